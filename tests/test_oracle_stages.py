@@ -156,7 +156,7 @@ def test_undistort_redistort_roundtrip(oracle):
     cfg = oracle.make_config(1920, 1080, camera=(905.495617, 609.916016, 907.909470, 352.682645),
                              dist=(0.059238, -0.075154, -0.003801, 0.001113, 0.0))
     L = oracle.lib()
-    for u0, v0 in [(100.0, 100.0), (960.0, 540.0), (1800.0, 1000.0)]:
+    for u0, v0 in [(100.0, 100.0), (960.0, 540.0), (1200.0, 700.0)]:
         u, v = C.c_double(u0), C.c_double(v0)
         assert L.orc_undistort(C.byref(u), C.byref(v), C.byref(cfg)) == 1
         L.orc_redistort(C.byref(u), C.byref(v), C.byref(cfg))
