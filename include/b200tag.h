@@ -1,0 +1,235 @@
+/*
+ * b200tag -- C ABI of the B200-native AprilTag detection engine.
+ *
+ * This is the drop-in boundary for the hot path of Team766/ros_vision's
+ * `apriltags_cuda` package: everything frc971::apriltag::GpuDetector does per
+ * frame (reference: src/apriltags_cuda/include/apriltags_cuda/apriltag_gpu.h:77-359,
+ * src/apriltags_cuda/src/apriltag_gpu.cu:725-1166, src/apriltags_cuda/src/apriltag_detect.cu).
+ * The C++ class with the reference's own name and members is layered on these
+ * entry points in include/apriltags_cuda/apriltag_gpu.h; INTEGRATION.md shows how
+ * the ROS 2 node links it.
+ *
+ * Plain C types only: pointers, sizes, PODs.  All functions return 0 on success
+ * or a negative B200TAG_E_* code; b200tag_error_string() describes it.  There is
+ * no CPU fallback: without a CUDA device b200tag_create fails with
+ * B200TAG_E_NO_DEVICE.
+ */
+#ifndef B200TAG_H_
+#define B200TAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TAG_ABI_VERSION 1
+
+/* Input pixel formats.  The reference accepts YUYV only (apriltag_gpu.h:89); the
+ * node converts bgr8 -> YUYV on the CPU first (apriltags_cuda_detector.cu:399-401),
+ * which B200TAG_FMT_BGR8 makes unnecessary. */
+enum { B200TAG_FMT_GRAY8 = 0, B200TAG_FMT_YUYV = 1, B200TAG_FMT_BGR8 = 2 };
+
+enum {
+  B200TAG_OK = 0,
+  B200TAG_E_INVALID = -1,    /* bad argument / unsupported configuration */
+  B200TAG_E_NO_DEVICE = -2,  /* no usable CUDA device */
+  B200TAG_E_CUDA = -3,       /* a CUDA call failed (see b200tag_last_error) */
+  B200TAG_E_OVERFLOW = -4,   /* a fixed-capacity device buffer overflowed on this frame */
+  B200TAG_E_NOMEM = -5,
+};
+
+/* Bits of b200tag_frame_info.status (non-zero => results for that frame are incomplete). */
+enum {
+  B200TAG_ST_POINTS_OVERFLOW = 1u << 0,
+  B200TAG_ST_HASH_OVERFLOW = 1u << 1,
+  B200TAG_ST_BLOBS_OVERFLOW = 1u << 2,
+  B200TAG_ST_QUADS_OVERFLOW = 1u << 3,
+  B200TAG_ST_DETS_OVERFLOW = 1u << 4,
+};
+
+/* Mirrors the fields of apriltag_detector_t / apriltag_quad_thresh_params that the
+ * reference reads (apriltag_gpu.cu:166-181,737,884,1084-1086; apriltag_detect.cu:229,
+ * 244,455,580) plus CameraMatrix / DistCoeffs (apriltag_gpu.h:61-74). */
+typedef struct b200tag_config {
+  int32_t abi_version;    /* B200TAG_ABI_VERSION */
+  int32_t width, height;  /* full-resolution frame; width/quad_decimate and height/quad_decimate
+                             must be multiples of 4 (the reference requires W%8==0, H%8==0 at decimate 2) */
+  int32_t format;         /* B200TAG_FMT_* */
+  int32_t quad_decimate;  /* integer >= 1 (the reference: exactly 2, apriltag_gpu.cu:166) */
+  float quad_sigma;       /* Gaussian blur of the quad image; 0 = off (ignored by the reference) */
+  int32_t refine_edges;
+  double decode_sharpening;
+  int32_t min_cluster_pixels;
+  int32_t max_nmaxima;    /* must be 10 (line_fit_filter.cu:1205) */
+  float cos_critical_rad;
+  float max_line_fit_mse;
+  int32_t min_white_black_diff;
+  double fx, cx, fy, cy;      /* CameraMatrix */
+  double k1, k2, p1, p2, k3;  /* DistCoeffs */
+  int32_t max_batch;      /* frames per call that buffers are sized for (>= 1) */
+  int32_t device;         /* CUDA device ordinal, -1 = current device */
+  int32_t keep_stages;    /* 1 = also keep debug-only stage arrays (filtered min/max, fit quads) */
+  uint32_t max_points;    /* capacity of the boundary-point list per frame; 0 = default (2 * quad pixels) */
+  uint32_t max_blobs;     /* capacity of the candidate-blob list per frame; 0 = default */
+  uint32_t max_detections;/* per frame; 0 = default (256) */
+  int32_t reserved[8];
+} b200tag_config;
+
+/* apriltag_detection_t (libapriltag apriltag.h) flattened: id, hamming, decision_margin,
+ * H (row-major 3x3), centre, corners. */
+typedef struct b200tag_detection {
+  int32_t id;
+  int32_t hamming;
+  float decision_margin;
+  int32_t frame; /* index within the batch */
+  double H[9];
+  double c[2];
+  double p[4][2];
+} b200tag_detection;
+
+/* frc971::apriltag::QuadCorners (apriltag_gpu.h:55-59). */
+typedef struct b200tag_quad {
+  float corners[4][2];
+  int32_t reversed_border;
+  uint32_t blob_index;
+  uint32_t rep0, rep1; /* the two component labels bounding the blob */
+} b200tag_quad;
+
+typedef struct b200tag_frame_info {
+  uint32_t status; /* B200TAG_ST_* */
+  uint32_t num_points;
+  uint32_t num_clusters;
+  uint32_t num_blobs;
+  uint32_t num_selected_points;
+  uint32_t num_fit_quads;
+  uint32_t num_quads;
+  uint32_t num_detections; /* before host-side reconcile */
+} b200tag_frame_info;
+
+/* Stage selectors for b200tag_copy_stage: the reference's Copy*To debug accessors
+ * (apriltag_gpu.h:98-183), generalised. */
+enum {
+  B200TAG_STAGE_GRAY = 0,        /* uint8[W*H]                      CopyGrayTo */
+  B200TAG_STAGE_QUAD_IMAGE = 1,  /* uint8[w*h]                      CopyDecimatedTo */
+  B200TAG_STAGE_THRESHOLD = 2,   /* uint8[w*h]                      CopyThresholdedTo */
+  B200TAG_STAGE_LABELS = 3,      /* uint32[w*h]                     CopyUnionMarkersTo */
+  B200TAG_STAGE_SIZES = 4,       /* uint32[w*h]                     CopyUnionMarkersSizeTo */
+  B200TAG_STAGE_POINTS = 5,      /* b200tag_point[num_points]       CopyCompressedUnionMarkerPairTo */
+  B200TAG_STAGE_BLOBS = 6,       /* b200tag_blob[num_blobs]         CopySelectedExtents */
+  B200TAG_STAGE_SORTED_POINTS = 7,/* uint64[num_selected_points]    CopySortedSelectedBlobs */
+  B200TAG_STAGE_LINE_FIT_POINTS = 8, /* b200tag_lfp[...]            CopyLineFitPoints */
+  B200TAG_STAGE_ERRORS = 9,      /* float[num_selected_points]      CopyErrors */
+  B200TAG_STAGE_FILTERED_ERRORS = 10, /* double[...]                CopyFilteredErrors */
+  B200TAG_STAGE_FIT_QUADS = 11,  /* b200tag_fit_quad[num_fit_quads] CopyFitQuads */
+  B200TAG_STAGE_QUADS = 12,      /* b200tag_quad[num_quads]         FitQuads() */
+  B200TAG_STAGE_RAW_DETECTIONS = 13, /* b200tag_detection[num_detections] before reconcile */
+  B200TAG_STAGE_MINMAX = 14,     /* uint8[(w/4)*(h/4)*2] filtered tile min,max */
+  B200TAG_STAGE_CLUSTERS = 15,   /* b200tag_blob[num_clusters] every blob pair, selected or not (keep_stages) */
+};
+
+typedef struct b200tag_point { /* one boundary point; QuadBoundaryPoint (points.h:25-161) unpacked */
+  uint32_t slot;  /* cluster slot (engine-internal id of the blob pair) */
+  uint16_t x, y;  /* half-pixel coordinates 2*base + d */
+  uint8_t dir, black_to_white, pad[2];
+} b200tag_point;
+
+typedef struct b200tag_blob { /* MinMaxExtents (line_fit_filter.h:14-59) + selection */
+  uint32_t rep0, rep1;
+  uint32_t min_x, min_y, max_x, max_y;
+  uint32_t count;
+  uint32_t offset; /* first point of this blob in the sorted-point arrays (selected blobs) */
+  int32_t gx_sum, gy_sum;
+  int64_t pxgx_plus_pygy_sum;
+  uint32_t slot;
+  int32_t selected;
+} b200tag_blob;
+
+typedef struct b200tag_lfp { /* LineFitPoint (line_fit_filter.h:61-83), inclusive per-blob prefix sums */
+  int64_t Mxx, Myy, Mxy, Mx, My, W;
+} b200tag_lfp;
+
+typedef struct b200tag_moments { /* LineFitMoments (line_fit_filter.h:85-94) */
+  int64_t Mx, My, W, Mxx, Myy, Mxy;
+  int32_t N, pad;
+} b200tag_moments;
+
+typedef struct b200tag_fit_quad { /* FitQuad (line_fit_filter.h:130-135) */
+  uint32_t blob_index;
+  int32_t valid;
+  int32_t num_peaks;
+  uint32_t indices[4];
+  uint32_t pad;
+  b200tag_moments moments[4];
+  double err;
+} b200tag_fit_quad;
+
+typedef struct b200tag_detector b200tag_detector;
+
+/* Fills `cfg` with libapriltag's apriltag_detector_create() defaults as the node sets them
+ * (apriltags_cuda_detector.cu:142-147): decimate 2, sigma 0, refine_edges on. */
+int b200tag_default_config(b200tag_config *cfg, int width, int height, int format);
+
+/* GpuDetector::GpuDetector (apriltag_gpu.cu:111-188): allocates every device buffer up front. */
+int b200tag_create(const b200tag_config *cfg, b200tag_detector **out);
+/* GpuDetector::~GpuDetector (apriltag_gpu.cu:190-200). */
+void b200tag_destroy(b200tag_detector *det);
+
+/* GpuDetector::Detect (apriltag_gpu.cu:725): `host_image` is one tightly packed frame in
+ * cfg.format (pageable or pinned); returns with detections ready. */
+int b200tag_detect(b200tag_detector *det, const uint8_t *host_image);
+/* `count` <= cfg.max_batch frames, each from its own host buffer. */
+int b200tag_detect_batch(b200tag_detector *det, const uint8_t *const *host_images, int count);
+/* Frames already resident in device memory, `count` frames `frame_stride_bytes` apart
+ * (0 = tightly packed).  Runs on the detector's stream and returns when results are on the host. */
+int b200tag_detect_device(b200tag_detector *det, const void *device_images, size_t frame_stride_bytes, int count);
+
+/* Asynchronous halves of b200tag_detect_device, for callers that time or overlap on the GPU:
+ * enqueue puts all device work + the result copy on the detector's stream, finish waits for it
+ * and builds the detection lists.  `stream_out` (optional) receives the cudaStream_t. */
+int b200tag_enqueue_device(b200tag_detector *det, const void *device_images, size_t frame_stride_bytes, int count);
+int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_images, int count);
+int b200tag_finish(b200tag_detector *det);
+void *b200tag_stream(b200tag_detector *det);
+
+/* GpuDetector::Detections(): detections of frame `frame` of the last call, after reconcile,
+ * sorted by id.  The array is owned by the detector and valid until the next detect call. */
+const b200tag_detection *b200tag_detections(const b200tag_detector *det, int frame, int *count);
+/* GpuDetector::FitQuads(). */
+const b200tag_quad *b200tag_quads(const b200tag_detector *det, int frame, int *count);
+int b200tag_frame_info_get(const b200tag_detector *det, int frame, b200tag_frame_info *info);
+
+/* Copies one intermediate stage of frame `frame` to `dst` (host).  `out_bytes` receives the
+ * stage size; returns B200TAG_E_INVALID if cap_bytes is too small. */
+int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, size_t cap_bytes, size_t *out_bytes);
+
+/* SetCameraMatrix / SetDistortionCoefficients (apriltag_gpu.h:189-195). */
+int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, double cy);
+int b200tag_set_distortion(b200tag_detector *det, double k1, double k2, double p1, double p2, double k3);
+
+/* GpuDetector::UnDistort (apriltag_gpu.h:199-200, apriltag_detect.cu:335-402). Pure host helper. */
+int b200tag_undistort(double *u, double *v, double fx, double cx, double fy, double cy, double k1, double k2,
+                      double p1, double p2, double k3);
+
+/* Pinned host staging memory, so b200tag_detect* can overlap H2D with compute. */
+void *b200tag_alloc_pinned(size_t bytes);
+void b200tag_free_pinned(void *p);
+
+/* Number of this library's kernels launched per frame batch (for benchmarks' gpu_launches). */
+int b200tag_kernels_per_batch(const b200tag_detector *det);
+/* Per-kernel device time of the last b200tag_profile_device call (ms); names are static strings. */
+int b200tag_profile_device(b200tag_detector *det, const void *device_images, size_t frame_stride_bytes, int count,
+                           int iters, const char **names, float *ms, int cap, int *n);
+
+/* Test hook: out[i] = atan2f(a[i], b[i]) (op 0) or hypotf(a[i], b[i]) (op 1) evaluated on the device. */
+int b200tag_debug_math(int op, const float *a, const float *b, float *out, int n);
+
+const char *b200tag_error_string(int code);
+const char *b200tag_last_error(const b200tag_detector *det);
+int b200tag_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TAG_H_ */

@@ -1,0 +1,714 @@
+// Host side of the C ABI (include/b200tag.h): device-buffer arena, stream, launch sequence,
+// result hand-off.  Mirrors the life cycle of frc971::apriltag::GpuDetector
+// (reference: src/apriltags_cuda/src/apriltag_gpu.cu:111-220,725-1166) without any of its seven
+// mid-frame host synchronisations: every data-dependent size stays in device counters.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200tag.h"
+#include "dev_types.h"
+#include "kernels.h"
+
+namespace b200tag {
+int upload_family();
+}
+
+using namespace b200tag;
+
+struct b200tag_detector {
+  b200tag_config cfg;
+  FrameParams fp;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
+  uint8_t *d_in = nullptr;  // internal input staging (frames copied from the host)
+  size_t in_bytes = 0;      // bytes per frame of input
+  // host-visible results
+  Counters *h_counters = nullptr;          // pinned, max_batch
+  b200tag_detection *h_dets = nullptr;     // pinned + mapped, max_batch * det_cap (kernels write here)
+  b200tag_detection *d_dets_alias = nullptr;
+  std::vector<std::vector<b200tag_detection>> dets;  // after reconcile
+  std::vector<std::vector<b200tag_quad>> quads;
+  std::vector<bool> quads_valid;
+  int last_count = 0;
+  bool pending = false;
+  int kernels_per_batch = 0;
+  std::string err;
+  KernelTimer timer;
+};
+
+namespace b200tag {
+// test hook: evaluates the device libm routines the hot path depends on (atan2f / hypotf)
+__global__ void k_debug_math(int op, const float *a, const float *b, float *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = op == 0 ? atan2f(a[i], b[i]) : hypotf(a[i], b[i]);
+}
+}  // namespace b200tag
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char buf_[512];                                                                             \
+      snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      det->err = buf_;                                                                            \
+      return B200TAG_E_CUDA;                                                                      \
+    }                                                                                             \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ArenaPlan {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+int blur_kernel(float quad_sigma, uint8_t *k) {  // image_u8_gaussian_blur's kernel (libapriltag, recalled)
+  const float sigma = fabsf(quad_sigma);
+  int ksz = static_cast<int>(4 * sigma);
+  if ((ksz & 1) == 0) ksz++;
+  if (ksz <= 1) return 0;
+  if (ksz > 31) ksz = 31;
+  double dk[32], acc = 0;
+  for (int i = 0; i < ksz; i++) {
+    const int x = -ksz / 2 + i;
+    const double q = x / sigma;
+    dk[i] = exp(-.5 * q * q);
+    acc += dk[i];
+  }
+  for (int i = 0; i < ksz; i++) k[i] = static_cast<uint8_t>(dk[i] / acc * 255);
+  return ksz;
+}
+
+// reconcile_detections (libapriltag; declared at apriltag_detect.cu:31-32, called at :660) ------
+bool seg_intersect(const double *a0, const double *a1, const double *b0, const double *b1) {
+  const double d1x = a1[0] - a0[0], d1y = a1[1] - a0[1];
+  const double d2x = b1[0] - b0[0], d2y = b1[1] - b0[1];
+  const double den = d1x * d2y - d1y * d2x;
+  if (den == 0) return false;
+  const double t = ((b0[0] - a0[0]) * d2y - (b0[1] - a0[1]) * d2x) / den;
+  const double u = ((b0[0] - a0[0]) * d1y - (b0[1] - a0[1]) * d1x) / den;
+  return t >= 0 && t <= 1 && u >= 0 && u <= 1;
+}
+bool poly_contains(const double p[4][2], const double *q) {
+  bool c = false;
+  for (int i = 0, j = 3; i < 4; j = i++) {
+    if (((p[i][1] > q[1]) != (p[j][1] > q[1])) &&
+        (q[0] < (p[j][0] - p[i][0]) * (q[1] - p[i][1]) / (p[j][1] - p[i][1]) + p[i][0]))
+      c = !c;
+  }
+  return c;
+}
+bool polys_overlap(const double a[4][2], const double b[4][2]) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      if (seg_intersect(a[i], a[(i + 1) & 3], b[j], b[(j + 1) & 3])) return true;
+  double ca[2] = {0, 0}, cb[2] = {0, 0};
+  for (int i = 0; i < 4; i++) {
+    ca[0] += a[i][0] / 4; ca[1] += a[i][1] / 4;
+    cb[0] += b[i][0] / 4; cb[1] += b[i][1] / 4;
+  }
+  return poly_contains(a, cb) || poly_contains(b, ca);
+}
+int prefer_smaller(int pref, double q0, double q1) {
+  if (pref) return pref;
+  if (q0 < q1) return -1;
+  if (q1 < q0) return 1;
+  return 0;
+}
+bool det_less(const b200tag_detection &a, const b200tag_detection &b) {  // detection_compare_function + tie-break
+  if (a.id != b.id) return a.id < b.id;
+  if (a.c[0] != b.c[0]) return a.c[0] < b.c[0];
+  if (a.c[1] != b.c[1]) return a.c[1] < b.c[1];
+  return a.hamming < b.hamming;
+}
+void reconcile(std::vector<b200tag_detection> &d) {
+  std::sort(d.begin(), d.end(), det_less);  // device append order is arbitrary: fix it first
+  int n = static_cast<int>(d.size());
+  for (int i0 = 0; i0 < n; i0++) {
+    for (int i1 = i0 + 1; i1 < n; i1++) {
+      if (d[i0].id != d[i1].id) continue;
+      if (!polys_overlap(d[i0].p, d[i1].p)) continue;
+      int pref = 0;
+      pref = prefer_smaller(pref, d[i0].hamming, d[i1].hamming);
+      pref = prefer_smaller(pref, -d[i0].decision_margin, -d[i1].decision_margin);
+      for (int i = 0; i < 4; i++) {
+        pref = prefer_smaller(pref, d[i0].p[i][0], d[i1].p[i][0]);
+        pref = prefer_smaller(pref, d[i0].p[i][1], d[i1].p[i][1]);
+      }
+      if (pref < 0) {
+        d[i1] = d[n - 1];
+        n--;
+        i1--;
+      } else {
+        d[i0] = d[n - 1];
+        n--;
+        i0--;
+        break;
+      }
+    }
+  }
+  d.resize(n);
+  std::sort(d.begin(), d.end(), det_less);
+}
+
+int validate(const b200tag_config &c, std::string *why) {
+  auto bad = [&](const char *m) { *why = m; return B200TAG_E_INVALID; };
+  if (c.abi_version != B200TAG_ABI_VERSION) return bad("abi_version mismatch");
+  if (c.width <= 0 || c.height <= 0) return bad("width/height must be positive");
+  if (c.format < B200TAG_FMT_GRAY8 || c.format > B200TAG_FMT_BGR8) return bad("unknown format");
+  if (c.quad_decimate < 1 || c.quad_decimate > 8) return bad("quad_decimate must be an integer in [1, 8]");
+  if (c.width % c.quad_decimate || c.height % c.quad_decimate) return bad("frame size must be divisible by quad_decimate");
+  const int w = c.width / c.quad_decimate, h = c.height / c.quad_decimate;
+  if (w % 4 || h % 4 || w < 8 || h < 8) return bad("quad image dimensions must be multiples of 4 (threshold.cu:156-157)");
+  if (w > 4096 || h > 4096) return bad("quad image larger than 4096x4096 (12-bit point coordinates)");
+  if (c.format == B200TAG_FMT_YUYV && (c.width % 8)) return bad("YUYV frames need width % 8 == 0");
+  if (c.max_nmaxima != 10) return bad("max_nmaxima must be 10 (line_fit_filter.cu:1205)");
+  if (c.max_batch < 1 || c.max_batch > 4096) return bad("max_batch out of range");
+  return 0;
+}
+
+void build_params(b200tag_detector *det) {
+  const b200tag_config &c = det->cfg;
+  FrameParams &p = det->fp;
+  memset(&p, 0, sizeof(p));
+  p.W = c.width; p.H = c.height; p.f = c.quad_decimate;
+  p.w = c.width / p.f; p.h = c.height / p.f;
+  p.fmt = c.format;
+  p.tiles_x = p.w / 4; p.tiles_y = p.h / 4;
+  p.blur_ksz = c.quad_sigma != 0 ? blur_kernel(c.quad_sigma, p.blur_k) : 0;
+  p.sharpen = c.quad_sigma < 0;
+  p.min_white_black_diff = c.min_white_black_diff;
+  p.min_cluster_pixels = static_cast<uint32_t>(std::max(24, c.min_cluster_pixels));  // apriltag_gpu.cu:529
+  p.max_cluster_pixels = static_cast<uint32_t>(4 * (p.w + p.h));                      // :871 in quad-image units
+  int mtw = 8;  // tag36h11 width_at_border; apriltag_gpu.cu:169-181
+  mtw = static_cast<int>(static_cast<float>(mtw) / static_cast<float>(p.f));
+  if (mtw < 3) mtw = 3;
+  p.min_tag_width = mtw;
+  p.normal_border = 1; p.reversed_border = 0;
+  p.cos_critical_rad = c.cos_critical_rad;
+  p.max_line_fit_mse = c.max_line_fit_mse;
+  p.refine_edges = c.refine_edges;
+  p.decode_sharpening = c.decode_sharpening;
+  p.fx = c.fx; p.cx = c.cx; p.fy = c.fy; p.cy = c.cy;
+  p.k1 = c.k1; p.k2 = c.k2; p.p1 = c.p1; p.p2 = c.p2; p.k3 = c.k3;
+  p.keep_stages = c.keep_stages;
+}
+
+int finish_impl(b200tag_detector *det) {
+  if (!det->pending) return 0;
+  CK(cudaStreamSynchronize(det->stream));
+  det->pending = false;
+  int rc = 0;
+  for (int f = 0; f < det->last_count; f++) {
+    const Counters &c = det->h_counters[f];
+    const uint32_t nd = std::min(c.num_detections, det->fp.det_cap);
+    const b200tag_detection *src = det->h_dets + static_cast<size_t>(f) * det->fp.det_cap;
+    det->dets[f].assign(src, src + nd);
+    reconcile(det->dets[f]);
+    det->quads_valid[f] = false;
+    if (c.status) rc = B200TAG_E_OVERFLOW;
+  }
+  if (rc) det->err = "a fixed-capacity device buffer overflowed; see b200tag_frame_info.status";
+  return rc;
+}
+
+int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt) {
+  FrameParams p = det->fp;
+  p.in = static_cast<const uint8_t *>(device_images);
+  p.in_stride = stride ? stride : det->in_bytes;
+  if (det->cfg.format == B200TAG_FMT_GRAY8) {
+    p.gray = const_cast<uint8_t *>(p.in);
+    p.gray_stride = p.in_stride;
+  }
+  CK(cudaMemsetAsync(p.counters, 0, sizeof(Counters) * count, det->stream));
+  int launches = 0;
+  launches += launch_frontend(p, count, det->stream, kt);
+  launches += launch_blobs(p, count, det->stream, kt);
+  launches += launch_decode(p, count, det->stream, kt);
+  det->kernels_per_batch = launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(det->h_counters, p.counters, sizeof(Counters) * count, cudaMemcpyDeviceToHost, det->stream));
+  det->last_count = count;
+  det->pending = true;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200tag_version(void) { return B200TAG_ABI_VERSION; }
+
+const char *b200tag_error_string(int code) {
+  switch (code) {
+    case B200TAG_OK: return "ok";
+    case B200TAG_E_INVALID: return "invalid argument or unsupported configuration";
+    case B200TAG_E_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
+    case B200TAG_E_CUDA: return "CUDA error";
+    case B200TAG_E_OVERFLOW: return "device buffer overflow on this frame";
+    case B200TAG_E_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+const char *b200tag_last_error(const b200tag_detector *det) { return det ? det->err.c_str() : g_create_error.c_str(); }
+
+int b200tag_default_config(b200tag_config *cfg, int width, int height, int format) {
+  if (!cfg) return B200TAG_E_INVALID;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = B200TAG_ABI_VERSION;
+  cfg->width = width;
+  cfg->height = height;
+  cfg->format = format;
+  cfg->quad_decimate = 2;
+  cfg->quad_sigma = 0.0f;
+  cfg->refine_edges = 1;
+  cfg->decode_sharpening = 0.25;
+  cfg->min_cluster_pixels = 5;
+  cfg->max_nmaxima = 10;
+  cfg->cos_critical_rad = cosf(static_cast<float>(10 * 3.14159265358979323846 / 180));
+  cfg->max_line_fit_mse = 10.0f;
+  cfg->min_white_black_diff = 5;
+  cfg->fx = 1.0; cfg->fy = 1.0; cfg->cx = 0.0; cfg->cy = 0.0;
+  cfg->max_batch = 1;
+  cfg->device = -1;
+  cfg->keep_stages = 0;
+  return 0;
+}
+
+int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
+  if (!cfg || !out) return B200TAG_E_INVALID;
+  *out = nullptr;
+  std::string why;
+  if (int rc = validate(*cfg, &why)) {
+    g_create_error = why;
+    return rc;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device visible";
+    return B200TAG_E_NO_DEVICE;
+  }
+  b200tag_detector *det = new b200tag_detector();
+  det->cfg = *cfg;
+  auto fail = [&](int rc) {
+    g_create_error = det->err;
+    b200tag_destroy(det);
+    return rc;
+  };
+  if (cfg->device >= 0) {
+    if (cudaSetDevice(cfg->device) != cudaSuccess) {
+      det->err = "cudaSetDevice failed";
+      return fail(B200TAG_E_NO_DEVICE);
+    }
+  }
+  if (cudaGetDevice(&det->device) != cudaSuccess) {
+    det->err = "cudaGetDevice failed";
+    return fail(B200TAG_E_NO_DEVICE);
+  }
+  build_params(det);
+  FrameParams &p = det->fp;
+  const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
+  const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
+  const int B = cfg->max_batch;
+  const int bpp = cfg->format == B200TAG_FMT_GRAY8 ? 1 : (cfg->format == B200TAG_FMT_YUYV ? 2 : 3);
+  det->in_bytes = N * bpp;
+  p.point_cap = cfg->max_points ? cfg->max_points : static_cast<uint32_t>(2 * n);
+  uint32_t hc = 4096;
+  while (hc < n / 8) hc <<= 1;
+  p.hash_cap = hc;
+  p.blob_cap = cfg->max_blobs ? cfg->max_blobs : static_cast<uint32_t>(std::min<size_t>(65536, std::max<size_t>(4096, n / 32)));
+  p.quad_cap = std::min<uint32_t>(p.blob_cap, 8192);
+  p.det_cap = cfg->max_detections ? cfg->max_detections : 256;
+  p.cluster_cap = cfg->keep_stages ? hc : 0;
+
+  ArenaPlan plan;
+  const size_t o_in = plan.take(align_up(det->in_bytes, 256) * B);
+  const size_t in_stride = align_up(det->in_bytes, 256);
+  const size_t o_gray = cfg->format == B200TAG_FMT_GRAY8 ? 0 : plan.take(N * B);
+  const size_t o_quad = plan.take(n * B);
+  const size_t o_quad_tmp = p.blur_ksz ? plan.take(n * B) : 0;
+  const size_t o_mmr = plan.take(tiles * 2 * B);
+  const size_t o_mm = plan.take(tiles * 2 * B);
+  const size_t o_th = plan.take(n * B);
+  const size_t o_lab = plan.take(n * 4 * B);
+  const size_t o_sz = plan.take(n * 4 * B);
+  const size_t o_pts = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
+  const size_t HB = static_cast<size_t>(hc) * B;
+  const size_t o_hkey = plan.take(HB * 8);
+  const size_t o_hcnt = plan.take(HB * 4), o_hminx = plan.take(HB * 4), o_hminy = plan.take(HB * 4);
+  const size_t o_hmaxx = plan.take(HB * 4), o_hmaxy = plan.take(HB * 4), o_hgx = plan.take(HB * 4), o_hgy = plan.take(HB * 4);
+  const size_t o_hdot = plan.take(HB * 8);
+  const size_t o_sb = plan.take(HB * 4);
+  const size_t o_blobs = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_blob) * B);
+  const size_t o_fill = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
+  const size_t o_clusters = p.cluster_cap ? plan.take(static_cast<size_t>(p.cluster_cap) * sizeof(b200tag_blob) * B) : 0;
+  const size_t o_seg = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
+  const size_t o_lfp = plan.take(static_cast<size_t>(p.point_cap) * sizeof(b200tag_lfp) * B);
+  const size_t o_errs = plan.take(static_cast<size_t>(p.point_cap) * 4 * B);
+  const size_t o_filt = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
+  const size_t o_fq = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_fit_quad) * B);
+  const size_t o_quads = plan.take(static_cast<size_t>(p.quad_cap) * sizeof(b200tag_quad) * B);
+  const size_t o_ctr = plan.take(sizeof(Counters) * B);
+  det->arena_bytes = plan.off;
+  cudaError_t e = cudaMalloc(&det->arena, det->arena_bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cudaMalloc of %zu bytes failed: %s", det->arena_bytes, cudaGetErrorString(e));
+    det->err = buf;
+    det->arena = nullptr;
+    return fail(e == cudaErrorMemoryAllocation ? B200TAG_E_NOMEM : B200TAG_E_NO_DEVICE);
+  }
+  uint8_t *base = static_cast<uint8_t *>(det->arena);
+  det->d_in = base + o_in;
+  p.in = det->d_in; p.in_stride = in_stride;
+  det->in_bytes = N * bpp;
+  if (cfg->format == B200TAG_FMT_GRAY8) { p.gray = det->d_in; p.gray_stride = in_stride; }
+  else { p.gray = base + o_gray; p.gray_stride = N; }
+  p.quad = base + o_quad; p.quad_stride = n;
+  p.quad_tmp = p.blur_ksz ? base + o_quad_tmp : nullptr;
+  p.minmax_raw = base + o_mmr; p.minmax_stride = tiles * 2;
+  p.minmax = base + o_mm;
+  p.thresh = base + o_th;
+  p.labels = reinterpret_cast<uint32_t *>(base + o_lab);
+  p.sizes = reinterpret_cast<uint32_t *>(base + o_sz);
+  p.points = reinterpret_cast<uint64_t *>(base + o_pts);
+  p.h_key = reinterpret_cast<unsigned long long *>(base + o_hkey);
+  p.h_count = reinterpret_cast<uint32_t *>(base + o_hcnt);
+  p.h_minx = reinterpret_cast<uint32_t *>(base + o_hminx);
+  p.h_miny = reinterpret_cast<uint32_t *>(base + o_hminy);
+  p.h_maxx = reinterpret_cast<uint32_t *>(base + o_hmaxx);
+  p.h_maxy = reinterpret_cast<uint32_t *>(base + o_hmaxy);
+  p.h_gx = reinterpret_cast<int32_t *>(base + o_hgx);
+  p.h_gy = reinterpret_cast<int32_t *>(base + o_hgy);
+  p.h_dot = reinterpret_cast<long long *>(base + o_hdot);
+  p.slot_blob = reinterpret_cast<int32_t *>(base + o_sb);
+  p.blobs = reinterpret_cast<b200tag_blob *>(base + o_blobs);
+  p.blob_fill = reinterpret_cast<uint32_t *>(base + o_fill);
+  p.clusters = p.cluster_cap ? reinterpret_cast<b200tag_blob *>(base + o_clusters) : nullptr;
+  p.seg_keys = reinterpret_cast<uint64_t *>(base + o_seg);
+  p.lfp = reinterpret_cast<b200tag_lfp *>(base + o_lfp);
+  p.errs = reinterpret_cast<float *>(base + o_errs);
+  p.filt = reinterpret_cast<double *>(base + o_filt);
+  p.fit_quads = reinterpret_cast<b200tag_fit_quad *>(base + o_fq);
+  p.quads = reinterpret_cast<b200tag_quad *>(base + o_quads);
+  p.counters = reinterpret_cast<Counters *>(base + o_ctr);
+
+  auto ck = [&](cudaError_t ce, const char *what) {
+    if (ce != cudaSuccess) {
+      det->err = std::string(what) + ": " + cudaGetErrorString(ce);
+      return false;
+    }
+    return true;
+  };
+  if (!ck(cudaStreamCreateWithFlags(&det->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(B200TAG_E_CUDA);
+  if (!ck(cudaHostAlloc(reinterpret_cast<void **>(&det->h_counters), sizeof(Counters) * B, cudaHostAllocDefault), "cudaHostAlloc"))
+    return fail(B200TAG_E_CUDA);
+  if (!ck(cudaHostAlloc(reinterpret_cast<void **>(&det->h_dets), sizeof(b200tag_detection) * p.det_cap * B, cudaHostAllocMapped),
+          "cudaHostAlloc(mapped)"))
+    return fail(B200TAG_E_CUDA);
+  if (!ck(cudaHostGetDevicePointer(reinterpret_cast<void **>(&det->d_dets_alias), det->h_dets, 0), "cudaHostGetDevicePointer"))
+    return fail(B200TAG_E_CUDA);
+  p.dets = det->d_dets_alias;  // the decode kernel writes detections straight into pinned host memory
+  if (upload_family() != 0) {
+    det->err = "uploading the tag family failed";
+    return fail(B200TAG_E_CUDA);
+  }
+  launch_hash_clear(p, B, det->stream);
+  if (!ck(cudaStreamSynchronize(det->stream), "initial hash clear")) return fail(B200TAG_E_CUDA);
+  det->dets.resize(B);
+  det->quads.resize(B);
+  det->quads_valid.assign(B, false);
+  memset(det->h_counters, 0, sizeof(Counters) * B);
+  *out = det;
+  return 0;
+}
+
+void b200tag_destroy(b200tag_detector *det) {
+  if (!det) return;
+  if (det->stream) {
+    cudaStreamSynchronize(det->stream);
+    cudaStreamDestroy(det->stream);
+  }
+  if (det->arena) cudaFree(det->arena);
+  if (det->h_counters) cudaFreeHost(det->h_counters);
+  if (det->h_dets) cudaFreeHost(det->h_dets);
+  delete det;
+}
+
+int b200tag_enqueue_device(b200tag_detector *det, const void *device_images, size_t stride, int count) {
+  if (!det || !device_images || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  if (det->pending) {
+    if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
+  }
+  return enqueue_impl(det, device_images, stride, count, nullptr);
+}
+
+int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_images, int count) {
+  if (!det || !host_images || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  if (det->pending) {
+    if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
+  }
+  for (int f = 0; f < count; f++) {
+    if (!host_images[f]) return B200TAG_E_INVALID;
+    // GpuMemory::MemcpyAsyncFrom, apriltag_gpu.cu:729 (works for pageable and pinned buffers)
+    CK(cudaMemcpyAsync(det->d_in + static_cast<size_t>(f) * det->fp.in_stride, host_images[f], det->in_bytes,
+                       cudaMemcpyHostToDevice, det->stream));
+  }
+  return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+}
+
+int b200tag_finish(b200tag_detector *det) {
+  if (!det) return B200TAG_E_INVALID;
+  return finish_impl(det);
+}
+
+void *b200tag_stream(b200tag_detector *det) { return det ? static_cast<void *>(det->stream) : nullptr; }
+
+int b200tag_detect_device(b200tag_detector *det, const void *device_images, size_t stride, int count) {
+  if (int rc = b200tag_enqueue_device(det, device_images, stride, count)) return rc;
+  return b200tag_finish(det);
+}
+
+int b200tag_detect_batch(b200tag_detector *det, const uint8_t *const *host_images, int count) {
+  if (int rc = b200tag_enqueue_host(det, host_images, count)) return rc;
+  return b200tag_finish(det);
+}
+
+int b200tag_detect(b200tag_detector *det, const uint8_t *host_image) {
+  const uint8_t *imgs[1] = {host_image};
+  return b200tag_detect_batch(det, imgs, 1);
+}
+
+const b200tag_detection *b200tag_detections(const b200tag_detector *det, int frame, int *count) {
+  if (count) *count = 0;
+  if (!det || frame < 0 || frame >= det->last_count || det->pending) return nullptr;
+  if (count) *count = static_cast<int>(det->dets[frame].size());
+  return det->dets[frame].data();
+}
+
+int b200tag_frame_info_get(const b200tag_detector *det, int frame, b200tag_frame_info *info) {
+  if (!det || !info || frame < 0 || frame >= det->last_count || det->pending) return B200TAG_E_INVALID;
+  const Counters &c = det->h_counters[frame];
+  info->status = c.status;
+  info->num_points = std::min(c.num_points, det->fp.point_cap);
+  info->num_clusters = c.num_clusters;
+  info->num_blobs = std::min(c.num_blobs, det->fp.blob_cap);
+  info->num_selected_points = c.num_selected_points;
+  info->num_fit_quads = std::min(c.num_fit_quads, det->fp.blob_cap);
+  info->num_quads = std::min(c.num_quads, det->fp.quad_cap);
+  info->num_detections = std::min(c.num_detections, det->fp.det_cap);
+  return 0;
+}
+
+const b200tag_quad *b200tag_quads(const b200tag_detector *cdet, int frame, int *count) {
+  if (count) *count = 0;
+  b200tag_detector *det = const_cast<b200tag_detector *>(cdet);
+  if (!det || frame < 0 || frame >= det->last_count || det->pending) return nullptr;
+  if (!det->quads_valid[frame]) {
+    const uint32_t nq = std::min(det->h_counters[frame].num_quads, det->fp.quad_cap);
+    det->quads[frame].resize(nq);
+    if (nq) {
+      if (cudaMemcpy(det->quads[frame].data(), det->fp.quads + static_cast<size_t>(frame) * det->fp.quad_cap,
+                     nq * sizeof(b200tag_quad), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return nullptr;
+      std::sort(det->quads[frame].begin(), det->quads[frame].end(), [](const b200tag_quad &a, const b200tag_quad &b) {
+        return a.rep0 != b.rep0 ? a.rep0 < b.rep0 : a.rep1 < b.rep1;
+      });
+    }
+    det->quads_valid[frame] = true;
+  }
+  if (count) *count = static_cast<int>(det->quads[frame].size());
+  return det->quads[frame].data();
+}
+
+int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, size_t cap, size_t *out_bytes) {
+  if (!det || frame < 0 || frame >= det->last_count || det->pending) return B200TAG_E_INVALID;
+  const FrameParams &p = det->fp;
+  const Counters &c = det->h_counters[frame];
+  const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
+  const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
+  const size_t f = static_cast<size_t>(frame);
+  const void *src = nullptr;
+  size_t bytes = 0;
+  const uint32_t np = std::min(c.num_points, p.point_cap);
+  const uint32_t nsel = std::min(c.num_selected_points, p.point_cap);
+  switch (stage) {
+    case B200TAG_STAGE_GRAY:
+      if (det->cfg.format == B200TAG_FMT_GRAY8) return B200TAG_E_INVALID;  // the gray image is the caller's input
+      src = p.gray + f * N; bytes = N; break;
+    case B200TAG_STAGE_QUAD_IMAGE: src = p.quad + f * n; bytes = n; break;
+    case B200TAG_STAGE_THRESHOLD: src = p.thresh + f * n; bytes = n; break;
+    case B200TAG_STAGE_LABELS: src = p.labels + f * n; bytes = n * 4; break;
+    case B200TAG_STAGE_SIZES: src = p.sizes + f * n; bytes = n * 4; break;
+    case B200TAG_STAGE_MINMAX:
+      if (!p.keep_stages) return B200TAG_E_INVALID;
+      src = p.minmax + f * tiles * 2; bytes = tiles * 2; break;
+    case B200TAG_STAGE_POINTS: {
+      bytes = static_cast<size_t>(np) * sizeof(b200tag_point);
+      if (out_bytes) *out_bytes = bytes;
+      if (!dst) return 0;
+      if (cap < bytes) return B200TAG_E_INVALID;
+      std::vector<uint64_t> raw(np);
+      if (np) CK(cudaMemcpy(raw.data(), p.points + f * p.point_cap, np * 8ull, cudaMemcpyDeviceToHost));
+      b200tag_point *o = static_cast<b200tag_point *>(dst);
+      for (uint32_t i = 0; i < np; i++) {
+        o[i].slot = point_slot(raw[i]);
+        o[i].x = static_cast<uint16_t>(point_x(raw[i]));
+        o[i].y = static_cast<uint16_t>(point_y(raw[i]));
+        o[i].dir = static_cast<uint8_t>(point_dir(raw[i]));
+        o[i].black_to_white = static_cast<uint8_t>(point_b2w(raw[i]));
+        o[i].pad[0] = o[i].pad[1] = 0;
+      }
+      return 0;
+    }
+    case B200TAG_STAGE_BLOBS: src = p.blobs + f * p.blob_cap; bytes = std::min(c.num_blobs, p.blob_cap) * sizeof(b200tag_blob); break;
+    case B200TAG_STAGE_CLUSTERS:
+      if (!p.clusters) return B200TAG_E_INVALID;
+      src = p.clusters + f * p.cluster_cap; bytes = std::min(c.num_clusters, p.cluster_cap) * sizeof(b200tag_blob); break;
+    case B200TAG_STAGE_SORTED_POINTS: src = p.seg_keys + f * p.point_cap; bytes = nsel * 8ull; break;
+    case B200TAG_STAGE_LINE_FIT_POINTS: src = p.lfp + f * p.point_cap; bytes = nsel * sizeof(b200tag_lfp); break;
+    case B200TAG_STAGE_ERRORS: src = p.errs + f * p.point_cap; bytes = nsel * 4ull; break;
+    case B200TAG_STAGE_FILTERED_ERRORS: src = p.filt + f * p.point_cap; bytes = nsel * 8ull; break;
+    case B200TAG_STAGE_FIT_QUADS: src = p.fit_quads + f * p.blob_cap; bytes = std::min(c.num_fit_quads, p.blob_cap) * sizeof(b200tag_fit_quad); break;
+    case B200TAG_STAGE_QUADS: src = p.quads + f * p.quad_cap; bytes = std::min(c.num_quads, p.quad_cap) * sizeof(b200tag_quad); break;
+    case B200TAG_STAGE_RAW_DETECTIONS: {
+      bytes = std::min(c.num_detections, p.det_cap) * sizeof(b200tag_detection);
+      if (out_bytes) *out_bytes = bytes;
+      if (!dst) return 0;
+      if (cap < bytes) return B200TAG_E_INVALID;
+      memcpy(dst, det->h_dets + f * p.det_cap, bytes);
+      return 0;
+    }
+    default: return B200TAG_E_INVALID;
+  }
+  if (out_bytes) *out_bytes = bytes;
+  if (!dst) return 0;
+  if (cap < bytes) return B200TAG_E_INVALID;
+  if (bytes) CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, double cy) {
+  if (!det) return B200TAG_E_INVALID;
+  det->cfg.fx = det->fp.fx = fx; det->cfg.cx = det->fp.cx = cx;
+  det->cfg.fy = det->fp.fy = fy; det->cfg.cy = det->fp.cy = cy;
+  return 0;
+}
+
+int b200tag_set_distortion(b200tag_detector *det, double k1, double k2, double p1, double p2, double k3) {
+  if (!det) return B200TAG_E_INVALID;
+  det->cfg.k1 = det->fp.k1 = k1; det->cfg.k2 = det->fp.k2 = k2; det->cfg.p1 = det->fp.p1 = p1;
+  det->cfg.p2 = det->fp.p2 = p2; det->cfg.k3 = det->fp.k3 = k3;
+  return 0;
+}
+
+int b200tag_undistort(double *u, double *v, double fx, double cx, double fy, double cy, double k1, double k2, double p1,
+                      double p2, double k3) {
+  // GpuDetector::UnDistort, apriltag_detect.cu:335-402
+  if (!u || !v) return B200TAG_E_INVALID;
+  int converged = 1;
+  const double xPP = (*u - cx) / fx, yPP = (*v - cy) / fy;
+  double xP = xPP, yP = yPP;
+  const double x0 = xP, y0 = yP;
+  double prev_x = 0, prev_y = 0;
+  int iterations = 0;
+  do {
+    prev_x = xP;
+    prev_y = yP;
+    const double rSq = xP * xP + yP * yP;
+    const double radial = 1 + (k1 * rSq) + (k2 * rSq * rSq) + (k3 * rSq * rSq * rSq);
+    const double radial_inv = 1 / radial;
+    const double tdx = 2 * p1 * xP * yP + p2 * (rSq + k3 * rSq * rSq * rSq);
+    const double tdy = p1 * (rSq + 2 * yP * yP) + 2 * p2 * xP * yP;
+    xP = (x0 - tdx) * radial_inv;
+    yP = (y0 - tdy) * radial_inv;
+    if (iterations > 100) { converged = 0; break; }
+    iterations++;
+  } while (std::fabs(xP - prev_x) > 1e-6 || std::fabs(yP - prev_y) > 1e-6);
+  *u = xP * fx + cx;
+  *v = yP * fy + cy;
+  return converged;
+}
+
+void *b200tag_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void b200tag_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int b200tag_debug_math(int op, const float *a, const float *b, float *out, int n) {
+  if (!a || !b || !out || n <= 0 || (op != 0 && op != 1)) return B200TAG_E_INVALID;
+  float *d = nullptr;
+  if (cudaMalloc(&d, sizeof(float) * 3 * static_cast<size_t>(n)) != cudaSuccess) {
+    cudaGetLastError();
+    return B200TAG_E_NO_DEVICE;
+  }
+  int rc = 0;
+  if (cudaMemcpy(d, a, sizeof(float) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d + n, b, sizeof(float) * n, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = B200TAG_E_CUDA;
+  if (!rc) {
+    b200tag::k_debug_math<<<(n + 255) / 256, 256>>>(op, d, d + n, d + 2 * static_cast<size_t>(n), n);
+    if (cudaMemcpy(out, d + 2 * static_cast<size_t>(n), sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200TAG_E_CUDA;
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int b200tag_kernels_per_batch(const b200tag_detector *det) { return det ? det->kernels_per_batch : 0; }
+
+int b200tag_profile_device(b200tag_detector *det, const void *device_images, size_t stride, int count, int iters,
+                           const char **names, float *ms, int cap, int *n_out) {
+  if (!det || !device_images || count < 1 || count > det->cfg.max_batch || iters < 1) return B200TAG_E_INVALID;
+  if (det->pending) finish_impl(det);
+  std::vector<double> acc;
+  for (int it = 0; it < iters; it++) {
+    det->timer.rewind();
+    if (int rc = enqueue_impl(det, device_images, stride, count, &det->timer)) return rc;
+    CK(cudaStreamSynchronize(det->stream));
+    const size_t ns = det->timer.cursor;
+    if (acc.size() < ns) acc.resize(ns, 0.0);
+    for (size_t i = 0; i < ns; i++) {
+      float t = 0;
+      CK(cudaEventElapsedTime(&t, det->timer.spans[i].a, det->timer.spans[i].b));
+      acc[i] += t;
+    }
+  }
+  finish_impl(det);
+  const int ns = static_cast<int>(acc.size());
+  if (n_out) *n_out = ns;
+  for (int i = 0; i < ns && i < cap; i++) {
+    if (names) names[i] = det->timer.spans[i].name;
+    if (ms) ms[i] = static_cast<float>(acc[i] / iters);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Device-side data layout of the B200 AprilTag engine (shared by all .cu files).
+//
+// One `FrameParams` describes the HBM layout of a batch: every per-frame array is
+// `base + frame * stride`; kernels take the struct by value and use blockIdx.y
+// (or a device-side loop) as the frame index.  See DESIGN.md "Data layout in HBM".
+#ifndef B200TAG_DEV_TYPES_H_
+#define B200TAG_DEV_TYPES_H_
+
+#include <stdint.h>
+
+#include "../../include/b200tag.h"
+
+namespace b200tag {
+
+constexpr uint32_t kMinBlobPixels = 25;      // apriltag_gpu.cu:284,306 (union_markers_size >= 25)
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kMaxPeaks = 10;                // line_fit_filter.cu:630 (kNMaxima)
+constexpr int kNumCombos = 210;              // line_fit_filter.h:160
+
+// Packed boundary point, 64 bit:  [63:40] cluster slot | [28:16] x | [15:3] y | [2:1] dir | [0] black_to_white
+// (the reference's QuadBoundaryPoint, points.h:25-161, carries 20-bit blob ids and
+// 10-bit coordinates; the slot indirection and 13-bit half-pixel coordinates lift
+// its 1024x1024 quad-image limit to 4096x4096).
+__host__ __device__ inline uint64_t pack_point(uint32_t slot, uint32_t x, uint32_t y, uint32_t dir, uint32_t b2w) {
+  return (static_cast<uint64_t>(slot) << 40) | (static_cast<uint64_t>(x) << 16) | (static_cast<uint64_t>(y) << 3) |
+         (static_cast<uint64_t>(dir) << 1) | b2w;
+}
+__host__ __device__ inline uint32_t point_slot(uint64_t p) { return static_cast<uint32_t>(p >> 40); }
+__host__ __device__ inline uint32_t point_x(uint64_t p) { return static_cast<uint32_t>(p >> 16) & 0x1fff; }
+__host__ __device__ inline uint32_t point_y(uint64_t p) { return static_cast<uint32_t>(p >> 3) & 0x1fff; }
+__host__ __device__ inline uint32_t point_dir(uint64_t p) { return static_cast<uint32_t>(p >> 1) & 3; }
+__host__ __device__ inline uint32_t point_b2w(uint64_t p) { return static_cast<uint32_t>(p) & 1; }
+
+// Sort key of a selected point inside its blob, 64 bit:
+//   [53:26] theta (28 bit, IndexPoint::theta, points.h:195-202) | [25:24] dir | [23:12] base y | [11:0] base x
+// Ascending key order == the reference's stable radix sort on (blob, theta) over the
+// (dir, y, x)-ordered compaction (apriltag_gpu.cu:788-825,944-956).
+__host__ __device__ inline uint64_t pack_sort_key(uint32_t theta, uint32_t dir, uint32_t by, uint32_t bx) {
+  return (static_cast<uint64_t>(theta) << 26) | (static_cast<uint64_t>(dir) << 24) | (static_cast<uint64_t>(by) << 12) | bx;
+}
+__host__ __device__ inline uint32_t key_theta(uint64_t k) { return static_cast<uint32_t>(k >> 26) & 0xfffffff; }
+__host__ __device__ inline uint32_t key_dir(uint64_t k) { return static_cast<uint32_t>(k >> 24) & 3; }
+__host__ __device__ inline uint32_t key_by(uint64_t k) { return static_cast<uint32_t>(k >> 12) & 0xfff; }
+__host__ __device__ inline uint32_t key_bx(uint64_t k) { return static_cast<uint32_t>(k) & 0xfff; }
+__host__ __device__ inline int dir_dx(uint32_t d) { return d == 2 ? 0 : (d == 3 ? -1 : 1); }
+__host__ __device__ inline int dir_dy(uint32_t d) { return d == 0 ? 0 : 1; }
+
+struct Counters {  // one per frame, zeroed before each frame
+  uint32_t status;
+  uint32_t num_points;
+  uint32_t num_clusters;
+  uint32_t num_blobs;
+  uint32_t num_selected_points;
+  uint32_t num_fit_quads;
+  uint32_t num_quads;
+  uint32_t num_detections;
+  uint32_t next_blob;  // dynamic work counters
+  uint32_t next_quad;
+  uint32_t pad[6];
+};
+static_assert(sizeof(Counters) == 64, "Counters layout");
+
+struct FrameParams {
+  // geometry
+  int32_t W, H;        // full resolution
+  int32_t w, h;        // quad image
+  int32_t f;           // quad_decimate
+  int32_t fmt;
+  int32_t tiles_x, tiles_y;  // 4x4 threshold tiles
+  int32_t blur_ksz;    // 0 = no blur
+  uint8_t blur_k[32];
+  int32_t sharpen;     // quad_sigma < 0
+  // detector parameters
+  int32_t min_white_black_diff;
+  uint32_t min_cluster_pixels;  // max(24, qtp.min_cluster_pixels)
+  uint32_t max_cluster_pixels;  // 4 * (w + h)
+  int32_t min_tag_width;
+  int32_t normal_border, reversed_border;
+  float cos_critical_rad;
+  float max_line_fit_mse;
+  int32_t refine_edges;
+  double decode_sharpening;
+  double fx, cx, fy, cy, k1, k2, p1, p2, k3;
+  int32_t keep_stages;
+  // capacities
+  uint32_t point_cap, hash_cap /* pow2 */, blob_cap, quad_cap, det_cap, cluster_cap;
+  // buffers (frame 0) and per-frame strides in elements
+  const uint8_t *in;    size_t in_stride;
+  uint8_t *gray;        size_t gray_stride;      // W*H (aliases `in` for GRAY8)
+  uint8_t *quad;        size_t quad_stride;      // w*h
+  uint8_t *quad_tmp;                              // w*h, blur scratch (same stride)
+  uint8_t *minmax_raw;  size_t minmax_stride;    // tiles*2
+  uint8_t *minmax;                                // tiles*2 filtered (keep_stages)
+  uint8_t *thresh;                                // w*h (quad_stride)
+  uint32_t *labels;                               // w*h (quad_stride)
+  uint32_t *sizes;                                // w*h
+  uint64_t *points;     // point_cap
+  // cluster hash (hash_cap each)
+  unsigned long long *h_key;
+  uint32_t *h_count, *h_minx, *h_miny, *h_maxx, *h_maxy;
+  int32_t *h_gx, *h_gy;
+  long long *h_dot;
+  int32_t *slot_blob;   // hash_cap
+  b200tag_blob *blobs;  // blob_cap
+  uint32_t *blob_fill;  // blob_cap
+  b200tag_blob *clusters;  // cluster_cap (keep_stages)
+  uint64_t *seg_keys;   // point_cap
+  b200tag_lfp *lfp;     // point_cap
+  float *errs;          // point_cap
+  double *filt;         // point_cap
+  b200tag_fit_quad *fit_quads;  // blob_cap
+  b200tag_quad *quads;  // quad_cap
+  b200tag_detection *dets;  // det_cap
+  Counters *counters;
+};
+
+}  // namespace b200tag
+
+#endif

@@ -1,0 +1,54 @@
+// Launch entry points of the engine's kernels (one translation unit per pipeline phase).
+#ifndef B200TAG_KERNELS_H_
+#define B200TAG_KERNELS_H_
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "dev_types.h"
+
+namespace b200tag {
+
+// Optional per-kernel CUDA-event timing (b200tag_profile_device); null in normal runs.
+struct KernelTimer {
+  struct Span {
+    const char *name;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
+  size_t cursor = 0;
+  bool recording = false;
+  void begin(const char *name, cudaStream_t s) {
+    if (cursor == spans.size()) {
+      Span sp{name, nullptr, nullptr};
+      cudaEventCreate(&sp.a);
+      cudaEventCreate(&sp.b);
+      spans.push_back(sp);
+    }
+    spans[cursor].name = name;
+    cudaEventRecord(spans[cursor].a, s);
+  }
+  void end(cudaStream_t s) {
+    cudaEventRecord(spans[cursor].b, s);
+    cursor++;
+  }
+  void rewind() { cursor = 0; }
+  ~KernelTimer() {
+    for (auto &sp : spans) {
+      cudaEventDestroy(sp.a);
+      cudaEventDestroy(sp.b);
+    }
+  }
+};
+
+// Each returns the number of kernels it launched.
+int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
+int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
+int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
+void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s);
+
+}  // namespace b200tag
+
+#endif

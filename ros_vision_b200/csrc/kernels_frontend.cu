@@ -1,0 +1,733 @@
+// Front-end kernels of the B200 AprilTag engine (sm_100a):
+//   K1  gray conversion + decimation + 4x4 tile min/max      (reference: threshold.cu:16-80)
+//   K1b Gaussian quad_sigma filter                            (upstream image_u8_gaussian_blur)
+//   K2  3x3 tile min/max dilation + adaptive threshold        (threshold.cu:84-147)
+//   K3  tile-local union-find in shared memory                (labeling_allegretti_2019_BKE.cu:114-300)
+//   K4  cross-tile merge with global atomicMin                (:302-338)
+//   K5  pointer-jumping compression + component sizes         (:287-300,340-462)
+//   K6  boundary points, ballot/match compaction, blob-pair hash with extents
+//                                                            (apriltag_gpu.cu:226-360,788-862)
+// All integer work: bit-exact against oracle/ by construction.  No tensor cores: nothing
+// here is a contraction; the bound is HBM/L2 bandwidth and atomics latency.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_types.h"
+#include "kernels.h"
+
+namespace b200tag {
+
+// ---------------------------------------------------------------------------------------------
+// K1: YUYV, decimate 2.  One thread = one threshold tile = 8x8 full-res pixels (128 B of YUYV):
+// eight independent 16-byte loads in flight per thread, 8-byte gray stores, 4-byte quad stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pre_yuyv_dec2(FrameParams p) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *in = p.in + frame * p.in_stride;
+  uint8_t *gray = p.gray + frame * N;
+  uint8_t *quad = p.quad + frame * n;
+  uint4 v[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const size_t row = static_cast<size_t>(ty) * 8 + r;
+    v[r] = __ldcs(reinterpret_cast<const uint4 *>(in + (row * p.W + static_cast<size_t>(tx) * 8) * 2));
+  }
+  uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const size_t row = static_cast<size_t>(ty) * 8 + r;
+    const uint32_t lo = __byte_perm(v[r].x, v[r].y, 0x6420);
+    const uint32_t hi = __byte_perm(v[r].z, v[r].w, 0x6420);
+    *reinterpret_cast<uint2 *>(gray + row * p.W + static_cast<size_t>(tx) * 8) = make_uint2(lo, hi);
+    if ((r & 1) == 0) {
+      const uint32_t d = __byte_perm(lo, hi, 0x6420);
+      const size_t qrow = static_cast<size_t>(ty) * 4 + (r >> 1);
+      *reinterpret_cast<uint32_t *>(quad + qrow * p.w + static_cast<size_t>(tx) * 4) = d;
+      mn = __vminu4(mn, d);
+      mx = __vmaxu4(mx, d);
+    }
+  }
+  mn = __vminu4(mn, mn >> 16);
+  mn = __vminu4(mn, mn >> 8);
+  mx = __vmaxu4(mx, mx >> 16);
+  mx = __vmaxu4(mx, mx >> 8);
+  uint8_t *mm = p.minmax_raw + (frame * static_cast<size_t>(p.tiles_x) * p.tiles_y + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+  *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn & 0xff, mx & 0xff);
+}
+
+__device__ __forceinline__ uint8_t luma_of(const uint8_t *in, int fmt, size_t i) {
+  if (fmt == B200TAG_FMT_GRAY8) return in[i];
+  if (fmt == B200TAG_FMT_YUYV) return in[2 * i];
+  const int b = in[3 * i], g = in[3 * i + 1], r = in[3 * i + 2];
+  // Y of cv::COLOR_BGR2YUV_YUYV, the conversion the node applies before Detect
+  // (apriltags_cuda_detector.cu:401)
+  return static_cast<uint8_t>((4211 * r + 8258 * g + 1606 * b + (1 << 13) + (16 << 14)) >> 14);
+}
+
+// K1 generic: any format, any integer decimation.  One thread = one threshold tile
+// (4f x 4f full-res pixels).  `dst_quad` is quad_tmp when a blur follows.
+__global__ void __launch_bounds__(128) k_pre_generic(FrameParams p, int write_minmax) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *in = p.in + frame * p.in_stride;
+  uint8_t *gray = p.gray + frame * N;
+  uint8_t *quad = (p.blur_ksz ? p.quad_tmp : p.quad) + frame * n;
+  const int f = p.f, span = 4 * f;
+  int mn = 255, mx = 0;
+  for (int r = 0; r < span; r++) {
+    const size_t row = static_cast<size_t>(ty) * span + r;
+    for (int c = 0; c < span; c++) {
+      const size_t col = static_cast<size_t>(tx) * span + c;
+      const uint8_t g = luma_of(in, p.fmt, row * p.W + col);
+      if (p.fmt != B200TAG_FMT_GRAY8) gray[row * p.W + col] = g;
+      if ((r % f) == 0 && (c % f) == 0) {
+        quad[(row / f) * p.w + col / f] = g;
+        mn = min(mn, static_cast<int>(g));
+        mx = max(mx, static_cast<int>(g));
+      }
+    }
+  }
+  if (write_minmax) {
+    uint8_t *mm = p.minmax_raw + (frame * static_cast<size_t>(p.tiles_x) * p.tiles_y + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+    mm[0] = static_cast<uint8_t>(mn);
+    mm[1] = static_cast<uint8_t>(mx);
+  }
+}
+
+// K1 for GRAY8 / BGR8 at decimate 1 with 16-byte accesses: one thread = 16 pixels of one row.
+// (config 3's input shape; tile min/max is computed by k_tile_minmax afterwards.)
+__global__ void __launch_bounds__(256) k_pre_bgr_dec1(FrameParams p) {
+  const size_t N = static_cast<size_t>(p.W) * p.H;
+  const int frame = blockIdx.y;
+  const size_t g16 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // group of 16 pixels
+  if (g16 * 16 >= N) return;
+  const uint8_t *in = p.in + frame * p.in_stride;
+  const uint4 *src = reinterpret_cast<const uint4 *>(in + g16 * 48);
+  const uint4 a = __ldcs(src), b = __ldcs(src + 1), c = __ldcs(src + 2);
+  const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int px = q * 4 + k, byte = px * 3;
+      const uint32_t bb = (wds[byte >> 2] >> ((byte & 3) * 8)) & 0xff;
+      const uint32_t gg = (wds[(byte + 1) >> 2] >> (((byte + 1) & 3) * 8)) & 0xff;
+      const uint32_t rr = (wds[(byte + 2) >> 2] >> (((byte + 2) & 3) * 8)) & 0xff;
+      const uint32_t y = (4211u * rr + 8258u * gg + 1606u * bb + (1u << 13) + (16u << 14)) >> 14;
+      o |= y << (8 * k);
+    }
+    out[q] = o;
+  }
+  const uint4 o4 = make_uint4(out[0], out[1], out[2], out[3]);
+  *reinterpret_cast<uint4 *>(p.gray + frame * N + g16 * 16) = o4;
+  uint8_t *quad = (p.blur_ksz ? p.quad_tmp : p.quad) + frame * N;
+  *reinterpret_cast<uint4 *>(quad + g16 * 16) = o4;
+}
+
+// K1b: separable Gaussian with upstream's border rule (convolve(): indices [ksz/2, sz-ksz+ksz/2)
+// are filtered, the rest copied), rows first then columns.
+__device__ __forceinline__ uint32_t blur_row(const uint8_t *src, int w, int x, int y, int ksz, const uint8_t *k) {
+  const int r = ksz >> 1;
+  if (x < r || x >= w - ksz + r) return src[static_cast<size_t>(y) * w + x];
+  uint32_t acc = 0;
+  for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(k[j]) * src[static_cast<size_t>(y) * w + x - r + j];
+  return (acc >> 8) & 0xff;
+}
+
+__global__ void __launch_bounds__(256) k_blur(FrameParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (x >= p.w) return;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *src = p.quad_tmp + frame * n;
+  uint8_t *dst = p.quad + frame * n;
+  const int ksz = p.blur_ksz, r = ksz >> 1;
+  uint32_t v;
+  if (y < r || y >= p.h - ksz + r) {
+    v = blur_row(src, p.w, x, y, ksz, p.blur_k);
+  } else {
+    uint32_t acc = 0;
+    for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * blur_row(src, p.w, x, y - r + j, ksz, p.blur_k);
+    v = (acc >> 8) & 0xff;
+  }
+  if (p.sharpen) {
+    int s = 2 * static_cast<int>(src[static_cast<size_t>(y) * p.w + x]) - static_cast<int>(v);
+    s = max(0, min(255, s));
+    v = static_cast<uint32_t>(s);
+  }
+  dst[static_cast<size_t>(y) * p.w + x] = static_cast<uint8_t>(v);
+}
+
+// 4x4 tile min/max of the quad image (threshold.cu:60-80).  One thread per tile.
+__global__ void __launch_bounds__(128) k_tile_minmax(FrameParams p) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *quad = p.quad + frame * n;
+  uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t d = *reinterpret_cast<const uint32_t *>(quad + (static_cast<size_t>(ty) * 4 + r) * p.w + static_cast<size_t>(tx) * 4);
+    mn = __vminu4(mn, d);
+    mx = __vmaxu4(mx, d);
+  }
+  mn = __vminu4(mn, mn >> 16);
+  mn = __vminu4(mn, mn >> 8);
+  mx = __vmaxu4(mx, mx >> 16);
+  mx = __vmaxu4(mx, mx >> 8);
+  uint8_t *mm = p.minmax_raw + (frame * static_cast<size_t>(p.tiles_x) * p.tiles_y + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+  *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn & 0xff, mx & 0xff);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: 3x3 dilation of the tile min/max (edge tiles skip missing neighbours) + threshold.
+// One thread per tile: 9 cached uchar2 reads, 4 x 4-byte pixel loads, 4 x 4-byte stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_threshold(FrameParams p) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
+  const uchar2 *raw = reinterpret_cast<const uchar2 *>(p.minmax_raw + frame * tiles * 2);
+  int mn = 255, mx = 0;
+#pragma unroll
+  for (int j = -1; j <= 1; j++) {
+    const int ry = ty + j;
+    if (ry < 0 || ry >= p.tiles_y) continue;
+#pragma unroll
+    for (int i = -1; i <= 1; i++) {
+      const int rx = tx + i;
+      if (rx < 0 || rx >= p.tiles_x) continue;
+      const uchar2 m = raw[static_cast<size_t>(ry) * p.tiles_x + rx];
+      mn = min(mn, static_cast<int>(m.x));
+      mx = max(mx, static_cast<int>(m.y));
+    }
+  }
+  if (p.keep_stages) {
+    uint8_t *mm = p.minmax + (frame * tiles + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+    *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn, mx);
+  }
+  const uint8_t *quad = p.quad + frame * n;
+  uint8_t *th = p.thresh + frame * n;
+  const bool flat = (mx - mn) < p.min_white_black_diff;
+  const int thr = mn + (mx - mn) / 2;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const size_t off = (static_cast<size_t>(ty) * 4 + r) * p.w + static_cast<size_t>(tx) * 4;
+    const uint32_t d = *reinterpret_cast<const uint32_t *>(quad + off);
+    uint32_t o = 0x7f7f7f7fu;
+    if (!flat) {
+      o = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (static_cast<int>((d >> (8 * k)) & 0xff) > thr) o |= 0xffu << (8 * k);
+    }
+    *reinterpret_cast<uint32_t *>(th + off) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Connected components.  255 is 8-connected, 0 is 4-connected, 127 joins nothing.
+// Label of a component = its smallest pixel index (roots are kept minimal by atomicMin
+// links), size[root] = pixel count.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCclTW = 64;  // tile width  (two 32-lane halves per row)
+constexpr int kCclTH = 32;  // tile height
+constexpr int kCclThreads = 256;
+
+__device__ __forceinline__ uint32_t sfind(volatile uint32_t *par, uint32_t a) {
+  uint32_t q = par[a];
+  while (q != a) {
+    a = q;
+    q = par[a];
+  }
+  return a;
+}
+
+__device__ __forceinline__ void sunite(uint32_t *par, uint32_t a, uint32_t b) {
+  while (true) {
+    a = sfind(par, a);
+    b = sfind(par, b);
+    if (a == b) return;
+    if (a < b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    const uint32_t old = atomicMin(&par[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// Start (x index) of the maximal run of set bits of `m` that contains bit x.
+__device__ __forceinline__ int run_start64(unsigned long long m, int x) {
+  const unsigned long long below = (~m) & ((1ull << x) - 1ull);
+  return below ? 64 - __clzll(static_cast<long long>(below)) : 0;
+}
+
+// K3: one CTA labels a 64x32 tile entirely in shared memory.  Rows are turned into run
+// bitmasks with __ballot_sync, every pixel starts out pointing at the first pixel of its
+// run, and only the pixels that begin an overlap with a run in the row above issue a union.
+__global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
+  __shared__ uint8_t s_px[kCclTH][kCclTW];
+  __shared__ unsigned long long s_white[kCclTH], s_black[kCclTH];
+  __shared__ uint32_t s_par[kCclTH * kCclTW];
+  __shared__ uint32_t s_cnt[kCclTH * kCclTW];
+
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *th = p.thresh + frame * n;
+  uint32_t *labels = p.labels + frame * n;
+  uint32_t *sizes = p.sizes + frame * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tw = min(kCclTW, p.w - x0), thh = min(kCclTH, p.h - y0);
+
+  // stage the tile: 16 pixels (16 bytes) per thread-iteration; quad width is a multiple of 4
+  for (int i = tid; i < kCclTH * (kCclTW / 4); i += kCclThreads) {
+    const int r = i / (kCclTW / 4), c4 = (i % (kCclTW / 4)) * 4;
+    uint32_t v = 0x7f7f7f7fu;  // outside the image: 127 (joins nothing)
+    if (r < thh && c4 < tw) v = *reinterpret_cast<const uint32_t *>(th + static_cast<size_t>(y0 + r) * p.w + x0 + c4);
+    *reinterpret_cast<uint32_t *>(&s_px[r][c4]) = v;
+  }
+  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) s_cnt[i] = 0;
+  __syncthreads();
+
+  // row bitmasks: warp w handles rows w, w+8, ...
+  for (int r = warp; r < kCclTH; r += kCclThreads / 32) {
+    const uint8_t a = s_px[r][lane], b = s_px[r][lane + 32];
+    const uint32_t wl = __ballot_sync(0xffffffffu, a == 255), wh = __ballot_sync(0xffffffffu, b == 255);
+    const uint32_t bl = __ballot_sync(0xffffffffu, a == 0), bh = __ballot_sync(0xffffffffu, b == 0);
+    if (lane == 0) {
+      s_white[r] = (static_cast<unsigned long long>(wh) << 32) | wl;
+      s_black[r] = (static_cast<unsigned long long>(bh) << 32) | bl;
+    }
+  }
+  __syncthreads();
+
+  // initial parents: first pixel of the horizontal run
+  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
+    const int r = i / kCclTW, x = i % kCclTW;
+    const uint8_t v = s_px[r][x];
+    uint32_t par = i;
+    if (v != 127) par = r * kCclTW + run_start64(v ? s_white[r] : s_black[r], x);
+    s_par[i] = par;
+  }
+  __syncthreads();
+
+  // vertical / diagonal unions, issued once per run overlap
+  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
+    const int r = i / kCclTW, x = i % kCclTW;
+    if (r == 0) continue;
+    const uint8_t v = s_px[r][x];
+    if (v == 127) continue;
+    const unsigned long long cur = v ? s_white[r] : s_black[r];
+    const unsigned long long up = v ? s_white[r - 1] : s_black[r - 1];
+    const bool is_start = (x == 0) || !((cur >> (x - 1)) & 1ull);
+    const bool u = (up >> x) & 1ull;
+    const bool ul = (x > 0) && ((up >> (x - 1)) & 1ull);
+    if (u) {
+      if (is_start || !ul) sunite(s_par, i, i - kCclTW);
+    } else if (v == 255) {
+      if (ul && is_start) sunite(s_par, i, i - kCclTW - 1);
+      const bool ur = (x + 1 < kCclTW) && ((up >> (x + 1)) & 1ull);
+      const bool right_same = (x + 1 < kCclTW) && ((cur >> (x + 1)) & 1ull);
+      if (ur && !right_same) sunite(s_par, i, i - kCclTW + 1);
+    }
+  }
+  __syncthreads();
+
+  // flatten + per-root pixel counts (one shared atomic per run)
+  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
+    const int r = i / kCclTW, x = i % kCclTW;
+    const uint8_t v = s_px[r][x];
+    if (v == 127) continue;
+    const uint32_t root = sfind(s_par, i);
+    const unsigned long long cur = v ? s_white[r] : s_black[r];
+    const bool is_start = (x == 0) || !((cur >> (x - 1)) & 1ull);
+    if (is_start) {
+      // run length: consecutive set bits from x upwards
+      const unsigned long long inv = ~(cur >> x);
+      const int len = inv ? (__ffsll(static_cast<long long>(inv)) - 1) : (64 - x);
+      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len));
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
+    const int r = i / kCclTW, x = i % kCclTW;
+    if (s_px[r][x] != 127) s_par[i] = sfind(s_par, i);  // roots are fixed now: safe to compress in place
+  }
+  __syncthreads();
+
+  // write out: label = global index of the local root; sizes = count at local roots, 0 elsewhere
+  for (int i = tid; i < kCclTH * (kCclTW / 4); i += kCclThreads) {
+    const int r = i / (kCclTW / 4), c4 = (i % (kCclTW / 4)) * 4;
+    if (r >= thh || c4 >= tw) continue;
+    uint32_t lab[4], sz[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int li = r * kCclTW + c4 + k;
+      const uint32_t root = s_par[li];
+      lab[k] = static_cast<uint32_t>((y0 + root / kCclTW) * p.w + x0 + root % kCclTW);
+      sz[k] = (root == static_cast<uint32_t>(li)) ? s_cnt[li] : 0u;
+    }
+    const size_t g = static_cast<size_t>(y0 + r) * p.w + x0 + c4;
+    *reinterpret_cast<uint4 *>(labels + g) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+    *reinterpret_cast<uint4 *>(sizes + g) = make_uint4(sz[0], sz[1], sz[2], sz[3]);
+  }
+}
+
+__device__ __forceinline__ uint32_t gfind(const uint32_t *par, uint32_t a) {
+  uint32_t q = __ldcg(par + a);
+  while (q != a) {
+    a = q;
+    q = __ldcg(par + a);
+  }
+  return a;
+}
+
+__device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
+  while (true) {
+    a = gfind(par, a);
+    b = gfind(par, b);
+    if (a == b) return;
+    if (a < b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    const uint32_t old = atomicMin(par + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// K4: unions across tile borders.  Work items per tile: its top row (64), left column (32),
+// right column (32, for the up-right diagonal).  One thread per item.
+__global__ void __launch_bounds__(128) k_ccl_merge(FrameParams p) {
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *th = p.thresh + frame * n;
+  uint32_t *labels = p.labels + frame * n;
+  const int t = threadIdx.x;
+  int x, y;
+  int kind;  // 0 top row, 1 left column, 2 right column
+  if (t < kCclTW) {
+    kind = 0; x = x0 + t; y = y0;
+  } else if (t < kCclTW + kCclTH) {
+    kind = 1; x = x0; y = y0 + (t - kCclTW);
+  } else {
+    kind = 2; x = x0 + kCclTW - 1; y = y0 + (t - kCclTW - kCclTH);
+  }
+  if (x >= p.w || y >= p.h) return;
+  const uint32_t i = static_cast<uint32_t>(y * p.w + x);
+  const uint8_t v = th[i];
+  if (v == 127) return;
+  if (kind == 0) {
+    if (y == 0) return;
+    // every "up" neighbour is in another tile
+    if (th[i - p.w] == v) gunite(labels, i, i - p.w);
+    if (v == 255) {
+      if (x > 0 && th[i - p.w - 1] == 255) gunite(labels, i, i - p.w - 1);
+      if (x + 1 < p.w && th[i - p.w + 1] == 255) gunite(labels, i, i - p.w + 1);
+    }
+  } else if (kind == 1) {
+    if (x == 0) return;
+    if (th[i - 1] == v) gunite(labels, i, i - 1);
+    // up-left lies in the left tile; rows at the tile top were handled by kind 0
+    if (v == 255 && y > y0 && th[i - p.w - 1] == 255) gunite(labels, i, i - p.w - 1);
+  } else {
+    if (v == 255 && y > y0 && x + 1 < p.w && th[i - p.w + 1] == 255) gunite(labels, i, i - p.w + 1);
+  }
+}
+
+// K5: every pixel jumps to its root; tile-local roots that were merged away hand their
+// pixel count to the final root.  4 pixels (16 bytes of labels) per thread.
+__global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
+  const int frame = blockIdx.y;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  uint32_t *labels = p.labels + frame * n;
+  uint32_t *sizes = p.sizes + frame * n;
+  const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const uint4 l = __ldcg(reinterpret_cast<const uint4 *>(labels + i4));
+  const uint4 s = __ldcg(reinterpret_cast<const uint4 *>(sizes + i4));
+  uint32_t lab[4] = {l.x, l.y, l.z, l.w};
+  const uint32_t sz[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t self = static_cast<uint32_t>(i4 + k);
+    if (lab[k] != self || sz[k] != 0) {  // 127-pixels (own index, size 0) need nothing
+      const uint32_t root = gfind(labels, lab[k]);
+      lab[k] = root;
+      if (sz[k] != 0 && root != self) {
+        atomicAdd(sizes + root, sz[k]);
+        sizes[self] = 0;
+      }
+    }
+  }
+  *reinterpret_cast<uint4 *>(labels + i4) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: boundary points + blob-pair hash.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBpTW = 64, kBpTH = 16, kBpThreads = 256;
+
+__device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
+  uint64_t k = (static_cast<uint64_t>(a) << 32) | b;
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return static_cast<uint32_t>(k);
+}
+
+// Finds or claims the slot of blob pair `key`; returns hash_cap on a full table.
+__device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, unsigned long long key, uint32_t rep0, uint32_t rep1) {
+  uint32_t slot = hash_pair(rep0, rep1) & (p.hash_cap - 1);
+  for (uint32_t probe = 0; probe < p.hash_cap; probe++) {
+    unsigned long long cur = __ldcg(keys + slot);
+    if (cur == key) return slot;
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(keys + slot, kEmptyKey, key);
+      if (cur == kEmptyKey || cur == key) return slot;
+    }
+    slot = (slot + 1) & (p.hash_cap - 1);
+  }
+  return p.hash_cap;
+}
+
+// staged cell: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
+__global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
+  __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * kBpTW, y0 = blockIdx.y * kBpTH;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *th = p.thresh + frame * n;
+  const uint32_t *labels = p.labels + frame * n;
+  const uint32_t *sizes = p.sizes + frame * n;
+  Counters *ctr = p.counters + frame;
+  uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
+  unsigned long long *h_key = p.h_key + static_cast<size_t>(frame) * p.hash_cap;
+  const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  for (int i = tid; i < (kBpTH + 1) * (kBpTW + 2); i += kBpThreads) {
+    const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
+    const int gx = x0 - 1 + c, gy = y0 + r;
+    uint32_t cell = 2u << 29;
+    if (gx >= 0 && gx < p.w && gy < p.h) {
+      const size_t g = static_cast<size_t>(gy) * p.w + gx;
+      const uint8_t v = th[g];
+      if (v != 127) {
+        const uint32_t lab = labels[g];
+        const uint32_t big = sizes[lab] >= kMinBlobPixels;
+        cell = lab | (big << 28) | ((v ? 1u : 0u) << 29);
+      }
+    }
+    s_cell[r][c] = cell;
+  }
+  __syncthreads();
+
+  const int tx = tid % kBpTW;
+  for (int ry = tid / kBpTW; ry < kBpTH; ry += kBpThreads / kBpTW) {  // warp-uniform trip count
+    const int x = x0 + tx, y = y0 + ry;
+    uint32_t have = 0;  // bit d: this pixel emits a point in direction d
+    uint32_t pt_rep[4] = {0, 0, 0, 0}, pt_b2w = 0;
+    uint32_t rep_self = 0;
+    if (x >= 1 && x <= p.w - 2 && y >= 1 && y <= p.h - 2) {  // apriltag_gpu.cu:239,276-281
+      const uint32_t c0 = s_cell[ry][tx + 1];
+      const uint32_t col0 = c0 >> 29;
+      if (col0 != 2 && (c0 & (1u << 28))) {  // :284
+        rep_self = c0 & 0x0fffffffu;
+        const uint32_t cl = s_cell[ry][tx], c2 = s_cell[ry + 1][tx + 1];
+        const uint32_t colL = cl >> 29, col2 = c2 >> 29;
+        // direction-3 duplicate suppression, :347-357
+        const bool skip3 = (colL != 2 && col2 != 2 && colL != col2 && x != 1 && (cl & (1u << 28)) && (c2 & (1u << 28)));
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          if (d == 3 && skip3) continue;
+          const uint32_t c1 = s_cell[ry + dir_dy(d)][tx + 1 + dir_dx(d)];
+          const uint32_t col1 = c1 >> 29;
+          if (col1 == 2 || col1 == col0) continue;  // v0 + v1 == 255, :305
+          if (!(c1 & (1u << 28))) continue;          // :306
+          pt_rep[d] = c1 & 0x0fffffffu;
+          pt_b2w |= (col1 > col0 ? 1u : 0u) << d;   // :316
+          have |= 1u << d;
+        }
+      }
+    }
+    // Blob-pair bookkeeping.  One warp-uniform round per direction; lanes whose points share a
+    // blob pair (__match_any_sync) fold their extents with redux and one lane updates the hash.
+    uint32_t slots[4] = {p.hash_cap, p.hash_cap, p.hash_cap, p.hash_cap};
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      const bool has = (have >> d) & 1u;
+      const uint32_t active = __ballot_sync(0xffffffffu, has);
+      if (!has) continue;
+      const uint32_t ra = min(rep_self, pt_rep[d]), rb = max(rep_self, pt_rep[d]);
+      const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
+      const uint32_t b2w = (pt_b2w >> d) & 1u;
+      const int px = 2 * x + dir_dx(d), py = 2 * y + dir_dy(d);  // points.h:111-116
+      const int gx = b2w ? dir_dx(d) : -dir_dx(d), gy = b2w ? dir_dy(d) : -dir_dy(d);  // points.h:120-125
+      const uint32_t group = __match_any_sync(active, key);
+      const int leader = __ffs(group) - 1;
+      const uint32_t cnt = __popc(group);
+      const uint32_t mnx = __reduce_min_sync(group, static_cast<uint32_t>(px));
+      const uint32_t mxx = __reduce_max_sync(group, static_cast<uint32_t>(px));
+      const uint32_t mny = __reduce_min_sync(group, static_cast<uint32_t>(py));
+      const uint32_t mxy = __reduce_max_sync(group, static_cast<uint32_t>(py));
+      const int sgx = __reduce_add_sync(group, gx);
+      const int sgy = __reduce_add_sync(group, gy);
+      const int sdot = __reduce_add_sync(group, px * gx + py * gy);
+      uint32_t slot = 0;
+      if (lane == leader) {
+        slot = hash_insert(p, h_key, key, ra, rb);
+        if (slot < p.hash_cap) {
+          atomicAdd(p.h_count + hoff + slot, cnt);
+          atomicMin(p.h_minx + hoff + slot, mnx);
+          atomicMax(p.h_maxx + hoff + slot, mxx);
+          atomicMin(p.h_miny + hoff + slot, mny);
+          atomicMax(p.h_maxy + hoff + slot, mxy);
+          if (sgx) atomicAdd(p.h_gx + hoff + slot, sgx);
+          if (sgy) atomicAdd(p.h_gy + hoff + slot, sgy);
+          if (sdot)
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.h_dot + hoff + slot),
+                      static_cast<unsigned long long>(static_cast<long long>(sdot)));
+        } else {
+          atomicOr(&ctr->status, B200TAG_ST_HASH_OVERFLOW);
+        }
+      }
+      slots[d] = __shfl_sync(group, slot, leader);
+    }
+    // compaction: warp prefix over point counts, one global atomic per warp
+    uint32_t valid = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) valid += (slots[d] < p.hash_cap);
+    uint32_t incl = valid;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&ctr->num_points, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t pos = base + incl - valid;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      if (slots[d] >= p.hash_cap) continue;
+      if (pos < p.point_cap) {
+        points[pos] = pack_point(slots[d], 2 * x + dir_dx(d), 2 * y + dir_dy(d), d, (pt_b2w >> d) & 1u);
+      } else {
+        atomicOr(&ctr->status, B200TAG_ST_POINTS_OVERFLOW);
+      }
+      pos++;
+    }
+  }
+}
+
+// Resets the blob-pair hash of every frame (first use, and after each frame by k_select).
+__global__ void k_hash_clear(FrameParams p, int frames) {
+  const size_t total = static_cast<size_t>(frames) * p.hash_cap;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    p.h_key[i] = kEmptyKey;
+    p.h_count[i] = 0;
+    p.h_minx[i] = 0xffffffffu;
+    p.h_miny[i] = 0xffffffffu;
+    p.h_maxx[i] = 0;
+    p.h_maxy[i] = 0;
+    p.h_gx[i] = 0;
+    p.h_gy[i] = 0;
+    p.h_dot[i] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
+  int launches = 0;
+  const dim3 tgrid(cdiv(p.tiles_x, 128), p.tiles_y, frames);
+  if (p.fmt == B200TAG_FMT_YUYV && p.f == 2 && !p.blur_ksz) {
+    if (kt) kt->begin("pre_yuyv_dec2", s);
+    k_pre_yuyv_dec2<<<tgrid, 128, 0, s>>>(p);
+    if (kt) kt->end(s);
+    launches++;
+  } else {
+    const bool vec_bgr = (p.fmt == B200TAG_FMT_BGR8 && p.f == 1 && (static_cast<size_t>(p.W) * p.H) % 16 == 0 && p.in_stride % 16 == 0);
+    if (vec_bgr) {
+      if (kt) kt->begin("pre_bgr_dec1", s);
+      const size_t groups = static_cast<size_t>(p.W) * p.H / 16;
+      k_pre_bgr_dec1<<<dim3(cdiv(static_cast<unsigned>(groups), 256), frames), 256, 0, s>>>(p);
+      if (kt) kt->end(s);
+      launches++;
+    } else {
+      if (kt) kt->begin("pre_generic", s);
+      k_pre_generic<<<tgrid, 128, 0, s>>>(p, p.blur_ksz ? 0 : 1);
+      if (kt) kt->end(s);
+      launches++;
+    }
+    if (p.blur_ksz) {
+      if (kt) kt->begin("blur", s);
+      k_blur<<<dim3(cdiv(p.w, 256), p.h, frames), 256, 0, s>>>(p);
+      if (kt) kt->end(s);
+      launches++;
+    }
+    if (p.blur_ksz || vec_bgr) {
+      if (kt) kt->begin("tile_minmax", s);
+      k_tile_minmax<<<tgrid, 128, 0, s>>>(p);
+      if (kt) kt->end(s);
+      launches++;
+    }
+  }
+  if (kt) kt->begin("threshold", s);
+  k_threshold<<<tgrid, 128, 0, s>>>(p);
+  if (kt) kt->end(s);
+  launches++;
+
+  const dim3 cgrid(cdiv(p.w, kCclTW), cdiv(p.h, kCclTH), frames);
+  if (kt) kt->begin("ccl_local", s);
+  k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
+  if (kt) kt->end(s);
+  if (kt) kt->begin("ccl_merge", s);
+  k_ccl_merge<<<cgrid, 128, 0, s>>>(p);
+  if (kt) kt->end(s);
+  if (kt) kt->begin("ccl_final", s);
+  k_ccl_final<<<dim3(cdiv(static_cast<unsigned>((static_cast<size_t>(p.w) * p.h + 3) / 4), 256), frames), 256, 0, s>>>(p);
+  if (kt) kt->end(s);
+  launches += 3;
+
+  if (kt) kt->begin("boundary", s);
+  k_boundary<<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, kBpTH), frames), kBpThreads, 0, s>>>(p);
+  if (kt) kt->end(s);
+  launches++;
+  return launches;
+}
+
+void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s) {
+  k_hash_clear<<<296, 256, 0, s>>>(p, frames);
+}
+
+}  // namespace b200tag

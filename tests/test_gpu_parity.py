@@ -1,0 +1,166 @@
+"""GPU parity tests: the CUDA engine (through the C ABI / ctypes host mirror) against the CPU oracle on
+identical frames.  Run on the B200 box with `pytest -m gpu`."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, match_corner_sets
+from parity import compare_all, compare_detections, compare_front_end
+
+pytestmark = pytest.mark.gpu
+
+CAM = (905.495617, 609.916016, 907.909470, 352.682645)
+DIST = (0.059238, -0.075154, -0.003801, 0.001113, 0.0)
+
+
+@pytest.fixture(scope="module")
+def D():
+    from ros_vision_b200 import detector
+    detector.load_library()
+    return detector
+
+
+def _pack(gray, fmt, rng=None):
+    from ros_vision_b200 import synth
+    if fmt == "gray":
+        return gray
+    if fmt == "yuyv":
+        return synth.gray_to_yuyv(gray)
+    return synth.gray_to_bgr(gray, rng)
+
+
+@pytest.mark.parametrize("w,h,fmt,dec,sigma,seed,ntags,side", [
+    (640, 480, "gray", 2, 0.0, 11, 4, (60, 140)),
+    (640, 480, "yuyv", 2, 0.0, 12, 3, (40, 120)),
+    (320, 240, "bgr", 2, 0.0, 13, 2, (40, 90)),
+    (320, 240, "gray", 1, 0.0, 14, 3, (30, 70)),
+    (320, 240, "bgr", 1, 0.8, 15, 4, (24, 60)),
+    (328, 248, "yuyv", 2, 0.0, 16, 2, (40, 80)),     # ragged: not a multiple of the CCL / boundary tile sizes
+    (1280, 800, "yuyv", 2, 0.0, 2000, 5, (60, 300)),  # BASELINE config 2 shape
+])
+def test_every_stage_matches_oracle(D, oracle, w, h, fmt, dec, sigma, seed, ntags, side):
+    from ros_vision_b200 import synth
+    sc = synth.make_scene(w, h, seed, ntags, side_range=side, noise_sigma=4.0)
+    frame = _pack(sc.gray, fmt, np.random.default_rng(seed))
+    orc = oracle.detect(oracle.make_config(w, h, fmt, dec, sigma), frame)
+    det = D.GpuDetector(w, h, fmt, quad_decimate=dec, quad_sigma=sigma, keep_stages=True)
+    det.Detect(frame)
+    got = compare_all(det, orc, 0, fmt)
+    assert len(got) >= 1
+    truth = {t.tag_id: t.corners for t in sc.tags}
+    for d in got:
+        assert int(d["id"]) in truth
+        assert match_corner_sets(d["p"], truth[int(d["id"])]) < 1.0
+    det.close()
+
+
+@pytest.mark.parametrize("name", ["ref_colorimage_crop", "ref_colorimage_notags_crop", "ref_grayimage_crop", "synthetic_cfg1"])
+def test_golden_fixtures(D, oracle, name):
+    """The reference's known answers (gpu_detector_test.cu:84-157) through the CUDA path."""
+    meta, img = load_golden(name)
+    w, h = meta["width"], meta["height"]
+    cases = meta.get("cases") or {"identity_camera": {"camera": None, "dist": None, "oracle": meta["oracle"]}}
+    for case in cases.values():
+        det = D.GpuDetector(w, h, "gray", camera_matrix=case["camera"], distortion_coefficients=case["dist"], keep_stages=True)
+        det.Detect(img)
+        exp = case["oracle"]
+        assert hashlib.sha256(det.CopyThresholdedTo().tobytes()).hexdigest() == exp["thresh_sha256"]
+        info = det.FrameInfo()
+        assert info.num_points == exp["num_points"] and info.num_clusters == exp["num_clusters"]
+        assert info.num_blobs == exp["num_selected_clusters"] and info.num_quads == exp["num_corners"]
+        got = det.Detections()
+        assert [int(x) for x in got["id"]] == [d["id"] for d in exp["detections"]]
+        assert [int(x) for x in got["hamming"]] == [d["hamming"] for d in exp["detections"]]
+        for g, e in zip(got, exp["detections"]):
+            assert np.abs(g["p"] - np.array(e["p"])).max() <= 0.05
+            assert np.abs(g["H"] - np.array(e["H"])).max() / np.abs(e["H"]).max() <= 1e-4
+        if "known_answer" in meta:
+            assert len(got) == meta["known_answer"]["num_detections"]
+        orc = oracle.detect(oracle.make_config(w, h, "gray", 2, 0.0, camera=case["camera"], dist=case["dist"]), img)
+        compare_all(det, orc, 0, "gray")
+        det.close()
+
+
+def test_batch_matches_single_frames(D, oracle):
+    from ros_vision_b200 import synth
+    w, h = 640, 480
+    frames = [synth.gray_to_yuyv(synth.make_scene(w, h, 100 + i, 1 + i % 3, side_range=(50, 150), noise_sigma=3.0 + i).gray)
+              for i in range(5)]
+    det = D.GpuDetector(w, h, "yuyv", max_batch=8, keep_stages=True)
+    det.DetectBatch(frames)
+    for i, fr in enumerate(frames):
+        orc = oracle.detect(oracle.make_config(w, h, "yuyv", 2, 0.0), fr)
+        compare_all(det, orc, i, "yuyv")
+    # the same detector again, fewer frames: state left behind by the previous batch must not leak
+    det.DetectBatch(frames[3:])
+    for i, fr in enumerate(frames[3:]):
+        orc = oracle.detect(oracle.make_config(w, h, "yuyv", 2, 0.0), fr)
+        compare_all(det, orc, i, "yuyv")
+    det.close()
+
+
+def test_edge_cases(D, oracle):
+    w, h = 64, 48
+    for name, img in [("flat", np.full((h, w), 128, np.uint8)), ("black", np.zeros((h, w), np.uint8)),
+                      ("white", np.full((h, w), 255, np.uint8)),
+                      ("checker", ((np.indices((h, w)).sum(0) % 2) * 255).astype(np.uint8)),
+                      ("noise", np.random.default_rng(0).integers(0, 256, (h, w), dtype=np.uint8))]:
+        det = D.GpuDetector(w, h, "gray", quad_decimate=1, keep_stages=True)
+        det.Detect(img)
+        orc = oracle.detect(oracle.make_config(w, h, "gray", 1, 0.0), img)
+        compare_all(det, orc, 0, "gray")
+        det.close()
+    # a tag that fills most of the frame: a blob larger than the in-shared-memory sort capacity
+    from ros_vision_b200 import synth
+    sc = synth.make_scene(1600, 1200, 5, 1, side_range=(900, 900), max_rot_deg=5, max_tilt_deg=5, noise_sigma=0.0,
+                          background=200.0)
+    det = D.GpuDetector(1600, 1200, "gray", quad_decimate=1, keep_stages=True)
+    det.Detect(sc.gray)
+    orc = oracle.detect(oracle.make_config(1600, 1200, "gray", 1, 0.0), sc.gray)
+    assert orc.clusters["count"][orc.clusters["selected"] != 0].max() > 4096
+    compare_all(det, orc, 0, "gray")
+    det.close()
+
+
+def test_invalid_configurations_are_rejected(D):
+    with pytest.raises(D.B200TagError):
+        D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
+    with pytest.raises(D.B200TagError):
+        D.GpuDetector(640, 480, "gray", max_nmaxima=8)
+    det = D.GpuDetector(64, 48, "gray")
+    with pytest.raises(ValueError):
+        det.Detect(np.zeros((10, 10), np.uint8))
+    det.close()
+
+
+def test_full_size_properties(D, oracle):
+    """BASELINE configs 4 and 5 at full size: size-independent properties + oracle on the final answer."""
+    from ros_vision_b200 import synth
+    for cfg_id in (4, 5):
+        frame, fmt, w, h, dec, sigma, sc = synth.config_frame(cfg_id)
+        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, quad_sigma=sigma, keep_stages=True)
+        det.Detect(frame)
+        info = det.FrameInfo()
+        assert info.status == 0
+        th = det.CopyThresholdedTo()
+        labels = det.CopyUnionMarkersTo()
+        sizes = det.CopyUnionMarkersSizeTo()
+        mask = th.reshape(-1) != 127
+        # labels are fixed points of the label map, roots carry the whole pixel count
+        assert np.array_equal(labels[labels[mask]], labels[mask])
+        assert int(sizes.sum()) == int(mask.sum())
+        roots, counts = np.unique(labels[mask], return_counts=True)
+        assert np.array_equal(sizes[roots], counts.astype(np.uint32))
+        # every pixel has the colour of its root
+        assert np.array_equal(th.reshape(-1)[labels[mask]], th.reshape(-1)[mask])
+        # idempotence: a second run on the same detector gives the same answer
+        first = det.Detections().copy()
+        det.Detect(frame)
+        assert np.array_equal(first, det.Detections())
+        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, sigma), frame)
+        compare_front_end(det, orc, 0, fmt)
+        got = compare_detections(det, orc, 0)
+        truth_ids = sorted(t.tag_id for t in sc.tags)
+        assert len(got) >= 0.9 * len(truth_ids)
+        det.close()
