@@ -60,7 +60,8 @@ def kernel_bytes(name: str, P: float, Psel: float, nblobs: float) -> float:
         "boundary": n + 4 * n + 4 * n + 8 * P,
         "select": 0.0,
         "scatter": 8 * P + 8 * Psel,
-        "fit_blobs": 16 * Psel + 8 * Psel + 48 * Psel + 48 * Psel + 12 * Psel,
+        "fit_small": 8 * Psel,   # reads the unsorted segment once; everything else stays in shared memory
+        "fit_large": 8 * Psel,
         "decode": 0.0,
     }
     return table.get(name, 0.0)

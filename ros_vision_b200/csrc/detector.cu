@@ -360,11 +360,14 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_sb = plan.take(HB * 4);
   const size_t o_blobs = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_blob) * B);
   const size_t o_fill = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
+  const size_t o_small = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
+  const size_t o_large = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
   const size_t o_clusters = p.cluster_cap ? plan.take(static_cast<size_t>(p.cluster_cap) * sizeof(b200tag_blob) * B) : 0;
   const size_t o_seg = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
   const size_t o_lfp = plan.take(static_cast<size_t>(p.point_cap) * sizeof(b200tag_lfp) * B);
   const size_t o_errs = plan.take(static_cast<size_t>(p.point_cap) * 4 * B);
   const size_t o_filt = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
+  const size_t o_pkws = plan.take((static_cast<size_t>(p.point_cap) / 2 + 1) * 8 * B);
   const size_t o_fq = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_fit_quad) * B);
   const size_t o_quads = plan.take(static_cast<size_t>(p.quad_cap) * sizeof(b200tag_quad) * B);
   const size_t o_ctr = plan.take(sizeof(Counters) * B);
@@ -404,11 +407,14 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.slot_blob = reinterpret_cast<int32_t *>(base + o_sb);
   p.blobs = reinterpret_cast<b200tag_blob *>(base + o_blobs);
   p.blob_fill = reinterpret_cast<uint32_t *>(base + o_fill);
+  p.small_list = reinterpret_cast<uint32_t *>(base + o_small);
+  p.large_list = reinterpret_cast<uint32_t *>(base + o_large);
   p.clusters = p.cluster_cap ? reinterpret_cast<b200tag_blob *>(base + o_clusters) : nullptr;
   p.seg_keys = reinterpret_cast<uint64_t *>(base + o_seg);
   p.lfp = reinterpret_cast<b200tag_lfp *>(base + o_lfp);
   p.errs = reinterpret_cast<float *>(base + o_errs);
   p.filt = reinterpret_cast<double *>(base + o_filt);
+  p.peak_ws = reinterpret_cast<uint64_t *>(base + o_pkws);
   p.fit_quads = reinterpret_cast<b200tag_fit_quad *>(base + o_fq);
   p.quads = reinterpret_cast<b200tag_quad *>(base + o_quads);
   p.counters = reinterpret_cast<Counters *>(base + o_ctr);

@@ -16,6 +16,7 @@ constexpr uint32_t kMinBlobPixels = 25;      // apriltag_gpu.cu:284,306 (union_m
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kMaxPeaks = 10;                // line_fit_filter.cu:630 (kNMaxima)
 constexpr int kNumCombos = 210;              // line_fit_filter.h:160
+constexpr uint32_t kSmallBlobPoints = 256;   // blobs up to this size are fitted by a single warp
 
 // Packed boundary point, 64 bit:  [63:40] cluster slot | [28:16] x | [15:3] y | [2:1] dir | [0] black_to_white
 // (the reference's QuadBoundaryPoint, points.h:25-161, carries 20-bit blob ids and
@@ -54,9 +55,12 @@ struct Counters {  // one per frame, zeroed before each frame
   uint32_t num_fit_quads;
   uint32_t num_quads;
   uint32_t num_detections;
-  uint32_t next_blob;  // dynamic work counters
-  uint32_t next_quad;
-  uint32_t pad[6];
+  uint32_t next_quad;   // dynamic work counters
+  uint32_t num_small;   // selected blobs with <= kSmallBlobPoints points (one warp each)
+  uint32_t num_large;   // the rest (one CTA each)
+  uint32_t next_small;
+  uint32_t next_large;
+  uint32_t pad[3];
 };
 static_assert(sizeof(Counters) == 64, "Counters layout");
 
@@ -103,11 +107,14 @@ struct FrameParams {
   int32_t *slot_blob;   // hash_cap
   b200tag_blob *blobs;  // blob_cap
   uint32_t *blob_fill;  // blob_cap
+  uint32_t *small_list; // blob_cap: indices of blobs fitted by one warp
+  uint32_t *large_list; // blob_cap: indices of blobs fitted by one CTA
   b200tag_blob *clusters;  // cluster_cap (keep_stages)
   uint64_t *seg_keys;   // point_cap
   b200tag_lfp *lfp;     // point_cap
   float *errs;          // point_cap
   double *filt;         // point_cap
+  uint64_t *peak_ws;    // point_cap / 2 + 1: peak list of blobs too large for shared memory
   b200tag_fit_quad *fit_quads;  // blob_cap
   b200tag_quad *quads;  // quad_cap
   b200tag_detection *dets;  // det_cap

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   uint32_t *fill = p.blob_fill + static_cast<size_t>(frame) * p.blob_cap;
+  uint32_t *small_list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
+  uint32_t *large_list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   b200tag_blob *clusters = p.clusters ? p.clusters + static_cast<size_t>(frame) * p.cluster_cap : nullptr;
   const int lane = threadIdx.x & 31;
   // hash_cap is a multiple of the block size, so every warp runs the same trip count
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
         blobs[b] = rec;
         fill[b] = 0;
         blob_id = static_cast<int32_t>(b);
+        if (rec.count <= kSmallBlobPoints) small_list[atomicAdd(&ctr->num_small, 1u)] = b;
+        else large_list[atomicAdd(&ctr->num_large, 1u)] = b;
       } else {
         atomicOr(&ctr->status, B200TAG_ST_BLOBS_OVERFLOW);
       }
@@ -153,14 +157,30 @@ __global__ void __launch_bounds__(256) k_scatter(FrameParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9
+// K9: blob -> quad.  Two tiers share one code path (template parameter GS = threads per blob):
+//   small blobs (<= 256 points, ~3/4 of all blobs): ONE WARP per blob, everything in shared
+//     memory, only __syncwarp between phases;
+//   large blobs: one 256-thread CTA per blob; sort / errors / peaks in shared memory up to 4096
+//     points, prefix moments in shared memory up to 768 points, the rare bigger blob works in
+//     its own (L2-resident) segment of the global arrays.
+// Phases: bitonic angle sort -> weights + prefix moments -> windowed line-fit error -> 7-tap
+// smoothing -> peak list -> [one warp] 10 strongest peaks -> table of the <= 90 candidate side
+// fits -> [one warp] 210 corner combinations + argmin -> [one lane] corners and quad tests.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFitThreads = 256;
-constexpr int kSortCap = 4096;  // keys sorted in shared memory; larger blobs sort in place in L2
+constexpr int kLargeThreads = 256;
+constexpr int kSmallWarps = 4;          // warps (= blobs in flight) per small-tier CTA
+constexpr uint32_t kSortCap = 4096;     // large tier: points sorted / filtered in shared memory
+constexpr uint32_t kLfpCap = 768;       // large tier: prefix moments kept in shared memory
+
+template <int GS>
+__device__ __forceinline__ void gsync() {
+  if constexpr (GS == 32) __syncwarp();
+  else __syncthreads();
+}
 
 template <typename Ptr>
 __device__ __forceinline__ void cmpxchg(Ptr a, uint32_t i, uint32_t l) {
-  const uint64_t x = a[i], y = a[l];
+  const unsigned long long x = a[i], y = a[l];
   if (x > y) {
     a[i] = y;
     a[l] = x;
@@ -169,22 +189,22 @@ __device__ __forceinline__ void cmpxchg(Ptr a, uint32_t i, uint32_t l) {
 
 // All-ascending bitonic network over N = pow2 >= cnt slots; slots >= cnt are virtual +inf and
 // never move, so no padding is materialised.
-template <typename Ptr>
-__device__ void bitonic_sort(Ptr a, uint32_t cnt, uint32_t N) {
+template <int GS, typename Ptr>
+__device__ void bitonic_sort(Ptr a, uint32_t cnt, uint32_t N, uint32_t gt) {
   for (uint32_t k = 2; k <= N; k <<= 1) {
     const uint32_t hk = k >> 1;
-    for (uint32_t t = threadIdx.x; t < (N >> 1); t += kFitThreads) {
+    for (uint32_t t = gt; t < (N >> 1); t += GS) {
       const uint32_t blk = t / hk, w = t % hk;
       const uint32_t i = blk * k + w, l = blk * k + k - 1 - w;
       if (l < cnt) cmpxchg(a, i, l);
     }
-    __syncthreads();
+    gsync<GS>();
     for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-      for (uint32_t t = threadIdx.x; t < (N >> 1); t += kFitThreads) {
+      for (uint32_t t = gt; t < (N >> 1); t += GS) {
         const uint32_t i = 2 * j * (t / j) + (t % j), l = i + j;
         if (l < cnt) cmpxchg(a, i, l);
       }
-      __syncthreads();
+      gsync<GS>();
     }
   }
 }
@@ -194,33 +214,25 @@ struct Mom {
   int N;
 };
 
-__device__ __forceinline__ b200tag_lfp load_lfp(const b200tag_lfp *p) {
-  const longlong2 *q = reinterpret_cast<const longlong2 *>(p);
-  const longlong2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2);
-  b200tag_lfp r;
-  r.Mxx = a.x; r.Myy = a.y; r.Mxy = b.x; r.Mx = b.y; r.My = c.x; r.W = c.y;
-  return r;
-}
-
 // ReadMoments, line_fit_filter.cu:745-796 (== CalculateError's window logic, :230-274)
-__device__ Mom read_moments(const b200tag_lfp *lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
+__device__ __forceinline__ Mom read_moments(const volatile b200tag_lfp *lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
   Mom m;
   if (i0 < i1) {
     m.N = static_cast<int>(i1 - i0 + 1);
-    const b200tag_lfp a = load_lfp(lf + i1);
-    m.Mx = a.Mx; m.My = a.My; m.Mxx = a.Mxx; m.Mxy = a.Mxy; m.Myy = a.Myy; m.W = a.W;
+    const volatile b200tag_lfp *a = lf + i1;
+    m.Mx = a->Mx; m.My = a->My; m.Mxx = a->Mxx; m.Mxy = a->Mxy; m.Myy = a->Myy; m.W = a->W;
     if (i0 > 0) {
-      const b200tag_lfp b = load_lfp(lf + i0 - 1);
-      m.Mx -= b.Mx; m.My -= b.My; m.Mxx -= b.Mxx; m.Mxy -= b.Mxy; m.Myy -= b.Myy; m.W -= b.W;
+      const volatile b200tag_lfp *b = lf + i0 - 1;
+      m.Mx -= b->Mx; m.My -= b->My; m.Mxx -= b->Mxx; m.Mxy -= b->Mxy; m.Myy -= b->Myy; m.W -= b->W;
     }
   } else {
-    const b200tag_lfp b = load_lfp(lf + i0 - 1), z = load_lfp(lf + cnt - 1), a = load_lfp(lf + i1);
-    m.Mx = z.Mx - b.Mx + a.Mx;
-    m.My = z.My - b.My + a.My;
-    m.Mxx = z.Mxx - b.Mxx + a.Mxx;
-    m.Mxy = z.Mxy - b.Mxy + a.Mxy;
-    m.Myy = z.Myy - b.Myy + a.Myy;
-    m.W = z.W - b.W + a.W;
+    const volatile b200tag_lfp *b = lf + i0 - 1, *z = lf + cnt - 1, *a = lf + i1;
+    m.Mx = z->Mx - b->Mx + a->Mx;
+    m.My = z->My - b->My + a->My;
+    m.Mxx = z->Mxx - b->Mxx + a->Mxx;
+    m.Mxy = z->Mxy - b->Mxy + a->Mxy;
+    m.Myy = z->Myy - b->Myy + a->Myy;
+    m.W = z->W - b->W + a->W;
     m.N = static_cast<int>(cnt - i0 + i1 + 1);
   }
   return m;
@@ -268,8 +280,8 @@ __device__ void fit_line(const Mom &m, double *lp01, double *lp23, double *err, 
 __device__ __forceinline__ int point_weight(const uint8_t *im, int w, int h, int ix, int iy) {
   int W = 1;
   if (ix > 0 && ix + 1 < w && iy > 0 && iy + 1 < h) {
-    const int gx = static_cast<int>(im[iy * w + ix + 1]) - static_cast<int>(im[iy * w + ix - 1]);
-    const int gy = static_cast<int>(im[(iy + 1) * w + ix]) - static_cast<int>(im[(iy - 1) * w + ix]);
+    const int gx = static_cast<int>(__ldg(im + iy * w + ix + 1)) - static_cast<int>(__ldg(im + iy * w + ix - 1));
+    const int gy = static_cast<int>(__ldg(im + (iy + 1) * w + ix)) - static_cast<int>(__ldg(im + (iy - 1) * w + ix));
     W = static_cast<int>(hypotf(static_cast<float>(gx), static_cast<float>(gy)) + 1);
   }
   return W;
@@ -281,270 +293,294 @@ __device__ __forceinline__ uint32_t float_order(float f) {  // monotone float ->
 }
 
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr double kDblMax = 1.7976931348623157e308;
 
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *s_red) {
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
     v = t < v ? t : v;
   }
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    unsigned long long r = threadIdx.x < (kFitThreads / 32) ? s_red[threadIdx.x] : kNoKey;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      const unsigned long long t = __shfl_xor_sync(0xffffffffu, r, o);
-      r = t < r ? t : r;
-    }
-    if (threadIdx.x == 0) s_red[8] = r;
-  }
-  __syncthreads();
-  const unsigned long long out = s_red[8];
-  __syncthreads();
-  return out;
+  return v;
 }
 
-struct FitShared {
-  unsigned long long sort_buf[kSortCap];
-  long long scan[6][kFitThreads];
-  unsigned long long red[16];
-  double cand_err[kFitThreads];
+// Per-blob scratch that is always in shared memory.
+struct BlobScratch {
+  double seg_err[kMaxPeaks][kMaxPeaks];  // fit error of side (a -> b); kDblMax if mse > max_line_fit_mse
+  double seg_nx[kMaxPeaks][kMaxPeaks], seg_ny[kMaxPeaks][kMaxPeaks];
   uint32_t peak_idx[kMaxPeaks];
-  uint8_t combos[kNumCombos][4];
-  uint32_t cur_blob;
-  uint32_t npeaks;
+  uint32_t npeaks;   // all strict local maxima
+  uint32_t nsel;     // min(10, npeaks)
+  uint32_t cur;      // blob being processed
+  int best_combo;
+  double best_err;
 };
 
-__global__ void __launch_bounds__(kFitThreads) k_fit_blobs(FrameParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FitShared &S = *reinterpret_cast<FitShared *>(smem_raw);
-  const int frame = blockIdx.y;
-  const int tid = threadIdx.x;
-  Counters *ctr = p.counters + frame;
+// nested-loop (Unrank) order of the C(10,4) corner choices, line_fit_filter.cu:709-728
+__device__ uint8_t d_combos[kNumCombos][4];
+
+__global__ void k_init_combos() {
+  int c = 0;
+  for (int m0 = 0; m0 < kMaxPeaks - 3; m0++)
+    for (int m1 = m0 + 1; m1 < kMaxPeaks - 2; m1++)
+      for (int m2 = m1 + 1; m2 < kMaxPeaks - 1; m2++)
+        for (int m3 = m2 + 1; m3 < kMaxPeaks; m3++) {
+          d_combos[c][0] = m0; d_combos[c][1] = m1; d_combos[c][2] = m2; d_combos[c][3] = m3;
+          c++;
+        }
+}
+
+// Working storage of one blob: shared or global memory, chosen by the caller.
+struct BlobWork {
+  volatile unsigned long long *keys;  // cnt sort keys; dead after the moments phase
+  volatile b200tag_lfp *lf;           // cnt prefix moments
+  volatile float *errs;               // cnt errors, later overlaid by the peak list (cnt/2 x u64)
+  volatile double *filt;              // cnt filtered errors (may alias keys)
+  volatile unsigned long long *peaks; // <= cnt/2 peak keys (may alias errs, which is dead by then)
+};
+
+template <int GS>
+__device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
+                             const BlobWork &wk, BlobScratch &S, long long (*scan)[kLargeThreads], uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
-  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  uint64_t *seg_all = p.seg_keys + static_cast<size_t>(frame) * p.point_cap;
-  b200tag_lfp *lfp_all = p.lfp + static_cast<size_t>(frame) * p.point_cap;
-  float *errs_all = p.errs + static_cast<size_t>(frame) * p.point_cap;
-  double *filt_all = p.filt + static_cast<size_t>(frame) * p.point_cap;
-  b200tag_fit_quad *fit_quads = p.fit_quads + static_cast<size_t>(frame) * p.blob_cap;
-  b200tag_quad *quads = p.quads + static_cast<size_t>(frame) * p.quad_cap;
-  const uint32_t nblobs = min(ctr->num_blobs, p.blob_cap);
+  const uint32_t cnt = blob.count, off = blob.offset;
+  const size_t pbase = static_cast<size_t>(frame) * p.point_cap + off;
+  const uint64_t *seg = p.seg_keys + pbase;
+  const int lane = threadIdx.x & 31;
+  const bool first_warp = gt < 32;
 
-  if (tid == 0) {  // Unrank table: nested-loop order == line_fit_filter.cu:709-728
-    int c = 0;
-    for (int m0 = 0; m0 < kMaxPeaks - 3; m0++)
-      for (int m1 = m0 + 1; m1 < kMaxPeaks - 2; m1++)
-        for (int m2 = m1 + 1; m2 < kMaxPeaks - 1; m2++)
-          for (int m3 = m2 + 1; m3 < kMaxPeaks; m3++) {
-            S.combos[c][0] = m0; S.combos[c][1] = m1; S.combos[c][2] = m2; S.combos[c][3] = m3;
-            c++;
-          }
+  // (1) angle sort, C6 (apriltag_gpu.cu:944-956)
+  uint32_t N = 1;
+  while (N < cnt) N <<= 1;
+  if (wk.keys != reinterpret_cast<volatile unsigned long long *>(const_cast<uint64_t *>(seg))) {
+    for (uint32_t i = gt; i < cnt; i += GS) wk.keys[i] = __ldcg(reinterpret_cast<const unsigned long long *>(seg + i));
+  }
+  if (gt == 0) S.npeaks = 0;
+  gsync<GS>();
+  bitonic_sort<GS>(wk.keys, cnt, N, gt);
+  if (p.keep_stages && wk.keys != reinterpret_cast<volatile unsigned long long *>(const_cast<uint64_t *>(seg))) {
+    uint64_t *out = p.seg_keys + pbase;
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.keys[i];
   }
 
-  while (true) {
+  // (2) weights + inclusive prefix moments, C7 (apriltag_gpu.cu:631-687,984-987).  Each thread owns a
+  //     contiguous chunk; weights are parked in the (still unused) error buffer between the passes.
+  const uint32_t chunk = (cnt + GS - 1) / GS;
+  const uint32_t c_lo = min(cnt, gt * chunk), c_hi = min(cnt, c_lo + chunk);
+  long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0, t_Mx = 0, t_My = 0, t_W = 0;
+  volatile int *wbuf = reinterpret_cast<volatile int *>(wk.errs);
+  for (uint32_t i = c_lo; i < c_hi; i++) {
+    const unsigned long long k = wk.keys[i];
+    const uint32_t d = key_dir(k);
+    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
+    const int Wi = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
+    wbuf[i] = Wi;
+    const long long W = Wi;
+    t_Mx += W * ix2; t_My += W * iy2; t_Mxx += W * ix2 * ix2; t_Mxy += W * ix2 * iy2; t_Myy += W * iy2 * iy2; t_W += W;
+  }
+  long long a_Mxx, a_Myy, a_Mxy, a_Mx, a_My, a_W;
+  if constexpr (GS == 32) {
+    long long v[6] = {t_Mxx, t_Myy, t_Mxy, t_Mx, t_My, t_W};
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      long long incl = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      v[q] = incl - v[q];
+    }
+    a_Mxx = v[0]; a_Myy = v[1]; a_Mxy = v[2]; a_Mx = v[3]; a_My = v[4]; a_W = v[5];
+  } else {
+    scan[0][gt] = t_Mxx; scan[1][gt] = t_Myy; scan[2][gt] = t_Mxy;
+    scan[3][gt] = t_Mx;  scan[4][gt] = t_My;  scan[5][gt] = t_W;
     __syncthreads();
-    if (tid == 0) S.cur_blob = atomicAdd(&ctr->next_blob, 1u);
-    __syncthreads();
-    const uint32_t b = S.cur_blob;
-    if (b >= nblobs) break;
-    const b200tag_blob blob = blobs[b];
-    const uint32_t cnt = blob.count, off = blob.offset;
-    uint64_t *seg = seg_all + off;
-    b200tag_lfp *lf = lfp_all + off;
-    float *errs = errs_all + off;
-    double *filt = filt_all + off;
-
-    // (1) angle sort, C6 (apriltag_gpu.cu:944-956)
-    uint32_t N = 1;
-    while (N < cnt) N <<= 1;
-    if (cnt <= kSortCap) {
-      for (uint32_t i = tid; i < cnt; i += kFitThreads) S.sort_buf[i] = __ldcg(reinterpret_cast<const unsigned long long *>(seg + i));
-      __syncthreads();
-      bitonic_sort(S.sort_buf, cnt, N);
-      for (uint32_t i = tid; i < cnt; i += kFitThreads) seg[i] = S.sort_buf[i];
-    } else {
-      bitonic_sort(reinterpret_cast<volatile unsigned long long *>(seg), cnt, N);
+    const int warp = gt >> 5;
+    if (warp < 6) {  // exclusive scan of the 256 chunk totals: warp q scans quantity q
+      long long v[8], run = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { v[j] = scan[warp][lane * 8 + j]; run += v[j]; }
+      long long incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      long long ex = incl - run;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { scan[warp][lane * 8 + j] = ex; ex += v[j]; }
     }
     __syncthreads();
-
-    // (2) weighted moments + inclusive prefix sums, C7 (apriltag_gpu.cu:631-687,984-987)
-    const uint32_t chunk = (cnt + kFitThreads - 1) / kFitThreads;
-    const uint32_t c_lo = min(cnt, tid * chunk), c_hi = min(cnt, c_lo + chunk);
-    long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0, t_Mx = 0, t_My = 0, t_W = 0;
-    for (uint32_t i = c_lo; i < c_hi; i++) {
-      const uint64_t k = seg[i];
-      const uint32_t d = key_dir(k);
-      const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-      const long long W = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
-      t_Mx += W * ix2; t_My += W * iy2; t_Mxx += W * ix2 * ix2; t_Mxy += W * ix2 * iy2; t_Myy += W * iy2 * iy2; t_W += W;
+    a_Mxx = scan[0][gt]; a_Myy = scan[1][gt]; a_Mxy = scan[2][gt];
+    a_Mx = scan[3][gt];  a_My = scan[4][gt];  a_W = scan[5][gt];
+  }
+  for (uint32_t i = c_lo; i < c_hi; i++) {
+    const unsigned long long k = wk.keys[i];
+    const uint32_t d = key_dir(k);
+    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
+    const long long W = wbuf[i];
+    a_Mx += W * ix2; a_My += W * iy2; a_Mxx += W * ix2 * ix2; a_Mxy += W * ix2 * iy2; a_Myy += W * iy2 * iy2; a_W += W;
+    volatile b200tag_lfp *o = wk.lf + i;
+    o->Mxx = a_Mxx; o->Myy = a_Myy; o->Mxy = a_Mxy; o->Mx = a_Mx; o->My = a_My; o->W = a_W;
+  }
+  gsync<GS>();
+  if (p.keep_stages && wk.lf != p.lfp + pbase) {
+    b200tag_lfp *out = p.lfp + pbase;
+    for (uint32_t i = gt; i < cnt; i += GS) {
+      const volatile b200tag_lfp *s = wk.lf + i;
+      out[i].Mxx = s->Mxx; out[i].Myy = s->Myy; out[i].Mxy = s->Mxy; out[i].Mx = s->Mx; out[i].My = s->My; out[i].W = s->W;
     }
-    S.scan[0][tid] = t_Mxx; S.scan[1][tid] = t_Myy; S.scan[2][tid] = t_Mxy;
-    S.scan[3][tid] = t_Mx;  S.scan[4][tid] = t_My;  S.scan[5][tid] = t_W;
-    __syncthreads();
-    {  // exclusive scan of the 256 chunk totals: warp q scans quantity q
-      const int warp = tid >> 5, lane = tid & 31;
-      if (warp < 6) {
-        long long v[8], run = 0;
+  }
+
+  // (3) windowed line-fit error, K10 part 1 (line_fit_filter.cu:217-278)
+  const uint32_t ksz = min(20u, cnt / 12u);
+  for (uint32_t i = gt; i < cnt; i += GS) {
+    const uint32_t i0 = (i + 2 * cnt - ksz) % cnt, i1 = (i + cnt + ksz) % cnt;
+    const Mom m = read_moments(wk.lf, cnt, i0, i1);
+    const float eig = eig_small_of(m, nullptr, nullptr, nullptr, nullptr);
+    wk.errs[i] = static_cast<float>(m.N) * eig;
+  }
+  gsync<GS>();
+  if (p.keep_stages && wk.errs != p.errs + pbase) {
+    float *out = p.errs + pbase;
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.errs[i];
+  }
+  // (4) 7-tap smoothing in double (:504-525); filt may alias keys, which are dead by now
+  for (uint32_t i = gt; i < cnt; i += GS) {
+    const float kf[7] = {0.01110899634659290314f, 0.13533528149127960205f, 0.60653066635131835938f, 1.0f,
+                         0.60653066635131835938f, 0.13533528149127960205f, 0.01110899634659290314f};
+    double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { v[j] = S.scan[warp][lane * 8 + j]; run += v[j]; }
-        long long incl = run;
+    for (int j = 0; j < 7; j++) {
+      const double e = static_cast<double>(wk.errs[(i + cnt + j - 3) % cnt]);
+      acc += e * static_cast<double>(kf[j]);
+    }
+    wk.filt[i] = acc;
+  }
+  gsync<GS>();
+  if (p.keep_stages && wk.filt != p.filt + pbase) {
+    double *out = p.filt + pbase;
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.filt[i];
+  }
+
+  // (5) peak list: strict local maxima (:582), keyed by (-filtered as f32, index) -- C8/C9
+  //     (apriltag_gpu.cu:1001-1034).  The list overlays the error buffer (<= cnt/2 entries).
+  volatile unsigned long long *peaks = wk.peaks;
+  {
+    unsigned long long mine[8];  // a thread sees at most ceil(cnt / GS) points; batches of 8 keep it in registers
+    for (uint32_t base = gt; base < cnt; base += GS * 8) {
+      int nm = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
+      for (int j = 0; j < 8; j++) {
+        const uint32_t i = base + j * GS;
+        if (i < cnt) {
+          const double m = wk.filt[i];
+          const double bv = wk.filt[(i + cnt - 1) % cnt], av = wk.filt[(i + 1) % cnt];
+          if (m > bv && m > av) mine[nm++] = (static_cast<unsigned long long>(float_order(static_cast<float>(-m))) << 32) | i;
         }
-        long long ex = incl - run;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { S.scan[warp][lane * 8 + j] = ex; ex += v[j]; }
+      }
+      // errs is fully consumed only after every thread has computed its filtered values (gsync above)
+      if (nm) {
+        const uint32_t at = atomicAdd(&S.npeaks, static_cast<uint32_t>(nm));
+        for (int j = 0; j < nm; j++) peaks[at + j] = mine[j];
       }
     }
-    __syncthreads();
-    {
-      long long a_Mxx = S.scan[0][tid], a_Myy = S.scan[1][tid], a_Mxy = S.scan[2][tid];
-      long long a_Mx = S.scan[3][tid], a_My = S.scan[4][tid], a_W = S.scan[5][tid];
-      for (uint32_t i = c_lo; i < c_hi; i++) {
-        const uint64_t k = seg[i];
-        const uint32_t d = key_dir(k);
-        const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-        const long long W = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
-        a_Mx += W * ix2; a_My += W * iy2; a_Mxx += W * ix2 * ix2; a_Mxy += W * ix2 * iy2; a_Myy += W * iy2 * iy2; a_W += W;
-        longlong2 *q = reinterpret_cast<longlong2 *>(lf + i);
-        q[0] = make_longlong2(a_Mxx, a_Myy);
-        q[1] = make_longlong2(a_Mxy, a_Mx);
-        q[2] = make_longlong2(a_My, a_W);
-      }
-    }
-    __syncthreads();
+  }
+  gsync<GS>();
+  const uint32_t npk = S.npeaks;
+  if (npk == 0) return;  // no PeakExtents entry -> no FitQuad (uniform across the group)
 
-    // (3) windowed line-fit error, K10 part 1 (line_fit_filter.cu:217-278)
-    const uint32_t ksz = min(20u, cnt / 12u);
-    for (uint32_t i = tid; i < cnt; i += kFitThreads) {
-      const uint32_t i0 = (i + 2 * cnt - ksz) % cnt, i1 = (i + cnt + ksz) % cnt;
-      const Mom m = read_moments(lf, cnt, i0, i1);
-      const float eig = eig_small_of(m, nullptr, nullptr, nullptr, nullptr);
-      errs[i] = static_cast<float>(m.N) * eig;
-    }
-    __syncthreads();
-    // (4) 7-tap smoothing in double, (:504-525)
-    for (uint32_t i = tid; i < cnt; i += kFitThreads) {
-      const float kf[7] = {0.01110899634659290314f, 0.13533528149127960205f, 0.60653066635131835938f, 1.0f,
-                           0.60653066635131835938f, 0.13533528149127960205f, 0.01110899634659290314f};
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < 7; j++) {
-        const double e = static_cast<double>(__ldcg(errs + (i + cnt + j - 3) % cnt));
-        acc += e * static_cast<double>(kf[j]);
-      }
-      filt[i] = acc;
-    }
-    __syncthreads();
-
-    // (5) peaks: strict local maxima (:582); the 10 strongest by (-filtered as f32, index), C8-C10
-    //     (apriltag_gpu.cu:1001-1078).  Ten rounds of "smallest key above the previous one".
+  // (6) [first warp] the 10 strongest peaks, re-ordered by position, C9/C10 + line_fit_filter.cu:1104-1119
+  if (first_warp) {
     unsigned long long last = 0;
-    uint32_t npk_local = 0;
     uint32_t nsel = 0;
     for (int round = 0; round < kMaxPeaks; round++) {
       unsigned long long best = kNoKey;
-      for (uint32_t i = tid; i < cnt; i += kFitThreads) {
-        const double m = __ldcg(filt + i);
-        const double bv = __ldcg(filt + (i + cnt - 1) % cnt), av = __ldcg(filt + (i + 1) % cnt);
-        if (m > bv && m > av) {
-          if (round == 0) npk_local++;
-          const unsigned long long key = (static_cast<unsigned long long>(float_order(static_cast<float>(-m))) << 32) | i;
-          if ((round == 0 || key > last) && key < best) best = key;
-        }
+      for (uint32_t i = lane; i < npk; i += 32) {
+        const unsigned long long key = peaks[i];
+        if ((round == 0 || key > last) && key < best) best = key;
       }
-      best = block_min_u64(best, S.red);
+      best = warp_min_u64(best);
       if (best == kNoKey) break;
-      if (tid == 0) S.peak_idx[round] = static_cast<uint32_t>(best & 0xffffffffu);
+      if (lane == 0) S.peak_idx[round] = static_cast<uint32_t>(best & 0xffffffffu);
       last = best;
       nsel++;
     }
-    {  // total number of peaks (PeakExtents.count)
-      uint32_t v = npk_local;
+    __syncwarp();
+    if (lane == 0) {
+      for (uint32_t a = 1; a < nsel; a++) {
+        const uint32_t v2 = S.peak_idx[a];
+        int q = static_cast<int>(a) - 1;
+        while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
+        S.peak_idx[q + 1] = v2;
+      }
+      S.nsel = nsel;
+    }
+  }
+  gsync<GS>();
+
+  // (7) side-fit table: every ordered pair of chosen peaks (<= 90 fits instead of 4 per combination)
+  const int nm = static_cast<int>(S.nsel);
+  const double max_mse = static_cast<double>(p.max_line_fit_mse);
+  for (int t = gt; t < nm * nm; t += GS) {
+    const int a = t / nm, c = t % nm;
+    if (a == c) continue;
+    const Mom mo = read_moments(wk.lf, cnt, S.peak_idx[a], S.peak_idx[c]);
+    double err, mse, nrm[2];
+    fit_line(mo, nullptr, nrm, &err, &mse);
+    S.seg_err[a][c] = (mse > max_mse) ? kDblMax : err;  // line_fit_filter.cu:964-966,1009,1027,1035
+    S.seg_nx[a][c] = nrm[0];
+    S.seg_ny[a][c] = nrm[1];
+  }
+  gsync<GS>();
+
+  // (8) [first warp] exhaustive search over the C(10,4) corner choices, K11 (line_fit_filter.cu:976-1048,1161)
+  if (first_warp) {
+    const double max_dot = static_cast<double>(p.cos_critical_rad);
+    double my_err = kDblMax;
+    int my_rank = kNumCombos;
+    for (int c = lane; c < kNumCombos; c += 32) {
+      const int m0 = d_combos[c][0], m1 = d_combos[c][1], m2 = d_combos[c][2], m3 = d_combos[c][3];
+      if (m3 >= nm) continue;
+      const double e01 = S.seg_err[m0][m1];
+      if (e01 == kDblMax) continue;
+      const double e12 = S.seg_err[m1][m2];
+      if (e12 == kDblMax) continue;
+      const double dot = S.seg_nx[m0][m1] * S.seg_nx[m1][m2] + S.seg_ny[m0][m1] * S.seg_ny[m1][m2];
+      if (fabs(dot) > max_dot) continue;
+      const double e23 = S.seg_err[m2][m3];
+      if (e23 == kDblMax) continue;
+      const double e30 = S.seg_err[m3][m0];
+      if (e30 == kDblMax) continue;
+      const double tot = e01 + e12 + e23 + e30;
+      if (tot < my_err) { my_err = tot; my_rank = c; }  // ranks ascend per lane: ties keep the lowest
+    }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      __syncthreads();
-      if ((tid & 31) == 0) S.red[tid >> 5] = v;
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t s = 0;
-        for (int q = 0; q < kFitThreads / 32; q++) s += static_cast<uint32_t>(S.red[q]);
-        S.npeaks = s;
-        // re-order the chosen maxima by position (line_fit_filter.cu:1104-1119)
-        for (uint32_t a = 1; a < nsel; a++) {
-          const uint32_t v2 = S.peak_idx[a];
-          int q = static_cast<int>(a) - 1;
-          while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
-          S.peak_idx[q + 1] = v2;
-        }
-      }
-      __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oe = __shfl_xor_sync(0xffffffffu, my_err, o);
+      const int orank = __shfl_xor_sync(0xffffffffu, my_rank, o);
+      if (oe < my_err || (oe == my_err && orank < my_rank)) { my_err = oe; my_rank = orank; }
     }
-    if (S.npeaks == 0) continue;  // no PeakExtents entry -> no FitQuad
 
-    // (6) exhaustive search over the C(10,4) corner choices, K11 (line_fit_filter.cu:889-1061,1088-1193)
-    const int nm = static_cast<int>(nsel);
-    double my_err = 1.7976931348623157e308;
-    if (tid < kNumCombos) {
-      const int m0 = S.combos[tid][0], m1 = S.combos[tid][1], m2 = S.combos[tid][2], m3 = S.combos[tid][3];
-      if (m3 < nm) {
-        const double max_mse = static_cast<double>(p.max_line_fit_mse);
-        const double max_dot = static_cast<double>(p.cos_critical_rad);
-        double e01, mse01, p01[2], e12, mse12, p12[2], e23, mse23, e30, mse30;
-        bool ok = true;
-        Mom mo = read_moments(lf, cnt, S.peak_idx[m0], S.peak_idx[m1]);
-        fit_line(mo, nullptr, p01, &e01, &mse01);
-        if (mse01 > max_mse) ok = false;
-        if (ok) {
-          mo = read_moments(lf, cnt, S.peak_idx[m1], S.peak_idx[m2]);
-          fit_line(mo, nullptr, p12, &e12, &mse12);
-          if (mse12 > max_mse) ok = false;
-        }
-        if (ok) {
-          const double dot = p01[0] * p12[0] + p01[1] * p12[1];
-          if (fabs(dot) > max_dot) ok = false;
-        }
-        if (ok) {
-          mo = read_moments(lf, cnt, S.peak_idx[m2], S.peak_idx[m3]);
-          fit_line(mo, nullptr, nullptr, &e23, &mse23);
-          if (mse23 > max_mse) ok = false;
-        }
-        if (ok) {
-          mo = read_moments(lf, cnt, S.peak_idx[m3], S.peak_idx[m0]);
-          fit_line(mo, nullptr, nullptr, &e30, &mse30);
-          if (mse30 > max_mse) ok = false;
-        }
-        if (ok) my_err = e01 + e12 + e23 + e30;
-      }
-    }
-    S.cand_err[tid] = my_err;
-    __syncthreads();
-
-    // (7) finalisation by one thread: FitQuad, then UpdateFitQuads + AdjustPixelCenters
-    //     (apriltag_detect.cu:98-282)
-    if (tid == 0) {
-      double best = 1.7976931348623157e308;
-      int bi = 0;
-      for (int c = 0; c < kNumCombos; c++)
-        if (S.cand_err[c] < best) { best = S.cand_err[c]; bi = c; }  // ties keep the lowest rank
+    // (9) [one lane] FitQuad, then UpdateFitQuads + AdjustPixelCenters (apriltag_detect.cu:98-282)
+    if (lane == 0) {
+      const double best = my_err;
+      const int bi = my_rank < kNumCombos ? my_rank : 0;
       const bool valid = best < static_cast<double>(p.max_line_fit_mse * static_cast<float>(cnt));
       const uint32_t fq = atomicAdd(&ctr->num_fit_quads, 1u);
       Mom moms[4];
       uint32_t idx[4] = {0, 0, 0, 0};
       if (valid) {
-        for (int i = 0; i < 4; i++) idx[i] = S.peak_idx[S.combos[bi][i]];
-        for (int i = 0; i < 4; i++) moms[i] = read_moments(lf, cnt, idx[i], idx[(i + 1) & 3]);
+        for (int i = 0; i < 4; i++) idx[i] = S.peak_idx[d_combos[bi][i]];
+        for (int i = 0; i < 4; i++) moms[i] = read_moments(wk.lf, cnt, idx[i], idx[(i + 1) & 3]);
       }
-      if (fq < p.blob_cap) {
-        b200tag_fit_quad &o = fit_quads[fq];
+      if (fq < p.blob_cap && (p.keep_stages || true)) {
+        b200tag_fit_quad &o = (p.fit_quads + static_cast<size_t>(frame) * p.blob_cap)[fq];
         o.blob_index = b;
         o.valid = valid;
-        o.num_peaks = static_cast<int32_t>(S.npeaks);
+        o.num_peaks = static_cast<int32_t>(npk);
         o.err = best;
         for (int i = 0; i < 4; i++) {
           o.indices[i] = idx[i];
@@ -614,7 +650,7 @@ __global__ void __launch_bounds__(kFitThreads) k_fit_blobs(FrameParams p) {
           }
           const uint32_t qi = atomicAdd(&ctr->num_quads, 1u);
           if (qi < p.quad_cap) {
-            b200tag_quad &q = quads[qi];
+            b200tag_quad &q = (p.quads + static_cast<size_t>(frame) * p.quad_cap)[qi];
             for (int j = 0; j < 4; j++) { q.corners[j][0] = cr[j][0]; q.corners[j][1] = cr[j][1]; }
             q.reversed_border = p.reversed_border && !p.normal_border;
             q.blob_index = b;
@@ -629,22 +665,106 @@ __global__ void __launch_bounds__(kFitThreads) k_fit_blobs(FrameParams p) {
   }
 }
 
+// ---- small tier: one warp per blob ------------------------------------------------------------
+struct SmallWarpShared {
+  unsigned long long keys[kSmallBlobPoints];  // sort keys, later the filtered errors (same size)
+  b200tag_lfp lf[kSmallBlobPoints];
+  float errs[kSmallBlobPoints];               // weights -> errors -> peak list
+  BlobScratch scratch;
+};
+
+__global__ void __launch_bounds__(kSmallWarps * 32) k_fit_small(FrameParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  Counters *ctr = p.counters + frame;
+  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
+  const uint32_t *list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
+  const uint32_t nlist = min(ctr->num_small, p.blob_cap);
+  BlobWork wk;
+  wk.keys = S.keys;
+  wk.lf = S.lf;
+  wk.errs = S.errs;
+  wk.filt = reinterpret_cast<volatile double *>(S.keys);
+  wk.peaks = reinterpret_cast<volatile unsigned long long *>(S.errs);
+  while (true) {
+    __syncwarp();
+    if (lane == 0) S.scratch.cur = atomicAdd(&ctr->next_small, 1u);
+    __syncwarp();
+    const uint32_t li = S.scratch.cur;
+    if (li >= nlist) break;
+    const uint32_t b = list[li];
+    const b200tag_blob blob = blobs[b];
+    fit_one_blob<32>(p, frame, ctr, b, blob, wk, S.scratch, nullptr, lane);
+  }
+}
+
+// ---- large tier: one CTA per blob -------------------------------------------------------------
+struct LargeShared {
+  unsigned long long keys[kSortCap];
+  b200tag_lfp lf[kLfpCap];
+  float errs[kSortCap];
+  long long scan[6][kLargeThreads];
+  BlobScratch scratch;
+};
+
+__global__ void __launch_bounds__(kLargeThreads) k_fit_large(FrameParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LargeShared &S = *reinterpret_cast<LargeShared *>(smem_raw);
+  const int frame = blockIdx.y;
+  const int tid = threadIdx.x;
+  Counters *ctr = p.counters + frame;
+  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
+  const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
+  const uint32_t nlist = min(ctr->num_large, p.blob_cap);
+  while (true) {
+    __syncthreads();
+    if (tid == 0) S.scratch.cur = atomicAdd(&ctr->next_large, 1u);
+    __syncthreads();
+    const uint32_t li = S.scratch.cur;
+    if (li >= nlist) break;
+    const uint32_t b = list[li];
+    const b200tag_blob blob = blobs[b];
+    const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
+    BlobWork wk;
+    const bool in_smem = blob.count <= kSortCap;
+    wk.keys = in_smem ? S.keys : reinterpret_cast<volatile unsigned long long *>(p.seg_keys + pbase);
+    wk.errs = in_smem ? S.errs : p.errs + pbase;
+    wk.filt = in_smem ? reinterpret_cast<volatile double *>(S.keys) : p.filt + pbase;
+    wk.lf = blob.count <= kLfpCap ? S.lf : p.lfp + pbase;
+    wk.peaks = in_smem ? reinterpret_cast<volatile unsigned long long *>(S.errs)
+                       : reinterpret_cast<volatile unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
+    fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+  }
+}
+
+static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_fit_blobs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FitShared)));
-    attr_set = true;
+  static bool dev_ready[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !dev_ready[dev]) {
+    cudaFuncSetAttribute(k_fit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallWarpShared) * kSmallWarps));
+    cudaFuncSetAttribute(k_fit_large, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
+    k_init_combos<<<1, 1, 0, s>>>();
+    dev_ready[dev] = true;
   }
   if (kt) kt->begin("select", s);
   k_select<<<dim3(min(p.hash_cap / 256u, 296u), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("scatter", s);
-  k_scatter<<<dim3(592, frames), 256, 0, s>>>(p);
+  k_scatter<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
-  if (kt) kt->begin("fit_blobs", s);
-  k_fit_blobs<<<dim3(296, frames), kFitThreads, sizeof(FitShared), s>>>(p);
+  // resident capacity: 3 small-tier CTAs (4 warps = 4 blobs each) and 2 large-tier CTAs per SM
+  if (kt) kt->begin("fit_small", s);
+  k_fit_small<<<dim3(max(4u, min(444u, cdivu(1776u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
   if (kt) kt->end(s);
-  return 3;
+  if (kt) kt->begin("fit_large", s);
+  k_fit_large<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p);
+  if (kt) kt->end(s);
+  return 4;
 }
 
 }  // namespace b200tag
