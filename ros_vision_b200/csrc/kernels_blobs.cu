@@ -161,16 +161,16 @@ __global__ void __launch_bounds__(256) k_scatter(FrameParams p) {
 //   small blobs (<= 256 points, ~3/4 of all blobs): ONE WARP per blob, everything in shared
 //     memory, only __syncwarp between phases;
 //   large blobs: one 256-thread CTA per blob; sort / errors / peaks in shared memory up to 4096
-//     points, prefix moments in shared memory up to 768 points, the rare bigger blob works in
+//     points, prefix moments in shared memory up to 1024 points, the rare bigger blob works in
 //     its own (L2-resident) segment of the global arrays.
 // Phases: bitonic angle sort -> weights + prefix moments -> windowed line-fit error -> 7-tap
 // smoothing -> peak list -> [one warp] 10 strongest peaks -> table of the <= 90 candidate side
-// fits -> [one warp] 210 corner combinations + argmin -> [one lane] corners and quad tests.
+// fits -> [one warp] 210 corner combinations + argmin -> [4 lanes] lines and corners, quad tests.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLargeThreads = 256;
 constexpr int kSmallWarps = 4;          // warps (= blobs in flight) per small-tier CTA
 constexpr uint32_t kSortCap = 4096;     // large tier: points sorted / filtered in shared memory
-constexpr uint32_t kLfpCap = 768;       // large tier: prefix moments kept in shared memory
+constexpr uint32_t kLfpCap = 1024;      // large tier: prefix moments kept in shared memory
 
 template <int GS>
 __device__ __forceinline__ void gsync() {
@@ -178,8 +178,7 @@ __device__ __forceinline__ void gsync() {
   else __syncthreads();
 }
 
-template <typename Ptr>
-__device__ __forceinline__ void cmpxchg(Ptr a, uint32_t i, uint32_t l) {
+__device__ __forceinline__ void cmpxchg(unsigned long long *a, uint32_t i, uint32_t l) {
   const unsigned long long x = a[i], y = a[l];
   if (x > y) {
     a[i] = y;
@@ -188,25 +187,35 @@ __device__ __forceinline__ void cmpxchg(Ptr a, uint32_t i, uint32_t l) {
 }
 
 // All-ascending bitonic network over N = pow2 >= cnt slots; slots >= cnt are virtual +inf and
-// never move, so no padding is materialised.
-template <int GS, typename Ptr>
-__device__ void bitonic_sort(Ptr a, uint32_t cnt, uint32_t N, uint32_t gt) {
-  for (uint32_t k = 2; k <= N; k <<= 1) {
+// never move, so no padding is materialised.  Pair index t always belongs to the same warp
+// (t = gt + it * GS) and, for compare distances <= 32, touches only the 64 elements of chunk
+// t / 32, so those stages need no block-wide barrier.
+template <int GS>
+__device__ __forceinline__ void bitonic_sort(unsigned long long *a, uint32_t cnt, uint32_t N, uint32_t gt) {
+  const uint32_t half = N >> 1;
+  for (uint32_t k = 2, lk = 1; k <= N; k <<= 1, lk++) {
     const uint32_t hk = k >> 1;
-    for (uint32_t t = gt; t < (N >> 1); t += GS) {
-      const uint32_t blk = t / hk, w = t % hk;
-      const uint32_t i = blk * k + w, l = blk * k + k - 1 - w;
+    for (uint32_t t = gt; t < half; t += GS) {
+      const uint32_t blk = t >> (lk - 1), w = t & (hk - 1);
+      const uint32_t i = (blk << lk) + w, l = (blk << lk) + k - 1 - w;
       if (l < cnt) cmpxchg(a, i, l);
     }
-    gsync<GS>();
+    // this flip is wide iff k > 64; the following stage (j = k/4, or the next flip if k == 2) is wide iff j >= 64
+    if (GS > 32 && (k > 64 || (k == 2 ? false : (k >> 2) >= 64))) __syncthreads();
+    else __syncwarp();
     for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-      for (uint32_t t = gt; t < (N >> 1); t += GS) {
-        const uint32_t i = 2 * j * (t / j) + (t % j), l = i + j;
+      for (uint32_t t = gt; t < half; t += GS) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i + j;
         if (l < cnt) cmpxchg(a, i, l);
       }
-      gsync<GS>();
+      // next stage: distance j/2, or (after j == 1) the flip of 2k
+      const bool this_wide = j >= 64;
+      const bool next_wide = (j > 1) ? ((j >> 1) >= 64) : ((k << 1) > 64);
+      if (GS > 32 && (this_wide || next_wide)) __syncthreads();
+      else __syncwarp();
     }
   }
+  gsync<GS>();
 }
 
 struct Mom {
@@ -215,24 +224,24 @@ struct Mom {
 };
 
 // ReadMoments, line_fit_filter.cu:745-796 (== CalculateError's window logic, :230-274)
-__device__ __forceinline__ Mom read_moments(const volatile b200tag_lfp *lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
+__device__ __forceinline__ Mom read_moments(const b200tag_lfp *lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
   Mom m;
   if (i0 < i1) {
     m.N = static_cast<int>(i1 - i0 + 1);
-    const volatile b200tag_lfp *a = lf + i1;
-    m.Mx = a->Mx; m.My = a->My; m.Mxx = a->Mxx; m.Mxy = a->Mxy; m.Myy = a->Myy; m.W = a->W;
+    const b200tag_lfp a = lf[i1];
+    m.Mx = a.Mx; m.My = a.My; m.Mxx = a.Mxx; m.Mxy = a.Mxy; m.Myy = a.Myy; m.W = a.W;
     if (i0 > 0) {
-      const volatile b200tag_lfp *b = lf + i0 - 1;
-      m.Mx -= b->Mx; m.My -= b->My; m.Mxx -= b->Mxx; m.Mxy -= b->Mxy; m.Myy -= b->Myy; m.W -= b->W;
+      const b200tag_lfp b = lf[i0 - 1];
+      m.Mx -= b.Mx; m.My -= b.My; m.Mxx -= b.Mxx; m.Mxy -= b.Mxy; m.Myy -= b.Myy; m.W -= b.W;
     }
   } else {
-    const volatile b200tag_lfp *b = lf + i0 - 1, *z = lf + cnt - 1, *a = lf + i1;
-    m.Mx = z->Mx - b->Mx + a->Mx;
-    m.My = z->My - b->My + a->My;
-    m.Mxx = z->Mxx - b->Mxx + a->Mxx;
-    m.Mxy = z->Mxy - b->Mxy + a->Mxy;
-    m.Myy = z->Myy - b->Myy + a->Myy;
-    m.W = z->W - b->W + a->W;
+    const b200tag_lfp b = lf[i0 - 1], z = lf[cnt - 1], a = lf[i1];
+    m.Mx = z.Mx - b.Mx + a.Mx;
+    m.My = z.My - b.My + a.My;
+    m.Mxx = z.Mxx - b.Mxx + a.Mxx;
+    m.Mxy = z.Mxy - b.Mxy + a.Mxy;
+    m.Myy = z.Myy - b.Myy + a.Myy;
+    m.W = z.W - b.W + a.W;
     m.N = static_cast<int>(cnt - i0 + i1 + 1);
   }
   return m;
@@ -251,7 +260,7 @@ __device__ __forceinline__ float eig_small_of(const Mom &m, float *hyp_out, long
   return eig;
 }
 
-__device__ void fit_line(const Mom &m, double *lp01, double *lp23, double *err, double *mse) {
+__device__ __forceinline__ void fit_line(const Mom &m, double *lp01, double *lp23, double *err, double *mse) {
   float hyp;
   long long Cxx, Cxy, Cyy;
   const float eig = eig_small_of(m, &hyp, &Cxx, &Cxy, &Cyy);
@@ -308,12 +317,12 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 struct BlobScratch {
   double seg_err[kMaxPeaks][kMaxPeaks];  // fit error of side (a -> b); kDblMax if mse > max_line_fit_mse
   double seg_nx[kMaxPeaks][kMaxPeaks], seg_ny[kMaxPeaks][kMaxPeaks];
+  double lines[4][4];
+  float corners[4][2];
   uint32_t peak_idx[kMaxPeaks];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
   uint32_t cur;      // blob being processed
-  int best_combo;
-  double best_err;
 };
 
 // nested-loop (Unrank) order of the C(10,4) corner choices, line_fit_filter.cu:709-728
@@ -330,53 +339,61 @@ __global__ void k_init_combos() {
         }
 }
 
-// Working storage of one blob: shared or global memory, chosen by the caller.
+// Working storage of one blob: shared or global memory, chosen by the caller.  Cross-thread hand-offs
+// always go through gsync<GS>(), so plain (non-volatile) accesses are sufficient.
 struct BlobWork {
-  volatile unsigned long long *keys;  // cnt sort keys; dead after the moments phase
-  volatile b200tag_lfp *lf;           // cnt prefix moments
-  volatile float *errs;               // cnt errors, later overlaid by the peak list (cnt/2 x u64)
-  volatile double *filt;              // cnt filtered errors (may alias keys)
-  volatile unsigned long long *peaks; // <= cnt/2 peak keys (may alias errs, which is dead by then)
+  unsigned long long *keys;  // cnt sort keys; dead after the moments phase
+  b200tag_lfp *lf;           // cnt prefix moments
+  float *errs;               // cnt weights, then errors
+  double *filt;              // cnt filtered errors (may alias keys)
+  unsigned long long *peaks; // <= cnt/2 peak keys (may alias errs, which is dead by then)
+  bool keys_in_place;        // keys == the blob's segment of p.seg_keys (sorted in place)
 };
 
 template <int GS>
-__device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
-                             const BlobWork &wk, BlobScratch &S, long long (*scan)[kLargeThreads], uint32_t gt) {
+__device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
+                                             const BlobWork &wk, BlobScratch &S, long long (*scan)[kLargeThreads], uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
   const uint32_t cnt = blob.count, off = blob.offset;
   const size_t pbase = static_cast<size_t>(frame) * p.point_cap + off;
-  const uint64_t *seg = p.seg_keys + pbase;
   const int lane = threadIdx.x & 31;
   const bool first_warp = gt < 32;
 
   // (1) angle sort, C6 (apriltag_gpu.cu:944-956)
   uint32_t N = 1;
   while (N < cnt) N <<= 1;
-  if (wk.keys != reinterpret_cast<volatile unsigned long long *>(const_cast<uint64_t *>(seg))) {
-    for (uint32_t i = gt; i < cnt; i += GS) wk.keys[i] = __ldcg(reinterpret_cast<const unsigned long long *>(seg + i));
+  if (!wk.keys_in_place) {
+    const unsigned long long *seg = reinterpret_cast<const unsigned long long *>(p.seg_keys + pbase);
+    for (uint32_t i = gt; i < cnt; i += GS) wk.keys[i] = __ldcg(seg + i);
   }
   if (gt == 0) S.npeaks = 0;
   gsync<GS>();
   bitonic_sort<GS>(wk.keys, cnt, N, gt);
-  if (p.keep_stages && wk.keys != reinterpret_cast<volatile unsigned long long *>(const_cast<uint64_t *>(seg))) {
+  if (p.keep_stages && !wk.keys_in_place) {
     uint64_t *out = p.seg_keys + pbase;
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.keys[i];
   }
 
-  // (2) weights + inclusive prefix moments, C7 (apriltag_gpu.cu:631-687,984-987).  Each thread owns a
-  //     contiguous chunk; weights are parked in the (still unused) error buffer between the passes.
+  // (2) weights (independent gathers, strided) then inclusive prefix moments over contiguous chunks,
+  //     C7 (apriltag_gpu.cu:631-687,984-987).  Weights are parked in the still unused error buffer.
+  int *wbuf = reinterpret_cast<int *>(wk.errs);
+#pragma unroll 4
+  for (uint32_t i = gt; i < cnt; i += GS) {
+    const unsigned long long k = wk.keys[i];
+    const uint32_t d = key_dir(k);
+    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
+    wbuf[i] = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
+  }
+  gsync<GS>();
   const uint32_t chunk = (cnt + GS - 1) / GS;
   const uint32_t c_lo = min(cnt, gt * chunk), c_hi = min(cnt, c_lo + chunk);
   long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0, t_Mx = 0, t_My = 0, t_W = 0;
-  volatile int *wbuf = reinterpret_cast<volatile int *>(wk.errs);
   for (uint32_t i = c_lo; i < c_hi; i++) {
     const unsigned long long k = wk.keys[i];
     const uint32_t d = key_dir(k);
     const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-    const int Wi = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
-    wbuf[i] = Wi;
-    const long long W = Wi;
+    const long long W = wbuf[i];
     t_Mx += W * ix2; t_My += W * iy2; t_Mxx += W * ix2 * ix2; t_Mxy += W * ix2 * iy2; t_Myy += W * iy2 * iy2; t_W += W;
   }
   long long a_Mxx, a_Myy, a_Mxy, a_Mx, a_My, a_W;
@@ -422,22 +439,23 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
     const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
     const long long W = wbuf[i];
     a_Mx += W * ix2; a_My += W * iy2; a_Mxx += W * ix2 * ix2; a_Mxy += W * ix2 * iy2; a_Myy += W * iy2 * iy2; a_W += W;
-    volatile b200tag_lfp *o = wk.lf + i;
-    o->Mxx = a_Mxx; o->Myy = a_Myy; o->Mxy = a_Mxy; o->Mx = a_Mx; o->My = a_My; o->W = a_W;
+    b200tag_lfp o;
+    o.Mxx = a_Mxx; o.Myy = a_Myy; o.Mxy = a_Mxy; o.Mx = a_Mx; o.My = a_My; o.W = a_W;
+    wk.lf[i] = o;
   }
   gsync<GS>();
   if (p.keep_stages && wk.lf != p.lfp + pbase) {
     b200tag_lfp *out = p.lfp + pbase;
-    for (uint32_t i = gt; i < cnt; i += GS) {
-      const volatile b200tag_lfp *s = wk.lf + i;
-      out[i].Mxx = s->Mxx; out[i].Myy = s->Myy; out[i].Mxy = s->Mxy; out[i].Mx = s->Mx; out[i].My = s->My; out[i].W = s->W;
-    }
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.lf[i];
   }
 
   // (3) windowed line-fit error, K10 part 1 (line_fit_filter.cu:217-278)
   const uint32_t ksz = min(20u, cnt / 12u);
+#pragma unroll 2
   for (uint32_t i = gt; i < cnt; i += GS) {
-    const uint32_t i0 = (i + 2 * cnt - ksz) % cnt, i1 = (i + cnt + ksz) % cnt;
+    uint32_t i0 = i + cnt - ksz, i1 = i + ksz;  // (i + 2cnt - ksz) % cnt and (i + cnt + ksz) % cnt without division
+    if (i0 >= cnt) i0 -= cnt;
+    if (i1 >= cnt) i1 -= cnt;
     const Mom m = read_moments(wk.lf, cnt, i0, i1);
     const float eig = eig_small_of(m, nullptr, nullptr, nullptr, nullptr);
     wk.errs[i] = static_cast<float>(m.N) * eig;
@@ -452,10 +470,13 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
     const float kf[7] = {0.01110899634659290314f, 0.13533528149127960205f, 0.60653066635131835938f, 1.0f,
                          0.60653066635131835938f, 0.13533528149127960205f, 0.01110899634659290314f};
     double acc = 0.0;
+    uint32_t q = i + cnt - 3;  // cnt >= 24 > 3
+    if (q >= cnt) q -= cnt;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-      const double e = static_cast<double>(wk.errs[(i + cnt + j - 3) % cnt]);
+      const double e = static_cast<double>(wk.errs[q]);
       acc += e * static_cast<double>(kf[j]);
+      if (++q == cnt) q = 0;
     }
     wk.filt[i] = acc;
   }
@@ -466,26 +487,13 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
   }
 
   // (5) peak list: strict local maxima (:582), keyed by (-filtered as f32, index) -- C8/C9
-  //     (apriltag_gpu.cu:1001-1034).  The list overlays the error buffer (<= cnt/2 entries).
-  volatile unsigned long long *peaks = wk.peaks;
-  {
-    unsigned long long mine[8];  // a thread sees at most ceil(cnt / GS) points; batches of 8 keep it in registers
-    for (uint32_t base = gt; base < cnt; base += GS * 8) {
-      int nm = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint32_t i = base + j * GS;
-        if (i < cnt) {
-          const double m = wk.filt[i];
-          const double bv = wk.filt[(i + cnt - 1) % cnt], av = wk.filt[(i + 1) % cnt];
-          if (m > bv && m > av) mine[nm++] = (static_cast<unsigned long long>(float_order(static_cast<float>(-m))) << 32) | i;
-        }
-      }
-      // errs is fully consumed only after every thread has computed its filtered values (gsync above)
-      if (nm) {
-        const uint32_t at = atomicAdd(&S.npeaks, static_cast<uint32_t>(nm));
-        for (int j = 0; j < nm; j++) peaks[at + j] = mine[j];
-      }
+  //     (apriltag_gpu.cu:1001-1034).  At most cnt/2 entries.
+  for (uint32_t i = gt; i < cnt; i += GS) {
+    const double m = wk.filt[i];
+    const double bv = wk.filt[i == 0 ? cnt - 1 : i - 1], av = wk.filt[i + 1 == cnt ? 0 : i + 1];
+    if (m > bv && m > av) {
+      const uint32_t at = atomicAdd(&S.npeaks, 1u);
+      wk.peaks[at] = (static_cast<unsigned long long>(float_order(static_cast<float>(-m))) << 32) | i;
     }
   }
   gsync<GS>();
@@ -499,34 +507,31 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
     for (int round = 0; round < kMaxPeaks; round++) {
       unsigned long long best = kNoKey;
       for (uint32_t i = lane; i < npk; i += 32) {
-        const unsigned long long key = peaks[i];
+        const unsigned long long key = wk.peaks[i];
         if ((round == 0 || key > last) && key < best) best = key;
       }
       best = warp_min_u64(best);
       if (best == kNoKey) break;
-      if (lane == 0) S.peak_idx[round] = static_cast<uint32_t>(best & 0xffffffffu);
       last = best;
       nsel++;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      for (uint32_t a = 1; a < nsel; a++) {
-        const uint32_t v2 = S.peak_idx[a];
-        int q = static_cast<int>(a) - 1;
+      // insertion into the position-ordered list (lane 0), one element per round
+      if (lane == 0) {
+        const uint32_t v2 = static_cast<uint32_t>(best & 0xffffffffu);
+        int q = static_cast<int>(nsel) - 2;
         while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
         S.peak_idx[q + 1] = v2;
       }
-      S.nsel = nsel;
     }
+    if (lane == 0) S.nsel = nsel;
   }
   gsync<GS>();
 
   // (7) side-fit table: every ordered pair of chosen peaks (<= 90 fits instead of 4 per combination)
   const int nm = static_cast<int>(S.nsel);
   const double max_mse = static_cast<double>(p.max_line_fit_mse);
-  for (int t = gt; t < nm * nm; t += GS) {
-    const int a = t / nm, c = t % nm;
-    if (a == c) continue;
+  for (int t = gt; t < kMaxPeaks * kMaxPeaks; t += GS) {
+    const int a = t / kMaxPeaks, c = t % kMaxPeaks;
+    if (a == c || a >= nm || c >= nm) continue;
     const Mom mo = read_moments(wk.lf, cnt, S.peak_idx[a], S.peak_idx[c]);
     double err, mse, nrm[2];
     fit_line(mo, nullptr, nrm, &err, &mse);
@@ -542,7 +547,8 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
     double my_err = kDblMax;
     int my_rank = kNumCombos;
     for (int c = lane; c < kNumCombos; c += 32) {
-      const int m0 = d_combos[c][0], m1 = d_combos[c][1], m2 = d_combos[c][2], m3 = d_combos[c][3];
+      const uchar4 cm = *reinterpret_cast<const uchar4 *>(d_combos[c]);
+      const int m0 = cm.x, m1 = cm.y, m2 = cm.z, m3 = cm.w;
       if (m3 >= nm) continue;
       const double e01 = S.seg_err[m0][m1];
       if (e01 == kDblMax) continue;
@@ -564,56 +570,60 @@ __device__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uin
       if (oe < my_err || (oe == my_err && orank < my_rank)) { my_err = oe; my_rank = orank; }
     }
 
-    // (9) [one lane] FitQuad, then UpdateFitQuads + AdjustPixelCenters (apriltag_detect.cu:98-282)
-    if (lane == 0) {
-      const double best = my_err;
-      const int bi = my_rank < kNumCombos ? my_rank : 0;
-      const bool valid = best < static_cast<double>(p.max_line_fit_mse * static_cast<float>(cnt));
-      const uint32_t fq = atomicAdd(&ctr->num_fit_quads, 1u);
-      Mom moms[4];
-      uint32_t idx[4] = {0, 0, 0, 0};
+    // (9) FitQuad, then UpdateFitQuads + AdjustPixelCenters (apriltag_detect.cu:98-282): lanes 0..3 fit
+    //     one side each and intersect one corner each; lane 0 runs the quad tests.
+    const double best = my_err;
+    const int bi = my_rank < kNumCombos ? my_rank : 0;
+    const bool valid = best < static_cast<double>(p.max_line_fit_mse * static_cast<float>(cnt));
+    uint32_t fq = 0;
+    if (lane == 0) fq = atomicAdd(&ctr->num_fit_quads, 1u);
+    fq = __shfl_sync(0xffffffffu, fq, 0);
+    b200tag_fit_quad *fqo = (fq < p.blob_cap) ? (p.fit_quads + static_cast<size_t>(frame) * p.blob_cap + fq) : nullptr;
+    if (lane == 0 && fqo) {
+      fqo->blob_index = b;
+      fqo->valid = valid;
+      fqo->num_peaks = static_cast<int32_t>(npk);
+      fqo->err = best;
+    }
+    if (lane < 4) {
+      uint32_t i0 = 0, i1 = 0;
+      Mom mo;
       if (valid) {
-        for (int i = 0; i < 4; i++) idx[i] = S.peak_idx[d_combos[bi][i]];
-        for (int i = 0; i < 4; i++) moms[i] = read_moments(wk.lf, cnt, idx[i], idx[(i + 1) & 3]);
+        i0 = S.peak_idx[d_combos[bi][lane]];
+        i1 = S.peak_idx[d_combos[bi][(lane + 1) & 3]];
+        mo = read_moments(wk.lf, cnt, i0, i1);  // line_fit_filter.cu:1188-1191
+        double err, mse;
+        fit_line(mo, S.lines[lane], S.lines[lane] + 2, &err, &mse);
       }
-      if (fq < p.blob_cap && (p.keep_stages || true)) {
-        b200tag_fit_quad &o = (p.fit_quads + static_cast<size_t>(frame) * p.blob_cap)[fq];
-        o.blob_index = b;
-        o.valid = valid;
-        o.num_peaks = static_cast<int32_t>(npk);
-        o.err = best;
-        for (int i = 0; i < 4; i++) {
-          o.indices[i] = idx[i];
-          if (valid) {
-            o.moments[i].Mx = moms[i].Mx; o.moments[i].My = moms[i].My; o.moments[i].W = moms[i].W;
-            o.moments[i].Mxx = moms[i].Mxx; o.moments[i].Myy = moms[i].Myy; o.moments[i].Mxy = moms[i].Mxy;
-            o.moments[i].N = moms[i].N; o.moments[i].pad = 0;
-          } else {
-            o.moments[i] = b200tag_moments{0, 0, 0, 0, 0, 0, 0, 0};
-          }
-        }
+      if (fqo) {
+        fqo->indices[lane] = i0;
+        b200tag_moments mm = b200tag_moments{0, 0, 0, 0, 0, 0, 0, 0};
+        if (valid) { mm.Mx = mo.Mx; mm.My = mo.My; mm.W = mo.W; mm.Mxx = mo.Mxx; mm.Myy = mo.Myy; mm.Mxy = mo.Mxy; mm.N = mo.N; }
+        fqo->moments[lane] = mm;
       }
-      if (valid) {
-        double lines[4][4];
-        for (int i = 0; i < 4; i++) {
-          double err, mse;
-          fit_line(moms[i], lines[i], lines[i] + 2, &err, &mse);
-        }
+    }
+    __syncwarp();
+    if (valid) {
+      bool bad = false;
+      if (lane < 4) {  // apriltag_detect.cu:125-166
+        const int i = lane, nx = (lane + 1) & 3;
+        const double A00 = S.lines[i][3], A01 = -S.lines[nx][3];
+        const double A10 = -S.lines[i][2], A11 = S.lines[nx][2];
+        const double B0 = -S.lines[i][0] + S.lines[nx][0];
+        const double B1 = -S.lines[i][1] + S.lines[nx][1];
+        const double det = A00 * A11 - A10 * A01;
+        const double W00 = A11 / det, W01 = -A01 / det;
+        if (fabs(det) < 0.001) bad = true;
+        const double L0 = W00 * B0 + W01 * B1;
+        S.corners[i][0] = static_cast<float>(S.lines[i][0] + L0 * A00);
+        S.corners[i][1] = static_cast<float>(S.lines[i][1] + L0 * A10);
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      __syncwarp();
+      if (lane == 0 && !bad) {
         float cr[4][2];
-        bool bad = false;
-        for (int i = 0; i < 4 && !bad; i++) {  // apriltag_detect.cu:125-166
-          const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
-          const double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
-          const double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
-          const double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
-          const double det = A00 * A11 - A10 * A01;
-          const double W00 = A11 / det, W01 = -A01 / det;
-          if (fabs(det) < 0.001) { bad = true; break; }
-          const double L0 = W00 * B0 + W01 * B1;
-          cr[i][0] = static_cast<float>(lines[i][0] + L0 * A00);
-          cr[i][1] = static_cast<float>(lines[i][1] + L0 * A10);
-        }
-        if (!bad) {  // :171-207
+        for (int j = 0; j < 4; j++) { cr[j][0] = S.corners[j][0]; cr[j][1] = S.corners[j][1]; }
+        {  // :171-207
           float area = 0;
           float length[3], pp;
           for (int i = 0; i < 3; i++) {
@@ -673,7 +683,7 @@ struct SmallWarpShared {
   BlobScratch scratch;
 };
 
-__global__ void __launch_bounds__(kSmallWarps * 32) k_fit_small(FrameParams p) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
   const int frame = blockIdx.y;
@@ -686,8 +696,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32) k_fit_small(FrameParams p) {
   wk.keys = S.keys;
   wk.lf = S.lf;
   wk.errs = S.errs;
-  wk.filt = reinterpret_cast<volatile double *>(S.keys);
-  wk.peaks = reinterpret_cast<volatile unsigned long long *>(S.errs);
+  wk.filt = reinterpret_cast<double *>(S.keys);
+  wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
+  wk.keys_in_place = false;
   while (true) {
     __syncwarp();
     if (lane == 0) S.scratch.cur = atomicAdd(&ctr->next_small, 1u);
@@ -709,7 +720,7 @@ struct LargeShared {
   BlobScratch scratch;
 };
 
-__global__ void __launch_bounds__(kLargeThreads) k_fit_large(FrameParams p) {
+__global__ void __launch_bounds__(kLargeThreads, 2) k_fit_large(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LargeShared &S = *reinterpret_cast<LargeShared *>(smem_raw);
   const int frame = blockIdx.y;
@@ -728,14 +739,25 @@ __global__ void __launch_bounds__(kLargeThreads) k_fit_large(FrameParams p) {
     const b200tag_blob blob = blobs[b];
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
-    const bool in_smem = blob.count <= kSortCap;
-    wk.keys = in_smem ? S.keys : reinterpret_cast<volatile unsigned long long *>(p.seg_keys + pbase);
-    wk.errs = in_smem ? S.errs : p.errs + pbase;
-    wk.filt = in_smem ? reinterpret_cast<volatile double *>(S.keys) : p.filt + pbase;
-    wk.lf = blob.count <= kLfpCap ? S.lf : p.lfp + pbase;
-    wk.peaks = in_smem ? reinterpret_cast<volatile unsigned long long *>(S.errs)
-                       : reinterpret_cast<volatile unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
-    fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+    if (blob.count <= kLfpCap) {  // everything in shared memory
+      wk.keys = S.keys; wk.lf = S.lf; wk.errs = S.errs;
+      wk.filt = reinterpret_cast<double *>(S.keys);
+      wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
+      wk.keys_in_place = false;
+      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+    } else if (blob.count <= kSortCap) {  // prefix moments in the blob's global segment
+      wk.keys = S.keys; wk.lf = p.lfp + pbase; wk.errs = S.errs;
+      wk.filt = reinterpret_cast<double *>(S.keys);
+      wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
+      wk.keys_in_place = false;
+      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+    } else {  // too large for shared memory: work in place in the global arrays
+      wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
+      wk.lf = p.lfp + pbase; wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
+      wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
+      wk.keys_in_place = true;
+      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+    }
   }
 }
 

@@ -1,0 +1,15 @@
+#!/usr/bin/env python3
+"""Pretty-prints a bench.py JSON line (file or stdin)."""
+import json, sys
+txt = open(sys.argv[1]).read() if len(sys.argv) > 1 else sys.stdin.read()
+d = json.loads(txt.strip().splitlines()[-1])
+print(f"value {d['value']:.0f} {d['unit']}  ms/step {d['ms_per_step']:.3f}  e2e {d['e2e']['value']:.0f}  p50 {d.get('p50_latency_ms', 0):.3f} ms  gpus {d['n_gpus']}")
+r = d.get("roofline") or {}
+for k in r.get("kernels", []):
+    g = k["gbs"]
+    print(f"  {k['kernel']:16s} {k['ms']:8.3f} ms  {('%7.0f GB/s' % g) if g else ''}")
+if r:
+    print(f"  dominant {r['kernel']} frac {r['frac']}, whole-path {r['whole_path']['achieved']:.1f} GB/s")
+cb = d.get("cpu_baseline")
+if cb: print("  cpu", round(cb["value"], 1), cb["unit"], cb["cores"], "threads")
+print("  clocks", d.get("clocks"))
