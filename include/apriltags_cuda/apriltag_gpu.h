@@ -1,0 +1,114 @@
+// Header-compatible replacement for the reference's
+// src/apriltags_cuda/include/apriltags_cuda/apriltag_gpu.h (frc971::apriltag::GpuDetector, :77-359).
+//
+// Same namespace, class name, public members and ownership rules, so
+// ApriltagsDetector::setup_apriltags / imageCallback (apriltags_cuda_detector.cu:178-179,404,410,497),
+// gpu_detector_test.cu and the demos compile against it unchanged.  The implementation forwards to the
+// C ABI in include/b200tag.h (libb200tag.so); nothing CUDA-specific leaks into this header, so callers no
+// longer need nvcc/clang-cuda to include it.
+//
+// Not carried over: the debug copies typed to the reference's packed device structs
+// (QuadBoundaryPoint / IndexPoint / LineFitPoint / Peak, apriltag_gpu.h:111-183) -- their 20-bit blob ids
+// and 10-bit coordinates cannot represent frames beyond 1024x1024 quad pixels.  The same stages are
+// available, unpacked, through b200tag_copy_stage().
+#ifndef B200TAG_APRILTAGS_CUDA_APRILTAG_GPU_H_
+#define B200TAG_APRILTAGS_CUDA_APRILTAG_GPU_H_
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+extern "C" {
+#include "apriltag.h"
+}
+#include "b200tag.h"
+
+namespace frc971::apriltag {
+
+struct QuadCorners {  // apriltag_gpu.h:55-59
+  float corners[4][2];
+  bool reversed_border;
+  uint32_t blob_index;
+};
+
+struct CameraMatrix {  // apriltag_gpu.h:61-66 (note the field order)
+  double fx;
+  double cx;
+  double fy;
+  double cy;
+};
+
+struct DistCoeffs {  // apriltag_gpu.h:68-74
+  double k1;
+  double k2;
+  double p1;
+  double p2;
+  double k3;
+};
+
+class GpuDetector {
+ public:
+  // The number of blobs we will consider when counting april tags (apriltag_gpu.h:80).  The reference
+  // silently overflows beyond this; this engine sizes its lists from the frame and reports overflow.
+  static constexpr size_t kMaxBlobs = 2048;
+
+  // apriltag_gpu.h:84-85.  `tag_detector` stays owned by the caller and is read at construction
+  // (quad_decimate, quad_sigma, refine_edges, decode_sharpening, qtp, tag_families).
+  // Violated preconditions abort, like the reference's CHECK/LOG(FATAL) (cuda_frc971.h:14-17).
+  GpuDetector(size_t width, size_t height, apriltag_detector_t *tag_detector, CameraMatrix camera_matrix,
+              DistCoeffs distortion_coefficients);
+  // Extension: frames in another pixel format (B200TAG_FMT_*), e.g. the node's bgr8 image directly.
+  GpuDetector(size_t width, size_t height, apriltag_detector_t *tag_detector, CameraMatrix camera_matrix,
+              DistCoeffs distortion_coefficients, int pixel_format);
+  virtual ~GpuDetector();
+  GpuDetector(const GpuDetector &) = delete;
+  GpuDetector &operator=(const GpuDetector &) = delete;
+
+  // Detects april tags in the provided image (host pointer, YUYV 4:2:2 unless constructed otherwise).
+  void Detect(const uint8_t *image);
+
+  const std::vector<QuadCorners> &FitQuads() const;
+  const zarray_t *Detections() const { return detections_; }
+  void ReinitializeDetections();
+
+  // Debug methods to expose internal state for testing (apriltag_gpu.h:98-109,131-133).
+  void CopyGrayTo(uint8_t *output) const;
+  void CopyDecimatedTo(uint8_t *output) const;
+  void CopyThresholdedTo(uint8_t *output) const;
+  void CopyUnionMarkersTo(uint32_t *output) const;
+  void CopyUnionMarkersSizeTo(uint32_t *output) const;
+  int NumCompressedUnionMarkerPairs() const;  // :127
+  int NumQuads() const;                       // :135  number of blob pairs
+  int NumSelectedPairs() const;               // :146  points of the selected blobs
+  int NumFitQuads() const;                    // :179
+
+  void AdjustCenter(float corners[4][2]) const;  // :185
+
+  void SetCameraMatrix(CameraMatrix camera_matrix);                       // :189-191
+  void SetDistortionCoefficients(DistCoeffs distortion_coefficients);     // :193-195
+
+  // Undistort pixels based on our camera model, using iterative algorithm.  Returns false if we fail
+  // to converge (:199-200).
+  static bool UnDistort(double *u, double *v, const CameraMatrix *camera_matrix,
+                        const DistCoeffs *distortion_coefficients);
+
+  // The underlying C-ABI handle (batching, stage copies, profiling).
+  b200tag_detector *handle() const { return handle_; }
+
+ private:
+  void Init(size_t width, size_t height, apriltag_detector_t *td, CameraMatrix cam, DistCoeffs dist, int fmt);
+  void ClearDetections();
+
+  const size_t width_;
+  const size_t height_;
+  apriltag_detector_t *tag_detector_;
+  b200tag_detector *handle_ = nullptr;
+  CameraMatrix camera_matrix_;
+  DistCoeffs distortion_coefficients_;
+  mutable std::vector<QuadCorners> quad_corners_host_;
+  zarray_t *detections_ = nullptr;
+};
+
+}  // namespace frc971::apriltag
+
+#endif
