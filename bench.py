@@ -236,24 +236,49 @@ def run_ours(args):
     value = total_frames / (ms * 1e-3)
 
     # --- end to end: pinned host frames -> detections on the host -------------------------------
+    # `lanes` detectors (one CUDA stream each) take turns, so lane k's host->device copies overlap
+    # lane k-1's kernels; every frame still crosses PCIe inside the timed region and its detections
+    # are collected on the host (Finish) before the lane is reused.
+    L = max(1, args.lanes)
+    per_lane = B // L
+    lanes = [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=per_lane, device=local)
+             for _ in range(L)]
     pinned = [D.PinnedBuffer(frame_bytes) for _ in range(B)]
     for i, pb in enumerate(pinned):
         pb.array[:] = host_batch[i]
     ptrs = [pb.ptr for pb in pinned]
+    lane_ptrs = [ptrs[l * per_lane:(l + 1) * per_lane] for l in range(L)]
+
+    def e2e_step():
+        n = 0
+        for l, ld in enumerate(lanes):
+            ld.EnqueuePointers(lane_ptrs[l])   # waits for + collects this lane's previous batch first
+        return n
+
     for _ in range(3):
-        det.DetectPointers(ptrs)
+        e2e_step()
+    for ld in lanes:
+        ld.Finish()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        det.DetectPointers(ptrs)  # H2D of B frames + all kernels + result read-back, synchronous
+        e2e_step()
+    e2e_dets = 0
+    for ld in lanes:
+        ld.Finish()
+        e2e_dets += sum(len(ld.Detections(f)) for f in range(per_lane))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = total_frames / e2e_s
-    d2h = 64 * B + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
+    e2e_frames = per_lane * L * args.steps * world
+    e2e_value = e2e_frames / e2e_s
+    assert e2e_dets == sum(len(det.Detections(f)) for f in range(per_lane * L)), "end-to-end path lost detections"
+    d2h = 64 * per_lane * L + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
+    for ld in lanes:
+        ld.close()
 
     # --- single-frame latency (host frame in, detections out) -----------------------------------
     det1 = D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=1, device=local)
@@ -297,7 +322,8 @@ def run_ours(args):
                        "l2": "inputs (262 MB/step/GPU) and intermediates exceed the 126 MB L2; no explicit flush",
                        "sharding": "frames by rank, no collective"},
             "p50_latency_ms": p50, "p99_latency_ms": p99,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * B, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
+                    "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cb, "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs,
@@ -320,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--latency-iters", type=int, default=200)
+    ap.add_argument("--lanes", type=int, default=2, help="detector instances (CUDA streams) used by the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

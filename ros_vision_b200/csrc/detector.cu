@@ -333,7 +333,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   det->in_bytes = N * bpp;
   p.point_cap = cfg->max_points ? cfg->max_points : static_cast<uint32_t>(2 * n);
   uint32_t hc = 4096;
-  while (hc < n / 8) hc <<= 1;
+  while (hc < n / 8 && hc < (1u << 19)) hc <<= 1;  // 20-bit blob indices in Counters::alloc
   p.hash_cap = hc;
   p.blob_cap = cfg->max_blobs ? cfg->max_blobs : static_cast<uint32_t>(std::min<size_t>(65536, std::max<size_t>(4096, n / 32)));
   p.quad_cap = std::min<uint32_t>(p.blob_cap, 8192);
@@ -358,6 +358,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_hmaxx = plan.take(HB * 4), o_hmaxy = plan.take(HB * 4), o_hgx = plan.take(HB * 4), o_hgy = plan.take(HB * 4);
   const size_t o_hdot = plan.take(HB * 8);
   const size_t o_sb = plan.take(HB * 4);
+  const size_t o_occ = plan.take(HB * 4);
   const size_t o_blobs = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_blob) * B);
   const size_t o_fill = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
   const size_t o_small = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
@@ -405,6 +406,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.h_gy = reinterpret_cast<int32_t *>(base + o_hgy);
   p.h_dot = reinterpret_cast<long long *>(base + o_hdot);
   p.slot_blob = reinterpret_cast<int32_t *>(base + o_sb);
+  p.occupied = reinterpret_cast<uint32_t *>(base + o_occ);
   p.blobs = reinterpret_cast<b200tag_blob *>(base + o_blobs);
   p.blob_fill = reinterpret_cast<uint32_t *>(base + o_fill);
   p.small_list = reinterpret_cast<uint32_t *>(base + o_small);
@@ -517,8 +519,8 @@ int b200tag_frame_info_get(const b200tag_detector *det, int frame, b200tag_frame
   const Counters &c = det->h_counters[frame];
   info->status = c.status;
   info->num_points = std::min(c.num_points, det->fp.point_cap);
-  info->num_clusters = c.num_clusters;
-  info->num_blobs = std::min(c.num_blobs, det->fp.blob_cap);
+  info->num_clusters = alloc_clusters(c.alloc);
+  info->num_blobs = std::min(alloc_blobs(c.alloc), det->fp.blob_cap);
   info->num_selected_points = c.num_selected_points;
   info->num_fit_quads = std::min(c.num_fit_quads, det->fp.blob_cap);
   info->num_quads = std::min(c.num_quads, det->fp.quad_cap);
@@ -587,10 +589,10 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
       }
       return 0;
     }
-    case B200TAG_STAGE_BLOBS: src = p.blobs + f * p.blob_cap; bytes = std::min(c.num_blobs, p.blob_cap) * sizeof(b200tag_blob); break;
+    case B200TAG_STAGE_BLOBS: src = p.blobs + f * p.blob_cap; bytes = std::min(alloc_blobs(c.alloc), p.blob_cap) * sizeof(b200tag_blob); break;
     case B200TAG_STAGE_CLUSTERS:
       if (!p.clusters) return B200TAG_E_INVALID;
-      src = p.clusters + f * p.cluster_cap; bytes = std::min(c.num_clusters, p.cluster_cap) * sizeof(b200tag_blob); break;
+      src = p.clusters + f * p.cluster_cap; bytes = std::min(alloc_clusters(c.alloc), p.cluster_cap) * sizeof(b200tag_blob); break;
     case B200TAG_STAGE_SORTED_POINTS: src = p.seg_keys + f * p.point_cap; bytes = nsel * 8ull; break;
     case B200TAG_STAGE_LINE_FIT_POINTS: src = p.lfp + f * p.point_cap; bytes = nsel * sizeof(b200tag_lfp); break;
     case B200TAG_STAGE_ERRORS: src = p.errs + f * p.point_cap; bytes = nsel * 4ull; break;

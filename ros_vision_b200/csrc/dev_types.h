@@ -49,19 +49,20 @@ __host__ __device__ inline int dir_dy(uint32_t d) { return d == 0 ? 0 : 1; }
 struct Counters {  // one per frame, zeroed before each frame
   uint32_t status;
   uint32_t num_points;
-  uint32_t num_clusters;
-  uint32_t num_blobs;
+  unsigned long long alloc;  // [63:40] blob pairs | [39:20] selected blobs | [19:0] small blobs (k_select)
   uint32_t num_selected_points;
   uint32_t num_fit_quads;
   uint32_t num_quads;
   uint32_t num_detections;
   uint32_t next_quad;   // dynamic work counters
-  uint32_t num_small;   // selected blobs with <= kSmallBlobPoints points (one warp each)
-  uint32_t num_large;   // the rest (one CTA each)
   uint32_t next_small;
   uint32_t next_large;
-  uint32_t pad[3];
+  uint32_t num_occupied;  // claimed hash slots (listed in FrameParams::occupied)
+  uint32_t pad[4];
 };
+__host__ __device__ inline uint32_t alloc_clusters(unsigned long long a) { return static_cast<uint32_t>(a >> 40); }
+__host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return static_cast<uint32_t>(a >> 20) & 0xfffffu; }
+__host__ __device__ inline uint32_t alloc_small(unsigned long long a) { return static_cast<uint32_t>(a) & 0xfffffu; }
 static_assert(sizeof(Counters) == 64, "Counters layout");
 
 struct FrameParams {
@@ -105,6 +106,7 @@ struct FrameParams {
   int32_t *h_gx, *h_gy;
   long long *h_dot;
   int32_t *slot_blob;   // hash_cap
+  uint32_t *occupied;   // hash_cap: slots claimed this frame, in claim order
   b200tag_blob *blobs;  // blob_cap
   uint32_t *blob_fill;  // blob_cap
   uint32_t *small_list; // blob_cap: indices of blobs fitted by one warp

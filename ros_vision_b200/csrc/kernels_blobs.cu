@@ -17,6 +17,8 @@
 
 namespace b200tag {
 
+static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
 // ---------------------------------------------------------------------------------------------
 // K7
 // ---------------------------------------------------------------------------------------------
@@ -36,7 +38,15 @@ __device__ __forceinline__ bool select_blob(const FrameParams &p, uint32_t count
   return true;
 }
 
+// One atomic pair per CTA: the per-frame allocation state is packed as
+//   alloc = [63:40] clusters | [39:20] blobs | [19:0] small blobs      (large index = blob - small)
+// so cluster index, blob index and work-list positions of 256 hash slots come from a single
+// 64-bit atomicAdd (the first version issued ~4 returning atomics per warp on one cache line and
+// spent 97 % of its time waiting for them).
 __global__ void __launch_bounds__(256) k_select(FrameParams p) {
+  __shared__ uint32_t s_warp[8][4];  // per-warp totals: occupied, selected, small, points
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_pbase;
   const int frame = blockIdx.y;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
   Counters *ctr = p.counters + frame;
@@ -45,11 +55,15 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
   uint32_t *small_list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
   uint32_t *large_list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   b200tag_blob *clusters = p.clusters ? p.clusters + static_cast<size_t>(frame) * p.cluster_cap : nullptr;
-  const int lane = threadIdx.x & 31;
-  // hash_cap is a multiple of the block size, so every warp runs the same trip count
-  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < p.hash_cap; slot += gridDim.x * blockDim.x) {
-    const unsigned long long key = p.h_key[hoff + slot];
-    const bool occ = key != kEmptyKey;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nocc = min(ctr->num_occupied, p.hash_cap);
+  const uint32_t *occupied = p.occupied + hoff;
+  // every thread of a CTA runs the same trip count (the loop bound is rounded up to the block size)
+  const uint32_t nround = (nocc + blockDim.x - 1) / blockDim.x * blockDim.x;
+  for (uint32_t oi = blockIdx.x * blockDim.x + threadIdx.x; oi < nround; oi += gridDim.x * blockDim.x) {
+    const bool occ = oi < nocc;
+    const uint32_t slot = occ ? occupied[oi] : 0u;
+    const unsigned long long key = occ ? p.h_key[hoff + slot] : kEmptyKey;
     b200tag_blob rec;
     bool sel = false;
     if (occ) {
@@ -78,47 +92,74 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       p.h_gy[hoff + slot] = 0;
       p.h_dot[hoff + slot] = 0;
     }
-    // warp-aggregated allocation: cluster index, blob index, point offset
+    const bool small = sel && rec.count <= kSmallBlobPoints;
     const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
     const uint32_t sel_mask = __ballot_sync(0xffffffffu, sel);
+    const uint32_t small_mask = __ballot_sync(0xffffffffu, small);
     uint32_t incl = sel ? rec.count : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    const uint32_t total_pts = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t cbase = 0, bbase = 0, pbase = 0;
+    const uint32_t warp_pts = __shfl_sync(0xffffffffu, incl, 31);
     if (lane == 0) {
-      if (occ_mask) cbase = atomicAdd(&ctr->num_clusters, __popc(occ_mask));
-      if (sel_mask) {
-        bbase = atomicAdd(&ctr->num_blobs, __popc(sel_mask));
-        pbase = atomicAdd(&ctr->num_selected_points, total_pts);
-      }
+      s_warp[warp][0] = __popc(occ_mask);
+      s_warp[warp][1] = __popc(sel_mask);
+      s_warp[warp][2] = __popc(small_mask);
+      s_warp[warp][3] = warp_pts;
     }
-    cbase = __shfl_sync(0xffffffffu, cbase, 0);
-    bbase = __shfl_sync(0xffffffffu, bbase, 0);
-    pbase = __shfl_sync(0xffffffffu, pbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      for (int w = 0; w < 8; w++) {
+        const uint32_t a0 = s_warp[w][0], a1 = s_warp[w][1], a2 = s_warp[w][2], a3 = s_warp[w][3];
+        s_warp[w][0] = t0; s_warp[w][1] = t1; s_warp[w][2] = t2; s_warp[w][3] = t3;  // exclusive prefixes
+        t0 += a0; t1 += a1; t2 += a2; t3 += a3;
+      }
+      unsigned long long base = 0;
+      uint32_t pb = 0;
+      if (t0) {
+        const unsigned long long add = (static_cast<unsigned long long>(t0) << 40) | (static_cast<unsigned long long>(t1) << 20) | t2;
+        base = atomicAdd(&ctr->alloc, add);
+        if (t3) pb = atomicAdd(&ctr->num_selected_points, t3);
+      }
+      s_base = base;
+      s_pbase = pb;
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    const uint32_t cbase = static_cast<uint32_t>(base >> 40) + s_warp[warp][0];
+    const uint32_t bbase = static_cast<uint32_t>(base >> 20) & 0xfffffu;
+    const uint32_t sbase = static_cast<uint32_t>(base) & 0xfffffu;
     int32_t blob_id = -1;
     if (sel) {
-      const uint32_t b = bbase + __popc(sel_mask & ((1u << lane) - 1u));
-      const uint32_t off = pbase + incl - rec.count;
+      const uint32_t bw = s_warp[warp][1] + __popc(sel_mask & ((1u << lane) - 1u));    // rank among this CTA's blobs
+      const uint32_t sw = s_warp[warp][2] + __popc(small_mask & ((1u << lane) - 1u));  // ... among its small blobs
+      const uint32_t b = bbase + bw;
+      const uint32_t off = s_pbase + s_warp[warp][3] + incl - rec.count;
       if (b < p.blob_cap && static_cast<uint64_t>(off) + rec.count <= p.point_cap) {
         rec.offset = off;
         blobs[b] = rec;
         fill[b] = 0;
         blob_id = static_cast<int32_t>(b);
-        if (rec.count <= kSmallBlobPoints) small_list[atomicAdd(&ctr->num_small, 1u)] = b;
-        else large_list[atomicAdd(&ctr->num_large, 1u)] = b;
+        if (small) small_list[sbase + sw] = b;
+        else large_list[(bbase - sbase) + (bw - sw)] = b;
       } else {
         atomicOr(&ctr->status, B200TAG_ST_BLOBS_OVERFLOW);
+        // keep the work lists dense: an overflowing blob still occupies its list slot, flagged invalid
+        if (b < p.blob_cap) {
+          if (small) small_list[sbase + sw] = 0xffffffffu;
+          else large_list[(bbase - sbase) + (bw - sw)] = 0xffffffffu;
+        }
       }
     }
     if (occ && clusters) {
       const uint32_t c = cbase + __popc(occ_mask & ((1u << lane) - 1u));
       if (c < p.cluster_cap) clusters[c] = rec;
     }
-    p.slot_blob[hoff + slot] = blob_id;
+    if (occ) p.slot_blob[hoff + slot] = blob_id;
+    __syncthreads();  // s_warp / s_base are reused by the next trip
   }
 }
 
@@ -691,7 +732,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
   Counters *ctr = p.counters + frame;
   const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t nlist = min(ctr->num_small, p.blob_cap);
+  const uint32_t nlist = min(alloc_small(ctr->alloc), p.blob_cap);
   BlobWork wk;
   wk.keys = S.keys;
   wk.lf = S.lf;
@@ -706,6 +747,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
     const uint32_t b = list[li];
+    if (b == 0xffffffffu) continue;
     const b200tag_blob blob = blobs[b];
     fit_one_blob<32>(p, frame, ctr, b, blob, wk, S.scratch, nullptr, lane);
   }
@@ -728,7 +770,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) k_fit_large(FrameParams p) {
   Counters *ctr = p.counters + frame;
   const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t nlist = min(ctr->num_large, p.blob_cap);
+  const uint32_t nlist = min(alloc_blobs(ctr->alloc) - alloc_small(ctr->alloc), p.blob_cap);
   while (true) {
     __syncthreads();
     if (tid == 0) S.scratch.cur = atomicAdd(&ctr->next_large, 1u);
@@ -736,6 +778,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) k_fit_large(FrameParams p) {
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
     const uint32_t b = list[li];
+    if (b == 0xffffffffu) continue;
     const b200tag_blob blob = blobs[b];
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
@@ -761,8 +804,6 @@ __global__ void __launch_bounds__(kLargeThreads, 2) k_fit_large(FrameParams p) {
   }
 }
 
-static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
-
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
   static bool dev_ready[64] = {false};
   int dev = 0;
@@ -774,7 +815,7 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
     dev_ready[dev] = true;
   }
   if (kt) kt->begin("select", s);
-  k_select<<<dim3(min(p.hash_cap / 256u, 296u), frames), 256, 0, s>>>(p);
+  k_select<<<dim3(max(1u, min(16u, cdivu(148u * 4u, frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("scatter", s);
   k_scatter<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);

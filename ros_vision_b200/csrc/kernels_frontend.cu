@@ -245,11 +245,12 @@ __global__ void __launch_bounds__(128) k_threshold(FrameParams p) {
 // Label of a component = its smallest pixel index (roots are kept minimal by atomicMin
 // links), size[root] = pixel count.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCclTW = 64;  // tile width  (two 32-lane halves per row)
-constexpr int kCclTH = 32;  // tile height
+constexpr int kCclTW = 32;  // tile width: one lane per column, rows are 32-bit run masks
+constexpr int kCclTH = 64;  // tile height
 constexpr int kCclThreads = 256;
+constexpr int kCclRowsPerThread = kCclTH / (kCclThreads / 32);
 
-__device__ __forceinline__ uint32_t sfind(volatile uint32_t *par, uint32_t a) {
+__device__ __forceinline__ uint32_t sfind(const uint32_t *par, uint32_t a) {
   uint32_t q = par[a];
   while (q != a) {
     a = q;
@@ -274,18 +275,13 @@ __device__ __forceinline__ void sunite(uint32_t *par, uint32_t a, uint32_t b) {
   }
 }
 
-// Start (x index) of the maximal run of set bits of `m` that contains bit x.
-__device__ __forceinline__ int run_start64(unsigned long long m, int x) {
-  const unsigned long long below = (~m) & ((1ull << x) - 1ull);
-  return below ? 64 - __clzll(static_cast<long long>(below)) : 0;
-}
-
-// K3: one CTA labels a 64x32 tile entirely in shared memory.  Rows are turned into run
-// bitmasks with __ballot_sync, every pixel starts out pointing at the first pixel of its
-// run, and only the pixels that begin an overlap with a run in the row above issue a union.
+// K3: one CTA labels a 32x64 tile entirely in shared memory.  Lane = column, so a row's white /
+// black pixels are two __ballot_sync masks; every pixel starts out pointing at the first pixel of
+// its horizontal run (one __clz), and only pixels that begin an overlap with a run in the row
+// above issue a union.  Pixel values stay in registers; shared memory holds the masks, the parent
+// array and the per-root counts.
 __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
-  __shared__ uint8_t s_px[kCclTH][kCclTW];
-  __shared__ unsigned long long s_white[kCclTH], s_black[kCclTH];
+  __shared__ uint32_t s_white[kCclTH], s_black[kCclTH];
   __shared__ uint32_t s_par[kCclTH * kCclTW];
   __shared__ uint32_t s_cnt[kCclTH * kCclTW];
 
@@ -296,99 +292,98 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   uint32_t *labels = p.labels + frame * n;
   uint32_t *sizes = p.sizes + frame * n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tw = min(kCclTW, p.w - x0), thh = min(kCclTH, p.h - y0);
+  const int gx = x0 + lane;
+  const bool col_ok = gx < p.w;
 
-  // stage the tile: 16 pixels (16 bytes) per thread-iteration; quad width is a multiple of 4
-  for (int i = tid; i < kCclTH * (kCclTW / 4); i += kCclThreads) {
-    const int r = i / (kCclTW / 4), c4 = (i % (kCclTW / 4)) * 4;
-    uint32_t v = 0x7f7f7f7fu;  // outside the image: 127 (joins nothing)
-    if (r < thh && c4 < tw) v = *reinterpret_cast<const uint32_t *>(th + static_cast<size_t>(y0 + r) * p.w + x0 + c4);
-    *reinterpret_cast<uint32_t *>(&s_px[r][c4]) = v;
-  }
-  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) s_cnt[i] = 0;
-  __syncthreads();
-
-  // row bitmasks: warp w handles rows w, w+8, ...
-  for (int r = warp; r < kCclTH; r += kCclThreads / 32) {
-    const uint8_t a = s_px[r][lane], b = s_px[r][lane + 32];
-    const uint32_t wl = __ballot_sync(0xffffffffu, a == 255), wh = __ballot_sync(0xffffffffu, b == 255);
-    const uint32_t bl = __ballot_sync(0xffffffffu, a == 0), bh = __ballot_sync(0xffffffffu, b == 0);
+  // rows warp, warp + 8, ...: pixel values in registers, run masks to shared memory
+  uint32_t v[kCclRowsPerThread];
+#pragma unroll
+  for (int k = 0; k < kCclRowsPerThread; k++) {
+    const int r = warp + k * (kCclThreads / 32);
+    const int gy = y0 + r;
+    uint32_t px = 127;  // outside the image: joins nothing
+    if (col_ok && gy < p.h) px = th[static_cast<size_t>(gy) * p.w + gx];
+    v[k] = px;
+    const uint32_t wm = __ballot_sync(0xffffffffu, px == 255), bm = __ballot_sync(0xffffffffu, px == 0);
     if (lane == 0) {
-      s_white[r] = (static_cast<unsigned long long>(wh) << 32) | wl;
-      s_black[r] = (static_cast<unsigned long long>(bh) << 32) | bl;
+      s_white[r] = wm;
+      s_black[r] = bm;
     }
+    s_cnt[r * kCclTW + lane] = 0;
   }
   __syncthreads();
 
   // initial parents: first pixel of the horizontal run
-  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
-    const int r = i / kCclTW, x = i % kCclTW;
-    const uint8_t v = s_px[r][x];
+  const uint32_t below_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < kCclRowsPerThread; k++) {
+    const int r = warp + k * (kCclThreads / 32);
+    const int i = r * kCclTW + lane;
     uint32_t par = i;
-    if (v != 127) par = r * kCclTW + run_start64(v ? s_white[r] : s_black[r], x);
+    if (v[k] != 127) {
+      const uint32_t m = v[k] ? s_white[r] : s_black[r];
+      const uint32_t below = ~m & below_mask;
+      par = r * kCclTW + (below ? 32 - __clz(below) : 0);
+    }
     s_par[i] = par;
   }
   __syncthreads();
 
   // vertical / diagonal unions, issued once per run overlap
-  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
-    const int r = i / kCclTW, x = i % kCclTW;
-    if (r == 0) continue;
-    const uint8_t v = s_px[r][x];
-    if (v == 127) continue;
-    const unsigned long long cur = v ? s_white[r] : s_black[r];
-    const unsigned long long up = v ? s_white[r - 1] : s_black[r - 1];
-    const bool is_start = (x == 0) || !((cur >> (x - 1)) & 1ull);
-    const bool u = (up >> x) & 1ull;
-    const bool ul = (x > 0) && ((up >> (x - 1)) & 1ull);
+#pragma unroll
+  for (int k = 0; k < kCclRowsPerThread; k++) {
+    const int r = warp + k * (kCclThreads / 32);
+    if (r == 0 || v[k] == 127) continue;
+    const int i = r * kCclTW + lane;
+    const bool white = v[k] != 0;
+    const uint32_t cur = white ? s_white[r] : s_black[r];
+    const uint32_t up = white ? s_white[r - 1] : s_black[r - 1];
+    const bool is_start = (lane == 0) || !((cur >> (lane - 1)) & 1u);
+    const bool u = (up >> lane) & 1u;
+    const bool ul = (lane > 0) && ((up >> (lane - 1)) & 1u);
     if (u) {
       if (is_start || !ul) sunite(s_par, i, i - kCclTW);
-    } else if (v == 255) {
+    } else if (white) {
       if (ul && is_start) sunite(s_par, i, i - kCclTW - 1);
-      const bool ur = (x + 1 < kCclTW) && ((up >> (x + 1)) & 1ull);
-      const bool right_same = (x + 1 < kCclTW) && ((cur >> (x + 1)) & 1ull);
+      const bool ur = (lane + 1 < kCclTW) && ((up >> (lane + 1)) & 1u);
+      const bool right_same = (lane + 1 < kCclTW) && ((cur >> (lane + 1)) & 1u);
       if (ur && !right_same) sunite(s_par, i, i - kCclTW + 1);
     }
   }
   __syncthreads();
 
-  // flatten + per-root pixel counts (one shared atomic per run)
-  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
-    const int r = i / kCclTW, x = i % kCclTW;
-    const uint8_t v = s_px[r][x];
-    if (v == 127) continue;
-    const uint32_t root = sfind(s_par, i);
-    const unsigned long long cur = v ? s_white[r] : s_black[r];
-    const bool is_start = (x == 0) || !((cur >> (x - 1)) & 1ull);
+  // per-root pixel counts: one shared atomic per run
+#pragma unroll
+  for (int k = 0; k < kCclRowsPerThread; k++) {
+    const int r = warp + k * (kCclThreads / 32);
+    if (v[k] == 127) continue;
+    const uint32_t cur = v[k] ? s_white[r] : s_black[r];
+    const bool is_start = (lane == 0) || !((cur >> (lane - 1)) & 1u);
     if (is_start) {
-      // run length: consecutive set bits from x upwards
-      const unsigned long long inv = ~(cur >> x);
-      const int len = inv ? (__ffsll(static_cast<long long>(inv)) - 1) : (64 - x);
-      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len));
+      const uint32_t inv = ~(cur >> lane);
+      const int len = inv ? (__ffs(inv) - 1) : (32 - lane);
+      atomicAdd(&s_cnt[sfind(s_par, r * kCclTW + lane)], static_cast<uint32_t>(len));
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < kCclTH * kCclTW; i += kCclThreads) {
-    const int r = i / kCclTW, x = i % kCclTW;
-    if (s_px[r][x] != 127) s_par[i] = sfind(s_par, i);  // roots are fixed now: safe to compress in place
   }
   __syncthreads();
 
-  // write out: label = global index of the local root; sizes = count at local roots, 0 elsewhere
-  for (int i = tid; i < kCclTH * (kCclTW / 4); i += kCclThreads) {
-    const int r = i / (kCclTW / 4), c4 = (i % (kCclTW / 4)) * 4;
-    if (r >= thh || c4 >= tw) continue;
-    uint32_t lab[4], sz[4];
+  // write out: label = global index of the local root; sizes = count at local roots, 0 elsewhere.
+  // Each warp writes one 128-byte row segment per array.
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int li = r * kCclTW + c4 + k;
-      const uint32_t root = s_par[li];
-      lab[k] = static_cast<uint32_t>((y0 + root / kCclTW) * p.w + x0 + root % kCclTW);
-      sz[k] = (root == static_cast<uint32_t>(li)) ? s_cnt[li] : 0u;
+  for (int k = 0; k < kCclRowsPerThread; k++) {
+    const int r = warp + k * (kCclThreads / 32);
+    const int gy = y0 + r;
+    if (!col_ok || gy >= p.h) continue;
+    const uint32_t i = r * kCclTW + lane;
+    const size_t g = static_cast<size_t>(gy) * p.w + gx;
+    uint32_t lab = static_cast<uint32_t>(g), sz = 0;
+    if (v[k] != 127) {
+      const uint32_t root = sfind(s_par, i);
+      lab = static_cast<uint32_t>((y0 + (root >> 5)) * p.w + x0 + (root & 31));
+      if (root == i) sz = s_cnt[i];
     }
-    const size_t g = static_cast<size_t>(y0 + r) * p.w + x0 + c4;
-    *reinterpret_cast<uint4 *>(labels + g) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
-    *reinterpret_cast<uint4 *>(sizes + g) = make_uint4(sz[0], sz[1], sz[2], sz[3]);
+    labels[g] = lab;
+    sizes[g] = sz;
   }
 }
 
@@ -417,9 +412,10 @@ __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
   }
 }
 
-// K4: unions across tile borders.  Work items per tile: its top row (64), left column (32),
-// right column (32, for the up-right diagonal).  One thread per item.
-__global__ void __launch_bounds__(128) k_ccl_merge(FrameParams p) {
+// K4: unions across tile borders.  Work items per tile: its top row (TW), left column (TH),
+// right column (TH, for the up-right diagonal).  One thread per item.
+constexpr int kCclMergeThreads = ((kCclTW + 2 * kCclTH + 31) / 32) * 32;
+__global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
@@ -432,8 +428,10 @@ __global__ void __launch_bounds__(128) k_ccl_merge(FrameParams p) {
     kind = 0; x = x0 + t; y = y0;
   } else if (t < kCclTW + kCclTH) {
     kind = 1; x = x0; y = y0 + (t - kCclTW);
-  } else {
+  } else if (t < kCclTW + 2 * kCclTH) {
     kind = 2; x = x0 + kCclTW - 1; y = y0 + (t - kCclTW - kCclTH);
+  } else {
+    return;
   }
   if (x >= p.w || y >= p.h) return;
   const uint32_t i = static_cast<uint32_t>(y * p.w + x);
@@ -501,14 +499,19 @@ __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
 }
 
 // Finds or claims the slot of blob pair `key`; returns hash_cap on a full table.
-__device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, unsigned long long key, uint32_t rep0, uint32_t rep1) {
+__device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, unsigned long long key, uint32_t rep0, uint32_t rep1,
+                                Counters *ctr, uint32_t *occupied) {
   uint32_t slot = hash_pair(rep0, rep1) & (p.hash_cap - 1);
   for (uint32_t probe = 0; probe < p.hash_cap; probe++) {
     unsigned long long cur = __ldcg(keys + slot);
     if (cur == key) return slot;
     if (cur == kEmptyKey) {
       cur = atomicCAS(keys + slot, kEmptyKey, key);
-      if (cur == kEmptyKey || cur == key) return slot;
+      if (cur == kEmptyKey) {  // we claimed it: list the slot so k_select never scans the whole table
+        occupied[atomicAdd(&ctr->num_occupied, 1u)] = slot;
+        return slot;
+      }
+      if (cur == key) return slot;
     }
     slot = (slot + 1) & (p.hash_cap - 1);
   }
@@ -528,6 +531,7 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
   unsigned long long *h_key = p.h_key + static_cast<size_t>(frame) * p.hash_cap;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
+  uint32_t *occupied = p.occupied + hoff;
   const int tid = threadIdx.x, lane = tid & 31;
 
   for (int i = tid; i < (kBpTH + 1) * (kBpTW + 2); i += kBpThreads) {
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
       const int sdot = __reduce_add_sync(group, px * gx + py * gy);
       uint32_t slot = 0;
       if (lane == leader) {
-        slot = hash_insert(p, h_key, key, ra, rb);
+        slot = hash_insert(p, h_key, key, ra, rb, ctr, occupied);
         if (slot < p.hash_cap) {
           atomicAdd(p.h_count + hoff + slot, cnt);
           atomicMin(p.h_minx + hoff + slot, mnx);
@@ -712,7 +716,7 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_merge", s);
-  k_ccl_merge<<<cgrid, 128, 0, s>>>(p);
+  k_ccl_merge<<<cgrid, kCclMergeThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_final", s);
   k_ccl_final<<<dim3(cdiv(static_cast<unsigned>((static_cast<size_t>(p.w) * p.h + 3) / 4), 256), frames), 256, 0, s>>>(p);
