@@ -61,6 +61,7 @@ def kernel_bytes(name: str, P: float, Psel: float, nblobs: float) -> float:
         "select": 0.0,
         "scatter": 8 * P + 8 * Psel,
         "fit_small": 8 * Psel,   # reads the unsorted segment once; everything else stays in shared memory
+        "fit_medium": 8 * Psel,
         "fit_large": 8 * Psel,
         "decode": 0.0,
     }

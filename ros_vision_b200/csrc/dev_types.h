@@ -58,7 +58,8 @@ struct Counters {  // one per frame, zeroed before each frame
   uint32_t next_small;
   uint32_t next_large;
   uint32_t num_occupied;  // claimed hash slots (listed in FrameParams::occupied)
-  uint32_t pad[4];
+  uint32_t next_medium;
+  uint32_t pad[3];
 };
 __host__ __device__ inline uint32_t alloc_clusters(unsigned long long a) { return static_cast<uint32_t>(a >> 40); }
 __host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return static_cast<uint32_t>(a >> 20) & 0xfffffu; }

@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(256) k_scatter(FrameParams p) {
 constexpr int kLargeThreads = 256;
 constexpr int kSmallWarps = 4;          // warps (= blobs in flight) per small-tier CTA
 constexpr uint32_t kSortCap = 4096;     // large tier: points sorted / filtered in shared memory
-constexpr uint32_t kLfpCap = 1024;      // large tier: prefix moments kept in shared memory
 
 template <int GS>
 __device__ __forceinline__ void gsync() {
@@ -393,7 +392,7 @@ struct BlobWork {
 
 template <int GS>
 __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
-                                             const BlobWork &wk, BlobScratch &S, long long (*scan)[kLargeThreads], uint32_t gt) {
+                                             const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
   const uint32_t cnt = blob.count, off = blob.offset;
@@ -452,14 +451,14 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     }
     a_Mxx = v[0]; a_Myy = v[1]; a_Mxy = v[2]; a_Mx = v[3]; a_My = v[4]; a_W = v[5];
   } else {
-    scan[0][gt] = t_Mxx; scan[1][gt] = t_Myy; scan[2][gt] = t_Mxy;
-    scan[3][gt] = t_Mx;  scan[4][gt] = t_My;  scan[5][gt] = t_W;
+    scan[0 * GS + gt] = t_Mxx; scan[1 * GS + gt] = t_Myy; scan[2 * GS + gt] = t_Mxy;
+    scan[3 * GS + gt] = t_Mx;  scan[4 * GS + gt] = t_My;  scan[5 * GS + gt] = t_W;
     __syncthreads();
-    const int warp = gt >> 5;
-    if (warp < 6) {  // exclusive scan of the 256 chunk totals: warp q scans quantity q
-      long long v[8], run = 0;
+    constexpr int kPer = GS / 32;  // chunk totals per lane
+    for (int q = gt >> 5; q < 6; q += GS / 32) {  // exclusive scan of the GS chunk totals of quantity q by one warp
+      long long v[kPer], run = 0;
 #pragma unroll
-      for (int j = 0; j < 8; j++) { v[j] = scan[warp][lane * 8 + j]; run += v[j]; }
+      for (int j = 0; j < kPer; j++) { v[j] = scan[q * GS + lane * kPer + j]; run += v[j]; }
       long long incl = run;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -468,11 +467,11 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       }
       long long ex = incl - run;
 #pragma unroll
-      for (int j = 0; j < 8; j++) { scan[warp][lane * 8 + j] = ex; ex += v[j]; }
+      for (int j = 0; j < kPer; j++) { scan[q * GS + lane * kPer + j] = ex; ex += v[j]; }
     }
     __syncthreads();
-    a_Mxx = scan[0][gt]; a_Myy = scan[1][gt]; a_Mxy = scan[2][gt];
-    a_Mx = scan[3][gt];  a_My = scan[4][gt];  a_W = scan[5][gt];
+    a_Mxx = scan[0 * GS + gt]; a_Myy = scan[1 * GS + gt]; a_Mxy = scan[2 * GS + gt];
+    a_Mx = scan[3 * GS + gt];  a_My = scan[4 * GS + gt];  a_W = scan[5 * GS + gt];
   }
   for (uint32_t i = c_lo; i < c_hi; i++) {
     const unsigned long long k = wk.keys[i];
@@ -551,7 +550,13 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
         const unsigned long long key = wk.peaks[i];
         if ((round == 0 || key > last) && key < best) best = key;
       }
-      best = warp_min_u64(best);
+      {  // 64-bit warp minimum as two 32-bit redux steps
+        const uint32_t hi = static_cast<uint32_t>(best >> 32);
+        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+        const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(best) : 0xffffffffu;
+        const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+        best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+      }
       if (best == kNoKey) break;
       last = best;
       nsel++;
@@ -753,56 +758,71 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
   }
 }
 
-// ---- large tier: one CTA per blob -------------------------------------------------------------
-struct LargeShared {
-  unsigned long long keys[kSortCap];
-  b200tag_lfp lf[kLfpCap];
-  float errs[kSortCap];
-  long long scan[6][kLargeThreads];
+// ---- CTA tiers: one CTA per blob ----------------------------------------------------------------
+//   medium: 128 threads, blobs of 257..1024 points, everything in shared memory (3 CTAs per SM)
+//   large : 256 threads, blobs above 1024 points; sort / errors / peaks in shared memory up to 4096 points,
+//           prefix moments in the blob's own L2-resident segment
+// Both pull from the same work list and skip the blobs of the other tier.
+template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP>
+struct CtaShared {
+  unsigned long long keys[KEY_CAP];
+  b200tag_lfp lf[LF_CAP > 0 ? LF_CAP : 1];
+  float errs[KEY_CAP];
+  long long scan[6 * THREADS];
   BlobScratch scratch;
 };
 
-__global__ void __launch_bounds__(kLargeThreads, 2) k_fit_large(FrameParams p) {
+template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP, uint32_t MIN_CNT, uint32_t MAX_CNT, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, int tier) {
+  using Shared = CtaShared<THREADS, KEY_CAP, LF_CAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  LargeShared &S = *reinterpret_cast<LargeShared *>(smem_raw);
+  Shared &S = *reinterpret_cast<Shared *>(smem_raw);
   const int frame = blockIdx.y;
   const int tid = threadIdx.x;
   Counters *ctr = p.counters + frame;
   const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(alloc_blobs(ctr->alloc) - alloc_small(ctr->alloc), p.blob_cap);
+  uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
   while (true) {
     __syncthreads();
-    if (tid == 0) S.scratch.cur = atomicAdd(&ctr->next_large, 1u);
+    if (tid == 0) S.scratch.cur = atomicAdd(next, 1u);
     __syncthreads();
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
     const uint32_t b = list[li];
     if (b == 0xffffffffu) continue;
     const b200tag_blob blob = blobs[b];
+    if (blob.count < MIN_CNT || blob.count > MAX_CNT) continue;  // the other tier's blob
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
-    if (blob.count <= kLfpCap) {  // everything in shared memory
+    if (blob.count <= LF_CAP) {  // everything in shared memory
       wk.keys = S.keys; wk.lf = S.lf; wk.errs = S.errs;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
-    } else if (blob.count <= kSortCap) {  // prefix moments in the blob's global segment
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+    } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.lf = p.lfp + pbase; wk.errs = S.errs;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
     } else {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf = p.lfp + pbase; wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
       wk.keys_in_place = true;
-      fit_one_blob<kLargeThreads>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
     }
   }
 }
+
+constexpr uint32_t kMediumCap = 1024;
+using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
+using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
+#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 3>
+#define K_FIT_LARGE k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2>
 
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
   static bool dev_ready[64] = {false};
@@ -810,7 +830,8 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !dev_ready[dev]) {
     cudaFuncSetAttribute(k_fit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallWarpShared) * kSmallWarps));
-    cudaFuncSetAttribute(k_fit_large, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
+    cudaFuncSetAttribute(K_FIT_MEDIUM, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MediumShared)));
+    cudaFuncSetAttribute(K_FIT_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
     k_init_combos<<<1, 1, 0, s>>>();
     dev_ready[dev] = true;
   }
@@ -824,10 +845,13 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (kt) kt->begin("fit_small", s);
   k_fit_small<<<dim3(max(4u, min(444u, cdivu(1776u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
   if (kt) kt->end(s);
-  if (kt) kt->begin("fit_large", s);
-  k_fit_large<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p);
+  if (kt) kt->begin("fit_medium", s);
+  K_FIT_MEDIUM<<<dim3(max(3u, min(444u, cdivu(1776u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
   if (kt) kt->end(s);
-  return 4;
+  if (kt) kt->begin("fit_large", s);
+  K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
+  if (kt) kt->end(s);
+  return 5;
 }
 
 }  // namespace b200tag
