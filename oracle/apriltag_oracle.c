@@ -1042,6 +1042,7 @@ static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, c
 
 static void decode_quads(const orc_config *c, orc_result *r) {
   r->detections = (orc_detection *)calloc((size_t)r->num_corners + 1, sizeof(orc_detection));
+  r->refined = (orc_quadcorners *)calloc((size_t)r->num_corners + 1, sizeof(orc_quadcorners));
   int nd = 0;
   /* cos/sin(rotation * M_PI / 2.0) as libm returns them for k = 0..3 */
   static const double kc[4] = {1.0, 6.123233995736766e-17, -1.0, -1.8369701987210297e-16};
@@ -1050,6 +1051,8 @@ static void decode_quads(const orc_config *c, orc_result *r) {
     float p[4][2];
     memcpy(p, r->corners[qi].corners, sizeof(p));
     if (c->refine_edges) refine_edges(c, r->gray, r->W, r->H, p, r->corners[qi].reversed_border);
+    r->refined[qi] = r->corners[qi]; /* the quad as handed to quad_decode_index, apriltag_detect.cu:613 */
+    memcpy(r->refined[qi].corners, p, sizeof(p));
     double corr[4][4];
     for (int i = 0; i < 4; i++) {
       corr[i][0] = (i == 0 || i == 3) ? -1 : 1;
@@ -1212,6 +1215,6 @@ void orc_free_result(orc_result *r) {
   if (!r) return;
   free(r->gray); free(r->quad_im); free(r->minmax); free(r->thresh); free(r->labels); free(r->sizes);
   free(r->points); free(r->clusters); free(r->spoints); free(r->lfps); free(r->errs); free(r->filtered_errs);
-  free(r->is_peak); free(r->fitquads); free(r->corners); free(r->detections);
+  free(r->is_peak); free(r->fitquads); free(r->corners); free(r->detections); free(r->refined);
   free(r);
 }

@@ -152,6 +152,7 @@ typedef struct {
   orc_quadcorners *corners;
   int num_detections;
   orc_detection *detections; /* after reconcile, sorted by id */
+  orc_quadcorners *refined;  /* num_corners: corners[] after RefineEdges (apriltag_detect.cu:405-564) */
 } orc_result;
 
 void orc_default_config(orc_config *cfg, int width, int height, int format);

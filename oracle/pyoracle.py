@@ -61,6 +61,7 @@ class OrcResult(C.Structure):
         ("num_fitquads", C.c_int), ("fitquads", C.c_void_p),
         ("num_corners", C.c_int), ("corners", C.c_void_p),
         ("num_detections", C.c_int), ("detections", C.c_void_p),
+        ("refined", C.c_void_p),
     ]
 
 
@@ -149,6 +150,7 @@ class Result:
         self.fitquads = _arr(r.fitquads, FITQUAD_DT, r.num_fitquads)
         self.corners = _arr(r.corners, CORNERS_DT, r.num_corners)
         self.detections = _arr(r.detections, DET_DT, r.num_detections)
+        self.refined = _arr(r.refined, CORNERS_DT, r.num_corners if r.refined else 0)
 
 
 def detect(cfg: OrcConfig, image: np.ndarray) -> Result:
