@@ -138,6 +138,25 @@ def cpu_baseline(frames, seconds_budget=12.0, threads=None):
             "sample": f"{n} frames of the bench workload ({len(frames)} distinct), oracle/liboracle.so, {threads} threads, {dt:.1f} s"}
 
 
+def reference_gpu_leg(frames, iters=300):
+    """The reference's own GpuDetector (its kernels recompiled for sm_100a into oracle/_ref by
+    oracle/build_ref.sh), one synchronous Detect per frame exactly as the node calls it (pageable H2D
+    included).  libapriltag is absent, so quad decode is stubbed: the figure EXCLUDES decode and is
+    therefore an upper bound on the reference's frame rate.  Reported beside the headline, never as it."""
+    try:
+        from oracle import pyrefgpu
+        if not pyrefgpu.available():
+            return None
+        ref = pyrefgpu.ReferenceGpuDetector(W, H)
+        ms = ref.time_detect([f.reshape(H, W * 2) for f in frames], iters=iters, warmup=20)
+        ref.close()
+        return {"value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "kind": "reference kernels recompiled for sm_100a "
+                "(oracle/_ref/librefgpu.so), synchronous Detect per frame, pageable H2D, decode excluded",
+                "sample": f"{iters} frames, {len(frames)} distinct"}
+    except Exception as e:  # reporting leg only
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args):
     rank, world, local = dist_setup(args.gpus)
     if rank != 0:
@@ -326,7 +345,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cb, "clocks": clocks.summary(),
+            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if world == 1 else None,
+            "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs,
                       "detections_per_batch": ndet_per_batch},
         }

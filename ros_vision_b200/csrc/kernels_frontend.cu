@@ -245,16 +245,23 @@ __global__ void __launch_bounds__(128) k_threshold(FrameParams p) {
 // Label of a component = its smallest pixel index (roots are kept minimal by atomicMin
 // links), size[root] = pixel count.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCclTW = 32;  // tile width: one lane per column, rows are 32-bit run masks
+constexpr int kCclTW = 32;  // tile width: one 32-bit run mask per row and colour
 constexpr int kCclTH = 64;  // tile height
-constexpr int kCclThreads = 256;
-constexpr int kCclRowsPerThread = kCclTH / (kCclThreads / 32);
+constexpr int kCclThreads = 128;
+constexpr int kCclWarps = kCclThreads / 32;
+static_assert(kCclThreads == 2 * kCclTH, "one thread per (row, colour)");
 
-__device__ __forceinline__ uint32_t sfind(const uint32_t *par, uint32_t a) {
+// Find with path halving.  Parent links only ever move to an ancestor (a smaller index of the same
+// component), so the plain stores are safe next to the atomicMin links of concurrent unions.  On
+// thresholded noise the white (8-connected) pixels percolate into one tile-spanning component;
+// without halving its parent chains grow to hundreds of dependent shared-memory hops.
+__device__ __forceinline__ uint32_t sfind(uint32_t *par, uint32_t a) {
   uint32_t q = par[a];
   while (q != a) {
+    const uint32_t qq = par[q];
+    if (qq != q) par[a] = qq;
     a = q;
-    q = par[a];
+    q = qq;
   }
   return a;
 }
@@ -275,13 +282,20 @@ __device__ __forceinline__ void sunite(uint32_t *par, uint32_t a, uint32_t b) {
   }
 }
 
-// K3: one CTA labels a 32x64 tile entirely in shared memory.  Lane = column, so a row's white /
-// black pixels are two __ballot_sync masks; every pixel starts out pointing at the first pixel of
-// its horizontal run (one __clz), and only pixels that begin an overlap with a run in the row
-// above issue a union.  Pixel values stay in registers; shared memory holds the masks, the parent
-// array and the per-root counts.
+// bits [lo, lo + len) of a 32-bit word, 1 <= len <= 32
+__device__ __forceinline__ uint32_t bit_span(int lo, int len) {
+  return (len >= 32 ? ~0u : ((1u << len) - 1u)) << lo;
+}
+
+// K3: one CTA labels a 32x64 tile entirely in shared memory, working on RUNS instead of pixels.
+// A row of the tile is two 32-bit masks (white, black).  The union-find nodes are the first
+// pixels of the horizontal runs; one thread per (row, colour) walks the runs of its mask with
+// ffs/clz and unites each with the runs it touches in the row above (white: 8-connected, i.e.
+// the run dilated by one pixel; black: 4-connected).  A second walk compresses every run start
+// to its root and adds the run length to the root's pixel count.  Only the final write-out is
+// per pixel: label = global index of the root of the pixel's run, 16-byte stores.
 __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
-  __shared__ uint32_t s_white[kCclTH], s_black[kCclTH];
+  __shared__ uint32_t s_mask[2][kCclTH];  // [0] black, [1] white
   __shared__ uint32_t s_par[kCclTH * kCclTW];
   __shared__ uint32_t s_cnt[kCclTH * kCclTW];
 
@@ -292,98 +306,93 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   uint32_t *labels = p.labels + frame * n;
   uint32_t *sizes = p.sizes + frame * n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gx = x0 + lane;
-  const bool col_ok = gx < p.w;
 
-  // rows warp, warp + 8, ...: pixel values in registers, run masks to shared memory
-  uint32_t v[kCclRowsPerThread];
-#pragma unroll
-  for (int k = 0; k < kCclRowsPerThread; k++) {
-    const int r = warp + k * (kCclThreads / 32);
+  // (A) run masks: lane = column, rows strided over the warps; pixels outside the image count as
+  //     127 (join nothing)
+  for (int r = warp; r < kCclTH; r += kCclWarps) {
     const int gy = y0 + r;
-    uint32_t px = 127;  // outside the image: joins nothing
-    if (col_ok && gy < p.h) px = th[static_cast<size_t>(gy) * p.w + gx];
-    v[k] = px;
-    const uint32_t wm = __ballot_sync(0xffffffffu, px == 255), bm = __ballot_sync(0xffffffffu, px == 0);
+    uint32_t a = 127;
+    if (gy < p.h && x0 + lane < p.w) a = th[static_cast<size_t>(gy) * p.w + x0 + lane];
+    const uint32_t wm = __ballot_sync(0xffffffffu, a == 255), bm = __ballot_sync(0xffffffffu, a == 0);
     if (lane == 0) {
-      s_white[r] = wm;
-      s_black[r] = bm;
+      s_mask[1][r] = wm;
+      s_mask[0][r] = bm;
     }
-    s_cnt[r * kCclTW + lane] = 0;
+  }
+  for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
+    reinterpret_cast<uint4 *>(s_par)[i] = make_uint4(4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3);
+    reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
 
-  // initial parents: first pixel of the horizontal run
-  const uint32_t below_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int k = 0; k < kCclRowsPerThread; k++) {
-    const int r = warp + k * (kCclThreads / 32);
-    const int i = r * kCclTW + lane;
-    uint32_t par = i;
-    if (v[k] != 127) {
-      const uint32_t m = v[k] ? s_white[r] : s_black[r];
-      const uint32_t below = ~m & below_mask;
-      par = r * kCclTW + (below ? 32 - __clz(below) : 0);
-    }
-    s_par[i] = par;
-  }
-  __syncthreads();
-
-  // vertical / diagonal unions, issued once per run overlap
-#pragma unroll
-  for (int k = 0; k < kCclRowsPerThread; k++) {
-    const int r = warp + k * (kCclThreads / 32);
-    if (r == 0 || v[k] == 127) continue;
-    const int i = r * kCclTW + lane;
-    const bool white = v[k] != 0;
-    const uint32_t cur = white ? s_white[r] : s_black[r];
-    const uint32_t up = white ? s_white[r - 1] : s_black[r - 1];
-    const bool is_start = (lane == 0) || !((cur >> (lane - 1)) & 1u);
-    const bool u = (up >> lane) & 1u;
-    const bool ul = (lane > 0) && ((up >> (lane - 1)) & 1u);
-    if (u) {
-      if (is_start || !ul) sunite(s_par, i, i - kCclTW);
-    } else if (white) {
-      if (ul && is_start) sunite(s_par, i, i - kCclTW - 1);
-      const bool ur = (lane + 1 < kCclTW) && ((up >> (lane + 1)) & 1u);
-      const bool right_same = (lane + 1 < kCclTW) && ((cur >> (lane + 1)) & 1u);
-      if (ur && !right_same) sunite(s_par, i, i - kCclTW + 1);
+  // (B) unions with the row above: thread = (row, colour)
+  const int row = tid >> 1, colour = tid & 1;
+  const uint32_t mine = s_mask[colour][row];
+  if (row > 0) {
+    const uint32_t up = s_mask[colour][row - 1];
+    uint32_t m = mine;
+    while (m) {
+      const int s = __ffs(static_cast<int>(m)) - 1;
+      const uint32_t inv = ~(m >> s);
+      const int len = inv ? __ffs(static_cast<int>(inv)) - 1 : 32 - s;
+      const uint32_t run = bit_span(s, len);
+      m &= ~run;
+      uint32_t ov = up & (colour ? (run | (run << 1) | (run >> 1)) : run);
+      const uint32_t node = row * kCclTW + s;
+      while (ov) {
+        const int bpos = __ffs(static_cast<int>(ov)) - 1;
+        const uint32_t below = ~up & ((1u << bpos) - 1u);
+        const int us = below ? 32 - __clz(static_cast<int>(below)) : 0;
+        const uint32_t above = ~up >> bpos;
+        const int ulen = above ? __ffs(static_cast<int>(above)) - 1 : 32 - bpos;
+        ov &= ~bit_span(bpos, ulen);
+        sunite(s_par, node, (row - 1) * kCclTW + us);
+      }
     }
   }
   __syncthreads();
 
-  // per-root pixel counts: one shared atomic per run
-#pragma unroll
-  for (int k = 0; k < kCclRowsPerThread; k++) {
-    const int r = warp + k * (kCclThreads / 32);
-    if (v[k] == 127) continue;
-    const uint32_t cur = v[k] ? s_white[r] : s_black[r];
-    const bool is_start = (lane == 0) || !((cur >> (lane - 1)) & 1u);
-    if (is_start) {
-      const uint32_t inv = ~(cur >> lane);
-      const int len = inv ? (__ffs(inv) - 1) : (32 - lane);
-      atomicAdd(&s_cnt[sfind(s_par, r * kCclTW + lane)], static_cast<uint32_t>(len));
+  // (C) compress run starts to their roots, per-root pixel counts
+  {
+    uint32_t m = mine;
+    while (m) {
+      const int s = __ffs(static_cast<int>(m)) - 1;
+      const uint32_t inv = ~(m >> s);
+      const int len = inv ? __ffs(static_cast<int>(inv)) - 1 : 32 - s;
+      m &= ~bit_span(s, len);
+      const uint32_t node = row * kCclTW + s;
+      const uint32_t root = sfind(s_par, node);
+      if (root != node) s_par[node] = root;
+      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len));
     }
   }
   __syncthreads();
 
-  // write out: label = global index of the local root; sizes = count at local roots, 0 elsewhere.
-  // Each warp writes one 128-byte row segment per array.
-#pragma unroll
-  for (int k = 0; k < kCclRowsPerThread; k++) {
-    const int r = warp + k * (kCclThreads / 32);
-    const int gy = y0 + r;
-    if (!col_ok || gy >= p.h) continue;
-    const uint32_t i = r * kCclTW + lane;
+  // (D) write out, 4 pixels (16 bytes of labels) per thread: label = global index of the root of
+  //     the pixel's run; sizes = count at local roots, 0 elsewhere
+  for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
+    const int r = i / (kCclTW / 4), xq = (i % (kCclTW / 4)) * 4;
+    const int gy = y0 + r, gx = x0 + xq;
+    if (gy >= p.h || gx >= p.w) continue;
+    const uint32_t wm = s_mask[1][r], bm = s_mask[0][r];
     const size_t g = static_cast<size_t>(gy) * p.w + gx;
-    uint32_t lab = static_cast<uint32_t>(g), sz = 0;
-    if (v[k] != 127) {
-      const uint32_t root = sfind(s_par, i);
-      lab = static_cast<uint32_t>((y0 + (root >> 5)) * p.w + x0 + (root & 31));
-      if (root == i) sz = s_cnt[i];
+    uint32_t lab[4], sz[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int x = xq + k;
+      lab[k] = static_cast<uint32_t>(g + k);
+      sz[k] = 0;
+      const bool isw = (wm >> x) & 1u, isb = (bm >> x) & 1u;
+      if (isw || isb) {
+        const uint32_t below = ~(isw ? wm : bm) & ((1u << x) - 1u);
+        const int s = below ? 32 - __clz(static_cast<int>(below)) : 0;
+        const uint32_t root = s_par[r * kCclTW + s];
+        lab[k] = static_cast<uint32_t>((y0 + (root / kCclTW)) * p.w + x0 + (root % kCclTW));
+        if (root == static_cast<uint32_t>(r * kCclTW + x)) sz[k] = s_cnt[root];
+      }
     }
-    labels[g] = lab;
-    sizes[g] = sz;
+    *reinterpret_cast<uint4 *>(labels + g) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+    *reinterpret_cast<uint4 *>(sizes + g) = make_uint4(sz[0], sz[1], sz[2], sz[3]);
   }
 }
 

@@ -7,6 +7,10 @@ frames -- images and integer stages bit-exact, component labels up to relabellin
 exact or within the stated tolerance (the reference build contracts some expressions into FMAs).
 The quads the reference hands to quad_decode_index (after its own RefineEdges) pin the refine
 stage; decode itself is libapriltag, absent from the reference tree, and stays unpinned.
+
+(A frame without any boundary point cannot be part of this test: the reference hands CUB zero items and
+aborts in its CHECK_CUDA at apriltag_gpu.cu:788-802 -- observed here on a flat 640x480 frame.  The product
+and the oracle handle that case; see test_gpu_parity.py::test_edge_cases.)
 """
 import numpy as np
 import pytest
@@ -182,12 +186,3 @@ def test_reference_pins_oracle_and_product(R, oracle):
         det.close()
         ref.close()
     assert total_quads > 10 and total_dets > 5
-
-
-def test_reference_on_a_flat_frame(R):
-    """A frame without contrast: every pixel thresholds to 127, no boundary points, no quads."""
-    ref = R.ReferenceGpuDetector(640, 480)
-    ref.Detect(np.full((480, 1280), 128, np.uint8))
-    assert np.all(ref.thresholded() == 127)
-    assert len(ref.quad_corners()) == 0
-    ref.close()
