@@ -117,8 +117,9 @@ enum {
   B200TAG_STAGE_LABELS = 3,      /* uint32[w*h]                     CopyUnionMarkersTo */
   B200TAG_STAGE_SIZES = 4,       /* uint32[w*h]                     CopyUnionMarkersSizeTo */
   B200TAG_STAGE_POINTS = 5,      /* b200tag_point[num_points]       CopyCompressedUnionMarkerPairTo */
-  B200TAG_STAGE_BLOBS = 6,       /* b200tag_blob[num_blobs]         CopySelectedExtents */
-  B200TAG_STAGE_SORTED_POINTS = 7,/* uint64[num_selected_points]    CopySortedSelectedBlobs */
+  B200TAG_STAGE_BLOBS = 6,       /* b200tag_blob[candidates]: every blob pair within the point-count limits;
+                                    .selected tells whether it also passed SelectBlobs      CopySelectedExtents */
+  B200TAG_STAGE_SORTED_POINTS = 7,/* uint64[...] indexed by b200tag_blob.offset             CopySortedSelectedBlobs */
   B200TAG_STAGE_LINE_FIT_POINTS = 8, /* b200tag_lfp[...]            CopyLineFitPoints */
   B200TAG_STAGE_ERRORS = 9,      /* float[num_selected_points]      CopyErrors */
   B200TAG_STAGE_FILTERED_ERRORS = 10, /* double[...]                CopyFilteredErrors */
@@ -139,7 +140,7 @@ typedef struct b200tag_blob { /* MinMaxExtents (line_fit_filter.h:14-59) + selec
   uint32_t rep0, rep1;
   uint32_t min_x, min_y, max_x, max_y;
   uint32_t count;
-  uint32_t offset; /* first point of this blob in the sorted-point arrays (selected blobs) */
+  uint32_t offset; /* first point of this blob in the sorted-point arrays (candidate blobs) */
   int32_t gx_sum, gy_sum;
   int64_t pxgx_plus_pygy_sum;
   uint32_t slot;

@@ -354,13 +354,12 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_pts = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
   const size_t HB = static_cast<size_t>(hc) * B;
   const size_t o_hkey = plan.take(HB * 8);
-  const size_t o_hcnt = plan.take(HB * 4), o_hminx = plan.take(HB * 4), o_hminy = plan.take(HB * 4);
-  const size_t o_hmaxx = plan.take(HB * 4), o_hmaxy = plan.take(HB * 4), o_hgx = plan.take(HB * 4), o_hgy = plan.take(HB * 4);
-  const size_t o_hdot = plan.take(HB * 8);
-  const size_t o_sb = plan.take(HB * 4);
+  const size_t o_hcnt = plan.take(HB * 4);
+  const size_t o_soff = plan.take(HB * 4);
+  const size_t o_sclu = cfg->keep_stages ? plan.take(HB * 4) : 0;
   const size_t o_occ = plan.take(HB * 4);
   const size_t o_blobs = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_blob) * B);
-  const size_t o_fill = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
+  const size_t o_segp = plan.take(static_cast<size_t>(p.point_cap) * 4 * B);
   const size_t o_small = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
   const size_t o_large = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
   const size_t o_clusters = p.cluster_cap ? plan.take(static_cast<size_t>(p.cluster_cap) * sizeof(b200tag_blob) * B) : 0;
@@ -398,17 +397,11 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.points = reinterpret_cast<uint64_t *>(base + o_pts);
   p.h_key = reinterpret_cast<unsigned long long *>(base + o_hkey);
   p.h_count = reinterpret_cast<uint32_t *>(base + o_hcnt);
-  p.h_minx = reinterpret_cast<uint32_t *>(base + o_hminx);
-  p.h_miny = reinterpret_cast<uint32_t *>(base + o_hminy);
-  p.h_maxx = reinterpret_cast<uint32_t *>(base + o_hmaxx);
-  p.h_maxy = reinterpret_cast<uint32_t *>(base + o_hmaxy);
-  p.h_gx = reinterpret_cast<int32_t *>(base + o_hgx);
-  p.h_gy = reinterpret_cast<int32_t *>(base + o_hgy);
-  p.h_dot = reinterpret_cast<long long *>(base + o_hdot);
-  p.slot_blob = reinterpret_cast<int32_t *>(base + o_sb);
+  p.slot_off = reinterpret_cast<uint32_t *>(base + o_soff);
+  p.slot_cluster = cfg->keep_stages ? reinterpret_cast<uint32_t *>(base + o_sclu) : nullptr;
+  p.seg_pts = reinterpret_cast<uint32_t *>(base + o_segp);
   p.occupied = reinterpret_cast<uint32_t *>(base + o_occ);
   p.blobs = reinterpret_cast<b200tag_blob *>(base + o_blobs);
-  p.blob_fill = reinterpret_cast<uint32_t *>(base + o_fill);
   p.small_list = reinterpret_cast<uint32_t *>(base + o_small);
   p.large_list = reinterpret_cast<uint32_t *>(base + o_large);
   p.clusters = p.cluster_cap ? reinterpret_cast<b200tag_blob *>(base + o_clusters) : nullptr;
@@ -520,7 +513,7 @@ int b200tag_frame_info_get(const b200tag_detector *det, int frame, b200tag_frame
   info->status = c.status;
   info->num_points = std::min(c.num_points, det->fp.point_cap);
   info->num_clusters = alloc_clusters(c.alloc);
-  info->num_blobs = std::min(alloc_blobs(c.alloc), det->fp.blob_cap);
+  info->num_blobs = c.num_selected_blobs;
   info->num_selected_points = c.num_selected_points;
   info->num_fit_quads = std::min(c.num_fit_quads, det->fp.blob_cap);
   info->num_quads = std::min(c.num_quads, det->fp.quad_cap);
@@ -559,7 +552,7 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
   const void *src = nullptr;
   size_t bytes = 0;
   const uint32_t np = std::min(c.num_points, p.point_cap);
-  const uint32_t nsel = std::min(c.num_selected_points, p.point_cap);
+  const uint32_t nsel = std::min(c.num_seg_points, p.point_cap);  // segments of all candidate blobs
   switch (stage) {
     case B200TAG_STAGE_GRAY:
       if (det->cfg.format == B200TAG_FMT_GRAY8) return B200TAG_E_INVALID;  // the gray image is the caller's input
@@ -580,11 +573,12 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
       if (np) CK(cudaMemcpy(raw.data(), p.points + f * p.point_cap, np * 8ull, cudaMemcpyDeviceToHost));
       b200tag_point *o = static_cast<b200tag_point *>(dst);
       for (uint32_t i = 0; i < np; i++) {
+        const uint32_t sp = point_seg(raw[i]);
         o[i].slot = point_slot(raw[i]);
-        o[i].x = static_cast<uint16_t>(point_x(raw[i]));
-        o[i].y = static_cast<uint16_t>(point_y(raw[i]));
-        o[i].dir = static_cast<uint8_t>(point_dir(raw[i]));
-        o[i].black_to_white = static_cast<uint8_t>(point_b2w(raw[i]));
+        o[i].x = static_cast<uint16_t>(sp_x(sp));
+        o[i].y = static_cast<uint16_t>(sp_y(sp));
+        o[i].dir = static_cast<uint8_t>(sp_dir(sp));
+        o[i].black_to_white = static_cast<uint8_t>(sp_b2w(sp));
         o[i].pad[0] = o[i].pad[1] = 0;
       }
       return 0;

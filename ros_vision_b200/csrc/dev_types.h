@@ -18,19 +18,33 @@ constexpr int kMaxPeaks = 10;                // line_fit_filter.cu:630 (kNMaxima
 constexpr int kNumCombos = 210;              // line_fit_filter.h:160
 constexpr uint32_t kSmallBlobPoints = 256;   // blobs up to this size are fitted by a single warp
 
-// Packed boundary point, 64 bit:  [63:40] cluster slot | [28:16] x | [15:3] y | [2:1] dir | [0] black_to_white
-// (the reference's QuadBoundaryPoint, points.h:25-161, carries 20-bit blob ids and
-// 10-bit coordinates; the slot indirection and 13-bit half-pixel coordinates lift
-// its 1024x1024 quad-image limit to 4096x4096).
-__host__ __device__ inline uint64_t pack_point(uint32_t slot, uint32_t x, uint32_t y, uint32_t dir, uint32_t b2w) {
-  return (static_cast<uint64_t>(slot) << 40) | (static_cast<uint64_t>(x) << 16) | (static_cast<uint64_t>(y) << 3) |
-         (static_cast<uint64_t>(dir) << 1) | b2w;
+// Packed boundary point, 64 bit:
+//   [62:43] cluster slot | [42:27] rank of the point inside its cluster (saturating) | [26:15] base x |
+//   [14:3] base y | [2:1] dir | [0] black_to_white
+// (the reference's QuadBoundaryPoint, points.h:25-161, carries 20-bit blob ids and 10-bit
+// coordinates; the slot indirection and 12-bit base coordinates lift its 1024x1024 quad-image
+// limit to 4096x4096).  The rank is handed out while the point is counted, so the scatter into
+// per-blob segments needs no second atomic; clusters with more than 65535 points are far above
+// max_cluster_pixels (<= 4 * (4096 + 4096)) and never selected, so saturation is harmless.
+// The low 27 bits are what travels on into the blob segments ("segment point").
+constexpr uint32_t kPointRankMax = 0xffffu;
+constexpr uint32_t kInvalidSlot = 0xfffffu;
+__host__ __device__ inline uint64_t pack_point(uint32_t slot, uint32_t rank, uint32_t bx, uint32_t by, uint32_t dir, uint32_t b2w) {
+  return (static_cast<uint64_t>(slot) << 43) | (static_cast<uint64_t>(rank < kPointRankMax ? rank : kPointRankMax) << 27) |
+         (static_cast<uint64_t>(bx) << 15) | (static_cast<uint64_t>(by) << 3) | (static_cast<uint64_t>(dir) << 1) | b2w;
 }
-__host__ __device__ inline uint32_t point_slot(uint64_t p) { return static_cast<uint32_t>(p >> 40); }
-__host__ __device__ inline uint32_t point_x(uint64_t p) { return static_cast<uint32_t>(p >> 16) & 0x1fff; }
-__host__ __device__ inline uint32_t point_y(uint64_t p) { return static_cast<uint32_t>(p >> 3) & 0x1fff; }
-__host__ __device__ inline uint32_t point_dir(uint64_t p) { return static_cast<uint32_t>(p >> 1) & 3; }
-__host__ __device__ inline uint32_t point_b2w(uint64_t p) { return static_cast<uint32_t>(p) & 1; }
+__host__ __device__ inline int dir_dx(uint32_t d) { return d == 2 ? 0 : (d == 3 ? -1 : 1); }
+__host__ __device__ inline int dir_dy(uint32_t d) { return d == 0 ? 0 : 1; }
+__host__ __device__ inline uint32_t point_slot(uint64_t p) { return static_cast<uint32_t>(p >> 43) & 0xfffffu; }
+__host__ __device__ inline uint32_t point_rank(uint64_t p) { return static_cast<uint32_t>(p >> 27) & 0xffffu; }
+__host__ __device__ inline uint32_t point_seg(uint64_t p) { return static_cast<uint32_t>(p) & 0x7ffffffu; }
+__host__ __device__ inline uint32_t sp_bx(uint32_t s) { return (s >> 15) & 0xfffu; }
+__host__ __device__ inline uint32_t sp_by(uint32_t s) { return (s >> 3) & 0xfffu; }
+__host__ __device__ inline uint32_t sp_dir(uint32_t s) { return (s >> 1) & 3u; }
+__host__ __device__ inline uint32_t sp_b2w(uint32_t s) { return s & 1u; }
+// half-pixel coordinates, points.h:111-116
+__host__ __device__ inline uint32_t sp_x(uint32_t s) { return 2 * sp_bx(s) + dir_dx(sp_dir(s)); }
+__host__ __device__ inline uint32_t sp_y(uint32_t s) { return 2 * sp_by(s) + dir_dy(sp_dir(s)); }
 
 // Sort key of a selected point inside its blob, 64 bit:
 //   [53:26] theta (28 bit, IndexPoint::theta, points.h:195-202) | [25:24] dir | [23:12] base y | [11:0] base x
@@ -43,13 +57,11 @@ __host__ __device__ inline uint32_t key_theta(uint64_t k) { return static_cast<u
 __host__ __device__ inline uint32_t key_dir(uint64_t k) { return static_cast<uint32_t>(k >> 24) & 3; }
 __host__ __device__ inline uint32_t key_by(uint64_t k) { return static_cast<uint32_t>(k >> 12) & 0xfff; }
 __host__ __device__ inline uint32_t key_bx(uint64_t k) { return static_cast<uint32_t>(k) & 0xfff; }
-__host__ __device__ inline int dir_dx(uint32_t d) { return d == 2 ? 0 : (d == 3 ? -1 : 1); }
-__host__ __device__ inline int dir_dy(uint32_t d) { return d == 0 ? 0 : 1; }
 
 struct Counters {  // one per frame, zeroed before each frame
   uint32_t status;
   uint32_t num_points;
-  unsigned long long alloc;  // [63:40] blob pairs | [39:20] selected blobs | [19:0] small blobs (k_select)
+  unsigned long long alloc;  // [63:40] blob pairs | [39:20] candidate blobs | [19:0] small blobs (k_select)
   uint32_t num_selected_points;
   uint32_t num_fit_quads;
   uint32_t num_quads;
@@ -59,7 +71,9 @@ struct Counters {  // one per frame, zeroed before each frame
   uint32_t next_large;
   uint32_t num_occupied;  // claimed hash slots (listed in FrameParams::occupied)
   uint32_t next_medium;
-  uint32_t pad[3];
+  uint32_t num_seg_points;      // points of all candidate blobs (count filter only): segment allocation
+  uint32_t num_selected_blobs;  // candidates that also pass SelectBlobs' extent / polarity tests
+  uint32_t pad[1];
 };
 __host__ __device__ inline uint32_t alloc_clusters(unsigned long long a) { return static_cast<uint32_t>(a >> 40); }
 __host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return static_cast<uint32_t>(a >> 20) & 0xfffffu; }
@@ -101,15 +115,14 @@ struct FrameParams {
   uint32_t *labels;                               // w*h (quad_stride)
   uint32_t *sizes;                                // w*h
   uint64_t *points;     // point_cap
-  // cluster hash (hash_cap each)
+  // blob-pair hash (hash_cap each): key and point count; extents are computed per blob later
   unsigned long long *h_key;
-  uint32_t *h_count, *h_minx, *h_miny, *h_maxx, *h_maxy;
-  int32_t *h_gx, *h_gy;
-  long long *h_dot;
-  int32_t *slot_blob;   // hash_cap
+  uint32_t *h_count;
+  uint32_t *slot_off;   // hash_cap: first segment position of the slot's blob, 0xffffffff = not a candidate
+  uint32_t *slot_cluster;  // hash_cap: index into clusters[] (keep_stages)
   uint32_t *occupied;   // hash_cap: slots claimed this frame, in claim order
   b200tag_blob *blobs;  // blob_cap
-  uint32_t *blob_fill;  // blob_cap
+  uint32_t *seg_pts;    // point_cap: segment points (27 bit) of candidate blobs, unsorted
   uint32_t *small_list; // blob_cap: indices of blobs fitted by one warp
   uint32_t *large_list; // blob_cap: indices of blobs fitted by one CTA
   b200tag_blob *clusters;  // cluster_cap (keep_stages)

@@ -1,8 +1,10 @@
 // Blob stage of the B200 AprilTag engine (sm_100a):
-//   K7  blob selection straight off the blob-pair hash     (reference: apriltag_gpu.cu:522-629,873-905)
-//   K8  scatter of surviving points into per-blob segments, keyed by angle (:380-412,909-942)
-//   K9  one CTA per blob: in-CTA bitonic angle sort, prefix moments, line-fit errors, 7-tap
-//       smoothing, peak selection, exhaustive 210-way quad search, corner/area/angle tests
+//   K7  candidate blobs straight off the blob-pair hash (count limits), segment allocation
+//                                                          (reference: apriltag_gpu.cu:522-629,873-905)
+//   K8  scatter of the candidates' points into per-blob segments (rank known: no atomics)  (:909-942)
+//   K9  one warp / CTA per blob: extents + SelectBlobs (:418-454,534-559), angle keys (:380-412),
+//       in-CTA bitonic angle sort, prefix moments, line-fit errors, 7-tap smoothing, peak
+//       selection, exhaustive 210-way quad search, corner/area/angle tests
 //       (:944-1097, line_fit_filter.cu:22-36,217-278,504-592,709-1193, apriltag_detect.cu:38-282)
 // The reference spends 10 CUB device-wide passes and 5 host round trips here; per-blob work is
 // independent, so each blob is carried from unsorted points to QuadCorners by a single CTA with
@@ -39,19 +41,20 @@ __device__ __forceinline__ bool select_blob(const FrameParams &p, uint32_t count
 }
 
 // One atomic pair per CTA: the per-frame allocation state is packed as
-//   alloc = [63:40] clusters | [39:20] blobs | [19:0] small blobs      (large index = blob - small)
+//   alloc = [63:40] clusters | [39:20] candidate blobs | [19:0] small blobs      (large index = blob - small)
 // so cluster index, blob index and work-list positions of 256 hash slots come from a single
 // 64-bit atomicAdd (the first version issued ~4 returning atomics per warp on one cache line and
-// spent 97 % of its time waiting for them).
+// spent 97 % of its time waiting for them).  Only the count limits of SelectBlobs
+// (apriltag_gpu.cu:536-541) are applied here; the extent and polarity tests need the blob's
+// points and run at the top of the fit kernels.
 __global__ void __launch_bounds__(256) k_select(FrameParams p) {
-  __shared__ uint32_t s_warp[8][4];  // per-warp totals: occupied, selected, small, points
+  __shared__ uint32_t s_warp[8][4];  // per-warp totals: occupied, candidates, small, points
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_pbase;
   const int frame = blockIdx.y;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  uint32_t *fill = p.blob_fill + static_cast<size_t>(frame) * p.blob_cap;
   uint32_t *small_list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
   uint32_t *large_list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   b200tag_blob *clusters = p.clusters ? p.clusters + static_cast<size_t>(frame) * p.cluster_cap : nullptr;
@@ -69,28 +72,16 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
     if (occ) {
       rec.rep0 = static_cast<uint32_t>(key >> 32);
       rec.rep1 = static_cast<uint32_t>(key);
-      rec.min_x = p.h_minx[hoff + slot];
-      rec.min_y = p.h_miny[hoff + slot];
-      rec.max_x = p.h_maxx[hoff + slot];
-      rec.max_y = p.h_maxy[hoff + slot];
+      rec.min_x = 0xffffffffu; rec.min_y = 0xffffffffu; rec.max_x = 0; rec.max_y = 0;
       rec.count = p.h_count[hoff + slot];
-      rec.gx_sum = p.h_gx[hoff + slot];
-      rec.gy_sum = p.h_gy[hoff + slot];
-      rec.pxgx_plus_pygy_sum = p.h_dot[hoff + slot];
+      rec.gx_sum = 0; rec.gy_sum = 0; rec.pxgx_plus_pygy_sum = 0;
       rec.slot = slot;
       rec.offset = 0;
-      sel = select_blob(p, rec.count, rec.min_x, rec.min_y, rec.max_x, rec.max_y, rec.gx_sum, rec.gy_sum, rec.pxgx_plus_pygy_sum);
-      rec.selected = sel;
+      sel = rec.count >= p.min_cluster_pixels && rec.count <= p.max_cluster_pixels;
+      rec.selected = 0;
       // leave the table empty for the next frame
       p.h_key[hoff + slot] = kEmptyKey;
       p.h_count[hoff + slot] = 0;
-      p.h_minx[hoff + slot] = 0xffffffffu;
-      p.h_miny[hoff + slot] = 0xffffffffu;
-      p.h_maxx[hoff + slot] = 0;
-      p.h_maxy[hoff + slot] = 0;
-      p.h_gx[hoff + slot] = 0;
-      p.h_gy[hoff + slot] = 0;
-      p.h_dot[hoff + slot] = 0;
     }
     const bool small = sel && rec.count <= kSmallBlobPoints;
     const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
@@ -122,7 +113,7 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       if (t0) {
         const unsigned long long add = (static_cast<unsigned long long>(t0) << 40) | (static_cast<unsigned long long>(t1) << 20) | t2;
         base = atomicAdd(&ctr->alloc, add);
-        if (t3) pb = atomicAdd(&ctr->num_selected_points, t3);
+        if (t3) pb = atomicAdd(&ctr->num_seg_points, t3);
       }
       s_base = base;
       s_pbase = pb;
@@ -132,7 +123,7 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
     const uint32_t cbase = static_cast<uint32_t>(base >> 40) + s_warp[warp][0];
     const uint32_t bbase = static_cast<uint32_t>(base >> 20) & 0xfffffu;
     const uint32_t sbase = static_cast<uint32_t>(base) & 0xfffffu;
-    int32_t blob_id = -1;
+    uint32_t seg_off = 0xffffffffu;
     if (sel) {
       const uint32_t bw = s_warp[warp][1] + __popc(sel_mask & ((1u << lane) - 1u));    // rank among this CTA's blobs
       const uint32_t sw = s_warp[warp][2] + __popc(small_mask & ((1u << lane) - 1u));  // ... among its small blobs
@@ -141,8 +132,7 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       if (b < p.blob_cap && static_cast<uint64_t>(off) + rec.count <= p.point_cap) {
         rec.offset = off;
         blobs[b] = rec;
-        fill[b] = 0;
-        blob_id = static_cast<int32_t>(b);
+        seg_off = off;
         if (small) small_list[sbase + sw] = b;
         else large_list[(bbase - sbase) + (bw - sw)] = b;
       } else {
@@ -157,43 +147,74 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
     if (occ && clusters) {
       const uint32_t c = cbase + __popc(occ_mask & ((1u << lane) - 1u));
       if (c < p.cluster_cap) clusters[c] = rec;
+      p.slot_cluster[hoff + slot] = c;
     }
-    if (occ) p.slot_blob[hoff + slot] = blob_id;
+    if (occ) p.slot_off[hoff + slot] = seg_off;
     __syncthreads();  // s_warp / s_base are reused by the next trip
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K8
+// K8: a candidate blob's points move to its segment; the position is segment start + the rank
+// the point was given when it was counted (k_boundary), so there is no atomic and no ordering
+// dependence here.  Only the 27 point bits travel on.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(FrameParams p) {
   const int frame = blockIdx.y;
   const Counters *ctr = p.counters + frame;
   const uint32_t np = min(ctr->num_points, p.point_cap);
   const uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
-  const int32_t *slot_blob = p.slot_blob + static_cast<size_t>(frame) * p.hash_cap;
-  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  uint32_t *fill = p.blob_fill + static_cast<size_t>(frame) * p.blob_cap;
-  uint64_t *seg = p.seg_keys + static_cast<size_t>(frame) * p.point_cap;
+  const uint32_t *slot_off = p.slot_off + static_cast<size_t>(frame) * p.hash_cap;
+  uint32_t *seg = p.seg_pts + static_cast<size_t>(frame) * p.point_cap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+    const uint64_t pt = __ldcs(points + i);
+    const uint32_t slot = point_slot(pt);
+    if (slot >= p.hash_cap) continue;  // hash overflow (frame already flagged)
+    const uint32_t off = __ldg(slot_off + slot);
+    if (off == 0xffffffffu) continue;  // NonzeroBlobs, apriltag_gpu.cu:505-518
+    seg[off + point_rank(pt)] = point_seg(pt);
+  }
+}
+
+// Debug stages (keep_stages): extents of EVERY blob pair, selected or not, as the reference's C3
+// reduce produces them (apriltag_gpu.cu:418-454,829-862), by plain global atomics.
+__global__ void __launch_bounds__(256) k_cluster_extents(FrameParams p) {
+  const int frame = blockIdx.y;
+  const Counters *ctr = p.counters + frame;
+  const uint32_t np = min(ctr->num_points, p.point_cap);
+  const uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
+  const uint32_t *slot_cluster = p.slot_cluster + static_cast<size_t>(frame) * p.hash_cap;
+  b200tag_blob *clusters = p.clusters + static_cast<size_t>(frame) * p.cluster_cap;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
     const uint64_t pt = points[i];
-    const int32_t b = slot_blob[point_slot(pt)];
-    if (b < 0) continue;  // NonzeroBlobs, apriltag_gpu.cu:505-518
-    const uint32_t minx = blobs[b].min_x, maxx = blobs[b].max_x, miny = blobs[b].min_y, maxy = blobs[b].max_y;
-    const uint32_t x = point_x(pt), y = point_y(pt), d = point_dir(pt);
-    // MinMaxExtents::cx/cy, line_fit_filter.h:44-49
-    const double cx = static_cast<double>(static_cast<float>(static_cast<int>(minx + maxx)) * 0.5f) + 0.05118;
-    const double cy = static_cast<double>(static_cast<float>(static_cast<int>(miny + maxy)) * 0.5f) + -0.028581;
-    // AddThetaToIndexPoint, apriltag_gpu.cu:400-408
-    const float fy = static_cast<float>(static_cast<double>(y) - cy);
-    const float fx = static_cast<float>(static_cast<double>(x) - cx);
-    const float theta = static_cast<float>((static_cast<double>(atan2f(fy, fx)) + 3.14159265358979323846) * 8e6);
-    long long ti = llrintf(theta);
-    if (ti < 0) ti = 0;
-    const uint32_t th = static_cast<uint32_t>(ti & 0xfffffff);
-    const uint32_t bx = (x - dir_dx(d)) >> 1, by = (y - dir_dy(d)) >> 1;
-    const uint32_t pos = blobs[b].offset + atomicAdd(&fill[b], 1u);
-    seg[pos] = pack_sort_key(th, d, by, bx);
+    const uint32_t slot = point_slot(pt);
+    if (slot >= p.hash_cap) continue;
+    const uint32_t c = slot_cluster[slot];
+    if (c >= p.cluster_cap) continue;
+    const uint32_t sp = point_seg(pt);
+    const int x = static_cast<int>(sp_x(sp)), y = static_cast<int>(sp_y(sp));
+    const int d = static_cast<int>(sp_dir(sp));
+    const int gx = sp_b2w(sp) ? dir_dx(d) : -dir_dx(d), gy = sp_b2w(sp) ? dir_dy(d) : -dir_dy(d);  // points.h:120-125
+    b200tag_blob *r = clusters + c;
+    atomicMin(&r->min_x, static_cast<uint32_t>(x));
+    atomicMax(&r->max_x, static_cast<uint32_t>(x));
+    atomicMin(&r->min_y, static_cast<uint32_t>(y));
+    atomicMax(&r->max_y, static_cast<uint32_t>(y));
+    if (gx) atomicAdd(&r->gx_sum, gx);
+    if (gy) atomicAdd(&r->gy_sum, gy);
+    const int dot = x * gx + y * gy;
+    if (dot) atomicAdd(reinterpret_cast<unsigned long long *>(&r->pxgx_plus_pygy_sum), static_cast<unsigned long long>(static_cast<long long>(dot)));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cluster_finish(FrameParams p) {
+  const int frame = blockIdx.y;
+  const Counters *ctr = p.counters + frame;
+  const uint32_t nc = min(alloc_clusters(ctr->alloc), p.cluster_cap);
+  b200tag_blob *clusters = p.clusters + static_cast<size_t>(frame) * p.cluster_cap;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    b200tag_blob *r = clusters + c;
+    r->selected = select_blob(p, r->count, r->min_x, r->min_y, r->max_x, r->max_y, r->gx_sum, r->gy_sum, r->pxgx_plus_pygy_sum);
   }
 }
 
@@ -360,6 +381,8 @@ struct BlobScratch {
   double lines[4][4];
   float corners[4][2];
   uint32_t peak_idx[kMaxPeaks];
+  uint32_t red_u[8][4];  // per-warp partial extents (CTA tiers)
+  int red_i[8][3];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
   uint32_t cur;      // blob being processed
@@ -392,7 +415,7 @@ struct BlobWork {
 
 template <int GS>
 __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
-                                             const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
+                                             b200tag_blob *blob_rec, const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
   const uint32_t cnt = blob.count, off = blob.offset;
@@ -400,13 +423,72 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
   const int lane = threadIdx.x & 31;
   const bool first_warp = gt < 32;
 
+  // (0) the blob's points: extents (MinMaxExtents, apriltag_gpu.cu:418-454) by warp reductions, the
+  //     extent / polarity tests of SelectBlobs (:534-559), then the angle keys (:380-412).  The raw
+  //     points are parked in the still unused error buffer.
+  uint32_t *raw = reinterpret_cast<uint32_t *>(wk.errs);
+  {
+    const uint32_t *sp = p.seg_pts + pbase;
+    uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
+    int sgx = 0, sgy = 0, sdot = 0;
+    for (uint32_t i = gt; i < cnt; i += GS) {
+      const uint32_t v = __ldcg(sp + i);
+      raw[i] = v;
+      const uint32_t x = sp_x(v), y = sp_y(v);
+      const int d = static_cast<int>(sp_dir(v));
+      const int gx = sp_b2w(v) ? dir_dx(d) : -dir_dx(d), gy = sp_b2w(v) ? dir_dy(d) : -dir_dy(d);  // points.h:120-125
+      mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y);
+      sgx += gx; sgy += gy;
+      sdot += static_cast<int>(x) * gx + static_cast<int>(y) * gy;  // |sum| <= 32768 points * 16382
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    sgx = __reduce_add_sync(0xffffffffu, sgx); sgy = __reduce_add_sync(0xffffffffu, sgy);
+    sdot = __reduce_add_sync(0xffffffffu, sdot);
+    if constexpr (GS > 32) {
+      const int wi = gt >> 5;
+      if (lane == 0) {
+        S.red_u[wi][0] = mnx; S.red_u[wi][1] = mxx; S.red_u[wi][2] = mny; S.red_u[wi][3] = mxy;
+        S.red_i[wi][0] = sgx; S.red_i[wi][1] = sgy; S.red_i[wi][2] = sdot;
+      }
+      __syncthreads();
+      mnx = 0xffffffffu; mxx = 0; mny = 0xffffffffu; mxy = 0; sgx = 0; sgy = 0; sdot = 0;
+#pragma unroll
+      for (int w = 0; w < GS / 32; w++) {
+        mnx = min(mnx, S.red_u[w][0]); mxx = max(mxx, S.red_u[w][1]); mny = min(mny, S.red_u[w][2]); mxy = max(mxy, S.red_u[w][3]);
+        sgx += S.red_i[w][0]; sgy += S.red_i[w][1]; sdot += S.red_i[w][2];
+      }
+    }
+    const bool sel = select_blob(p, cnt, mnx, mny, mxx, mxy, sgx, sgy, static_cast<long long>(sdot));
+    if (gt == 0) {
+      blob_rec->min_x = mnx; blob_rec->min_y = mny; blob_rec->max_x = mxx; blob_rec->max_y = mxy;
+      blob_rec->gx_sum = sgx; blob_rec->gy_sum = sgy; blob_rec->pxgx_plus_pygy_sum = sdot;
+      blob_rec->selected = sel;
+      if (sel) {
+        atomicAdd(&ctr->num_selected_blobs, 1u);
+        atomicAdd(&ctr->num_selected_points, cnt);
+      }
+    }
+    if (!sel) return;  // uniform across the group
+    gsync<GS>();
+    // MinMaxExtents::cx/cy, line_fit_filter.h:44-49
+    const double cx = static_cast<double>(static_cast<float>(static_cast<int>(mnx + mxx)) * 0.5f) + 0.05118;
+    const double cy = static_cast<double>(static_cast<float>(static_cast<int>(mny + mxy)) * 0.5f) + -0.028581;
+    for (uint32_t i = gt; i < cnt; i += GS) {
+      const uint32_t v = raw[i];
+      // AddThetaToIndexPoint, apriltag_gpu.cu:400-408
+      const float fy = static_cast<float>(static_cast<double>(sp_y(v)) - cy);
+      const float fx = static_cast<float>(static_cast<double>(sp_x(v)) - cx);
+      const float theta = static_cast<float>((static_cast<double>(atan2f(fy, fx)) + 3.14159265358979323846) * 8e6);
+      long long ti = llrintf(theta);
+      if (ti < 0) ti = 0;
+      wk.keys[i] = pack_sort_key(static_cast<uint32_t>(ti & 0xfffffff), sp_dir(v), sp_by(v), sp_bx(v));
+    }
+  }
+
   // (1) angle sort, C6 (apriltag_gpu.cu:944-956)
   uint32_t N = 1;
   while (N < cnt) N <<= 1;
-  if (!wk.keys_in_place) {
-    const unsigned long long *seg = reinterpret_cast<const unsigned long long *>(p.seg_keys + pbase);
-    for (uint32_t i = gt; i < cnt; i += GS) wk.keys[i] = __ldcg(seg + i);
-  }
   if (gt == 0) S.npeaks = 0;
   gsync<GS>();
   bitonic_sort<GS>(wk.keys, cnt, N, gt);
@@ -735,7 +817,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
   Counters *ctr = p.counters + frame;
-  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
+  b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(alloc_small(ctr->alloc), p.blob_cap);
   BlobWork wk;
@@ -754,7 +836,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
     const uint32_t b = list[li];
     if (b == 0xffffffffu) continue;
     const b200tag_blob blob = blobs[b];
-    fit_one_blob<32>(p, frame, ctr, b, blob, wk, S.scratch, nullptr, lane);
+    fit_one_blob<32>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, nullptr, lane);
   }
 }
 
@@ -780,7 +862,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   const int frame = blockIdx.y;
   const int tid = threadIdx.x;
   Counters *ctr = p.counters + frame;
-  const b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
+  b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(alloc_blobs(ctr->alloc) - alloc_small(ctr->alloc), p.blob_cap);
   uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
@@ -801,19 +883,19 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.lf = p.lfp + pbase; wk.errs = S.errs;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf = p.lfp + pbase; wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
       wk.keys_in_place = true;
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     }
   }
 }
@@ -841,6 +923,12 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (kt) kt->begin("scatter", s);
   k_scatter<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
+  int launches = 5;
+  if (p.clusters) {  // debug stage only (keep_stages)
+    k_cluster_extents<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
+    k_cluster_finish<<<dim3(16, frames), 256, 0, s>>>(p);
+    launches += 2;
+  }
   // resident capacity: 3 small-tier CTAs (4 warps = 4 blobs each) and 2 large-tier CTAs per SM
   if (kt) kt->begin("fit_small", s);
   k_fit_small<<<dim3(max(4u, min(444u, cdivu(1776u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
@@ -851,7 +939,7 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (kt) kt->begin("fit_large", s);
   K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
   if (kt) kt->end(s);
-  return 5;
+  return launches;
 }
 
 }  // namespace b200tag

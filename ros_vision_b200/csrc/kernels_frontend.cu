@@ -493,21 +493,35 @@ __global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6: boundary points + blob-pair hash.
+// K6: boundary points, grouped by blob pair.
+//
+// One CTA = one 64x16 pixel tile (halo staged in shared memory as label | big | colour).
+//   (1) per pixel: which of the 4 directions emit a point (apriltag_gpu.cu:276-357); the points
+//       are compacted into a shared-memory list, so everything after this runs with full warps;
+//   (2) per point: blob-pair key -> entry of a CTA-local hash table, local rank by one
+//       shared-memory atomicAdd on the entry's count;
+//   (3) per local entry: ONE find-or-claim in the frame's global blob-pair hash and ONE global
+//       atomicAdd of the entry's count, which returns the base rank of this tile's points;
+//   (4) per point: 8-byte record (slot, rank, x, y, dir, polarity), coalesced stores.
+// The reference writes a dense 32-byte-per-pixel array, compacts it and radix-sorts it by blob
+// pair (C1, C2); extents (C3) are computed per blob by the fit kernels, where a whole blob sits
+// in one warp / CTA and the reductions are shuffles instead of atomics.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBpTW = 64, kBpTH = 16, kBpThreads = 256;
+constexpr int kBpMaxPts = kBpTW * kBpTH * 4;
+constexpr uint32_t kBpLH = 1024;        // local blob-pair table (power of two)
+constexpr uint32_t kBpMaxProbe = 48;    // longer probe sequences take the direct-to-global path
+constexpr uint32_t kBpDirect = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
-  uint64_t k = (static_cast<uint64_t>(a) << 32) | b;
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return static_cast<uint32_t>(k);
+  uint32_t h = a * 0x9E3779B1u ^ (b * 0x85EBCA77u + 0x165667B1u);
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 13;
+  return h;
 }
 
-// Finds or claims the slot of blob pair `key`; returns hash_cap on a full table.
+// Finds or claims the slot of blob pair `key`; returns kInvalidSlot on a full table.
 __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, unsigned long long key, uint32_t rep0, uint32_t rep1,
                                 Counters *ctr, uint32_t *occupied) {
   uint32_t slot = hash_pair(rep0, rep1) & (p.hash_cap - 1);
@@ -524,12 +538,18 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
     }
     slot = (slot + 1) & (p.hash_cap - 1);
   }
-  return p.hash_cap;
+  atomicOr(&ctr->status, B200TAG_ST_HASH_OVERFLOW);
+  return kInvalidSlot;
 }
 
 // staged cell: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
 __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
+  __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
+  __shared__ uint32_t s_loc[kBpMaxPts];             // [9:0] local entry | [31:10] rank among the tile's points of that entry
+  __shared__ unsigned long long s_lkey[kBpLH];      // blob-pair key; after (3): the global slot
+  __shared__ uint32_t s_lcnt[kBpLH];                // points of the entry in this tile; after (3): base rank
+  __shared__ uint32_t s_npts, s_gbase;
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kBpTW, y0 = blockIdx.y * kBpTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
@@ -538,11 +558,17 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   const uint32_t *sizes = p.sizes + frame * n;
   Counters *ctr = p.counters + frame;
   uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
-  unsigned long long *h_key = p.h_key + static_cast<size_t>(frame) * p.hash_cap;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
+  unsigned long long *h_key = p.h_key + hoff;
+  uint32_t *h_count = p.h_count + hoff;
   uint32_t *occupied = p.occupied + hoff;
   const int tid = threadIdx.x, lane = tid & 31;
 
+  if (tid == 0) s_npts = 0;
+  for (int i = tid; i < static_cast<int>(kBpLH); i += kBpThreads) {
+    s_lkey[i] = kEmptyKey;
+    s_lcnt[i] = 0;
+  }
   for (int i = tid; i < (kBpTH + 1) * (kBpTW + 2); i += kBpThreads) {
     const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
     const int gx = x0 - 1 + c, gy = y0 + r;
@@ -560,17 +586,15 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   }
   __syncthreads();
 
+  // (1) which directions emit a point; compaction into s_pts
   const int tx = tid % kBpTW;
   for (int ry = tid / kBpTW; ry < kBpTH; ry += kBpThreads / kBpTW) {  // warp-uniform trip count
     const int x = x0 + tx, y = y0 + ry;
-    uint32_t have = 0;  // bit d: this pixel emits a point in direction d
-    uint32_t pt_rep[4] = {0, 0, 0, 0}, pt_b2w = 0;
-    uint32_t rep_self = 0;
+    uint32_t have = 0, b2w = 0;
     if (x >= 1 && x <= p.w - 2 && y >= 1 && y <= p.h - 2) {  // apriltag_gpu.cu:239,276-281
       const uint32_t c0 = s_cell[ry][tx + 1];
       const uint32_t col0 = c0 >> 29;
       if (col0 != 2 && (c0 & (1u << 28))) {  // :284
-        rep_self = c0 & 0x0fffffffu;
         const uint32_t cl = s_cell[ry][tx], c2 = s_cell[ry + 1][tx + 1];
         const uint32_t colL = cl >> 29, col2 = c2 >> 29;
         // direction-3 duplicate suppression, :347-357
@@ -582,60 +606,13 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
           const uint32_t col1 = c1 >> 29;
           if (col1 == 2 || col1 == col0) continue;  // v0 + v1 == 255, :305
           if (!(c1 & (1u << 28))) continue;          // :306
-          pt_rep[d] = c1 & 0x0fffffffu;
-          pt_b2w |= (col1 > col0 ? 1u : 0u) << d;   // :316
+          b2w |= (col1 > col0 ? 1u : 0u) << d;      // :316
           have |= 1u << d;
         }
       }
     }
-    // Blob-pair bookkeeping.  One warp-uniform round per direction; lanes whose points share a
-    // blob pair (__match_any_sync) fold their extents with redux and one lane updates the hash.
-    uint32_t slots[4] = {p.hash_cap, p.hash_cap, p.hash_cap, p.hash_cap};
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-      const bool has = (have >> d) & 1u;
-      const uint32_t active = __ballot_sync(0xffffffffu, has);
-      if (!has) continue;
-      const uint32_t ra = min(rep_self, pt_rep[d]), rb = max(rep_self, pt_rep[d]);
-      const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
-      const uint32_t b2w = (pt_b2w >> d) & 1u;
-      const int px = 2 * x + dir_dx(d), py = 2 * y + dir_dy(d);  // points.h:111-116
-      const int gx = b2w ? dir_dx(d) : -dir_dx(d), gy = b2w ? dir_dy(d) : -dir_dy(d);  // points.h:120-125
-      const uint32_t group = __match_any_sync(active, key);
-      const int leader = __ffs(group) - 1;
-      const uint32_t cnt = __popc(group);
-      const uint32_t mnx = __reduce_min_sync(group, static_cast<uint32_t>(px));
-      const uint32_t mxx = __reduce_max_sync(group, static_cast<uint32_t>(px));
-      const uint32_t mny = __reduce_min_sync(group, static_cast<uint32_t>(py));
-      const uint32_t mxy = __reduce_max_sync(group, static_cast<uint32_t>(py));
-      const int sgx = __reduce_add_sync(group, gx);
-      const int sgy = __reduce_add_sync(group, gy);
-      const int sdot = __reduce_add_sync(group, px * gx + py * gy);
-      uint32_t slot = 0;
-      if (lane == leader) {
-        slot = hash_insert(p, h_key, key, ra, rb, ctr, occupied);
-        if (slot < p.hash_cap) {
-          atomicAdd(p.h_count + hoff + slot, cnt);
-          atomicMin(p.h_minx + hoff + slot, mnx);
-          atomicMax(p.h_maxx + hoff + slot, mxx);
-          atomicMin(p.h_miny + hoff + slot, mny);
-          atomicMax(p.h_maxy + hoff + slot, mxy);
-          if (sgx) atomicAdd(p.h_gx + hoff + slot, sgx);
-          if (sgy) atomicAdd(p.h_gy + hoff + slot, sgy);
-          if (sdot)
-            atomicAdd(reinterpret_cast<unsigned long long *>(p.h_dot + hoff + slot),
-                      static_cast<unsigned long long>(static_cast<long long>(sdot)));
-        } else {
-          atomicOr(&ctr->status, B200TAG_ST_HASH_OVERFLOW);
-        }
-      }
-      slots[d] = __shfl_sync(group, slot, leader);
-    }
-    // compaction: warp prefix over point counts, one global atomic per warp
-    uint32_t valid = 0;
-#pragma unroll
-    for (int d = 0; d < 4; d++) valid += (slots[d] < p.hash_cap);
-    uint32_t incl = valid;
+    const uint32_t cnt = __popc(have);
+    uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -643,35 +620,86 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&ctr->num_points, total);
+    if (lane == 31 && total) base = atomicAdd(&s_npts, total);
     base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t pos = base + incl - valid;
+    uint32_t pos = base + incl - cnt;
+    const uint32_t pix = static_cast<uint32_t>(ry * kBpTW + tx) << 3;
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
-      if (slots[d] >= p.hash_cap) continue;
-      if (pos < p.point_cap) {
-        points[pos] = pack_point(slots[d], 2 * x + dir_dx(d), 2 * y + dir_dy(d), d, (pt_b2w >> d) & 1u);
-      } else {
-        atomicOr(&ctr->status, B200TAG_ST_POINTS_OVERFLOW);
+    for (int d = 0; d < 4; d++)
+      if ((have >> d) & 1u) s_pts[pos++] = static_cast<uint16_t>(pix | (d << 1) | ((b2w >> d) & 1u));
+  }
+  __syncthreads();
+  const uint32_t npts = s_npts;
+  if (npts == 0) return;
+  if (tid == 0) s_gbase = atomicAdd(&ctr->num_points, npts);
+
+  // (2) local blob-pair table: entry + local rank per point
+  for (uint32_t i = tid; i < npts; i += kBpThreads) {
+    const uint32_t e = s_pts[i];
+    const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
+    const int ry = pix / kBpTW, txp = pix % kBpTW;
+    const uint32_t r0 = s_cell[ry][txp + 1] & 0x0fffffffu;
+    const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
+    const uint32_t ra = min(r0, r1), rb = max(r0, r1);
+    const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
+    uint32_t h = hash_pair(ra, rb) & (kBpLH - 1);
+    uint32_t loc = kBpDirect;  // crowded local table (adversarial input): handled in (4)
+    for (uint32_t probe = 0; probe < kBpMaxProbe; probe++) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_lkey[h]);
+      if (cur == kEmptyKey) cur = atomicCAS(&s_lkey[h], kEmptyKey, key);
+      if (cur == key || cur == kEmptyKey) {
+        loc = h | (atomicAdd(&s_lcnt[h], 1u) << 10);
+        break;
       }
-      pos++;
+      h = (h + 1) & (kBpLH - 1);
+    }
+    s_loc[i] = loc;
+  }
+  __syncthreads();
+
+  // (3) one global find-or-claim and one global count update per local entry
+  for (uint32_t e = tid; e < kBpLH; e += kBpThreads) {
+    const unsigned long long key = s_lkey[e];
+    if (key == kEmptyKey) continue;
+    const uint32_t slot = hash_insert(p, h_key, key, static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(key), ctr, occupied);
+    s_lkey[e] = slot;
+    s_lcnt[e] = slot != kInvalidSlot ? atomicAdd(h_count + slot, s_lcnt[e]) : 0u;
+  }
+  __syncthreads();
+
+  // (4) point records
+  const uint32_t gbase = s_gbase;
+  for (uint32_t i = tid; i < npts; i += kBpThreads) {
+    const uint32_t e = s_pts[i];
+    const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
+    const int ry = pix / kBpTW, txp = pix % kBpTW;
+    const uint32_t loc = s_loc[i];
+    uint32_t slot, rank;
+    if (loc != kBpDirect) {
+      slot = static_cast<uint32_t>(s_lkey[loc & (kBpLH - 1)]);
+      rank = s_lcnt[loc & (kBpLH - 1)] + (loc >> 10);
+    } else {
+      const uint32_t r0 = s_cell[ry][txp + 1] & 0x0fffffffu;
+      const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
+      const uint32_t ra = min(r0, r1), rb = max(r0, r1);
+      slot = hash_insert(p, h_key, (static_cast<unsigned long long>(ra) << 32) | rb, ra, rb, ctr, occupied);
+      rank = slot != kInvalidSlot ? atomicAdd(h_count + slot, 1u) : 0u;
+    }
+    const uint32_t pos = gbase + i;
+    if (pos < p.point_cap) {
+      points[pos] = pack_point(slot, rank, static_cast<uint32_t>(x0 + txp), static_cast<uint32_t>(y0 + ry), d, e & 1u);
+    } else {
+      atomicOr(&ctr->status, B200TAG_ST_POINTS_OVERFLOW);
     }
   }
 }
 
-// Resets the blob-pair hash of every frame (first use, and after each frame by k_select).
+// Resets the blob-pair hash of every frame (first use; afterwards k_select leaves it empty).
 __global__ void k_hash_clear(FrameParams p, int frames) {
   const size_t total = static_cast<size_t>(frames) * p.hash_cap;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     p.h_key[i] = kEmptyKey;
     p.h_count[i] = 0;
-    p.h_minx[i] = 0xffffffffu;
-    p.h_miny[i] = 0xffffffffu;
-    p.h_maxx[i] = 0;
-    p.h_maxy[i] = 0;
-    p.h_gx[i] = 0;
-    p.h_gy[i] = 0;
-    p.h_dot[i] = 0;
   }
 }
 

@@ -77,13 +77,19 @@ def compare_line_fit(det: D.GpuDetector, orc, frame=0):
     filt = det.CopyStage(D.STAGE_FILTERED_ERRORS, frame)
     sel = orc.clusters[orc.clusters["selected"] != 0]
     okey = _key64(sel["rep0"], sel["rep1"])
-    bkey = _key64(blobs["rep0"], blobs["rep1"])
+    # STAGE_BLOBS lists every blob pair within the point-count limits; .selected = passed SelectBlobs
+    cand = orc.clusters[(orc.clusters["count"] >= 24) & (orc.clusters["count"] <= 4 * (orc.w + orc.h))]
+    assert np.array_equal(np.sort(_key64(blobs["rep0"], blobs["rep1"])), _key64(cand["rep0"], cand["rep1"])), "candidate blob set"
+    chosen = blobs[blobs["selected"] != 0]
+    bkey = _key64(chosen["rep0"], chosen["rep1"])
     assert np.array_equal(np.sort(bkey), okey), "selected blob set"
     lut = {int(k): i for i, k in enumerate(okey)}
-    for b in blobs:
+    for b in chosen:
         o = sel[lut[int(_key64(b["rep0"], b["rep1"]))]]
         cnt = int(b["count"])
         assert cnt == int(o["count"])
+        for fld in ("min_x", "min_y", "max_x", "max_y", "gx_sum", "gy_sum", "pxgx_plus_pygy_sum"):
+            assert int(b[fld]) == int(o[fld]), f"blob extents .{fld}"
         g0, o0 = int(b["offset"]), int(o["sel_start"])
         sp = orc.spoints[o0:o0 + cnt]
         ref_key = ((sp["theta"].astype(np.uint64) << np.uint64(26)) | (sp["dir"].astype(np.uint64) << np.uint64(24)) |
