@@ -333,7 +333,7 @@ def run_ours(args):
             "kernels": kern}
 
     if rank == 0:
-        cb = cpu_baseline(frames) if world == 1 or True else None
+        cb = cpu_baseline(frames) if not args.no_cpu else None
         line = {
             "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -345,7 +345,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if world == 1 else None,
+            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu) else None,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs,
                       "detections_per_batch": ndet_per_batch},
@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--lanes", type=int, default=2, help="detector instances (CUDA streams) used by the end-to-end leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU / reference-GPU reporting legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -411,7 +411,14 @@ struct BlobWork {
   double *filt;              // cnt filtered errors (may alias keys)
   unsigned long long *peaks; // <= cnt/2 peak keys (may alias errs, which is dead by then)
   bool keys_in_place;        // keys == the blob's segment of p.seg_keys (sorted in place)
+  // scratch of the bucket sort; all of it is dead before the prefix moments are written (may alias lf)
+  uint32_t *hist;            // hist_cap bucket counters
+  uint32_t hist_cap;         // power of two
+  uint32_t *tmp;             // 2 * cnt words: theta and in-bucket rank of every point
 };
+
+constexpr uint32_t kMaxBucketLoad = 24;  // fuller buckets (thin, elongated blobs) fall back to the bitonic network
+constexpr uint32_t kThetaSpan = 50265483u;  // theta = llrintf((atan2f + pi) * 8e6) < 2 * pi * 8e6 + 1
 
 template <int GS>
 __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
@@ -474,6 +481,18 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     // MinMaxExtents::cx/cy, line_fit_filter.h:44-49
     const double cx = static_cast<double>(static_cast<float>(static_cast<int>(mnx + mxx)) * 0.5f) + 0.05118;
     const double cy = static_cast<double>(static_cast<float>(static_cast<int>(mny + mxy)) * 0.5f) + -0.028581;
+
+    // (1) angle sort, C5/C6 (apriltag_gpu.cu:380-412,944-956).  The keys are (theta, dir, y, x); theta is
+    //     spread around the whole circle, so a bucket sort does it in O(cnt): B >= cnt buckets over the
+    //     theta range (monotone map), in-bucket rank from the counting atomicAdd, exclusive scan, scatter,
+    //     then each thread insertion-sorts the few elements of its own buckets on the full 64-bit key.
+    uint32_t N = 1;
+    while (N < cnt) N <<= 1;
+    const uint32_t B = min(N, wk.hist_cap);
+    for (uint32_t i = gt; i < B; i += GS) wk.hist[i] = 0;
+    if (gt == 0) S.npeaks = 0;
+    gsync<GS>();
+    uint32_t *th_tmp = wk.tmp, *rk_tmp = wk.tmp + cnt;
     for (uint32_t i = gt; i < cnt; i += GS) {
       const uint32_t v = raw[i];
       // AddThetaToIndexPoint, apriltag_gpu.cu:400-408
@@ -482,16 +501,80 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       const float theta = static_cast<float>((static_cast<double>(atan2f(fy, fx)) + 3.14159265358979323846) * 8e6);
       long long ti = llrintf(theta);
       if (ti < 0) ti = 0;
-      wk.keys[i] = pack_sort_key(static_cast<uint32_t>(ti & 0xfffffff), sp_dir(v), sp_by(v), sp_bx(v));
+      const uint32_t th = static_cast<uint32_t>(ti & 0xfffffff);
+      const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(th) * B / kThetaSpan));
+      th_tmp[i] = th;
+      rk_tmp[i] = atomicAdd(&wk.hist[bk], 1u);
+    }
+    gsync<GS>();
+    // exclusive scan of the bucket counts (B / GS consecutive buckets per thread) + fullest bucket
+    const uint32_t per = B / GS;  // B and GS are powers of two, B >= GS
+    uint32_t sum = 0, mx = 0;
+    for (uint32_t j = 0; j < per; j++) {
+      const uint32_t c = wk.hist[gt * per + j];
+      sum += c;
+      mx = max(mx, c);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if constexpr (GS > 32) {
+      const int wi = gt >> 5;
+      __syncthreads();  // red_u was read by every thread above
+      if (lane == 31) S.red_u[wi][0] = incl;
+      if (lane == 0) S.red_u[wi][1] = mx;
+      __syncthreads();
+      uint32_t before = 0;
+      mx = 0;
+#pragma unroll
+      for (int w = 0; w < GS / 32; w++) {
+        if (w < wi) before += S.red_u[w][0];
+        mx = max(mx, S.red_u[w][1]);
+      }
+      incl += before;
+    }
+    const bool bucketed = mx <= kMaxBucketLoad;
+    if (bucketed) {
+      uint32_t ex = incl - sum;
+      for (uint32_t j = 0; j < per; j++) {
+        const uint32_t c = wk.hist[gt * per + j];
+        wk.hist[gt * per + j] = ex;
+        ex += c;
+      }
+      gsync<GS>();
+      for (uint32_t i = gt; i < cnt; i += GS) {
+        const uint32_t v = raw[i], th = th_tmp[i];
+        const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(th) * B / kThetaSpan));
+        wk.keys[wk.hist[bk] + rk_tmp[i]] = pack_sort_key(th, sp_dir(v), sp_by(v), sp_bx(v));
+      }
+      gsync<GS>();
+      for (uint32_t j = 0; j < per; j++) {
+        const uint32_t bk = gt * per + j;
+        const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
+        for (uint32_t i = lo + 1; i < hi; i++) {
+          const unsigned long long key = wk.keys[i];
+          uint32_t q = i;
+          while (q > lo && wk.keys[q - 1] > key) {
+            wk.keys[q] = wk.keys[q - 1];
+            q--;
+          }
+          wk.keys[q] = key;
+        }
+      }
+      gsync<GS>();
+    } else {
+      for (uint32_t i = gt; i < cnt; i += GS) {
+        const uint32_t v = raw[i];
+        wk.keys[i] = pack_sort_key(th_tmp[i], sp_dir(v), sp_by(v), sp_bx(v));
+      }
+      gsync<GS>();
+      bitonic_sort<GS>(wk.keys, cnt, N, gt);
     }
   }
-
-  // (1) angle sort, C6 (apriltag_gpu.cu:944-956)
-  uint32_t N = 1;
-  while (N < cnt) N <<= 1;
-  if (gt == 0) S.npeaks = 0;
-  gsync<GS>();
-  bitonic_sort<GS>(wk.keys, cnt, N, gt);
   if (p.keep_stages && !wk.keys_in_place) {
     uint64_t *out = p.seg_keys + pbase;
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.keys[i];
@@ -827,6 +910,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
   wk.filt = reinterpret_cast<double *>(S.keys);
   wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
   wk.keys_in_place = false;
+  wk.hist = reinterpret_cast<uint32_t *>(S.lf);
+  wk.hist_cap = kSmallBlobPoints;
+  wk.tmp = wk.hist + kSmallBlobPoints;
   while (true) {
     __syncwarp();
     if (lane == 0) S.scratch.cur = atomicAdd(&ctr->next_small, 1u);
@@ -865,6 +951,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(alloc_blobs(ctr->alloc) - alloc_small(ctr->alloc), p.blob_cap);
+  // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
+  constexpr uint32_t kScanHist = (6u * THREADS * 2u >= 2048u) ? 2048u : ((6u * THREADS * 2u >= 1024u) ? 1024u : 512u);
   uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
   while (true) {
     __syncthreads();
@@ -883,18 +971,21 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
+      wk.hist = reinterpret_cast<uint32_t *>(S.lf); wk.hist_cap = LF_CAP > 0 ? LF_CAP : 1; wk.tmp = wk.hist + LF_CAP;
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.lf = p.lfp + pbase; wk.errs = S.errs;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
+      wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf = p.lfp + pbase; wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
       wk.keys_in_place = true;
+      wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     }
   }
