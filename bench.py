@@ -296,7 +296,7 @@ def run_ours(args):
     e2e_frames = per_lane * L * args.steps * world
     e2e_value = e2e_frames / e2e_s
     assert e2e_dets == sum(len(det.Detections(f)) for f in range(per_lane * L)), "end-to-end path lost detections"
-    d2h = 64 * per_lane * L + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
+    d2h = 128 * per_lane * L + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
     for ld in lanes:
         ld.close()
 
@@ -362,7 +362,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)

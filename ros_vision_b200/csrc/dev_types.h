@@ -73,12 +73,14 @@ struct Counters {  // one per frame, zeroed before each frame
   uint32_t next_medium;
   uint32_t num_seg_points;      // points of all candidate blobs (count filter only): segment allocation
   uint32_t num_selected_blobs;  // candidates that also pass SelectBlobs' extent / polarity tests
-  uint32_t pad[1];
+  uint32_t num_medium;          // candidates of the medium tier (front of large_list)
+  uint32_t num_large;           // candidates of the large tier (back of large_list)
+  uint32_t pad[15];
 };
 __host__ __device__ inline uint32_t alloc_clusters(unsigned long long a) { return static_cast<uint32_t>(a >> 40); }
 __host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return static_cast<uint32_t>(a >> 20) & 0xfffffu; }
 __host__ __device__ inline uint32_t alloc_small(unsigned long long a) { return static_cast<uint32_t>(a) & 0xfffffu; }
-static_assert(sizeof(Counters) == 64, "Counters layout");
+static_assert(sizeof(Counters) == 128, "Counters layout");
 
 struct FrameParams {
   // geometry

@@ -20,6 +20,7 @@
 namespace b200tag {
 
 static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
+constexpr uint32_t kMediumCap = 1024;   // blobs of 257..1024 points: 128-thread CTA, everything in shared memory
 
 // ---------------------------------------------------------------------------------------------
 // K7
@@ -48,9 +49,9 @@ __device__ __forceinline__ bool select_blob(const FrameParams &p, uint32_t count
 // (apriltag_gpu.cu:536-541) are applied here; the extent and polarity tests need the blob's
 // points and run at the top of the fit kernels.
 __global__ void __launch_bounds__(256) k_select(FrameParams p) {
-  __shared__ uint32_t s_warp[8][4];  // per-warp totals: occupied, candidates, small, points
+  __shared__ uint32_t s_warp[8][5];  // per-warp totals: occupied, candidates, small, points, medium
   __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_pbase;
+  __shared__ uint32_t s_pbase, s_mbase, s_lbase;
   const int frame = blockIdx.y;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
   Counters *ctr = p.counters + frame;
@@ -84,9 +85,11 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       p.h_count[hoff + slot] = 0;
     }
     const bool small = sel && rec.count <= kSmallBlobPoints;
+    const bool medium = sel && !small && rec.count <= kMediumCap;
     const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
     const uint32_t sel_mask = __ballot_sync(0xffffffffu, sel);
     const uint32_t small_mask = __ballot_sync(0xffffffffu, small);
+    const uint32_t medium_mask = __ballot_sync(0xffffffffu, medium);
     uint32_t incl = sel ? rec.count : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -99,24 +102,29 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       s_warp[warp][1] = __popc(sel_mask);
       s_warp[warp][2] = __popc(small_mask);
       s_warp[warp][3] = warp_pts;
+      s_warp[warp][4] = __popc(medium_mask);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
       for (int w = 0; w < 8; w++) {
-        const uint32_t a0 = s_warp[w][0], a1 = s_warp[w][1], a2 = s_warp[w][2], a3 = s_warp[w][3];
-        s_warp[w][0] = t0; s_warp[w][1] = t1; s_warp[w][2] = t2; s_warp[w][3] = t3;  // exclusive prefixes
-        t0 += a0; t1 += a1; t2 += a2; t3 += a3;
+        const uint32_t a0 = s_warp[w][0], a1 = s_warp[w][1], a2 = s_warp[w][2], a3 = s_warp[w][3], a4 = s_warp[w][4];
+        s_warp[w][0] = t0; s_warp[w][1] = t1; s_warp[w][2] = t2; s_warp[w][3] = t3; s_warp[w][4] = t4;  // exclusive prefixes
+        t0 += a0; t1 += a1; t2 += a2; t3 += a3; t4 += a4;
       }
       unsigned long long base = 0;
-      uint32_t pb = 0;
+      uint32_t pb = 0, mb = 0, lb = 0;
       if (t0) {
         const unsigned long long add = (static_cast<unsigned long long>(t0) << 40) | (static_cast<unsigned long long>(t1) << 20) | t2;
         base = atomicAdd(&ctr->alloc, add);
         if (t3) pb = atomicAdd(&ctr->num_seg_points, t3);
+        if (t4) mb = atomicAdd(&ctr->num_medium, t4);
+        if (t1 - t2 - t4) lb = atomicAdd(&ctr->num_large, t1 - t2 - t4);
       }
       s_base = base;
       s_pbase = pb;
+      s_mbase = mb;
+      s_lbase = lb;
     }
     __syncthreads();
     const unsigned long long base = s_base;
@@ -127,6 +135,9 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
     if (sel) {
       const uint32_t bw = s_warp[warp][1] + __popc(sel_mask & ((1u << lane) - 1u));    // rank among this CTA's blobs
       const uint32_t sw = s_warp[warp][2] + __popc(small_mask & ((1u << lane) - 1u));  // ... among its small blobs
+      const uint32_t mw = s_warp[warp][4] + __popc(medium_mask & ((1u << lane) - 1u)); // ... among its medium blobs
+      // the CTA tiers share one array: medium blobs fill it from the front, large blobs from the back
+      const uint32_t cta_pos = medium ? s_mbase + mw : p.blob_cap - 1u - (s_lbase + (bw - sw - mw));
       const uint32_t b = bbase + bw;
       const uint32_t off = s_pbase + s_warp[warp][3] + incl - rec.count;
       if (b < p.blob_cap && static_cast<uint64_t>(off) + rec.count <= p.point_cap) {
@@ -134,13 +145,14 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
         blobs[b] = rec;
         seg_off = off;
         if (small) small_list[sbase + sw] = b;
-        else large_list[(bbase - sbase) + (bw - sw)] = b;
+        else large_list[cta_pos] = b;
       } else {
         atomicOr(&ctr->status, B200TAG_ST_BLOBS_OVERFLOW);
         // keep the work lists dense: an overflowing blob still occupies its list slot, flagged invalid
-        if (b < p.blob_cap) {
-          if (small) small_list[sbase + sw] = 0xffffffffu;
-          else large_list[(bbase - sbase) + (bw - sw)] = 0xffffffffu;
+        if (small) {
+          if (sbase + sw < p.blob_cap) small_list[sbase + sw] = 0xffffffffu;
+        } else if (cta_pos < p.blob_cap) {
+          large_list[cta_pos] = 0xffffffffu;
         }
       }
     }
@@ -920,7 +932,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
     const uint32_t b = list[li];
-    if (b == 0xffffffffu) continue;
+    if (b >= p.blob_cap) continue;  // overflow marker
     const b200tag_blob blob = blobs[b];
     fit_one_blob<32>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, nullptr, lane);
   }
@@ -950,7 +962,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t nlist = min(alloc_blobs(ctr->alloc) - alloc_small(ctr->alloc), p.blob_cap);
+  const uint32_t nlist = min(tier == 0 ? ctr->num_medium : ctr->num_large, p.blob_cap);
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
   constexpr uint32_t kScanHist = (6u * THREADS * 2u >= 2048u) ? 2048u : ((6u * THREADS * 2u >= 1024u) ? 1024u : 512u);
   uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
@@ -960,10 +972,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
     __syncthreads();
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
-    const uint32_t b = list[li];
-    if (b == 0xffffffffu) continue;
+    const uint32_t b = list[tier == 0 ? li : p.blob_cap - 1u - li];
+    if (b >= p.blob_cap) continue;  // overflow marker
     const b200tag_blob blob = blobs[b];
-    if (blob.count < MIN_CNT || blob.count > MAX_CNT) continue;  // the other tier's blob
+    if (blob.count < MIN_CNT || blob.count > MAX_CNT) continue;  // (cannot happen: k_select sorts blobs into tiers)
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
     if (blob.count <= LF_CAP) {  // everything in shared memory
@@ -991,7 +1003,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   }
 }
 
-constexpr uint32_t kMediumCap = 1024;
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
 #define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 3>
