@@ -48,9 +48,11 @@ def algorithmic_bytes_per_frame(points_per_frame: float) -> float:
     return 2 * N + N + n + n + 4 * n + 8.0 * points_per_frame
 
 
-# per-kernel algorithmic bytes per frame ("Per-kernel algorithmic bytes")
-def kernel_bytes(name: str, P: float, Psel: float, nblobs: float) -> float:
+# per-kernel algorithmic bytes per frame ("Per-kernel algorithmic bytes"; the kernels of
+# the new engine move 8-byte point records and 4-byte segment points)
+def kernel_bytes(name: str, P: float, tiers: dict) -> float:
     N, n = W * H, (W // DECIMATE) * (H // DECIMATE)
+    Pseg = tiers["small"] + tiers["medium"] + tiers["large"]
     table = {
         "pre_yuyv_dec2": 2 * N + N + n + n / 8,
         "threshold": n + n / 8 + n,
@@ -59,10 +61,10 @@ def kernel_bytes(name: str, P: float, Psel: float, nblobs: float) -> float:
         "ccl_final": 4 * n + 4 * n + 4 * n,
         "boundary": n + 4 * n + 4 * n + 8 * P,
         "select": 0.0,
-        "scatter": 8 * P + 8 * Psel,
-        "fit_small": 8 * Psel,   # reads the unsorted segment once; everything else stays in shared memory
-        "fit_medium": 8 * Psel,
-        "fit_large": 8 * Psel,
+        "scatter": 8 * P + 4 * Pseg,
+        "fit_small": 4 * tiers["small"],   # reads its blobs' segment points once; everything else stays in shared memory
+        "fit_medium": 4 * tiers["medium"],
+        "fit_large": 4 * tiers["large"] + 2 * 48 * tiers["large"],  # + prefix moments written and read in its (L2-resident) segment
         "decode": 0.0,
     }
     return table.get(name, 0.0)
@@ -236,6 +238,14 @@ def run_ours(args):
     P = float(np.mean([i.num_points for i in infos]))
     Psel = float(np.mean([i.num_selected_points for i in infos]))
     nblobs = float(np.mean([i.num_blobs for i in infos]))
+    # points per blob tier (candidate blobs: within the point-count limits), from the blob lists of the distinct frames
+    tiers = {"small": 0.0, "medium": 0.0, "large": 0.0}
+    nd = min(B, len(frames))
+    for f in range(nd):
+        cnts = det.CopyStage(D.STAGE_BLOBS, f)["count"].astype(np.int64)
+        tiers["small"] += float(cnts[cnts <= 256].sum()) / nd
+        tiers["medium"] += float(cnts[(cnts > 256) & (cnts <= 1024)].sum()) / nd
+        tiers["large"] += float(cnts[cnts > 1024].sum()) / nd
     launches_per_step = det.kernels_per_batch()
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,12 +330,22 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     kern = []
     for name, kms in prof:
-        by = kernel_bytes(name, P, Psel, nblobs) * B
+        by = kernel_bytes(name, P, tiers) * B
         kern.append({"kernel": name, "ms": kms, "alg_bytes": by, "gbs": (by / (kms * 1e-3) / 1e9) if kms > 0 else None})
     step_kernel_ms = sum(k["ms"] for k in kern)
     dom = max(kern, key=lambda k: k["ms"])
+    # DRAM bytes per launch of the dominant kernel from its committed `ncu --set full` capture (profiles/traffic.json,
+    # written by tools/make_profile_summary.py); null when that kernel has no capture yet
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and B == BATCH:
+        t = json.load(open(tpath)).get(dom["kernel"])
+        if t:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+            traffic_src = f"profiles/summary_{t['tag']}.md ({t['report']})"
     roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": (dom["gbs"] / peak) if dom["gbs"] else None, "traffic": None, "peak_source": peak_src,
+            "frac": (dom["gbs"] / peak) if dom["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src,
+            "alg_bytes_per_launch": dom["alg_bytes"], "peak_source": peak_src,
             "share_of_step": dom["ms"] / step_kernel_ms if step_kernel_ms else None,
             "whole_path": {"alg_bytes_per_frame": algorithmic_bytes_per_frame(P),
                            "achieved": algorithmic_bytes_per_frame(P) * B / (ms / args.steps * 1e-3) / 1e9,
@@ -333,7 +353,7 @@ def run_ours(args):
             "kernels": kern}
 
     if rank == 0:
-        cb = cpu_baseline(frames) if not args.no_cpu else None
+        cb = cpu_baseline(frames) if (world == 1 and not args.no_cpu) else None  # rank 0 at N=1 only
         line = {
             "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -347,7 +367,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu) else None,
             "clocks": clocks.summary(),
-            "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs,
+            "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},
         }
         print(json.dumps(line))
