@@ -368,6 +368,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_errs = plan.take(static_cast<size_t>(p.point_cap) * 4 * B);
   const size_t o_filt = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
   const size_t o_pkws = plan.take((static_cast<size_t>(p.point_cap) / 2 + 1) * 8 * B);
+  const size_t o_ptab = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(PeakTable) * B);
   const size_t o_fq = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_fit_quad) * B);
   const size_t o_quads = plan.take(static_cast<size_t>(p.quad_cap) * sizeof(b200tag_quad) * B);
   const size_t o_ctr = plan.take(sizeof(Counters) * B);
@@ -410,6 +411,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.errs = reinterpret_cast<float *>(base + o_errs);
   p.filt = reinterpret_cast<double *>(base + o_filt);
   p.peak_ws = reinterpret_cast<uint64_t *>(base + o_pkws);
+  p.peak_tables = reinterpret_cast<PeakTable *>(base + o_ptab);
   p.fit_quads = reinterpret_cast<b200tag_fit_quad *>(base + o_fq);
   p.quads = reinterpret_cast<b200tag_quad *>(base + o_quads);
   p.counters = reinterpret_cast<Counters *>(base + o_ctr);

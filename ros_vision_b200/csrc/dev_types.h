@@ -82,6 +82,18 @@ __host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return s
 __host__ __device__ inline uint32_t alloc_small(unsigned long long a) { return static_cast<uint32_t>(a) & 0xfffffu; }
 static_assert(sizeof(Counters) == 128, "Counters layout");
 
+// What the fit kernels hand to k_quads for every blob with at least one peak: the (at most 10) strongest
+// peaks in position order and exactly the prefix-moment records ReadMoments (line_fit_filter.cu:745-796)
+// can touch for ranges between them -- lf[idx], lf[idx - 1] and lf[cnt - 1].
+struct PeakTable {
+  uint32_t blob, cnt, nsel, npk;
+  uint32_t rep0, rep1;
+  uint32_t idx[kMaxPeaks];
+  b200tag_lfp at[kMaxPeaks];      // lf[idx[k]]
+  b200tag_lfp before[kMaxPeaks];  // lf[idx[k] - 1] (zero when idx[k] == 0)
+  b200tag_lfp last;               // lf[cnt - 1]
+};
+
 struct FrameParams {
   // geometry
   int32_t W, H;        // full resolution
@@ -133,6 +145,7 @@ struct FrameParams {
   float *errs;          // point_cap
   double *filt;         // point_cap
   uint64_t *peak_ws;    // point_cap / 2 + 1: peak list of blobs too large for shared memory
+  PeakTable *peak_tables;       // blob_cap: hand-off from the fit kernels to k_quads
   b200tag_fit_quad *fit_quads;  // blob_cap
   b200tag_quad *quads;  // quad_cap
   b200tag_detection *dets;  // det_cap

@@ -386,18 +386,23 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
-// Per-blob scratch that is always in shared memory.
+// Per-blob scratch of the fit kernels (always in shared memory).
 struct BlobScratch {
-  double seg_err[kMaxPeaks][kMaxPeaks];  // fit error of side (a -> b); kDblMax if mse > max_line_fit_mse
-  double seg_nx[kMaxPeaks][kMaxPeaks], seg_ny[kMaxPeaks][kMaxPeaks];
-  double lines[4][4];
-  float corners[4][2];
   uint32_t peak_idx[kMaxPeaks];
   uint32_t red_u[8][4];  // per-warp partial extents (CTA tiers)
   int red_i[8][3];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
   uint32_t cur;      // blob being processed
+};
+
+// Scratch of k_quads, one per warp.
+struct QuadScratch {
+  double seg_err[kMaxPeaks][kMaxPeaks];  // fit error of side (a -> b); kDblMax if mse > max_line_fit_mse
+  double seg_nx[kMaxPeaks][kMaxPeaks], seg_ny[kMaxPeaks][kMaxPeaks];
+  double lines[4][4];
+  float corners[4][2];
+  PeakTable t;
 };
 
 // nested-loop (Unrank) order of the C(10,4) corner choices, line_fit_filter.cu:709-728
@@ -749,23 +754,95 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
   }
   gsync<GS>();
 
+  // hand-off to k_quads: the chosen peaks and the prefix-moment records around them
+  if (first_warp) {
+    const uint32_t nm = S.nsel;
+    uint32_t fq = 0;
+    if (lane == 0) fq = atomicAdd(&ctr->num_fit_quads, 1u);
+    fq = __shfl_sync(0xffffffffu, fq, 0);
+    if (fq < p.blob_cap) {
+      PeakTable *t = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap + fq;
+      if (lane == 0) {
+        t->blob = b; t->cnt = cnt; t->nsel = nm; t->npk = npk; t->rep0 = blob.rep0; t->rep1 = blob.rep1;
+        t->last = wk.lf[cnt - 1];
+      }
+      if (lane < static_cast<int>(nm)) {
+        const uint32_t i = S.peak_idx[lane];
+        t->idx[lane] = i;
+        t->at[lane] = wk.lf[i];
+        b200tag_lfp z;
+        z.Mxx = 0; z.Myy = 0; z.Mxy = 0; z.Mx = 0; z.My = 0; z.W = 0;
+        t->before[lane] = i > 0 ? wk.lf[i - 1] : z;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: quad search.  One warp per blob that has peaks, fed by the fit kernels' PeakTable: the work
+// per blob no longer depends on its size (<= 90 side fits, 210 corner choices, 4 corners), so it
+// runs as a separate, uniformly loaded kernel instead of as a serial tail of every fit CTA.
+// ---------------------------------------------------------------------------------------------
+// ReadMoments (line_fit_filter.cu:745-796) for the range from chosen peak a to chosen peak c.
+__device__ __forceinline__ Mom table_moments(const PeakTable &T, int a, int c) {
+  const uint32_t i0 = T.idx[a], i1 = T.idx[c];
+  const b200tag_lfp hi = T.at[c], lo = T.before[a];
+  Mom m;
+  if (i0 < i1) {
+    m.N = static_cast<int>(i1 - i0 + 1);
+    m.Mx = hi.Mx; m.My = hi.My; m.Mxx = hi.Mxx; m.Mxy = hi.Mxy; m.Myy = hi.Myy; m.W = hi.W;
+    if (i0 > 0) { m.Mx -= lo.Mx; m.My -= lo.My; m.Mxx -= lo.Mxx; m.Mxy -= lo.Mxy; m.Myy -= lo.Myy; m.W -= lo.W; }
+  } else {
+    const b200tag_lfp z = T.last;
+    m.Mx = z.Mx - lo.Mx + hi.Mx;
+    m.My = z.My - lo.My + hi.My;
+    m.Mxx = z.Mxx - lo.Mxx + hi.Mxx;
+    m.Mxy = z.Mxy - lo.Mxy + hi.Mxy;
+    m.Myy = z.Myy - lo.Myy + hi.Myy;
+    m.W = z.W - lo.W + hi.W;
+    m.N = static_cast<int>(T.cnt - i0 + i1 + 1);
+  }
+  return m;
+}
+
+constexpr int kQuadWarps = 4;
+
+__global__ void __launch_bounds__(kQuadWarps * 32) k_quads(FrameParams p) {
+  __shared__ QuadScratch s_q[kQuadWarps];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  QuadScratch &S = s_q[threadIdx.x >> 5];
+  Counters *ctr = p.counters + frame;
+  const uint32_t nfq = min(ctr->num_fit_quads, p.blob_cap);
+  const PeakTable *tables = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap;
+  for (uint32_t fq = blockIdx.x * kQuadWarps + (threadIdx.x >> 5); fq < nfq; fq += gridDim.x * kQuadWarps) {
+    __syncwarp();
+    {  // the table into shared memory, 8 bytes per lane and trip
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(tables + fq);
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&S.t);
+      for (uint32_t i = lane; i < sizeof(PeakTable) / 8; i += 32) dst[i] = __ldcg(src + i);
+    }
+    __syncwarp();
+    const PeakTable &T = S.t;
+    const uint32_t b = T.blob, cnt = T.cnt, npk = T.npk;
+
   // (7) side-fit table: every ordered pair of chosen peaks (<= 90 fits instead of 4 per combination)
-  const int nm = static_cast<int>(S.nsel);
+  const int nm = static_cast<int>(T.nsel);
   const double max_mse = static_cast<double>(p.max_line_fit_mse);
-  for (int t = gt; t < kMaxPeaks * kMaxPeaks; t += GS) {
+  for (int t = lane; t < kMaxPeaks * kMaxPeaks; t += 32) {
     const int a = t / kMaxPeaks, c = t % kMaxPeaks;
     if (a == c || a >= nm || c >= nm) continue;
-    const Mom mo = read_moments(wk.lf, cnt, S.peak_idx[a], S.peak_idx[c]);
+    const Mom mo = table_moments(T, a, c);
     double err, mse, nrm[2];
     fit_line(mo, nullptr, nrm, &err, &mse);
     S.seg_err[a][c] = (mse > max_mse) ? kDblMax : err;  // line_fit_filter.cu:964-966,1009,1027,1035
     S.seg_nx[a][c] = nrm[0];
     S.seg_ny[a][c] = nrm[1];
   }
-  gsync<GS>();
+  __syncwarp();
 
   // (8) [first warp] exhaustive search over the C(10,4) corner choices, K11 (line_fit_filter.cu:976-1048,1161)
-  if (first_warp) {
+  {
     const double max_dot = static_cast<double>(p.cos_critical_rad);
     double my_err = kDblMax;
     int my_rank = kNumCombos;
@@ -798,9 +875,6 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     const double best = my_err;
     const int bi = my_rank < kNumCombos ? my_rank : 0;
     const bool valid = best < static_cast<double>(p.max_line_fit_mse * static_cast<float>(cnt));
-    uint32_t fq = 0;
-    if (lane == 0) fq = atomicAdd(&ctr->num_fit_quads, 1u);
-    fq = __shfl_sync(0xffffffffu, fq, 0);
     b200tag_fit_quad *fqo = (fq < p.blob_cap) ? (p.fit_quads + static_cast<size_t>(frame) * p.blob_cap + fq) : nullptr;
     if (lane == 0 && fqo) {
       fqo->blob_index = b;
@@ -812,9 +886,9 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       uint32_t i0 = 0, i1 = 0;
       Mom mo;
       if (valid) {
-        i0 = S.peak_idx[d_combos[bi][lane]];
-        i1 = S.peak_idx[d_combos[bi][(lane + 1) & 3]];
-        mo = read_moments(wk.lf, cnt, i0, i1);  // line_fit_filter.cu:1188-1191
+        i0 = T.idx[d_combos[bi][lane]];
+        i1 = T.idx[d_combos[bi][(lane + 1) & 3]];
+        mo = table_moments(T, d_combos[bi][lane], d_combos[bi][(lane + 1) & 3]);  // line_fit_filter.cu:1188-1191
         double err, mse;
         fit_line(mo, S.lines[lane], S.lines[lane] + 2, &err, &mse);
       }
@@ -887,14 +961,15 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
             for (int j = 0; j < 4; j++) { q.corners[j][0] = cr[j][0]; q.corners[j][1] = cr[j][1]; }
             q.reversed_border = p.reversed_border && !p.normal_border;
             q.blob_index = b;
-            q.rep0 = blob.rep0;
-            q.rep1 = blob.rep1;
+            q.rep0 = T.rep0;
+            q.rep1 = T.rep1;
           } else {
             atomicOr(&ctr->status, B200TAG_ST_QUADS_OVERFLOW);
           }
         }
       }
     }
+  }
   }
 }
 
@@ -1041,7 +1116,10 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (kt) kt->begin("fit_large", s);
   K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
   if (kt) kt->end(s);
-  return launches;
+  if (kt) kt->begin("quads", s);
+  k_quads<<<dim3(max(2u, min(592u, cdivu(2368u, frames))), frames), kQuadWarps * 32, 0, s>>>(p);
+  if (kt) kt->end(s);
+  return launches + 1;
 }
 
 }  // namespace b200tag
