@@ -82,46 +82,59 @@ __device__ __forceinline__ void h_project(const double *H, double x, double y, d
   *oy = yy / zz;
 }
 
-// homography_compute2 (libapriltag common/homography.c): 8x9 Gaussian elimination, partial pivoting
-__device__ int homography_compute(const double c[4][4], double *Hout) {
-  double A[72];
-  for (int i = 0; i < 4; i++) {
+// homography_compute2 (libapriltag common/homography.c): 8x9 Gaussian elimination with partial pivoting,
+// run by one warp on a shared-memory matrix: lane = (row, quarter of the columns).  Every element sees
+// exactly the operations of the sequential routine in the same order, so the result is bit-identical;
+// only the independent row updates of one elimination step run side by side.  Returns 0 on success
+// (uniform across the warp).
+__device__ int homography_compute_warp(double *A /* shared, 72 */, const float p[4][2], double *Hout /* shared, 9 */, int lane) {
+  if (lane < 4) {
+    const int i = lane;
+    const double c0 = (i == 0 || i == 3) ? -1 : 1, c1 = (i == 0 || i == 1) ? -1 : 1;
+    const double c2 = p[i][0], c3 = p[i][1];
     double *r0 = &A[(2 * i) * 9], *r1 = &A[(2 * i + 1) * 9];
-    r0[0] = c[i][0]; r0[1] = c[i][1]; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0;
-    r0[6] = -c[i][0] * c[i][2]; r0[7] = -c[i][1] * c[i][2]; r0[8] = c[i][2];
-    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = c[i][0]; r1[4] = c[i][1]; r1[5] = 1;
-    r1[6] = -c[i][0] * c[i][3]; r1[7] = -c[i][1] * c[i][3]; r1[8] = c[i][3];
+    r0[0] = c0; r0[1] = c1; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0;
+    r0[6] = -c0 * c2; r0[7] = -c1 * c2; r0[8] = c2;
+    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = c0; r1[4] = c1; r1[5] = 1;
+    r1[6] = -c0 * c3; r1[7] = -c1 * c3; r1[8] = c3;
   }
+  __syncwarp();
   const double epsilon = 1e-10;
+  const int row = lane >> 2, sub = lane & 3;
   for (int col = 0; col < 8; col++) {
-    double max_val = 0;
-    int max_val_idx = -1;
-    for (int row = col; row < 8; row++) {
-      const double val = fabs(A[row * 9 + col]);
-      if (val > max_val) { max_val = val; max_val_idx = row; }
+    // pivot: the first row >= col holding the largest magnitude (strict > in the sequential scan)
+    const double val = (lane >= col && lane < 8) ? fabs(A[lane * 9 + col]) : -1.0;
+    double mx = val;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));  // lanes 0..7 fold among themselves
+    mx = __shfl_sync(0xffffffffu, mx, 0);
+    if (!(mx > 0.0) || mx < epsilon) return -1;
+    const int piv = __ffs(__ballot_sync(0xffffffffu, val == mx)) - 1;
+    if (piv != col && lane >= col && lane < 9) {
+      const double tmp = A[col * 9 + lane];
+      A[col * 9 + lane] = A[piv * 9 + lane];
+      A[piv * 9 + lane] = tmp;
     }
-    if (max_val_idx < 0) return -1;
-    if (max_val < epsilon) return -1;
-    if (max_val_idx != col) {
-      for (int i = col; i < 9; i++) {
-        const double tmp = A[col * 9 + i];
-        A[col * 9 + i] = A[max_val_idx * 9 + i];
-        A[max_val_idx * 9 + i] = tmp;
-      }
+    __syncwarp();
+    double f = 0;
+    if (row > col) f = A[row * 9 + col] / A[col * 9 + col];
+    __syncwarp();
+    if (row > col) {
+      if (sub == 0) A[row * 9 + col] = 0;
+      for (int j = col + 1 + sub; j < 9; j += 4) A[row * 9 + j] -= f * A[col * 9 + j];
     }
-    for (int i = col + 1; i < 8; i++) {
-      const double f = A[i * 9 + col] / A[col * 9 + col];
-      A[i * 9 + col] = 0;
-      for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
-    }
+    __syncwarp();
   }
-  for (int col = 7; col >= 0; col--) {
-    double sum = 0;
-    for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
-    A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+  if (lane == 0) {
+    for (int col = 7; col >= 0; col--) {
+      double sum = 0;
+      for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
+      A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+    }
+    for (int i = 0; i < 8; i++) Hout[i] = A[i * 9 + 8];
+    Hout[8] = 1;
   }
-  for (int i = 0; i < 8; i++) Hout[i] = A[i * 9 + 8];
-  Hout[8] = 1;
+  __syncwarp();
   return 0;
 }
 
@@ -182,6 +195,7 @@ struct DecodeShared {
   int gm_v[64];  // -1 = sample outside the image
   double values[100], sharp[100];
   double H[9];
+  double A[72];  // homography system
   GrayModel white, black;
   uint32_t cur;
   int ok;
@@ -304,23 +318,16 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
     }
 
     // quad_update_homographies
-    if (lane == 0) {
-      double corr[4][4];
-      for (int i = 0; i < 4; i++) {
-        corr[i][0] = (i == 0 || i == 3) ? -1 : 1;
-        corr[i][1] = (i == 0 || i == 1) ? -1 : 1;
-        corr[i][2] = S.p[i][0];
-        corr[i][3] = S.p[i][1];
-      }
-      double Hm[9];
-      int ok = homography_compute(corr, Hm) == 0;
+    {
+      int ok = homography_compute_warp(S.A, S.p, S.H, lane) == 0;
       if (ok) {
+        const double *Hm = S.H;
         const double det = Hm[0] * (Hm[4] * Hm[8] - Hm[5] * Hm[7]) - Hm[1] * (Hm[3] * Hm[8] - Hm[5] * Hm[6]) +
                            Hm[2] * (Hm[3] * Hm[7] - Hm[4] * Hm[6]);
         if (!(fabs(det) > 1e-300)) ok = 0;
       }
-      for (int i = 0; i < 9; i++) S.H[i] = ok ? Hm[i] : 0.0;
-      S.ok = ok;
+      __syncwarp();
+      if (lane == 0) S.ok = ok;
     }
     __syncwarp();
     if (!S.ok) continue;
