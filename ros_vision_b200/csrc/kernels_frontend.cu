@@ -569,20 +569,34 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
     s_lkey[i] = kEmptyKey;
     s_lcnt[i] = 0;
   }
-  for (int i = tid; i < (kBpTH + 1) * (kBpTW + 2); i += kBpThreads) {
-    const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
-    const int gx = x0 - 1 + c, gy = y0 + r;
-    uint32_t cell = 2u << 29;
-    if (gx >= 0 && gx < p.w && gy < p.h) {
-      const size_t g = static_cast<size_t>(gy) * p.w + gx;
-      const uint8_t v = th[g];
-      if (v != 127) {
-        const uint32_t lab = labels[g];
-        const uint32_t big = sizes[lab] >= kMinBlobPixels;
-        cell = lab | (big << 28) | ((v ? 1u : 0u) << 29);
+  {  // halo tile: all of a thread's pixel and label loads are issued before the dependent size gathers
+    constexpr int kCells = (kBpTH + 1) * (kBpTW + 2);
+    constexpr int kPer = (kCells + kBpThreads - 1) / kBpThreads;
+    uint32_t v[kPer], lab[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int i = tid + k * kBpThreads;
+      const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
+      const int gx = x0 - 1 + c, gy = y0 + r;
+      v[k] = 127;
+      lab[k] = 0;
+      if (i < kCells && gx >= 0 && gx < p.w && gy < p.h) {
+        const size_t g = static_cast<size_t>(gy) * p.w + gx;
+        v[k] = th[g];
+        lab[k] = labels[g];
       }
     }
-    s_cell[r][c] = cell;
+    uint32_t sz[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) sz[k] = v[k] != 127 ? __ldg(sizes + lab[k]) : 0u;
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int i = tid + k * kBpThreads;
+      if (i >= kCells) continue;
+      uint32_t cell = 2u << 29;
+      if (v[k] != 127) cell = lab[k] | ((sz[k] >= kMinBlobPixels ? 1u : 0u) << 28) | ((v[k] ? 1u : 0u) << 29);
+      (&s_cell[0][0])[i] = cell;
+    }
   }
   __syncthreads();
 
