@@ -296,19 +296,52 @@ struct Mom {
   int N;
 };
 
+// Prefix moments live either in global memory as b200tag_lfp records (large tiers) or, for blobs of at most
+// 1024 points, in shared memory as six separate arrays: Mxx/Myy/Mxy 64 bit, Mx/My/W 32 bit unsigned
+// (W <= 1024 * 362 and Mx, My <= W * 8192 < 2^32), 36 bytes per point instead of 48 and conflict-free.
+struct LfStore {
+  b200tag_lfp *aos;            // global records, or nullptr
+  unsigned long long *m64;     // shared: [3][cap]
+  uint32_t *m32;               // shared: [3][cap]
+  uint32_t cap;
+};
+__device__ __forceinline__ b200tag_lfp lf_load(const LfStore &L, uint32_t i) {
+  if (L.aos) return L.aos[i];
+  b200tag_lfp r;
+  r.Mxx = static_cast<long long>(L.m64[i]);
+  r.Myy = static_cast<long long>(L.m64[L.cap + i]);
+  r.Mxy = static_cast<long long>(L.m64[2 * L.cap + i]);
+  r.Mx = L.m32[i];
+  r.My = L.m32[L.cap + i];
+  r.W = L.m32[2 * L.cap + i];
+  return r;
+}
+__device__ __forceinline__ void lf_store(const LfStore &L, uint32_t i, const b200tag_lfp &r) {
+  if (L.aos) {
+    L.aos[i] = r;
+    return;
+  }
+  L.m64[i] = static_cast<unsigned long long>(r.Mxx);
+  L.m64[L.cap + i] = static_cast<unsigned long long>(r.Myy);
+  L.m64[2 * L.cap + i] = static_cast<unsigned long long>(r.Mxy);
+  L.m32[i] = static_cast<uint32_t>(r.Mx);
+  L.m32[L.cap + i] = static_cast<uint32_t>(r.My);
+  L.m32[2 * L.cap + i] = static_cast<uint32_t>(r.W);
+}
+
 // ReadMoments, line_fit_filter.cu:745-796 (== CalculateError's window logic, :230-274)
-__device__ __forceinline__ Mom read_moments(const b200tag_lfp *lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
+__device__ __forceinline__ Mom read_moments(const LfStore &lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
   Mom m;
   if (i0 < i1) {
     m.N = static_cast<int>(i1 - i0 + 1);
-    const b200tag_lfp a = lf[i1];
+    const b200tag_lfp a = lf_load(lf, i1);
     m.Mx = a.Mx; m.My = a.My; m.Mxx = a.Mxx; m.Mxy = a.Mxy; m.Myy = a.Myy; m.W = a.W;
     if (i0 > 0) {
-      const b200tag_lfp b = lf[i0 - 1];
+      const b200tag_lfp b = lf_load(lf, i0 - 1);
       m.Mx -= b.Mx; m.My -= b.My; m.Mxx -= b.Mxx; m.Mxy -= b.Mxy; m.Myy -= b.Myy; m.W -= b.W;
     }
   } else {
-    const b200tag_lfp b = lf[i0 - 1], z = lf[cnt - 1], a = lf[i1];
+    const b200tag_lfp b = lf_load(lf, i0 - 1), z = lf_load(lf, cnt - 1), a = lf_load(lf, i1);
     m.Mx = z.Mx - b.Mx + a.Mx;
     m.My = z.My - b.My + a.My;
     m.Mxx = z.Mxx - b.Mxx + a.Mxx;
@@ -423,7 +456,7 @@ __global__ void k_init_combos() {
 // always go through gsync<GS>(), so plain (non-volatile) accesses are sufficient.
 struct BlobWork {
   unsigned long long *keys;  // cnt sort keys; dead after the moments phase
-  b200tag_lfp *lf;           // cnt prefix moments
+  LfStore lf;                // cnt prefix moments
   float *errs;               // cnt weights, then errors
   double *filt;              // cnt filtered errors (may alias keys)
   unsigned long long *peaks; // <= cnt/2 peak keys (may alias errs, which is dead by then)
@@ -663,12 +696,12 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     a_Mx += W * ix2; a_My += W * iy2; a_Mxx += W * ix2 * ix2; a_Mxy += W * ix2 * iy2; a_Myy += W * iy2 * iy2; a_W += W;
     b200tag_lfp o;
     o.Mxx = a_Mxx; o.Myy = a_Myy; o.Mxy = a_Mxy; o.Mx = a_Mx; o.My = a_My; o.W = a_W;
-    wk.lf[i] = o;
+    lf_store(wk.lf, i, o);
   }
   gsync<GS>();
-  if (p.keep_stages && wk.lf != p.lfp + pbase) {
+  if (p.keep_stages && wk.lf.aos != p.lfp + pbase) {
     b200tag_lfp *out = p.lfp + pbase;
-    for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.lf[i];
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = lf_load(wk.lf, i);
   }
 
   // (3) windowed line-fit error, K10 part 1 (line_fit_filter.cu:217-278)
@@ -764,15 +797,15 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       PeakTable *t = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap + fq;
       if (lane == 0) {
         t->blob = b; t->cnt = cnt; t->nsel = nm; t->npk = npk; t->rep0 = blob.rep0; t->rep1 = blob.rep1;
-        t->last = wk.lf[cnt - 1];
+        t->last = lf_load(wk.lf, cnt - 1);
       }
       if (lane < static_cast<int>(nm)) {
         const uint32_t i = S.peak_idx[lane];
         t->idx[lane] = i;
-        t->at[lane] = wk.lf[i];
+        t->at[lane] = lf_load(wk.lf, i);
         b200tag_lfp z;
         z.Mxx = 0; z.Myy = 0; z.Mxy = 0; z.Mx = 0; z.My = 0; z.W = 0;
-        t->before[lane] = i > 0 ? wk.lf[i - 1] : z;
+        t->before[lane] = i > 0 ? lf_load(wk.lf, i - 1) : z;
       }
     }
   }
@@ -976,12 +1009,13 @@ __global__ void __launch_bounds__(kQuadWarps * 32) k_quads(FrameParams p) {
 // ---- small tier: one warp per blob ------------------------------------------------------------
 struct SmallWarpShared {
   unsigned long long keys[kSmallBlobPoints];  // sort keys, later the filtered errors (same size)
-  b200tag_lfp lf[kSmallBlobPoints];
-  float errs[kSmallBlobPoints];               // weights -> errors -> peak list
+  unsigned long long lf64[3 * kSmallBlobPoints];  // prefix moments (LfStore); bucket-sort scratch before that
+  uint32_t lf32[3 * kSmallBlobPoints];
+  alignas(16) float errs[kSmallBlobPoints];   // weights -> errors -> peak list (8-byte keys)
   BlobScratch scratch;
 };
 
-__global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 4) k_fit_small(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
   const int frame = blockIdx.y;
@@ -992,12 +1026,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
   const uint32_t nlist = min(alloc_small(ctr->alloc), p.blob_cap);
   BlobWork wk;
   wk.keys = S.keys;
-  wk.lf = S.lf;
+  wk.lf.aos = nullptr; wk.lf.m64 = S.lf64; wk.lf.m32 = S.lf32; wk.lf.cap = kSmallBlobPoints;
   wk.errs = S.errs;
   wk.filt = reinterpret_cast<double *>(S.keys);
   wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
   wk.keys_in_place = false;
-  wk.hist = reinterpret_cast<uint32_t *>(S.lf);
+  wk.hist = reinterpret_cast<uint32_t *>(S.lf64);
   wk.hist_cap = kSmallBlobPoints;
   wk.tmp = wk.hist + kSmallBlobPoints;
   while (true) {
@@ -1021,8 +1055,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3) k_fit_small(FrameParams p
 template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP>
 struct CtaShared {
   unsigned long long keys[KEY_CAP];
-  b200tag_lfp lf[LF_CAP > 0 ? LF_CAP : 1];
-  float errs[KEY_CAP];
+  unsigned long long lf64[LF_CAP > 0 ? 3 * LF_CAP : 1];  // prefix moments (LfStore); bucket-sort scratch before that
+  uint32_t lf32[LF_CAP > 0 ? 3 * LF_CAP : 1];
+  alignas(16) float errs[KEY_CAP];  // also holds 8-byte peak keys
   long long scan[6 * THREADS];
   BlobScratch scratch;
 };
@@ -1054,14 +1089,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
     if (blob.count <= LF_CAP) {  // everything in shared memory
-      wk.keys = S.keys; wk.lf = S.lf; wk.errs = S.errs;
+      wk.keys = S.keys; wk.errs = S.errs;
+      wk.lf.aos = nullptr; wk.lf.m64 = S.lf64; wk.lf.m32 = S.lf32; wk.lf.cap = LF_CAP;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      wk.hist = reinterpret_cast<uint32_t *>(S.lf); wk.hist_cap = LF_CAP > 0 ? LF_CAP : 1; wk.tmp = wk.hist + LF_CAP;
+      wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = LF_CAP > 0 ? LF_CAP : 1; wk.tmp = wk.hist + LF_CAP;
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
-      wk.keys = S.keys; wk.lf = p.lfp + pbase; wk.errs = S.errs;
+      wk.keys = S.keys; wk.errs = S.errs;
+      wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
@@ -1069,7 +1106,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
-      wk.lf = p.lfp + pbase; wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
+      wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
+      wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
       wk.keys_in_place = true;
       wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
@@ -1080,7 +1118,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
 
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
-#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 3>
+#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 4>
 #define K_FIT_LARGE k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2>
 
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
@@ -1106,12 +1144,12 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
     k_cluster_finish<<<dim3(16, frames), 256, 0, s>>>(p);
     launches += 2;
   }
-  // resident capacity: 3 small-tier CTAs (4 warps = 4 blobs each) and 2 large-tier CTAs per SM
+  // resident capacity per SM: 4 small-tier CTAs (4 warps = 4 blobs each), 4 medium-tier CTAs, 2 large-tier CTAs
   if (kt) kt->begin("fit_small", s);
-  k_fit_small<<<dim3(max(4u, min(444u, cdivu(1776u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
+  k_fit_small<<<dim3(max(4u, min(592u, cdivu(2368u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_medium", s);
-  K_FIT_MEDIUM<<<dim3(max(3u, min(444u, cdivu(1776u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
+  K_FIT_MEDIUM<<<dim3(max(4u, min(592u, cdivu(2368u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
   K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
