@@ -35,17 +35,36 @@ W, H, FMT, DECIMATE, SIGMA = 1280, 800, "yuyv", 2, 0.0
 WORKLOAD = "config2: 1280x800 YUYV stream, tag36h11, quad_decimate=2, 1-6 tags per frame, noise N(0,4)"
 UNIQUE_FRAMES = 16     # distinct synthetic frames (seeds 2000..2015), tiled to fill a batch
 BATCH = 128            # frames per step: 262 MB of input + ~3 GB of intermediates, far beyond the 126 MB L2
+CONFIG = 2
+
+# the other BASELINE.json configs (parity-test cases; `--config N` measures them for DESIGN.md, the default
+# bench line is always config 2): (W, H, fmt, decimate, sigma, workload, distinct frames, default batch)
+OTHER_CONFIGS = {
+    1: (640, 480, "gray", 2, 0.0, "config1: 640x480 gray, 4 tags", 8, 256),
+    3: (1920, 1080, "bgr", 1, 0.8, "config3: 1920x1080 BGR, 30 small tags, quad_decimate=1, quad_sigma=0.8", 4, 16),
+    4: (1600, 1200, "yuyv", 2, 0.0, "config4: 1600x1200 YUYV camera stream, 2-8 tags", 8, 64),
+    5: (3840, 2160, "yuyv", 2, 0.0, "config5: 3840x2160 YUYV cluttered scene, 100 tags, batch 16", 2, 16),
+}
 
 
-def make_frames(n_unique=UNIQUE_FRAMES):
+def select_config(cfg: int):
+    global W, H, FMT, DECIMATE, SIGMA, WORKLOAD, UNIQUE_FRAMES, BATCH, CONFIG
+    if cfg == 2:
+        return
+    W, H, FMT, DECIMATE, SIGMA, WORKLOAD, UNIQUE_FRAMES, BATCH = OTHER_CONFIGS[cfg]
+    CONFIG = cfg
+
+
+def make_frames(n_unique=None):
     from ros_vision_b200 import synth
-    return [np.ascontiguousarray(synth.config_frame(2, i)[0]).reshape(-1) for i in range(n_unique)]
+    return [np.ascontiguousarray(synth.config_frame(CONFIG, i)[0]).reshape(-1) for i in range(n_unique or UNIQUE_FRAMES)]
 
 
 def algorithmic_bytes_per_frame(points_per_frame: float) -> float:
     """B_frame of SURVEY.md section 8(d): input + gray + quad + thresholded + labels + 8 B per boundary point."""
     N, n = W * H, (W // DECIMATE) * (H // DECIMATE)
-    return 2 * N + N + n + n + 4 * n + 8.0 * points_per_frame
+    bpp = {"gray": 1, "yuyv": 2, "bgr": 3}[FMT]
+    return bpp * N + (N if FMT != "gray" else 0) + (n if (DECIMATE > 1 or SIGMA != 0) else 0) + n + 4 * n + 8.0 * points_per_frame
 
 
 # per-kernel algorithmic bytes per frame (SURVEY.md section 8(d), "Per-kernel algorithmic bytes"; the kernels of
@@ -53,8 +72,13 @@ def algorithmic_bytes_per_frame(points_per_frame: float) -> float:
 def kernel_bytes(name: str, P: float, tiers: dict) -> float:
     N, n = W * H, (W // DECIMATE) * (H // DECIMATE)
     Pseg = tiers["small"] + tiers["medium"] + tiers["large"]
+    bpp = {"gray": 1, "yuyv": 2, "bgr": 3}[FMT]
     table = {
         "pre_yuyv_dec2": 2 * N + N + n + n / 8,
+        "pre_generic": bpp * N + (N if FMT != "gray" else 0) + n + n / 8,
+        "pre_bgr_dec1": 3 * N + N + n,
+        "blur": n + n,
+        "tile_minmax": n + n / 8,
         "threshold": n + n / 8 + n,
         "ccl_local": n + 4 * n + 4 * n,
         "ccl_merge": 0.0,
@@ -359,13 +383,13 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "distinct_frames": len(frames),
-                       "l2": "inputs (262 MB/step/GPU) and intermediates exceed the 126 MB L2; no explicit flush",
+                       "l2": f"inputs ({frame_bytes * B / 1e6:.0f} MB/step/GPU) and intermediates exceed the 126 MB L2; no explicit flush",
                        "sharding": "frames by rank, no collective"},
             "p50_latency_ms": p50, "p99_latency_ms": p99,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu) else None,
+            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},
@@ -389,7 +413,12 @@ def main():
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--lanes", type=int, default=2, help="detector instances (CUDA streams) used by the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU / reference-GPU reporting legs (profiling runs)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config to measure; the contract line is config 2 (the default)")
     args = ap.parse_args()
+    select_config(args.config)
+    if args.batch == 128 and args.config != 2:
+        args.batch = BATCH
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -135,9 +135,9 @@ def test_invalid_configurations_are_rejected(D):
 
 
 def test_full_size_properties(D, oracle):
-    """BASELINE configs 4 and 5 at full size: size-independent properties + oracle on the final answer."""
+    """BASELINE configs 3, 4 and 5 at full size: size-independent properties + oracle on the final answer."""
     from ros_vision_b200 import synth
-    for cfg_id in (4, 5):
+    for cfg_id in (3, 4, 5):
         frame, fmt, w, h, dec, sigma, sc = synth.config_frame(cfg_id)
         det = D.GpuDetector(w, h, fmt, quad_decimate=dec, quad_sigma=sigma, keep_stages=True)
         det.Detect(frame)
