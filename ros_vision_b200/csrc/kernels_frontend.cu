@@ -59,6 +59,38 @@ __global__ void __launch_bounds__(128) k_pre_yuyv_dec2(FrameParams p) {
   *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn & 0xff, mx & 0xff);
 }
 
+// K1 for GRAY8 input, decimate 2 (the gray image is the caller's buffer, nothing to write back):
+// one thread = one threshold tile; only the even rows are read, 8 bytes each.
+__global__ void __launch_bounds__(128) k_pre_gray_dec2(FrameParams p) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *in = p.in + frame * p.in_stride;
+  uint8_t *quad = p.quad + frame * n;
+  uint2 v[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const size_t row = static_cast<size_t>(ty) * 8 + 2 * r;
+    v[r] = __ldcs(reinterpret_cast<const uint2 *>(in + row * p.W + static_cast<size_t>(tx) * 8));
+  }
+  uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t d = __byte_perm(v[r].x, v[r].y, 0x6420);
+    *reinterpret_cast<uint32_t *>(quad + (static_cast<size_t>(ty) * 4 + r) * p.w + static_cast<size_t>(tx) * 4) = d;
+    mn = __vminu4(mn, d);
+    mx = __vmaxu4(mx, d);
+  }
+  mn = __vminu4(mn, mn >> 16);
+  mn = __vminu4(mn, mn >> 8);
+  mx = __vmaxu4(mx, mx >> 16);
+  mx = __vmaxu4(mx, mx >> 8);
+  uint8_t *mm = p.minmax_raw + (frame * static_cast<size_t>(p.tiles_x) * p.tiles_y + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+  *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn & 0xff, mx & 0xff);
+}
+
 __device__ __forceinline__ uint8_t luma_of(const uint8_t *in, int fmt, size_t i) {
   if (fmt == B200TAG_FMT_GRAY8) return in[i];
   if (fmt == B200TAG_FMT_YUYV) return in[2 * i];
@@ -134,38 +166,57 @@ __global__ void __launch_bounds__(256) k_pre_bgr_dec1(FrameParams p) {
 }
 
 // K1b: separable Gaussian with upstream's border rule (convolve(): indices [ksz/2, sz-ksz+ksz/2)
-// are filtered, the rest copied), rows first then columns.
-__device__ __forceinline__ uint32_t blur_row(const uint8_t *src, int w, int x, int y, int ksz, const uint8_t *k) {
-  const int r = ksz >> 1;
-  if (x < r || x >= w - ksz + r) return src[static_cast<size_t>(y) * w + x];
-  uint32_t acc = 0;
-  for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(k[j]) * src[static_cast<size_t>(y) * w + x - r + j];
-  return (acc >> 8) & 0xff;
-}
-
+// are filtered, the rest copied), rows first then columns.  One CTA = 64x32 output pixels: the
+// input tile with its halo is staged in shared memory, the row pass writes a second shared tile
+// (all rows the column pass needs), the column pass writes the result.
+constexpr int kBlurTW = 64, kBlurTH = 32, kBlurMaxR = 15;
 __global__ void __launch_bounds__(256) k_blur(FrameParams p) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
+  extern __shared__ uint8_t s_blur[];
+  const int ksz = p.blur_ksz, r = ksz >> 1;
+  const int sw = kBlurTW + 2 * r, sh = kBlurTH + 2 * r;  // staged input tile
+  uint8_t *s_in = s_blur;                                  // [sh][sw]
+  uint8_t *s_row = s_blur + sh * sw;                       // [sh][kBlurTW]: row-filtered
+  const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
   const int frame = blockIdx.z;
-  if (x >= p.w) return;
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *src = p.quad_tmp + frame * n;
   uint8_t *dst = p.quad + frame * n;
-  const int ksz = p.blur_ksz, r = ksz >> 1;
-  uint32_t v;
-  if (y < r || y >= p.h - ksz + r) {
-    v = blur_row(src, p.w, x, y, ksz, p.blur_k);
-  } else {
-    uint32_t acc = 0;
-    for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * blur_row(src, p.w, x, y - r + j, ksz, p.blur_k);
-    v = (acc >> 8) & 0xff;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < sh * sw; i += 256) {
+    const int yy = i / sw, xx = i % sw;
+    const int gx = x0 - r + xx, gy = y0 - r + yy;
+    s_in[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h) ? src[static_cast<size_t>(gy) * p.w + gx] : 0;
   }
-  if (p.sharpen) {
-    int s = 2 * static_cast<int>(src[static_cast<size_t>(y) * p.w + x]) - static_cast<int>(v);
-    s = max(0, min(255, s));
-    v = static_cast<uint32_t>(s);
+  __syncthreads();
+  for (int i = tid; i < sh * kBlurTW; i += 256) {
+    const int yy = i / kBlurTW, xx = i % kBlurTW;
+    const int gx = x0 + xx;
+    uint32_t v = s_in[yy * sw + xx + r];
+    if (gx >= r && gx < p.w - ksz + r) {
+      uint32_t acc = 0;
+      for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * s_in[yy * sw + xx + j];
+      v = (acc >> 8) & 0xff;
+    }
+    s_row[i] = static_cast<uint8_t>(v);
   }
-  dst[static_cast<size_t>(y) * p.w + x] = static_cast<uint8_t>(v);
+  __syncthreads();
+  for (int i = tid; i < kBlurTH * kBlurTW; i += 256) {
+    const int yy = i / kBlurTW, xx = i % kBlurTW;
+    const int gx = x0 + xx, gy = y0 + yy;
+    if (gx >= p.w || gy >= p.h) continue;
+    uint32_t v = s_row[(yy + r) * kBlurTW + xx];
+    if (gy >= r && gy < p.h - ksz + r) {
+      uint32_t acc = 0;
+      for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * s_row[(yy + j) * kBlurTW + xx];
+      v = (acc >> 8) & 0xff;
+    }
+    if (p.sharpen) {
+      int sv = 2 * static_cast<int>(s_in[(yy + r) * sw + xx + r]) - static_cast<int>(v);
+      sv = max(0, min(255, sv));
+      v = static_cast<uint32_t>(sv);
+    }
+    dst[static_cast<size_t>(gy) * p.w + gx] = static_cast<uint8_t>(v);
+  }
 }
 
 // 4x4 tile min/max of the quad image (threshold.cu:60-80).  One thread per tile.
@@ -730,6 +781,11 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
     k_pre_yuyv_dec2<<<tgrid, 128, 0, s>>>(p);
     if (kt) kt->end(s);
     launches++;
+  } else if (p.fmt == B200TAG_FMT_GRAY8 && p.f == 2 && !p.blur_ksz && (reinterpret_cast<uintptr_t>(p.in) | p.in_stride) % 8 == 0) {
+    if (kt) kt->begin("pre_gray_dec2", s);
+    k_pre_gray_dec2<<<tgrid, 128, 0, s>>>(p);
+    if (kt) kt->end(s);
+    launches++;
   } else {
     const bool vec_bgr = (p.fmt == B200TAG_FMT_BGR8 && p.f == 1 && (static_cast<size_t>(p.W) * p.H) % 16 == 0 && p.in_stride % 16 == 0);
     if (vec_bgr) {
@@ -746,7 +802,9 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
     }
     if (p.blur_ksz) {
       if (kt) kt->begin("blur", s);
-      k_blur<<<dim3(cdiv(p.w, 256), p.h, frames), 256, 0, s>>>(p);
+      const int r = p.blur_ksz >> 1;
+      const size_t smem = static_cast<size_t>(kBlurTH + 2 * r) * (kBlurTW + 2 * r) + static_cast<size_t>(kBlurTH + 2 * r) * kBlurTW;
+      k_blur<<<dim3(cdiv(p.w, kBlurTW), cdiv(p.h, kBlurTH), frames), 256, smem, s>>>(p);
       if (kt) kt->end(s);
       launches++;
     }
