@@ -49,6 +49,12 @@ enum {
   B200TAG_ST_DETS_OVERFLOW = 1u << 4,
 };
 
+/* b200tag_config.test_flags: results must be identical with and without them. */
+enum {
+  B200TAG_TEST_DIRECT_HASH = 1,   /* k_boundary: every point bypasses the CTA-local blob-pair table */
+  B200TAG_TEST_BITONIC_SORT = 2,  /* fit kernels: angle sort by the bitonic network instead of the bucket sort */
+};
+
 /* Mirrors the fields of apriltag_detector_t / apriltag_quad_thresh_params that the
  * reference reads (apriltag_gpu.cu:166-181,737,884,1084-1086; apriltag_detect.cu:229,
  * 244,455,580) plus CameraMatrix / DistCoeffs (apriltag_gpu.h:61-74). */
@@ -74,7 +80,8 @@ typedef struct b200tag_config {
   uint32_t max_points;    /* capacity of the boundary-point list per frame; 0 = default (2 * quad pixels) */
   uint32_t max_blobs;     /* capacity of the candidate-blob list per frame; 0 = default */
   uint32_t max_detections;/* per frame; 0 = default (256) */
-  int32_t reserved[8];
+  int32_t test_flags;     /* B200TAG_TEST_*: force the rarely taken fallback paths (tests only), 0 in production */
+  int32_t reserved[7];
 } b200tag_config;
 
 /* apriltag_detection_t (libapriltag apriltag.h) flattened: id, hamming, decision_margin,

@@ -209,6 +209,7 @@ void build_params(b200tag_detector *det) {
   p.fx = c.fx; p.cx = c.cx; p.fy = c.fy; p.cy = c.cy;
   p.k1 = c.k1; p.k2 = c.k2; p.p1 = c.p1; p.p2 = c.p2; p.k3 = c.k3;
   p.keep_stages = c.keep_stages;
+  p.test_flags = c.test_flags;
 }
 
 int finish_impl(b200tag_detector *det) {

@@ -116,6 +116,7 @@ struct FrameParams {
   double decode_sharpening;
   double fx, cx, fy, cy, k1, k2, p1, p2, k3;
   int32_t keep_stages;
+  int32_t test_flags;  // B200TAG_TEST_*
   // capacities
   uint32_t point_cap, hash_cap /* pow2 */, blob_cap, quad_cap, det_cap, cluster_cap;
   // buffers (frame 0) and per-frame strides in elements

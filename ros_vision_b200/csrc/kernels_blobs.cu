@@ -587,7 +587,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       }
       incl += before;
     }
-    const bool bucketed = mx <= kMaxBucketLoad;
+    const bool bucketed = mx <= kMaxBucketLoad && !(p.test_flags & B200TAG_TEST_BITONIC_SORT);
     if (bucketed) {
       uint32_t ex = incl - sum;
       for (uint32_t j = 0; j < per; j++) {
@@ -602,17 +602,44 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
         wk.keys[wk.hist[bk] + rk_tmp[i]] = pack_sort_key(th, sp_dir(v), sp_by(v), sp_bx(v));
       }
       gsync<GS>();
-      for (uint32_t j = 0; j < per; j++) {
-        const uint32_t bk = gt * per + j;
-        const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
-        for (uint32_t i = lo + 1; i < hi; i++) {
-          const unsigned long long key = wk.keys[i];
-          uint32_t q = i;
-          while (q > lo && wk.keys[q - 1] > key) {
-            wk.keys[q] = wk.keys[q - 1];
-            q--;
+      constexpr uint32_t kRankPer = 8;  // elements a thread can hold in registers across the barrier
+      if (cnt <= kRankPer * GS) {
+        // every element finds its place inside its bucket by counting the smaller keys there (1-2 elements
+        // per bucket on average, at most kMaxBucketLoad): balanced across threads, unlike a sort per bucket
+        unsigned long long kreg[kRankPer];
+        uint32_t preg[kRankPer];
+#pragma unroll
+        for (uint32_t j = 0; j < kRankPer; j++) {
+          const uint32_t q = gt + j * GS;
+          kreg[j] = 0;
+          preg[j] = 0xffffffffu;
+          if (q < cnt) {
+            const unsigned long long key = wk.keys[q];
+            const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(key_theta(key)) * B / kThetaSpan));
+            const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
+            uint32_t pos = lo;
+            for (uint32_t i = lo; i < hi; i++) pos += wk.keys[i] < key;
+            kreg[j] = key;
+            preg[j] = pos;
           }
-          wk.keys[q] = key;
+        }
+        gsync<GS>();
+#pragma unroll
+        for (uint32_t j = 0; j < kRankPer; j++)
+          if (preg[j] != 0xffffffffu) wk.keys[preg[j]] = kreg[j];
+      } else {
+        for (uint32_t j = 0; j < per; j++) {
+          const uint32_t bk = gt * per + j;
+          const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
+          for (uint32_t i = lo + 1; i < hi; i++) {
+            const unsigned long long key = wk.keys[i];
+            uint32_t q = i;
+            while (q > lo && wk.keys[q - 1] > key) {
+              wk.keys[q] = wk.keys[q - 1];
+              q--;
+            }
+            wk.keys[q] = key;
+          }
         }
       }
       gsync<GS>();
@@ -641,62 +668,85 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     wbuf[i] = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
   }
   gsync<GS>();
-  const uint32_t chunk = (cnt + GS - 1) / GS;
-  const uint32_t c_lo = min(cnt, gt * chunk), c_hi = min(cnt, c_lo + chunk);
-  long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0, t_Mx = 0, t_My = 0, t_W = 0;
-  for (uint32_t i = c_lo; i < c_hi; i++) {
-    const unsigned long long k = wk.keys[i];
-    const uint32_t d = key_dir(k);
-    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-    const long long W = wbuf[i];
-    t_Mx += W * ix2; t_My += W * iy2; t_Mxx += W * ix2 * ix2; t_Mxy += W * ix2 * iy2; t_Myy += W * iy2 * iy2; t_W += W;
-  }
-  long long a_Mxx, a_Myy, a_Mxy, a_Mx, a_My, a_W;
-  if constexpr (GS == 32) {
-    long long v[6] = {t_Mxx, t_Myy, t_Mxy, t_Mx, t_My, t_W};
-#pragma unroll
-    for (int q = 0; q < 6; q++) {
-      long long incl = v[q];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+  // Inclusive prefix sums by warp scans over 32 consecutive points per step (consecutive lanes touch
+  // consecutive shared-memory words: no bank conflicts).  Each warp owns a contiguous range of the blob;
+  // in the CTA tiers a first sweep computes the warps' totals, their exclusive scan gives each warp its
+  // carry-in.  Products: W <= 361, coordinates <= 8192, so W*x fits 32 bits and W*x*x one 32x32->64 multiply.
+  {
+    constexpr int kWarps = GS / 32;
+    const int wi = static_cast<int>(gt >> 5);
+    const uint32_t per_warp = ((cnt + kWarps - 1) / kWarps + 31u) & ~31u;
+    const uint32_t w_lo = min(cnt, wi * per_warp), w_hi = min(cnt, w_lo + per_warp);
+    unsigned long long c_Mxx = 0, c_Myy = 0, c_Mxy = 0, c_Mx = 0, c_My = 0, c_W = 0;  // carry-in of this warp
+    if constexpr (GS > 32) {
+      unsigned long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0;
+      uint32_t t_Mx = 0, t_My = 0, t_W = 0;  // per lane: at most per_warp / 32 <= 128 points of < 2^22 each
+      for (uint32_t i = w_lo + lane; i < w_hi; i += 32) {
+        const unsigned long long k = wk.keys[i];
+        const uint32_t d = key_dir(k);
+        const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
+        const uint32_t W = static_cast<uint32_t>(wbuf[i]);
+        const uint32_t wx = W * ix2, wy = W * iy2;
+        t_Mx += wx; t_My += wy; t_W += W;
+        t_Mxx += static_cast<unsigned long long>(wx) * ix2;
+        t_Mxy += static_cast<unsigned long long>(wx) * iy2;
+        t_Myy += static_cast<unsigned long long>(wy) * iy2;
       }
-      v[q] = incl - v[q];
-    }
-    a_Mxx = v[0]; a_Myy = v[1]; a_Mxy = v[2]; a_Mx = v[3]; a_My = v[4]; a_W = v[5];
-  } else {
-    scan[0 * GS + gt] = t_Mxx; scan[1 * GS + gt] = t_Myy; scan[2 * GS + gt] = t_Mxy;
-    scan[3 * GS + gt] = t_Mx;  scan[4 * GS + gt] = t_My;  scan[5 * GS + gt] = t_W;
-    __syncthreads();
-    constexpr int kPer = GS / 32;  // chunk totals per lane
-    for (int q = gt >> 5; q < 6; q += GS / 32) {  // exclusive scan of the GS chunk totals of quantity q by one warp
-      long long v[kPer], run = 0;
+      unsigned long long r_Mx = t_Mx, r_My = t_My, r_W = t_W;
 #pragma unroll
-      for (int j = 0; j < kPer; j++) { v[j] = scan[q * GS + lane * kPer + j]; run += v[j]; }
-      long long incl = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+      for (int o = 16; o > 0; o >>= 1) {
+        t_Mxx += __shfl_xor_sync(0xffffffffu, t_Mxx, o);
+        t_Myy += __shfl_xor_sync(0xffffffffu, t_Myy, o);
+        t_Mxy += __shfl_xor_sync(0xffffffffu, t_Mxy, o);
+        r_Mx += __shfl_xor_sync(0xffffffffu, r_Mx, o);
+        r_My += __shfl_xor_sync(0xffffffffu, r_My, o);
+        r_W += __shfl_xor_sync(0xffffffffu, r_W, o);
       }
-      long long ex = incl - run;
-#pragma unroll
-      for (int j = 0; j < kPer; j++) { scan[q * GS + lane * kPer + j] = ex; ex += v[j]; }
+      unsigned long long *tot = reinterpret_cast<unsigned long long *>(scan);  // [kWarps][6]
+      if (lane == 0) {
+        tot[wi * 6 + 0] = t_Mxx; tot[wi * 6 + 1] = t_Myy; tot[wi * 6 + 2] = t_Mxy;
+        tot[wi * 6 + 3] = r_Mx;  tot[wi * 6 + 4] = r_My;  tot[wi * 6 + 5] = r_W;
+      }
+      __syncthreads();
+      for (int w = 0; w < wi; w++) {
+        c_Mxx += tot[w * 6 + 0]; c_Myy += tot[w * 6 + 1]; c_Mxy += tot[w * 6 + 2];
+        c_Mx += tot[w * 6 + 3];  c_My += tot[w * 6 + 4];  c_W += tot[w * 6 + 5];
+      }
     }
-    __syncthreads();
-    a_Mxx = scan[0 * GS + gt]; a_Myy = scan[1 * GS + gt]; a_Mxy = scan[2 * GS + gt];
-    a_Mx = scan[3 * GS + gt];  a_My = scan[4 * GS + gt];  a_W = scan[5 * GS + gt];
-  }
-  for (uint32_t i = c_lo; i < c_hi; i++) {
-    const unsigned long long k = wk.keys[i];
-    const uint32_t d = key_dir(k);
-    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-    const long long W = wbuf[i];
-    a_Mx += W * ix2; a_My += W * iy2; a_Mxx += W * ix2 * ix2; a_Mxy += W * ix2 * iy2; a_Myy += W * iy2 * iy2; a_W += W;
-    b200tag_lfp o;
-    o.Mxx = a_Mxx; o.Myy = a_Myy; o.Mxy = a_Mxy; o.Mx = a_Mx; o.My = a_My; o.W = a_W;
-    lf_store(wk.lf, i, o);
+    for (uint32_t base = w_lo; base < w_hi; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t s_Mx = 0, s_My = 0, s_W = 0;
+      unsigned long long s_Mxx = 0, s_Myy = 0, s_Mxy = 0;
+      if (i < w_hi) {
+        const unsigned long long k = wk.keys[i];
+        const uint32_t d = key_dir(k);
+        const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
+        const uint32_t W = static_cast<uint32_t>(wbuf[i]);
+        const uint32_t wx = W * ix2, wy = W * iy2;
+        s_Mx = wx; s_My = wy; s_W = W;
+        s_Mxx = static_cast<unsigned long long>(wx) * ix2;
+        s_Mxy = static_cast<unsigned long long>(wx) * iy2;
+        s_Myy = static_cast<unsigned long long>(wy) * iy2;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {  // 32 points of < 2^22 (Mx, My) stay below 2^27: 32-bit scans
+        const uint32_t u_Mx = __shfl_up_sync(0xffffffffu, s_Mx, o), u_My = __shfl_up_sync(0xffffffffu, s_My, o);
+        const uint32_t u_W = __shfl_up_sync(0xffffffffu, s_W, o);
+        const unsigned long long u_Mxx = __shfl_up_sync(0xffffffffu, s_Mxx, o), u_Myy = __shfl_up_sync(0xffffffffu, s_Myy, o);
+        const unsigned long long u_Mxy = __shfl_up_sync(0xffffffffu, s_Mxy, o);
+        if (lane >= o) { s_Mx += u_Mx; s_My += u_My; s_W += u_W; s_Mxx += u_Mxx; s_Myy += u_Myy; s_Mxy += u_Mxy; }
+      }
+      if (i < w_hi) {
+        b200tag_lfp o;
+        o.Mxx = static_cast<long long>(c_Mxx + s_Mxx); o.Myy = static_cast<long long>(c_Myy + s_Myy);
+        o.Mxy = static_cast<long long>(c_Mxy + s_Mxy);
+        o.Mx = static_cast<long long>(c_Mx + s_Mx); o.My = static_cast<long long>(c_My + s_My); o.W = static_cast<long long>(c_W + s_W);
+        lf_store(wk.lf, i, o);
+      }
+      c_Mxx += __shfl_sync(0xffffffffu, s_Mxx, 31); c_Myy += __shfl_sync(0xffffffffu, s_Myy, 31);
+      c_Mxy += __shfl_sync(0xffffffffu, s_Mxy, 31);
+      c_Mx += __shfl_sync(0xffffffffu, s_Mx, 31); c_My += __shfl_sync(0xffffffffu, s_My, 31); c_W += __shfl_sync(0xffffffffu, s_W, 31);
+    }
   }
   gsync<GS>();
   if (p.keep_stages && wk.lf.aos != p.lfp + pbase) {
@@ -755,44 +805,69 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
   const uint32_t npk = S.npeaks;
   if (npk == 0) return;  // no PeakExtents entry -> no FitQuad (uniform across the group)
 
-  // (6) [first warp] the 10 strongest peaks, re-ordered by position, C9/C10 + line_fit_filter.cu:1104-1119
+  // (6) [first warp] the 10 strongest peaks, re-ordered by position, C9/C10 + line_fit_filter.cu:1104-1119.
+  //     The slot in the hand-off table is requested now, so the atomic's round trip hides behind the selection.
+  uint32_t fq_slot = 0;
   if (first_warp) {
-    unsigned long long last = 0;
+    if (lane == 0) fq_slot = atomicAdd(&ctr->num_fit_quads, 1u);
     uint32_t nsel = 0;
-    for (int round = 0; round < kMaxPeaks; round++) {
-      unsigned long long best = kNoKey;
-      for (uint32_t i = lane; i < npk; i += 32) {
-        const unsigned long long key = wk.peaks[i];
-        if ((round == 0 || key > last) && key < best) best = key;
+    if (npk <= 32) {
+      // one key per lane: bitonic network across the warp, the 10 smallest keys end up in lanes 0..9
+      unsigned long long v = lane < static_cast<int>(npk) ? wk.peaks[lane] : kNoKey;
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, j);
+          const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+          v = (take_min == (other < v)) ? other : v;
+        }
       }
-      {  // 64-bit warp minimum as two 32-bit redux steps
-        const uint32_t hi = static_cast<uint32_t>(best >> 32);
-        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-        const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(best) : 0xffffffffu;
-        const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
-        best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+      nsel = min(npk, static_cast<uint32_t>(kMaxPeaks));
+      // position order: rank of this lane's point index among the chosen ones
+      const uint32_t my_idx = static_cast<uint32_t>(v & 0xffffffffu);
+      uint32_t rank = 0;
+#pragma unroll
+      for (int m = 0; m < kMaxPeaks; m++) {
+        const uint32_t o = __shfl_sync(0xffffffffu, my_idx, m);
+        rank += (m < static_cast<int>(nsel)) && (o < my_idx);
       }
-      if (best == kNoKey) break;
-      last = best;
-      nsel++;
-      // insertion into the position-ordered list (lane 0), one element per round
-      if (lane == 0) {
-        const uint32_t v2 = static_cast<uint32_t>(best & 0xffffffffu);
-        int q = static_cast<int>(nsel) - 2;
-        while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
-        S.peak_idx[q + 1] = v2;
+      if (lane < static_cast<int>(nsel)) S.peak_idx[rank] = my_idx;
+    } else {
+      unsigned long long last = 0;
+      for (int round = 0; round < kMaxPeaks; round++) {
+        unsigned long long best = kNoKey;
+        for (uint32_t i = lane; i < npk; i += 32) {
+          const unsigned long long key = wk.peaks[i];
+          if ((round == 0 || key > last) && key < best) best = key;
+        }
+        {  // 64-bit warp minimum as two 32-bit redux steps
+          const uint32_t hi = static_cast<uint32_t>(best >> 32);
+          const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+          const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(best) : 0xffffffffu;
+          const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+          best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+        }
+        if (best == kNoKey) break;
+        last = best;
+        nsel++;
+        // insertion into the position-ordered list (lane 0), one element per round
+        if (lane == 0) {
+          const uint32_t v2 = static_cast<uint32_t>(best & 0xffffffffu);
+          int q = static_cast<int>(nsel) - 2;
+          while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
+          S.peak_idx[q + 1] = v2;
+        }
       }
     }
     if (lane == 0) S.nsel = nsel;
+    __syncwarp();
   }
-  gsync<GS>();
 
   // hand-off to k_quads: the chosen peaks and the prefix-moment records around them
   if (first_warp) {
     const uint32_t nm = S.nsel;
-    uint32_t fq = 0;
-    if (lane == 0) fq = atomicAdd(&ctr->num_fit_quads, 1u);
-    fq = __shfl_sync(0xffffffffu, fq, 0);
+    const uint32_t fq = __shfl_sync(0xffffffffu, fq_slot, 0);
     if (fq < p.blob_cap) {
       PeakTable *t = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap + fq;
       if (lane == 0) {
@@ -1034,12 +1109,13 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_fit_small(FrameParams p
   wk.hist = reinterpret_cast<uint32_t *>(S.lf64);
   wk.hist_cap = kSmallBlobPoints;
   wk.tmp = wk.hist + kSmallBlobPoints;
+  uint32_t nxt = 0;
+  if (lane == 0) nxt = atomicAdd(&ctr->next_small, 1u);
   while (true) {
     __syncwarp();
-    if (lane == 0) S.scratch.cur = atomicAdd(&ctr->next_small, 1u);
-    __syncwarp();
-    const uint32_t li = S.scratch.cur;
+    const uint32_t li = __shfl_sync(0xffffffffu, nxt, 0);
     if (li >= nlist) break;
+    if (lane == 0) nxt = atomicAdd(&ctr->next_small, 1u);  // the next item's round trip overlaps this blob
     const uint32_t b = list[li];
     if (b >= p.blob_cap) continue;  // overflow marker
     const b200tag_blob blob = blobs[b];
@@ -1076,12 +1152,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
   constexpr uint32_t kScanHist = (6u * THREADS * 2u >= 2048u) ? 2048u : ((6u * THREADS * 2u >= 1024u) ? 1024u : 512u);
   uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
+  uint32_t nxt = 0;
+  if (tid == 0) nxt = atomicAdd(next, 1u);
   while (true) {
     __syncthreads();
-    if (tid == 0) S.scratch.cur = atomicAdd(next, 1u);
+    if (tid == 0) S.scratch.cur = nxt;
     __syncthreads();
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
+    if (tid == 0) nxt = atomicAdd(next, 1u);  // the next item's round trip overlaps this blob
     const uint32_t b = list[tier == 0 ? li : p.blob_cap - 1u - li];
     if (b >= p.blob_cap) continue;  // overflow marker
     const b200tag_blob blob = blobs[b];

@@ -709,7 +709,8 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
     const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
     uint32_t h = hash_pair(ra, rb) & (kBpLH - 1);
     uint32_t loc = kBpDirect;  // crowded local table (adversarial input): handled in (4)
-    for (uint32_t probe = 0; probe < kBpMaxProbe; probe++) {
+    const uint32_t max_probe = (p.test_flags & B200TAG_TEST_DIRECT_HASH) ? 0u : kBpMaxProbe;
+    for (uint32_t probe = 0; probe < max_probe; probe++) {
       unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_lkey[h]);
       if (cur == kEmptyKey) cur = atomicCAS(&s_lkey[h], kEmptyKey, key);
       if (cur == key || cur == kEmptyKey) {

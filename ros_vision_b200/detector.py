@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double), ("k3", C.c_double),
         ("max_batch", C.c_int32), ("device", C.c_int32), ("keep_stages", C.c_int32),
         ("max_points", C.c_uint32), ("max_blobs", C.c_uint32), ("max_detections", C.c_uint32),
-        ("reserved", C.c_int32 * 8),
+        ("test_flags", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -165,7 +165,7 @@ class GpuDetector:
 
     def __init__(self, width, height, fmt="yuyv", quad_decimate=2, quad_sigma=0.0, refine_edges=True,
                  camera_matrix=None, distortion_coefficients=None, max_batch=1, device=-1, keep_stages=False,
-                 max_points=0, max_blobs=0, max_detections=0, **qtp):
+                 max_points=0, max_blobs=0, max_detections=0, test_flags=0, **qtp):
         self._lib = load_library()
         cfg = default_config(width, height, fmt)
         cfg.quad_decimate = int(quad_decimate)
@@ -174,6 +174,7 @@ class GpuDetector:
         cfg.max_batch = int(max_batch)
         cfg.device = int(device)
         cfg.keep_stages = int(bool(keep_stages))
+        cfg.test_flags = int(test_flags)
         cfg.max_points, cfg.max_blobs, cfg.max_detections = int(max_points), int(max_blobs), int(max_detections)
         if camera_matrix is not None:
             cfg.fx, cfg.cx, cfg.fy, cfg.cy = camera_matrix  # CameraMatrix field order, apriltag_gpu.h:61-66

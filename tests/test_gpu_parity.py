@@ -123,6 +123,21 @@ def test_edge_cases(D, oracle):
     det.close()
 
 
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_fallback_paths_give_identical_results(D, oracle, flags):
+    """The rarely taken paths -- points counted straight in the global blob-pair hash (crowded CTA-local table)
+    and the bitonic angle sort (crowded theta buckets) -- forced on, every stage still equal to the oracle."""
+    from ros_vision_b200 import synth
+    for w, h, fmt, dec, seed, ntags, side in [(640, 480, "yuyv", 2, 31, 3, (50, 140)), (1280, 800, "gray", 1, 32, 2, (300, 600))]:
+        sc = synth.make_scene(w, h, seed, ntags, side_range=side, noise_sigma=4.0)
+        frame = _pack(sc.gray, fmt)
+        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, 0.0), frame)
+        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, keep_stages=True, test_flags=flags)
+        det.Detect(frame)
+        assert len(compare_all(det, orc, 0, fmt)) >= 1
+        det.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
