@@ -36,6 +36,7 @@ WORKLOAD = "config2: 1280x800 YUYV stream, tag36h11, quad_decimate=2, 1-6 tags p
 UNIQUE_FRAMES = 16     # distinct synthetic frames (seeds 2000..2015), tiled to fill a batch
 BATCH = 128            # frames per step: 262 MB of input + ~3 GB of intermediates, far beyond the 126 MB L2
 CONFIG = 2
+SMALL_CAP, MEDIUM_CAP = 192, 768   # blob tiers of the fit kernels (dev_types.h kSmallBlobPoints, kernels_blobs.cu kMediumCap)
 
 # the other BASELINE.json configs (parity-test cases; `--config N` measures them for DESIGN.md, the default
 # bench line is always config 2): (W, H, fmt, decimate, sigma, workload, distinct frames, default batch)
@@ -267,9 +268,9 @@ def run_ours(args):
     nd = min(B, len(frames))
     for f in range(nd):
         cnts = det.CopyStage(D.STAGE_BLOBS, f)["count"].astype(np.int64)
-        tiers["small"] += float(cnts[cnts <= 256].sum()) / nd
-        tiers["medium"] += float(cnts[(cnts > 256) & (cnts <= 1024)].sum()) / nd
-        tiers["large"] += float(cnts[cnts > 1024].sum()) / nd
+        tiers["small"] += float(cnts[cnts <= SMALL_CAP].sum()) / nd
+        tiers["medium"] += float(cnts[(cnts > SMALL_CAP) & (cnts <= MEDIUM_CAP)].sum()) / nd
+        tiers["large"] += float(cnts[cnts > MEDIUM_CAP].sum()) / nd
     launches_per_step = det.kernels_per_batch()
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -16,7 +16,7 @@ constexpr uint32_t kMinBlobPixels = 25;      // apriltag_gpu.cu:284,306 (union_m
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kMaxPeaks = 10;                // line_fit_filter.cu:630 (kNMaxima)
 constexpr int kNumCombos = 210;              // line_fit_filter.h:160
-constexpr uint32_t kSmallBlobPoints = 256;   // blobs up to this size are fitted by a single warp
+constexpr uint32_t kSmallBlobPoints = 192;   // blobs up to this size are fitted by a single warp
 
 // Packed boundary point, 64 bit:
 //   [62:43] cluster slot | [42:27] rank of the point inside its cluster (saturating) | [26:15] base x |

@@ -20,7 +20,8 @@
 namespace b200tag {
 
 static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
-constexpr uint32_t kMediumCap = 1024;   // blobs of 257..1024 points: 128-thread CTA, everything in shared memory
+__host__ __device__ constexpr uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
+constexpr uint32_t kMediumCap = 768;    // blobs of 257..1024 points: 128-thread CTA, everything in shared memory
 
 // ---------------------------------------------------------------------------------------------
 // K7
@@ -1090,7 +1091,7 @@ struct SmallWarpShared {
   BlobScratch scratch;
 };
 
-__global__ void __launch_bounds__(kSmallWarps * 32, 4) k_fit_small(FrameParams p) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
   const int frame = blockIdx.y;
@@ -1107,8 +1108,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_fit_small(FrameParams p
   wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
   wk.keys_in_place = false;
   wk.hist = reinterpret_cast<uint32_t *>(S.lf64);
-  wk.hist_cap = kSmallBlobPoints;
-  wk.tmp = wk.hist + kSmallBlobPoints;
+  wk.hist_cap = next_pow2(kSmallBlobPoints);
+  wk.tmp = wk.hist + next_pow2(kSmallBlobPoints);
   uint32_t nxt = 0;
   if (lane == 0) nxt = atomicAdd(&ctr->next_small, 1u);
   while (true) {
@@ -1173,7 +1174,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
-      wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = LF_CAP > 0 ? LF_CAP : 1; wk.tmp = wk.hist + LF_CAP;
+      wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = next_pow2(LF_CAP > 0 ? LF_CAP : 1); wk.tmp = wk.hist + next_pow2(LF_CAP > 0 ? LF_CAP : 1);
       fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.errs = S.errs;
@@ -1197,7 +1198,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
 
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
-#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 4>
+#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5>
 #define K_FIT_LARGE k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2>
 
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
@@ -1225,10 +1226,10 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   // resident capacity per SM: 4 small-tier CTAs (4 warps = 4 blobs each), 4 medium-tier CTAs, 2 large-tier CTAs
   if (kt) kt->begin("fit_small", s);
-  k_fit_small<<<dim3(max(4u, min(592u, cdivu(2368u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
+  k_fit_small<<<dim3(max(4u, min(740u, cdivu(2960u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_medium", s);
-  K_FIT_MEDIUM<<<dim3(max(4u, min(592u, cdivu(2368u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
+  K_FIT_MEDIUM<<<dim3(max(4u, min(740u, cdivu(2960u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
   K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
