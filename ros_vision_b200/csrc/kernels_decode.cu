@@ -213,12 +213,13 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
   const int W = p.W, H = p.H;
   const int wb = b200_tag36h11_WIDTH_AT_BORDER, tw = b200_tag36h11_TOTAL_WIDTH;
 
+  uint32_t nxt = 0;
+  if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);
   while (true) {
     __syncwarp();
-    if (lane == 0) S.cur = atomicAdd(&ctr->next_quad, 1u);
-    __syncwarp();
-    const uint32_t qi = S.cur;
+    const uint32_t qi = __shfl_sync(0xffffffffu, nxt, 0);
     if (qi >= nquads) break;
+    if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);  // the next item's round trip overlaps this quad
     const b200tag_quad quad = quads[qi];
     if (lane < 8) S.p[lane >> 1][lane & 1] = quad.corners[lane >> 1][lane & 1];
     __syncwarp();
@@ -245,20 +246,34 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
             const double y0 = alpha * pay + (1 - alpha) * pby;
             double Mn = 0, Mcount = 0;
             const double range = static_cast<double>(static_cast<float>(p.f)) + 1;
-            for (double n = -range; n <= range; n += 0.25) {
-              const double grange = 1;
-              const int x1 = static_cast<int>(x0 + (n + grange) * nx);
-              const int y1 = static_cast<int>(y0 + (n + grange) * ny);
-              if (x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) continue;
-              const int x2 = static_cast<int>(x0 + (n - grange) * nx);
-              const int y2 = static_cast<int>(y0 + (n - grange) * ny);
-              if (x2 < 0 || x2 >= W || y2 < 0 || y2 >= H) continue;
-              const int g1 = im[static_cast<size_t>(y1) * W + x1];
-              const int g2 = im[static_cast<size_t>(y2) * W + x2];
-              if (g1 < g2) continue;
-              const double weight = static_cast<double>((g2 - g1) * (g2 - g1));
-              Mn += weight * n;
-              Mcount += weight;
+            // n runs over -range, -range + 0.25, ..., range (multiples of 0.25: exact in double).  The two
+            // byte gathers of five consecutive n are issued together; the sums keep the order of n.
+            const int nt = static_cast<int>(8 * range) + 1;
+            for (int t0 = 0; t0 < nt; t0 += 5) {
+              int g1v[5], g2v[5];
+              double nv[5];
+              bool okv[5];
+#pragma unroll
+              for (int k = 0; k < 5; k++) {
+                const double n = -range + 0.25 * (t0 + k);
+                const double grange = 1;
+                const int x1 = static_cast<int>(x0 + (n + grange) * nx);
+                const int y1 = static_cast<int>(y0 + (n + grange) * ny);
+                const int x2 = static_cast<int>(x0 + (n - grange) * nx);
+                const int y2 = static_cast<int>(y0 + (n - grange) * ny);
+                const bool ok = (t0 + k < nt) && !(x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) && !(x2 < 0 || x2 >= W || y2 < 0 || y2 >= H);
+                nv[k] = n;
+                okv[k] = ok;
+                g1v[k] = ok ? im[static_cast<size_t>(y1) * W + x1] : 0;
+                g2v[k] = ok ? im[static_cast<size_t>(y2) * W + x2] : 0;
+              }
+#pragma unroll
+              for (int k = 0; k < 5; k++) {
+                if (!okv[k] || g1v[k] < g2v[k]) continue;
+                const double weight = static_cast<double>((g2v[k] - g1v[k]) * (g2v[k] - g1v[k]));
+                Mn += weight * nv[k];
+                Mcount += weight;
+              }
             }
             uint8_t valid = 0;
             double bestx = 0, besty = 0;
