@@ -138,6 +138,65 @@ def test_fallback_paths_give_identical_results(D, oracle, flags):
         det.close()
 
 
+def test_overflow_is_reported_not_fatal(D):
+    """Deliberately tiny device lists: the frame is flagged (B200TAG_E_OVERFLOW + status bits), nothing crashes,
+    and the same detector still gives the exact answer on the next frame when the lists are large enough."""
+    from ros_vision_b200 import synth
+    w, h = 640, 480
+    sc = synth.make_scene(w, h, 41, 3, side_range=(60, 140), noise_sigma=4.0)
+    for kw, bit in ((dict(max_points=2000), D.ST_POINTS_OVERFLOW), (dict(max_blobs=8), D.ST_BLOBS_OVERFLOW),
+                    (dict(max_detections=1), D.ST_DETS_OVERFLOW)):
+        det = D.GpuDetector(w, h, "gray", **kw)
+        with pytest.raises(D.B200TagError):
+            det.Detect(sc.gray)
+        assert det.FrameInfo().status & bit, (kw, det.FrameInfo().status)
+        det.close()
+    det = D.GpuDetector(w, h, "gray")
+    det.Detect(sc.gray)
+    assert det.FrameInfo().status == 0 and len(det.Detections()) == 3
+    det.close()
+
+
+def test_other_decimation_factors(D, oracle):
+    """quad_decimate 3 and 4 (the reference supports only 2): every stage against the oracle."""
+    from ros_vision_b200 import synth
+    for dec, w, h in ((3, 960, 720), (4, 1280, 960)):
+        sc = synth.make_scene(w, h, 50 + dec, 3, side_range=(150, 300), noise_sigma=3.0)
+        for fmt in ("gray", "yuyv"):
+            frame = _pack(sc.gray, fmt)
+            orc = oracle.detect(oracle.make_config(w, h, fmt, dec, 0.0), frame)
+            det = D.GpuDetector(w, h, fmt, quad_decimate=dec, keep_stages=True)
+            det.Detect(frame)
+            assert len(compare_all(det, orc, 0, fmt)) >= 2
+            det.close()
+
+
+def test_two_detectors_interleaved(D, oracle):
+    """Two detectors (two CUDA streams) with batches in flight at the same time do not disturb each other."""
+    from ros_vision_b200 import synth
+    w, h = 640, 480
+    fa = [synth.gray_to_yuyv(synth.make_scene(w, h, 60 + i, 2, side_range=(60, 140), noise_sigma=4.0).gray) for i in range(4)]
+    fb = [synth.gray_to_yuyv(synth.make_scene(w, h, 70 + i, 3, side_range=(50, 120), noise_sigma=3.0).gray) for i in range(4)]
+    da = D.GpuDetector(w, h, "yuyv", max_batch=4, keep_stages=True)
+    db = D.GpuDetector(w, h, "yuyv", max_batch=4, keep_stages=True)
+    pa = [D.PinnedBuffer(f.size) for f in fa]
+    pb = [D.PinnedBuffer(f.size) for f in fb]
+    for buf, f in zip(pa + pb, fa + fb):
+        buf.array[:] = f.reshape(-1)
+    for _ in range(3):
+        da.EnqueuePointers([b.ptr for b in pa])
+        db.EnqueuePointers([b.ptr for b in pb])
+    da.Finish()
+    db.Finish()
+    for det, frames in ((da, fa), (db, fb)):
+        for i, fr in enumerate(frames):
+            compare_all(det, oracle.detect(oracle.make_config(w, h, "yuyv", 2, 0.0), fr), i, "yuyv")
+    for b in pa + pb:
+        b.close()
+    da.close()
+    db.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
