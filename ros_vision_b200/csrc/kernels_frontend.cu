@@ -358,16 +358,25 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   uint32_t *sizes = p.sizes + frame * n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // (A) run masks: lane = column, rows strided over the warps; pixels outside the image count as
-  //     127 (join nothing)
-  for (int r = warp; r < kCclTH; r += kCclWarps) {
-    const int gy = y0 + r;
-    uint32_t a = 127;
-    if (gy < p.h && x0 + lane < p.w) a = th[static_cast<size_t>(gy) * p.w + x0 + lane];
-    const uint32_t wm = __ballot_sync(0xffffffffu, a == 255), bm = __ballot_sync(0xffffffffu, a == 0);
-    if (lane == 0) {
-      s_mask[1][r] = wm;
-      s_mask[0][r] = bm;
+  // (A) run masks: lane = column, rows strided over the warps (all of a warp's row loads are issued
+  //     before the first ballot); pixels outside the image count as 127 (join nothing)
+  {
+    constexpr int kRows = kCclTH / kCclWarps;
+    uint32_t a[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; k++) {
+      const int gy = y0 + warp + k * kCclWarps;
+      a[k] = 127;
+      if (gy < p.h && x0 + lane < p.w) a[k] = th[static_cast<size_t>(gy) * p.w + x0 + lane];
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; k++) {
+      const int r = warp + k * kCclWarps;
+      const uint32_t wm = __ballot_sync(0xffffffffu, a[k] == 255), bm = __ballot_sync(0xffffffffu, a[k] == 0);
+      if (lane == 0) {
+        s_mask[1][r] = wm;
+        s_mask[0][r] = bm;
+      }
     }
   }
   for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
