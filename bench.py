@@ -96,28 +96,62 @@ def kernel_bytes(name: str, P: float, tiers: dict) -> float:
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while a timed region runs: NVML every 10 ms (nvidia_ml_py), or
+    nvidia-smi every 200 ms when NVML is not importable.  Several regions can be sampled into one summary."""
+
+    _NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index = index
-        self.samples = []
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            self.index = int(vis.split(",")[index]) if vis else index
+        except ValueError:
+            self.index = index
+        self.samples = []   # (sm_mhz, sm_max_mhz, [reasons])
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _sample_nvml(self):
+        nv = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.samples.append((int(sm), int(mx), [n for bit, n in self._NVML_REASONS.items() if mask & bit]))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.samples.append((int(f[0]), int(f[1]), [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]))
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._nvml else 0.2)
 
     def __enter__(self):
+        self._stop.clear()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
@@ -129,11 +163,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = max((int(s[1]) for s in self.samples if s[1].isdigit()), default=None)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": sorted({r for s in self.samples for r in s[2]}), "samples": len(self.samples),
+                "source": "nvml" if self._nvml else "nvidia-smi", "regions": "device-resident and end-to-end timed regions"}
 
 
 def dist_setup(n_gpus: int):
@@ -315,15 +348,16 @@ def run_ours(args):
     for ld in lanes:
         ld.Finish()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_dets = 0
-    for ld in lanes:
-        ld.Finish()
-        e2e_dets += sum(len(ld.Detections(f)) for f in range(per_lane))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    with clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_dets = 0
+        for ld in lanes:
+            ld.Finish()
+            e2e_dets += sum(len(ld.Detections(f)) for f in range(per_lane))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -537,11 +537,20 @@ __global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
   const uint4 s = __ldcg(reinterpret_cast<const uint4 *>(sizes + i4));
   uint32_t lab[4] = {l.x, l.y, l.z, l.w};
   const uint32_t sz[4] = {s.x, s.y, s.z, s.w};
+  // neighbouring pixels mostly alternate between two tile roots (a white and a black component): chase each once
+  uint32_t m_lab0 = 0xffffffffu, m_root0 = 0, m_lab1 = 0xffffffffu, m_root1 = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const uint32_t self = static_cast<uint32_t>(i4 + k);
     if (lab[k] != self || sz[k] != 0) {  // 127-pixels (own index, size 0) need nothing
-      const uint32_t root = gfind(labels, lab[k]);
+      uint32_t root;
+      if (lab[k] == m_lab0) root = m_root0;
+      else if (lab[k] == m_lab1) root = m_root1;
+      else {
+        root = gfind(labels, lab[k]);
+        m_lab1 = m_lab0; m_root1 = m_root0;
+        m_lab0 = lab[k]; m_root0 = root;
+      }
       lab[k] = root;
       if (sz[k] != 0 && root != self) {
         atomicAdd(sizes + root, sz[k]);
