@@ -265,7 +265,7 @@ __device__ __forceinline__ void cmpxchg(unsigned long long *a, uint32_t i, uint3
 // (t = gt + it * GS) and, for compare distances <= 32, touches only the 64 elements of chunk
 // t / 32, so those stages need no block-wide barrier.
 template <int GS>
-__device__ __forceinline__ void bitonic_sort(unsigned long long *a, uint32_t cnt, uint32_t N, uint32_t gt) {
+__device__ __noinline__ void bitonic_sort(unsigned long long *a, uint32_t cnt, uint32_t N, uint32_t gt) {
   const uint32_t half = N >> 1;
   for (uint32_t k = 2, lk = 1; k <= N; k <<= 1, lk++) {
     const uint32_t hk = k >> 1;
@@ -306,8 +306,9 @@ struct LfStore {
   uint32_t *m32;               // shared: [3][cap]
   uint32_t cap;
 };
+template <bool AOS>
 __device__ __forceinline__ b200tag_lfp lf_load(const LfStore &L, uint32_t i) {
-  if (L.aos) return L.aos[i];
+  if constexpr (AOS) return L.aos[i];
   b200tag_lfp r;
   r.Mxx = static_cast<long long>(L.m64[i]);
   r.Myy = static_cast<long long>(L.m64[L.cap + i]);
@@ -317,8 +318,9 @@ __device__ __forceinline__ b200tag_lfp lf_load(const LfStore &L, uint32_t i) {
   r.W = L.m32[2 * L.cap + i];
   return r;
 }
+template <bool AOS>
 __device__ __forceinline__ void lf_store(const LfStore &L, uint32_t i, const b200tag_lfp &r) {
-  if (L.aos) {
+  if constexpr (AOS) {
     L.aos[i] = r;
     return;
   }
@@ -331,18 +333,19 @@ __device__ __forceinline__ void lf_store(const LfStore &L, uint32_t i, const b20
 }
 
 // ReadMoments, line_fit_filter.cu:745-796 (== CalculateError's window logic, :230-274)
+template <bool AOS>
 __device__ __forceinline__ Mom read_moments(const LfStore &lf, uint32_t cnt, uint32_t i0, uint32_t i1) {
   Mom m;
   if (i0 < i1) {
     m.N = static_cast<int>(i1 - i0 + 1);
-    const b200tag_lfp a = lf_load(lf, i1);
+    const b200tag_lfp a = lf_load<AOS>(lf, i1);
     m.Mx = a.Mx; m.My = a.My; m.Mxx = a.Mxx; m.Mxy = a.Mxy; m.Myy = a.Myy; m.W = a.W;
     if (i0 > 0) {
-      const b200tag_lfp b = lf_load(lf, i0 - 1);
+      const b200tag_lfp b = lf_load<AOS>(lf, i0 - 1);
       m.Mx -= b.Mx; m.My -= b.My; m.Mxx -= b.Mxx; m.Mxy -= b.Mxy; m.Myy -= b.Myy; m.W -= b.W;
     }
   } else {
-    const b200tag_lfp b = lf_load(lf, i0 - 1), z = lf_load(lf, cnt - 1), a = lf_load(lf, i1);
+    const b200tag_lfp b = lf_load<AOS>(lf, i0 - 1), z = lf_load<AOS>(lf, cnt - 1), a = lf_load<AOS>(lf, i1);
     m.Mx = z.Mx - b.Mx + a.Mx;
     m.My = z.My - b.My + a.My;
     m.Mxx = z.Mxx - b.Mxx + a.Mxx;
@@ -453,6 +456,40 @@ __global__ void k_init_combos() {
         }
 }
 
+// The 10 strongest of MANY (> 32) peaks: ten rounds of a warp-wide minimum over the list; position-ordered
+// insertion by lane 0.  Rare for small blobs, kept out of line so it does not sit in the hot instruction stream.
+__device__ __noinline__ uint32_t top_peaks_many(const unsigned long long *peaks, uint32_t npk, uint32_t *peak_idx, int lane) {
+  unsigned long long last = 0;
+  uint32_t nsel = 0;
+#pragma unroll 1
+  for (int round = 0; round < kMaxPeaks; round++) {
+    unsigned long long best = kNoKey;
+#pragma unroll 1
+    for (uint32_t i = lane; i < npk; i += 32) {
+      const unsigned long long key = peaks[i];
+      if ((round == 0 || key > last) && key < best) best = key;
+    }
+    {  // 64-bit warp minimum as two 32-bit redux steps
+      const uint32_t hi = static_cast<uint32_t>(best >> 32);
+      const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+      const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(best) : 0xffffffffu;
+      const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+      best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+    }
+    if (best == kNoKey) break;
+    last = best;
+    nsel++;
+    if (lane == 0) {
+      const uint32_t v2 = static_cast<uint32_t>(best & 0xffffffffu);
+      int q = static_cast<int>(nsel) - 2;
+      while (q >= 0 && peak_idx[q] > v2) { peak_idx[q + 1] = peak_idx[q]; q--; }
+      peak_idx[q + 1] = v2;
+    }
+    __syncwarp();
+  }
+  return nsel;
+}
+
 // Working storage of one blob: shared or global memory, chosen by the caller.  Cross-thread hand-offs
 // always go through gsync<GS>(), so plain (non-volatile) accesses are sufficient.
 struct BlobWork {
@@ -471,7 +508,10 @@ struct BlobWork {
 constexpr uint32_t kMaxBucketLoad = 24;  // fuller buckets (thin, elongated blobs) fall back to the bitonic network
 constexpr uint32_t kThetaSpan = 50265483u;  // theta = llrintf((atan2f + pi) * 8e6) < 2 * pi * 8e6 + 1
 
-template <int GS>
+// GS = threads per blob; AOS = prefix moments as records in global memory (else shared-memory arrays);
+// KEEP = also write the debug stage arrays (keep_stages) -- separate instantiations, so the production
+// kernels carry no debug code in their instruction stream.
+template <int GS, bool AOS, bool KEEP>
 __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
                                              b200tag_blob *blob_rec, const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
@@ -544,6 +584,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     if (gt == 0) S.npeaks = 0;
     gsync<GS>();
     uint32_t *th_tmp = wk.tmp, *rk_tmp = wk.tmp + cnt;
+#pragma unroll 1
     for (uint32_t i = gt; i < cnt; i += GS) {
       const uint32_t v = raw[i];
       // AddThetaToIndexPoint, apriltag_gpu.cu:400-408
@@ -603,7 +644,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
         wk.keys[wk.hist[bk] + rk_tmp[i]] = pack_sort_key(th, sp_dir(v), sp_by(v), sp_bx(v));
       }
       gsync<GS>();
-      constexpr uint32_t kRankPer = 8;  // elements a thread can hold in registers across the barrier
+      constexpr uint32_t kRankPer = 6;  // elements a thread can hold in registers across the barrier (192 / 32, 768 / 128)
       if (cnt <= kRankPer * GS) {
         // every element finds its place inside its bucket by counting the smaller keys there (1-2 elements
         // per bucket on average, at most kMaxBucketLoad): balanced across threads, unlike a sort per bucket
@@ -619,6 +660,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
             const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(key_theta(key)) * B / kThetaSpan));
             const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
             uint32_t pos = lo;
+#pragma unroll 1
             for (uint32_t i = lo; i < hi; i++) pos += wk.keys[i] < key;
             kreg[j] = key;
             preg[j] = pos;
@@ -653,15 +695,16 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       bitonic_sort<GS>(wk.keys, cnt, N, gt);
     }
   }
-  if (p.keep_stages && !wk.keys_in_place) {
+  if (KEEP && !wk.keys_in_place) {
     uint64_t *out = p.seg_keys + pbase;
+#pragma unroll 1
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.keys[i];
   }
 
   // (2) weights (independent gathers, strided) then inclusive prefix moments over contiguous chunks,
   //     C7 (apriltag_gpu.cu:631-687,984-987).  Weights are parked in the still unused error buffer.
   int *wbuf = reinterpret_cast<int *>(wk.errs);
-#pragma unroll 4
+#pragma unroll 2
   for (uint32_t i = gt; i < cnt; i += GS) {
     const unsigned long long k = wk.keys[i];
     const uint32_t d = key_dir(k);
@@ -714,6 +757,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
         c_Mx += tot[w * 6 + 3];  c_My += tot[w * 6 + 4];  c_W += tot[w * 6 + 5];
       }
     }
+#pragma unroll 1
     for (uint32_t base = w_lo; base < w_hi; base += 32) {
       const uint32_t i = base + lane;
       uint32_t s_Mx = 0, s_My = 0, s_W = 0;
@@ -742,7 +786,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
         o.Mxx = static_cast<long long>(c_Mxx + s_Mxx); o.Myy = static_cast<long long>(c_Myy + s_Myy);
         o.Mxy = static_cast<long long>(c_Mxy + s_Mxy);
         o.Mx = static_cast<long long>(c_Mx + s_Mx); o.My = static_cast<long long>(c_My + s_My); o.W = static_cast<long long>(c_W + s_W);
-        lf_store(wk.lf, i, o);
+        lf_store<AOS>(wk.lf, i, o);
       }
       c_Mxx += __shfl_sync(0xffffffffu, s_Mxx, 31); c_Myy += __shfl_sync(0xffffffffu, s_Myy, 31);
       c_Mxy += __shfl_sync(0xffffffffu, s_Mxy, 31);
@@ -750,28 +794,31 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     }
   }
   gsync<GS>();
-  if (p.keep_stages && wk.lf.aos != p.lfp + pbase) {
+  if (KEEP && !AOS) {
     b200tag_lfp *out = p.lfp + pbase;
-    for (uint32_t i = gt; i < cnt; i += GS) out[i] = lf_load(wk.lf, i);
+#pragma unroll 1
+    for (uint32_t i = gt; i < cnt; i += GS) out[i] = lf_load<AOS>(wk.lf, i);
   }
 
   // (3) windowed line-fit error, K10 part 1 (line_fit_filter.cu:217-278)
   const uint32_t ksz = min(20u, cnt / 12u);
-#pragma unroll 2
+#pragma unroll 1
   for (uint32_t i = gt; i < cnt; i += GS) {
     uint32_t i0 = i + cnt - ksz, i1 = i + ksz;  // (i + 2cnt - ksz) % cnt and (i + cnt + ksz) % cnt without division
     if (i0 >= cnt) i0 -= cnt;
     if (i1 >= cnt) i1 -= cnt;
-    const Mom m = read_moments(wk.lf, cnt, i0, i1);
+    const Mom m = read_moments<AOS>(wk.lf, cnt, i0, i1);
     const float eig = eig_small_of(m, nullptr, nullptr, nullptr, nullptr);
     wk.errs[i] = static_cast<float>(m.N) * eig;
   }
   gsync<GS>();
-  if (p.keep_stages && wk.errs != p.errs + pbase) {
+  if (KEEP && wk.errs != p.errs + pbase) {
     float *out = p.errs + pbase;
+#pragma unroll 1
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.errs[i];
   }
   // (4) 7-tap smoothing in double (:504-525); filt may alias keys, which are dead by now
+#pragma unroll 1
   for (uint32_t i = gt; i < cnt; i += GS) {
     const float kf[7] = {0.01110899634659290314f, 0.13533528149127960205f, 0.60653066635131835938f, 1.0f,
                          0.60653066635131835938f, 0.13533528149127960205f, 0.01110899634659290314f};
@@ -787,13 +834,15 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     wk.filt[i] = acc;
   }
   gsync<GS>();
-  if (p.keep_stages && wk.filt != p.filt + pbase) {
+  if (KEEP && wk.filt != p.filt + pbase) {
     double *out = p.filt + pbase;
+#pragma unroll 1
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.filt[i];
   }
 
   // (5) peak list: strict local maxima (:582), keyed by (-filtered as f32, index) -- C8/C9
   //     (apriltag_gpu.cu:1001-1034).  At most cnt/2 entries.
+#pragma unroll 1
   for (uint32_t i = gt; i < cnt; i += GS) {
     const double m = wk.filt[i];
     const double bv = wk.filt[i == 0 ? cnt - 1 : i - 1], av = wk.filt[i + 1 == cnt ? 0 : i + 1];
@@ -835,31 +884,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       }
       if (lane < static_cast<int>(nsel)) S.peak_idx[rank] = my_idx;
     } else {
-      unsigned long long last = 0;
-      for (int round = 0; round < kMaxPeaks; round++) {
-        unsigned long long best = kNoKey;
-        for (uint32_t i = lane; i < npk; i += 32) {
-          const unsigned long long key = wk.peaks[i];
-          if ((round == 0 || key > last) && key < best) best = key;
-        }
-        {  // 64-bit warp minimum as two 32-bit redux steps
-          const uint32_t hi = static_cast<uint32_t>(best >> 32);
-          const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-          const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(best) : 0xffffffffu;
-          const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
-          best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
-        }
-        if (best == kNoKey) break;
-        last = best;
-        nsel++;
-        // insertion into the position-ordered list (lane 0), one element per round
-        if (lane == 0) {
-          const uint32_t v2 = static_cast<uint32_t>(best & 0xffffffffu);
-          int q = static_cast<int>(nsel) - 2;
-          while (q >= 0 && S.peak_idx[q] > v2) { S.peak_idx[q + 1] = S.peak_idx[q]; q--; }
-          S.peak_idx[q + 1] = v2;
-        }
-      }
+      nsel = top_peaks_many(wk.peaks, npk, S.peak_idx, lane);
     }
     if (lane == 0) S.nsel = nsel;
     __syncwarp();
@@ -873,15 +898,15 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       PeakTable *t = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap + fq;
       if (lane == 0) {
         t->blob = b; t->cnt = cnt; t->nsel = nm; t->npk = npk; t->rep0 = blob.rep0; t->rep1 = blob.rep1;
-        t->last = lf_load(wk.lf, cnt - 1);
+        t->last = lf_load<AOS>(wk.lf, cnt - 1);
       }
       if (lane < static_cast<int>(nm)) {
         const uint32_t i = S.peak_idx[lane];
         t->idx[lane] = i;
-        t->at[lane] = lf_load(wk.lf, i);
+        t->at[lane] = lf_load<AOS>(wk.lf, i);
         b200tag_lfp z;
         z.Mxx = 0; z.Myy = 0; z.Mxy = 0; z.Mx = 0; z.My = 0; z.W = 0;
-        t->before[lane] = i > 0 ? lf_load(wk.lf, i - 1) : z;
+        t->before[lane] = i > 0 ? lf_load<AOS>(wk.lf, i - 1) : z;
       }
     }
   }
@@ -1091,6 +1116,7 @@ struct SmallWarpShared {
   BlobScratch scratch;
 };
 
+template <bool KEEP>
 __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
@@ -1120,7 +1146,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p
     const uint32_t b = list[li];
     if (b >= p.blob_cap) continue;  // overflow marker
     const b200tag_blob blob = blobs[b];
-    fit_one_blob<32>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, nullptr, lane);
+    fit_one_blob<32, false, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, nullptr, lane);
   }
 }
 
@@ -1139,7 +1165,7 @@ struct CtaShared {
   BlobScratch scratch;
 };
 
-template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP, uint32_t MIN_CNT, uint32_t MAX_CNT, int MIN_CTAS>
+template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP, uint32_t MIN_CNT, uint32_t MAX_CNT, int MIN_CTAS, bool KEEP>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, int tier) {
   using Shared = CtaShared<THREADS, KEY_CAP, LF_CAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1168,47 +1194,54 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
     if (blob.count < MIN_CNT || blob.count > MAX_CNT) continue;  // (cannot happen: k_select sorts blobs into tiers)
     const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
     BlobWork wk;
-    if (blob.count <= LF_CAP) {  // everything in shared memory
+    // branches that the tier's size limits rule out are not compiled (each one is a full copy of the fit code)
+    constexpr bool kHasSmemLf = LF_CAP > 0;
+    constexpr bool kHasGlobalLf = MAX_CNT > LF_CAP;
+    constexpr bool kHasInPlace = MAX_CNT > KEY_CAP;
+    if (kHasSmemLf && blob.count <= LF_CAP) {  // everything in shared memory
       wk.keys = S.keys; wk.errs = S.errs;
       wk.lf.aos = nullptr; wk.lf.m64 = S.lf64; wk.lf.m32 = S.lf32; wk.lf.cap = LF_CAP;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
       wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = next_pow2(LF_CAP > 0 ? LF_CAP : 1); wk.tmp = wk.hist + next_pow2(LF_CAP > 0 ? LF_CAP : 1);
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
-    } else if (blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
+      fit_one_blob<THREADS, false, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
+    } else if (kHasGlobalLf && KEY_CAP > LF_CAP && blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.errs = S.errs;
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
       wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
-    } else {  // too large for shared memory: work in place in the global arrays
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
+    } else if (kHasInPlace) {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
       wk.keys_in_place = true;
       wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
     }
   }
 }
 
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
-#define K_FIT_MEDIUM k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5>
-#define K_FIT_LARGE k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2>
+#define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
+#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2, KEEP>
 
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
   static bool dev_ready[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !dev_ready[dev]) {
-    cudaFuncSetAttribute(k_fit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallWarpShared) * kSmallWarps));
-    cudaFuncSetAttribute(K_FIT_MEDIUM, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MediumShared)));
-    cudaFuncSetAttribute(K_FIT_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
+    cudaFuncSetAttribute(k_fit_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallWarpShared) * kSmallWarps));
+    cudaFuncSetAttribute(k_fit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallWarpShared) * kSmallWarps));
+    cudaFuncSetAttribute(K_FIT_MEDIUM(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MediumShared)));
+    cudaFuncSetAttribute(K_FIT_MEDIUM(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MediumShared)));
+    cudaFuncSetAttribute(K_FIT_LARGE(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
+    cudaFuncSetAttribute(K_FIT_LARGE(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
     k_init_combos<<<1, 1, 0, s>>>();
     dev_ready[dev] = true;
   }
@@ -1226,13 +1259,25 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   // resident capacity per SM: 4 small-tier CTAs (4 warps = 4 blobs each), 4 medium-tier CTAs, 2 large-tier CTAs
   if (kt) kt->begin("fit_small", s);
-  k_fit_small<<<dim3(max(4u, min(740u, cdivu(2960u, frames))), frames), kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
+  {
+    const dim3 g(max(4u, min(740u, cdivu(2960u, frames))), frames);
+    if (p.keep_stages) k_fit_small<true><<<g, kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
+    else k_fit_small<false><<<g, kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
+  }
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_medium", s);
-  K_FIT_MEDIUM<<<dim3(max(4u, min(740u, cdivu(2960u, frames))), frames), 128, sizeof(MediumShared), s>>>(p, 0);
+  {
+    const dim3 g(max(4u, min(740u, cdivu(2960u, frames))), frames);
+    if (p.keep_stages) K_FIT_MEDIUM(true)<<<g, 128, sizeof(MediumShared), s>>>(p, 0);
+    else K_FIT_MEDIUM(false)<<<g, 128, sizeof(MediumShared), s>>>(p, 0);
+  }
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
-  K_FIT_LARGE<<<dim3(max(2u, min(296u, cdivu(1184u, frames))), frames), kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
+  {
+    const dim3 g(max(2u, min(296u, cdivu(1184u, frames))), frames);
+    if (p.keep_stages) K_FIT_LARGE(true)<<<g, kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
+    else K_FIT_LARGE(false)<<<g, kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
+  }
   if (kt) kt->end(s);
   if (kt) kt->begin("quads", s);
   k_quads<<<dim3(max(2u, min(592u, cdivu(2368u, frames))), frames), kQuadWarps * 32, 0, s>>>(p);
