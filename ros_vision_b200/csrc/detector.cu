@@ -26,6 +26,7 @@ struct b200tag_detector {
   FrameParams fp;
   int device = 0;
   cudaStream_t stream = nullptr;
+  SideStreams side;  // concurrent blob-tier kernels
   void *arena = nullptr;
   size_t arena_bytes = 0;
   uint8_t *d_in = nullptr;  // internal input staging (frames copied from the host)
@@ -241,7 +242,7 @@ int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride
   CK(cudaMemsetAsync(p.counters, 0, sizeof(Counters) * count, det->stream));
   int launches = 0;
   launches += launch_frontend(p, count, det->stream, kt);
-  launches += launch_blobs(p, count, det->stream, kt);
+  launches += launch_blobs(p, count, det->stream, kt, kt ? nullptr : &det->side);  // per-kernel timing runs serially
   launches += launch_decode(p, count, det->stream, kt);
   det->kernels_per_batch = launches;
   CK(cudaGetLastError());
@@ -425,6 +426,11 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
     return true;
   };
   if (!ck(cudaStreamCreateWithFlags(&det->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(B200TAG_E_CUDA);
+  for (int i = 0; i < 2; i++) {
+    if (!ck(cudaStreamCreateWithFlags(&det->side.s[i], cudaStreamNonBlocking), "cudaStreamCreate(side)")) return fail(B200TAG_E_CUDA);
+    if (!ck(cudaEventCreateWithFlags(&det->side.join[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(B200TAG_E_CUDA);
+  }
+  if (!ck(cudaEventCreateWithFlags(&det->side.fork, cudaEventDisableTiming), "cudaEventCreate")) return fail(B200TAG_E_CUDA);
   if (!ck(cudaHostAlloc(reinterpret_cast<void **>(&det->h_counters), sizeof(Counters) * B, cudaHostAllocDefault), "cudaHostAlloc"))
     return fail(B200TAG_E_CUDA);
   if (!ck(cudaHostAlloc(reinterpret_cast<void **>(&det->h_dets), sizeof(b200tag_detection) * p.det_cap * B, cudaHostAllocMapped),
@@ -453,6 +459,11 @@ void b200tag_destroy(b200tag_detector *det) {
     cudaStreamSynchronize(det->stream);
     cudaStreamDestroy(det->stream);
   }
+  for (int i = 0; i < 2; i++) {
+    if (det->side.s[i]) cudaStreamDestroy(det->side.s[i]);
+    if (det->side.join[i]) cudaEventDestroy(det->side.join[i]);
+  }
+  if (det->side.fork) cudaEventDestroy(det->side.fork);
   if (det->arena) cudaFree(det->arena);
   if (det->h_counters) cudaFreeHost(det->h_counters);
   if (det->h_dets) cudaFreeHost(det->h_dets);

@@ -43,9 +43,16 @@ struct KernelTimer {
   }
 };
 
+// Side streams + events that let the three independent blob-tier kernels run concurrently (fork after the
+// scatter, join before the quad search).  Owned by the detector; null = everything on the main stream.
+struct SideStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+
 // Each returns the number of kernels it launched.
 int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
-int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
+int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side);
 int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
 void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s);
 

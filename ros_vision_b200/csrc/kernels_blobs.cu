@@ -1231,7 +1231,7 @@ using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
 #define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
 #define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2, KEEP>
 
-int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
+int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side) {
   static bool dev_ready[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1257,7 +1257,30 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
     k_cluster_finish<<<dim3(16, frames), 256, 0, s>>>(p);
     launches += 2;
   }
-  // resident capacity per SM: 4 small-tier CTAs (4 warps = 4 blobs each), 4 medium-tier CTAs, 2 large-tier CTAs
+  // The three tiers are independent and each is latency bound at modest occupancy: with side streams they run
+  // concurrently (largest blobs first), so their tails overlap; the per-kernel timing mode runs them serially.
+  // Resident capacity per SM: 5 small-tier CTAs (4 warps = 4 blobs each), 5 medium-tier CTAs, 2 large-tier CTAs.
+  const bool fork = side && side->s[0] && side->s[1];
+  cudaStream_t s_large = fork ? side->s[0] : s, s_medium = fork ? side->s[1] : s;
+  if (fork) {
+    cudaEventRecord(side->fork, s);
+    cudaStreamWaitEvent(s_large, side->fork, 0);
+    cudaStreamWaitEvent(s_medium, side->fork, 0);
+  }
+  if (kt) kt->begin("fit_large", s);
+  {
+    const dim3 g(max(2u, min(296u, cdivu(1184u, frames))), frames);
+    if (p.keep_stages) K_FIT_LARGE(true)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);
+    else K_FIT_LARGE(false)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);
+  }
+  if (kt) kt->end(s);
+  if (kt) kt->begin("fit_medium", s);
+  {
+    const dim3 g(max(4u, min(740u, cdivu(2960u, frames))), frames);
+    if (p.keep_stages) K_FIT_MEDIUM(true)<<<g, 128, sizeof(MediumShared), s_medium>>>(p, 0);
+    else K_FIT_MEDIUM(false)<<<g, 128, sizeof(MediumShared), s_medium>>>(p, 0);
+  }
+  if (kt) kt->end(s);
   if (kt) kt->begin("fit_small", s);
   {
     const dim3 g(max(4u, min(740u, cdivu(2960u, frames))), frames);
@@ -1265,20 +1288,12 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
     else k_fit_small<false><<<g, kSmallWarps * 32, sizeof(SmallWarpShared) * kSmallWarps, s>>>(p);
   }
   if (kt) kt->end(s);
-  if (kt) kt->begin("fit_medium", s);
-  {
-    const dim3 g(max(4u, min(740u, cdivu(2960u, frames))), frames);
-    if (p.keep_stages) K_FIT_MEDIUM(true)<<<g, 128, sizeof(MediumShared), s>>>(p, 0);
-    else K_FIT_MEDIUM(false)<<<g, 128, sizeof(MediumShared), s>>>(p, 0);
+  if (fork) {
+    cudaEventRecord(side->join[0], s_large);
+    cudaEventRecord(side->join[1], s_medium);
+    cudaStreamWaitEvent(s, side->join[0], 0);
+    cudaStreamWaitEvent(s, side->join[1], 0);
   }
-  if (kt) kt->end(s);
-  if (kt) kt->begin("fit_large", s);
-  {
-    const dim3 g(max(2u, min(296u, cdivu(1184u, frames))), frames);
-    if (p.keep_stages) K_FIT_LARGE(true)<<<g, kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
-    else K_FIT_LARGE(false)<<<g, kLargeThreads, sizeof(LargeShared), s>>>(p, 1);
-  }
-  if (kt) kt->end(s);
   if (kt) kt->begin("quads", s);
   k_quads<<<dim3(max(2u, min(592u, cdivu(2368u, frames))), frames), kQuadWarps * 32, 0, s>>>(p);
   if (kt) kt->end(s);
