@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -27,6 +28,16 @@ struct b200tag_detector {
   int device = 0;
   cudaStream_t stream = nullptr;
   SideStreams side;  // concurrent blob-tier kernels
+  // CUDA graphs of the whole launch sequence, keyed by (input pointer, stride, frame count)
+  struct GraphEntry {
+    const void *images;
+    size_t stride;
+    int count;
+    int launches;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
   void *arena = nullptr;
   size_t arena_bytes = 0;
   uint8_t *d_in = nullptr;  // internal input staging (frames copied from the host)
@@ -231,7 +242,13 @@ int finish_impl(b200tag_detector *det) {
   return rc;
 }
 
-int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt) {
+void drop_graphs(b200tag_detector *det) {
+  for (auto &g : det->graphs) cudaGraphExecDestroy(g.exec);
+  det->graphs.clear();
+}
+
+// memset of the counters, every kernel, result counters to the host -- on det->stream (side streams fork/join inside)
+int record_sequence(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt, int *launches_out) {
   FrameParams p = det->fp;
   p.in = static_cast<const uint8_t *>(device_images);
   p.in_stride = stride ? stride : det->in_bytes;
@@ -244,9 +261,49 @@ int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride
   launches += launch_frontend(p, count, det->stream, kt);
   launches += launch_blobs(p, count, det->stream, kt, kt ? nullptr : &det->side);  // per-kernel timing runs serially
   launches += launch_decode(p, count, det->stream, kt);
+  *launches_out = launches;
+  CK(cudaMemcpyAsync(det->h_counters, p.counters, sizeof(Counters) * count, cudaMemcpyDeviceToHost, det->stream));
+  return 0;
+}
+
+// The launch sequence of a (input buffer, frame count) pair never changes, so it is captured once into a CUDA
+// graph and replayed: one graph launch instead of 15 stream operations per batch (what matters for the
+// single-frame latency path, where the kernels are short).
+int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt) {
+  int launches = 0;
+  bool done = false;
+  if (!kt && det->use_graphs) {
+    for (auto &g : det->graphs) {
+      if (g.images == device_images && g.stride == stride && g.count == count) {
+        CK(cudaGraphLaunch(g.exec, det->stream));
+        launches = g.launches;
+        done = true;
+        break;
+      }
+    }
+    if (!done && det->graphs.size() < 16) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(det->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = record_sequence(det, device_images, stride, count, nullptr, &launches);
+      const cudaError_t ce = cudaStreamEndCapture(det->stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        det->graphs.push_back({device_images, stride, count, launches, exec});
+        cudaGraphDestroy(graph);
+        CK(cudaGraphLaunch(exec, det->stream));
+        done = true;
+      } else {  // capture not possible here: fall back to plain stream launches from now on
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        det->use_graphs = false;
+      }
+    }
+  }
+  if (!done) {
+    if (int rc = record_sequence(det, device_images, stride, count, kt, &launches)) return rc;
+  }
   det->kernels_per_batch = launches;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(det->h_counters, p.counters, sizeof(Counters) * count, cudaMemcpyDeviceToHost, det->stream));
   det->last_count = count;
   det->pending = true;
   return 0;
@@ -443,6 +500,8 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
     det->err = "uploading the tag family failed";
     return fail(B200TAG_E_CUDA);
   }
+  if (const char *e = getenv("B200TAG_NO_GRAPH")) det->use_graphs = !(e[0] == '1');
+  launch_blobs_init(det->stream);  // one-time attributes / tables, outside any later graph capture
   launch_hash_clear(p, B, det->stream);
   if (!ck(cudaStreamSynchronize(det->stream), "initial hash clear")) return fail(B200TAG_E_CUDA);
   det->dets.resize(B);
@@ -457,6 +516,7 @@ void b200tag_destroy(b200tag_detector *det) {
   if (!det) return;
   if (det->stream) {
     cudaStreamSynchronize(det->stream);
+    drop_graphs(det);
     cudaStreamDestroy(det->stream);
   }
   for (int i = 0; i < 2; i++) {
@@ -626,6 +686,7 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
 
 int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, double cy) {
   if (!det) return B200TAG_E_INVALID;
+  drop_graphs(det);  // the parameters are baked into the captured launches
   det->cfg.fx = det->fp.fx = fx; det->cfg.cx = det->fp.cx = cx;
   det->cfg.fy = det->fp.fy = fy; det->cfg.cy = det->fp.cy = cy;
   return 0;
@@ -633,6 +694,7 @@ int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, d
 
 int b200tag_set_distortion(b200tag_detector *det, double k1, double k2, double p1, double p2, double k3) {
   if (!det) return B200TAG_E_INVALID;
+  drop_graphs(det);
   det->cfg.k1 = det->fp.k1 = k1; det->cfg.k2 = det->fp.k2 = k2; det->cfg.p1 = det->fp.p1 = p1;
   det->cfg.p2 = det->fp.p2 = p2; det->cfg.k3 = det->fp.k3 = k3;
   return 0;

@@ -55,6 +55,7 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side);
 int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
 void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s);
+void launch_blobs_init(cudaStream_t s);
 
 }  // namespace b200tag
 

@@ -1231,7 +1231,7 @@ using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
 #define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
 #define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2, KEEP>
 
-int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side) {
+void launch_blobs_init(cudaStream_t s) {
   static bool dev_ready[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1245,6 +1245,9 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
     k_init_combos<<<1, 1, 0, s>>>();
     dev_ready[dev] = true;
   }
+}
+
+int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side) {
   if (kt) kt->begin("select", s);
   k_select<<<dim3(max(1u, min(16u, cdivu(148u * 4u, frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
