@@ -159,6 +159,20 @@ void apriltag_detector_destroy(apriltag_detector_t *td);
 void apriltag_detection_destroy(apriltag_detection_t *det);
 void apriltag_detections_destroy(zarray_t *detections);
 
+/* ---- apriltag_pose.h ---- */
+typedef struct {
+  apriltag_detection_t *det;
+  double tagsize; /* in meters */
+  double fx, fy, cx, cy;
+} apriltag_detection_info_t;
+typedef struct {
+  matd_t *R; /* 3x3 */
+  matd_t *t; /* 3x1 */
+} apriltag_pose_t;
+/* The call the node makes per detection (apriltags_cuda_detector.cu:433).  Implemented in
+ * libapriltags_cuda_core.so over b200tag_estimate_pose, so the node's pose step no longer needs libapriltag. */
+double estimate_tag_pose(apriltag_detection_info_t *info, apriltag_pose_t *pose);
+
 /* ---- tag36h11.h ---- */
 apriltag_family_t *tag36h11_create(void);
 void tag36h11_destroy(apriltag_family_t *tf);

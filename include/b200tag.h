@@ -220,6 +220,22 @@ int b200tag_set_distortion(b200tag_detector *det, double k1, double k2, double p
 int b200tag_undistort(double *u, double *v, double fx, double cx, double fy, double cy, double k1, double k2,
                       double p1, double p2, double k3);
 
+/* Pose of a tag in the camera frame (x right, y down, z forward): X_cam = R * X_tag + t, tag corners at
+ * (+-tagsize/2, +-tagsize/2, 0).  The step the node runs on every detection right after Detect
+ * (libapriltag estimate_tag_pose, called at apriltags_cuda_detector.cu:433): initial pose from the homography,
+ * orthogonal iteration, the second local minimum of the object-space error, the better of the two returned.
+ * Restated from the published algorithm -- libapriltag is not vendored in the reference tree. */
+typedef struct b200tag_pose {
+  double R[9];       /* row-major 3x3 rotation */
+  double t[3];
+  double err;        /* object-space error of the returned pose (estimate_tag_pose's return value) */
+  double err_other;  /* error of the other local minimum, HUGE_VAL if there is none */
+} b200tag_pose;
+int b200tag_estimate_pose(const b200tag_detection *det, double tagsize, double fx, double fy, double cx, double cy,
+                          b200tag_pose *out);
+int b200tag_estimate_poses(const b200tag_detection *dets, int count, double tagsize, double fx, double fy, double cx,
+                           double cy, b200tag_pose *out);
+
 /* Pinned host staging memory, so b200tag_detect* can overlap H2D with compute. */
 void *b200tag_alloc_pinned(size_t bytes);
 void b200tag_free_pinned(void *p);

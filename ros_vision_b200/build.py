@@ -11,6 +11,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200tag.so")
 
 CU_SOURCES = ["kernels_frontend.cu", "kernels_blobs.cu", "kernels_decode.cu", "detector.cu"]
+CC_SOURCES = ["pose.cc"]   # host-only parts of the C ABI
 HEADERS = ["dev_types.h", "kernels.h", "tag36h11_data.h", os.path.join("..", "..", "include", "b200tag.h")]
 
 NVCC_FLAGS = [
@@ -31,7 +32,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in CU_SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in CU_SOURCES + CC_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -46,6 +47,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src in CC_SOURCES:
+        obj = os.path.join(LIBDIR, src.replace(".cc", ".o"))
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

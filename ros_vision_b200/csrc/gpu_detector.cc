@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 
 namespace frc971::apriltag {
@@ -186,3 +187,24 @@ bool GpuDetector::UnDistort(double *u, double *v, const CameraMatrix *m, const D
 }
 
 }  // namespace frc971::apriltag
+
+// libapriltag's estimate_tag_pose, for builds that link this library instead of libapriltag
+// (apriltags_cuda_detector.cu:425-462).  With the real libapriltag on the link line its own definition wins.
+extern "C" __attribute__((weak)) double estimate_tag_pose(apriltag_detection_info_t *info, apriltag_pose_t *pose) {
+  b200tag_detection d;
+  std::memset(&d, 0, sizeof(d));
+  const apriltag_detection_t *det = info->det;
+  d.id = det->id;
+  for (int i = 0; i < 9; i++) d.H[i] = det->H->data[i];
+  for (int i = 0; i < 4; i++) {
+    d.p[i][0] = det->p[i][0];
+    d.p[i][1] = det->p[i][1];
+  }
+  d.c[0] = det->c[0];
+  d.c[1] = det->c[1];
+  b200tag_pose out;
+  if (b200tag_estimate_pose(&d, info->tagsize, info->fx, info->fy, info->cx, info->cy, &out) != 0) return HUGE_VAL;
+  pose->R = matd_create_data(3, 3, out.R);
+  pose->t = matd_create_data(3, 1, out.t);
+  return out.err;
+}

@@ -72,6 +72,8 @@ _STAGE_DTYPES = {
     STAGE_CLUSTERS: BLOB_DT,
 }
 
+POSE_DT = np.dtype([("R", "<f8", (3, 3)), ("t", "<f8", (3,)), ("err", "<f8"), ("err_other", "<f8")])
+
 _lib = None
 
 
@@ -118,6 +120,7 @@ def load_library():
     L.b200tag_error_string.restype = C.c_char_p
     L.b200tag_last_error.argtypes = [vp]
     L.b200tag_last_error.restype = C.c_char_p
+    L.b200tag_estimate_poses.argtypes = [vp, i32] + [C.c_double] * 5 + [vp]
     L.b200tag_version.restype = i32
     _lib = L
     return L
@@ -129,6 +132,20 @@ def default_config(width: int, height: int, fmt: str = "yuyv") -> Config:
     if rc:
         raise B200TagError("b200tag_default_config failed")
     return cfg
+
+
+def estimate_poses(detections: np.ndarray, tagsize: float, fx: float, fy: float, cx: float, cy: float) -> np.ndarray:
+    """estimate_tag_pose for every detection (the node's step after Detect, apriltags_cuda_detector.cu:425-462):
+    returns POSE_DT records (R, t in the camera frame, object-space error).  Pure host math in libb200tag.so."""
+    lib = load_library()
+    dets = np.ascontiguousarray(detections, dtype=DETECTION_DT)
+    out = np.zeros(len(dets), dtype=POSE_DT)
+    if len(dets):
+        rc = lib.b200tag_estimate_poses(dets.ctypes.data_as(C.c_void_p), len(dets), float(tagsize), float(fx), float(fy),
+                                        float(cx), float(cy), out.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise B200TagError(f"b200tag_estimate_poses: {lib.b200tag_error_string(rc).decode()}")
+    return out
 
 
 class PinnedBuffer:

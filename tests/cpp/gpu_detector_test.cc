@@ -42,6 +42,14 @@ int main(int argc, char **argv) {
       std::printf("id=%d hamming=%d margin=%.3f c=(%.3f,%.3f) H22=%.3f\n", det->id, det->hamming, det->decision_margin, det->c[0],
                   det->c[1], matd_get(det->H, 2, 2));
       if (argc > 5 && det->id != std::atoi(argv[5])) rc = 1;
+      // the node's next step, apriltags_cuda_detector.cu:425-462: pose of the tag in the camera frame
+      apriltag_detection_info_t info{det, 0.1651, cam.fx, cam.fy, cam.cx, cam.cy};
+      apriltag_pose_t pose;
+      const double err = estimate_tag_pose(&info, &pose);
+      std::printf("pose t=(%.4f,%.4f,%.4f) err=%.3e\n", pose.t->data[0], pose.t->data[1], pose.t->data[2], err);
+      if (!(pose.t->data[2] > 0.1 && pose.t->data[2] < 20.0) || !(err < 1e-3)) rc = 7;  // in front of the camera, metres
+      matd_destroy(pose.R);
+      matd_destroy(pose.t);
     }
     std::vector<uint8_t> g2(gray.size());
     detector.CopyGrayTo(g2.data());

@@ -1,0 +1,159 @@
+"""Pose step: b200tag_estimate_poses against ground-truth poses and against an independent
+numpy restatement of the published algorithm (orthogonal iteration, Lu/Hager/Mjolsness 2000).  libapriltag's
+estimate_tag_pose is not available here (un-vendored dependency), so parity with it is unpinned; what is pinned is
+the geometry: a tag projected with a known (R, t) must come back with that pose.  Pure host code: runs without a GPU."""
+import numpy as np
+import pytest
+
+FX, FY, CX, CY = 905.5, 907.9, 640.0, 400.0
+TAGSIZE = 0.1651
+
+
+def _rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def _object_points(tagsize):
+    s = tagsize / 2
+    return np.array([[-s, s, 0], [s, s, 0], [s, -s, 0], [-s, -s, 0]], dtype=np.float64)
+
+
+def _homography(src, dst):
+    """DLT through 4 correspondences, H[2][2] = 1 (what quad_update_homographies produces)."""
+    A, b = [], []
+    for (x, y), (u, v) in zip(src, dst):
+        A.append([x, y, 1, 0, 0, 0, -x * u, -y * u]); b.append(u)
+        A.append([0, 0, 0, x, y, 1, -x * v, -y * v]); b.append(v)
+    h = np.linalg.solve(np.array(A, dtype=np.float64), np.array(b, dtype=np.float64))
+    return np.append(h, 1.0)
+
+
+def _detection(R, t, noise=None):
+    from ros_vision_b200 import detector as D
+    P = _object_points(TAGSIZE)
+    cam = (R @ P.T).T + t
+    px = np.stack([FX * cam[:, 0] / cam[:, 2] + CX, FY * cam[:, 1] / cam[:, 2] + CY], axis=1)
+    if noise is not None:
+        px = px + noise
+    det = np.zeros(1, dtype=D.DETECTION_DT)
+    det["p"][0] = px
+    det["H"][0] = _homography([(-1, 1), (1, 1), (1, -1), (-1, -1)], px)
+    det["c"][0] = px.mean(axis=0)
+    return det
+
+
+def _orthogonal_iteration_numpy(v, p, R, steps=50):
+    """Independent restatement (numpy SVD instead of the library's Jacobi sweeps)."""
+    n = len(p)
+    F = [np.outer(x, x) / (x @ x) for x in v]
+    I = np.eye(3)
+    M1inv = np.linalg.inv(I - sum(F) / n)
+    p_res = p - p.mean(axis=0)
+    t = np.zeros(3)
+    for _ in range(steps):
+        t = M1inv @ (sum((F[j] - I) @ R @ p[j] for j in range(n)) / n)
+        q = np.array([F[j] @ (R @ p[j] + t) for j in range(n)])
+        M3 = sum(np.outer(q[j] - q.mean(axis=0), p_res[j]) for j in range(n))
+        U, _, Vt = np.linalg.svd(M3)
+        R = U @ Vt
+        if np.linalg.det(R) < 0:
+            R[:, 2] *= -1
+    err = sum(np.sum(((I - F[j]) @ (R @ p[j] + t)) ** 2) for j in range(n))
+    return R, t, err
+
+
+@pytest.fixture(scope="module")
+def D():
+    from ros_vision_b200 import build, detector
+    build.build_native()
+    detector.load_library()
+    return detector
+
+
+def test_ground_truth_poses_are_recovered(D):
+    rng = np.random.default_rng(7)
+    worst_t = worst_r = 0.0
+    for _ in range(200):
+        R = _rot(np.pi + rng.uniform(-0.9, 0.9), rng.uniform(-0.9, 0.9), rng.uniform(-np.pi, np.pi))  # tag faces the camera
+        t = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.5, 0.5), rng.uniform(0.5, 4.0)])
+        pose = D.estimate_poses(_detection(R, t), TAGSIZE, FX, FY, CX, CY)[0]
+        assert pose["err"] < 1e-12, pose["err"]
+        worst_t = max(worst_t, float(np.abs(pose["t"] - t).max()))
+        worst_r = max(worst_r, float(np.abs(pose["R"] - R).max()))
+        assert abs(np.linalg.det(pose["R"]) - 1) < 1e-9 and np.abs(pose["R"] @ pose["R"].T - np.eye(3)).max() < 1e-9
+    assert worst_t < 1e-6 and worst_r < 1e-6, (worst_t, worst_r)
+
+
+def test_noisy_corners_and_the_second_minimum(D):
+    """With corner noise the returned pose is the better of the (up to) two local minima, and its error is in the
+    range of what orthogonal iteration started at the TRUE pose reaches."""
+    rng = np.random.default_rng(8)
+    close = 0
+    for _ in range(100):
+        R = _rot(np.pi + rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(-np.pi, np.pi))
+        t = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(1.0, 5.0)])
+        det = _detection(R, t, noise=rng.normal(0, 0.3, size=(4, 2)))
+        pose = D.estimate_poses(det, TAGSIZE, FX, FY, CX, CY)[0]
+        assert pose["err"] <= pose["err_other"]
+        v = np.stack([(det["p"][0][:, 0] - CX) / FX, (det["p"][0][:, 1] - CY) / FY, np.ones(4)], axis=1)
+        _, _, err_ref = _orthogonal_iteration_numpy(v, _object_points(TAGSIZE), R.copy())
+        close += pose["err"] <= 3 * err_ref + 1e-15
+        assert np.abs(pose["t"] - t).max() < 0.35 * t[2]  # depth is the weakly constrained direction
+    # far, small tags converge slowly: after the 50 sweeps libapriltag also uses, a few poses are still on their way
+    # (and when the error then shows two other minima, libapriltag's rule -- accept a UNIQUE second minimum only --
+    # keeps the first pose); the large majority must be at the level of the truth-started iteration
+    assert close >= 90, close
+
+
+def _pose_from_homography_numpy(H, tagsize):
+    """homography_to_pose(H, -fx, fy, cx, cy) + the y/z flip of estimate_pose_for_tag_homography, restated."""
+    H = np.asarray(H).reshape(3, 3)
+    fx = -FX
+    R20, R21, TZ = H[2]
+    R00, R01, TX = (H[0, 0] - CX * R20) / fx, (H[0, 1] - CX * R21) / fx, (H[0, 2] - CX * TZ) / fx
+    R10, R11, TY = (H[1, 0] - CY * R20) / FY, (H[1, 1] - CY * R21) / FY, (H[1, 2] - CY * TZ) / FY
+    s = 1.0 / np.sqrt(np.sqrt(R00**2 + R10**2 + R20**2) * np.sqrt(R01**2 + R11**2 + R21**2))
+    if TZ > 0:
+        s = -s
+    c0 = np.array([R00, R10, R20]) * s
+    c1 = np.array([R01, R11, R21]) * s
+    Rm = np.stack([c0, c1, np.cross(c0, c1)], axis=1)
+    U, _, Vt = np.linalg.svd(Rm)
+    fix = np.diag([1.0, -1.0, -1.0])
+    return fix @ (U @ Vt), fix @ (np.array([TX, TY, TZ]) * s * tagsize / 2)
+
+
+def test_matches_numpy_restatement(D):
+    """The first stage (homography start + 50 sweeps) restated in numpy: the library returns that pose, or -- when it
+    found a unique second minimum -- one with a smaller error."""
+    rng = np.random.default_rng(9)
+    same = 0
+    for _ in range(60):
+        R = _rot(np.pi + rng.uniform(-0.7, 0.7), rng.uniform(-0.7, 0.7), rng.uniform(-np.pi, np.pi))
+        t = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(0.8, 3.0)])
+        det = _detection(R, t, noise=rng.normal(0, 0.2, size=(4, 2)))
+        pose = D.estimate_poses(det, TAGSIZE, FX, FY, CX, CY)[0]
+        v = np.stack([(det["p"][0][:, 0] - CX) / FX, (det["p"][0][:, 1] - CY) / FY, np.ones(4)], axis=1)
+        R0, _ = _pose_from_homography_numpy(det["H"][0], TAGSIZE)
+        R1, t1, err1 = _orthogonal_iteration_numpy(v, _object_points(TAGSIZE), R0)
+        if np.abs(R1 - pose["R"]).max() < 1e-7 and np.abs(t1 - pose["t"]).max() < 1e-7:
+            same += 1
+            assert abs(err1 - pose["err"]) <= 1e-9 * max(err1, 1e-12)
+        else:
+            assert pose["err"] < err1 and np.isfinite(pose["err_other"])
+            assert abs(pose["err_other"] - err1) <= 1e-6 * err1 + 1e-15
+    assert same >= 30, same
+
+
+def test_bad_arguments(D):
+    import ctypes as C
+    lib = D.load_library()
+    out = np.zeros(1, dtype=D.POSE_DT)
+    det = np.zeros(1, dtype=D.DETECTION_DT)
+    assert lib.b200tag_estimate_poses(det.ctypes.data_as(C.c_void_p), 1, 0.0, FX, FY, CX, CY, out.ctypes.data_as(C.c_void_p)) != 0
+    assert lib.b200tag_estimate_poses(None, 1, TAGSIZE, FX, FY, CX, CY, out.ctypes.data_as(C.c_void_p)) != 0
+    assert len(D.estimate_poses(np.zeros(0, dtype=D.DETECTION_DT), TAGSIZE, FX, FY, CX, CY)) == 0
