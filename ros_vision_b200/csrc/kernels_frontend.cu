@@ -618,7 +618,11 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   __shared__ uint32_t s_loc[kBpMaxPts];             // [9:0] local entry | [31:10] rank among the tile's points of that entry
   __shared__ unsigned long long s_lkey[kBpLH];      // blob-pair key; after (3): the global slot
   __shared__ uint32_t s_lcnt[kBpLH];                // points of the entry in this tile; after (3): base rank
-  __shared__ uint32_t s_npts, s_gbase;
+  __shared__ uint32_t s_npts, s_gbase, s_half;
+  __shared__ uint32_t s_rowm[kBpTH + 1][3][2];      // white / black / big masks of a staged row, two 32-bit halves
+  __shared__ uint8_t s_halo[kBpTH + 1][2];          // the same three bits for the left / right halo column
+  __shared__ unsigned long long s_emit[kBpTH][4], s_b2w[kBpTH][4];
+  __shared__ uint32_t s_ebase[kBpTH][4];
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kBpTW, y0 = blockIdx.y * kBpTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
@@ -633,7 +637,6 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   uint32_t *occupied = p.occupied + hoff;
   const int tid = threadIdx.x, lane = tid & 31;
 
-  if (tid == 0) s_npts = 0;
   for (int i = tid; i < static_cast<int>(kBpLH); i += kBpThreads) {
     s_lkey[i] = kEmptyKey;
     s_lcnt[i] = 0;
@@ -669,47 +672,91 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   }
   __syncthreads();
 
-  // (1) which directions emit a point; compaction into s_pts
-  const int tx = tid % kBpTW;
-  for (int ry = tid / kBpTW; ry < kBpTH; ry += kBpThreads / kBpTW) {  // warp-uniform trip count
-    const int x = x0 + tx, y = y0 + ry;
-    uint32_t have = 0, b2w = 0;
-    if (x >= 1 && x <= p.w - 2 && y >= 1 && y <= p.h - 2) {  // apriltag_gpu.cu:239,276-281
-      const uint32_t c0 = s_cell[ry][tx + 1];
-      const uint32_t col0 = c0 >> 29;
-      if (col0 != 2 && (c0 & (1u << 28))) {  // :284
-        const uint32_t cl = s_cell[ry][tx], c2 = s_cell[ry + 1][tx + 1];
-        const uint32_t colL = cl >> 29, col2 = c2 >> 29;
-        // direction-3 duplicate suppression, :347-357
-        const bool skip3 = (colL != 2 && col2 != 2 && colL != col2 && x != 1 && (cl & (1u << 28)) && (c2 & (1u << 28)));
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-          if (d == 3 && skip3) continue;
-          const uint32_t c1 = s_cell[ry + dir_dy(d)][tx + 1 + dir_dx(d)];
-          const uint32_t col1 = c1 >> 29;
-          if (col1 == 2 || col1 == col0) continue;  // v0 + v1 == 255, :305
-          if (!(c1 & (1u << 28))) continue;          // :306
-          b2w |= (col1 > col0 ? 1u : 0u) << d;      // :316
-          have |= 1u << d;
-        }
-      }
+  // (1) which directions emit a point -- on row bit masks.  Three 64-bit masks per staged row (white, black,
+  //     component big enough) plus the two halo columns; one thread per (row, direction) combines them into the
+  //     emission mask of apriltag_gpu.cu:276-357 with shifts and ANDs; popcounts give every point its place in the
+  //     list without shuffles or atomics.
+  for (int t = tid >> 5; t < (kBpTH + 1) * 2; t += kBpThreads / 32) {
+    const int r = t >> 1, half = t & 1;
+    const uint32_t c = s_cell[r][1 + 32 * half + lane];
+    const uint32_t col = c >> 29;
+    const uint32_t wm = __ballot_sync(0xffffffffu, col == 1), bm = __ballot_sync(0xffffffffu, col == 0);
+    const uint32_t gm = __ballot_sync(0xffffffffu, (c >> 28) & 1u);
+    if (lane == 0) {
+      s_rowm[r][0][half] = wm;
+      s_rowm[r][1][half] = bm;
+      s_rowm[r][2][half] = gm;
     }
-    const uint32_t cnt = __popc(have);
+  }
+  if (tid < (kBpTH + 1) * 2) {  // halo columns: bit 0 white, 1 black, 2 big
+    const int r = tid >> 1, side = tid & 1;
+    const uint32_t c = s_cell[r][side ? kBpTW + 1 : 0];
+    const uint32_t col = c >> 29;
+    s_halo[r][side] = static_cast<uint8_t>((col == 1 ? 1u : 0u) | (col == 0 ? 2u : 0u) | (((c >> 28) & 1u) << 2));
+  }
+  __syncthreads();
+  if (tid < kBpTH * 4) {
+    const int ry = tid >> 2, d = tid & 3;
+    const int y = y0 + ry;
+    auto row64 = [&](int r, int k) { return (static_cast<unsigned long long>(s_rowm[r][k][1]) << 32) | s_rowm[r][k][0]; };
+    unsigned long long emit = 0, b2w = 0;
+    if (y >= 1 && y <= p.h - 2) {
+      const unsigned long long W0 = row64(ry, 0), B0 = row64(ry, 1), G0 = row64(ry, 2);
+      const int rn = ry + dir_dy(d), dx = dir_dx(d);
+      unsigned long long W1 = row64(rn, 0), B1 = row64(rn, 1), G1 = row64(rn, 2);
+      if (dx > 0) {  // neighbour column x + 1: shift right, the right halo enters at bit 63
+        const unsigned long long h = s_halo[rn][1];
+        W1 = (W1 >> 1) | ((h & 1ull) << 63); B1 = (B1 >> 1) | (((h >> 1) & 1ull) << 63); G1 = (G1 >> 1) | (((h >> 2) & 1ull) << 63);
+      } else if (dx < 0) {  // neighbour column x - 1: shift left, the left halo enters at bit 0
+        const unsigned long long h = s_halo[rn][0];
+        W1 = (W1 << 1) | (h & 1ull); B1 = (B1 << 1) | ((h >> 1) & 1ull); G1 = (G1 << 1) | ((h >> 2) & 1ull);
+      }
+      b2w = B0 & W1;                                   // :316
+      emit = ((W0 & B1) | b2w) & G0 & G1;              // :284,305,306
+      if (d == 3) {  // duplicate suppression, :347-357: left and lower neighbours non-gray, different colours, both big
+        const unsigned long long hl = s_halo[ry][0];
+        const unsigned long long WL = (W0 << 1) | (hl & 1ull), BL = (B0 << 1) | ((hl >> 1) & 1ull), GL = (G0 << 1) | ((hl >> 2) & 1ull);
+        const unsigned long long W2 = row64(ry + 1, 0), B2 = row64(ry + 1, 1), G2 = row64(ry + 1, 2);
+        unsigned long long skip = ((WL & B2) | (BL & W2)) & GL & G2;
+        if (x0 <= 1 && 1 < x0 + kBpTW) skip &= ~(1ull << (1 - x0));  // x != 1
+        emit &= ~skip;
+      }
+      // interior columns only, :239,276-281
+      const int xlo = max(1, x0) - x0, xhi = min(p.w - 2, x0 + kBpTW - 1) - x0;  // inclusive, tile-local
+      unsigned long long cols = 0;
+      if (xhi >= xlo) cols = (xhi - xlo + 1 >= 64 ? ~0ull : ((1ull << (xhi - xlo + 1)) - 1ull)) << xlo;
+      emit &= cols;
+    }
+    s_emit[ry][d] = emit;
+    s_b2w[ry][d] = b2w;
+    // exclusive prefix of the popcounts over the 64 (row, direction) words: two warps, then a fix-up
+    const uint32_t cnt = static_cast<uint32_t>(__popcll(emit));
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&s_npts, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t pos = base + incl - cnt;
-    const uint32_t pix = static_cast<uint32_t>(ry * kBpTW + tx) << 3;
+    s_ebase[ry][d] = incl - cnt;
+    if (tid == 31) s_half = incl;
+    if (tid == 63) s_npts = incl;  // second half only; completed below
+  }
+  __syncthreads();
+  if (tid >= 32 && tid < kBpTH * 4) s_ebase[tid >> 2][tid & 3] += s_half;
+  if (tid == 0) s_npts += s_half;
+  __syncthreads();
+  {
+    const int tx = tid % kBpTW;
+    const unsigned long long below = (1ull << tx) - 1ull;
+    for (int ry = tid / kBpTW; ry < kBpTH; ry += kBpThreads / kBpTW) {
+      const uint32_t pix = static_cast<uint32_t>(ry * kBpTW + tx) << 3;
 #pragma unroll
-    for (int d = 0; d < 4; d++)
-      if ((have >> d) & 1u) s_pts[pos++] = static_cast<uint16_t>(pix | (d << 1) | ((b2w >> d) & 1u));
+      for (int d = 0; d < 4; d++) {
+        const unsigned long long e = s_emit[ry][d];
+        if ((e >> tx) & 1ull)
+          s_pts[s_ebase[ry][d] + __popcll(e & below)] = static_cast<uint16_t>(pix | (d << 1) | ((s_b2w[ry][d] >> tx) & 1ull));
+      }
+    }
   }
   __syncthreads();
   const uint32_t npts = s_npts;
