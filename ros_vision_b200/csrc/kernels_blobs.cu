@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
 #define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
-#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 2, KEEP>
+#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 3, KEEP>
 
 void launch_blobs_init(cudaStream_t s) {
   static bool dev_ready[64] = {false};
@@ -1262,7 +1262,7 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   // The three tiers are independent and each is latency bound at modest occupancy: with side streams they run
   // concurrently (largest blobs first), so their tails overlap; the per-kernel timing mode runs them serially.
-  // Resident capacity per SM: 5 small-tier CTAs (4 warps = 4 blobs each), 5 medium-tier CTAs, 2 large-tier CTAs.
+  // Resident capacity per SM: 5 small-tier CTAs (4 warps = 4 blobs each), 5 medium-tier CTAs, 3 large-tier CTAs.
   const bool fork = side && side->s[0] && side->s[1];
   cudaStream_t s_large = fork ? side->s[0] : s, s_medium = fork ? side->s[1] : s;
   if (fork) {
@@ -1272,7 +1272,7 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   if (kt) kt->begin("fit_large", s);
   {
-    const dim3 g(max(2u, min(296u, cdivu(1184u, frames))), frames);
+    const dim3 g(max(3u, min(444u, cdivu(1776u, frames))), frames);
     if (p.keep_stages) K_FIT_LARGE(true)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);
     else K_FIT_LARGE(false)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);
   }
