@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 line = json.loads(open(bench_path).read().strip().splitlines()[-1])
 kern = line["roofline"]["kernels"]
 peak = line["roofline"]["peak"]
-B = line["config"]["frames_per_step_per_gpu"]
+B = line["config"].get("frames_per_batch", line["config"]["frames_per_step_per_gpu"])
 
 # launch list -> per kernel mean device time, only launches of full batches (grid z or y == B is not visible here,
 # so take the launches of the LAST complete step: the final `len(kern)` pipeline launches before the latency runs)
