@@ -348,16 +348,17 @@ def run_ours(args):
     per_lane = B // L
     lanes = [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=per_lane, device=local)
              for _ in range(L)]
-    pinned = [D.PinnedBuffer(frame_bytes) for _ in range(B)]
-    for i, pb in enumerate(pinned):
-        pb.array[:] = host_batch[i]
-    ptrs = [pb.ptr for pb in pinned]
-    lane_ptrs = [ptrs[l * per_lane:(l + 1) * per_lane] for l in range(L)]
+    # one pinned block holding the batch back to back, as a camera ring buffer would (the engine then moves each
+    # lane's frames with a single host->device copy)
+    pinned = [D.PinnedBuffer(frame_bytes * B)]
+    pinned[0].array[:] = host_batch.reshape(-1)
+    ptrs = [pinned[0].ptr + i * frame_bytes for i in range(B)]
+    lane_ptrs = [ptrs[l * per_lane] for l in range(L)]
 
     def e2e_step():
         n = 0
         for l, ld in enumerate(lanes):
-            ld.EnqueuePointers(lane_ptrs[l])   # waits for + collects this lane's previous batch first
+            ld.EnqueueHostBlock(lane_ptrs[l], per_lane)   # waits for + collects this lane's previous batch first
         return n
 
     for _ in range(3):

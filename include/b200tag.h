@@ -198,6 +198,9 @@ int b200tag_detect_device(b200tag_detector *det, const void *device_images, size
  * and builds the detection lists.  `stream_out` (optional) receives the cudaStream_t. */
 int b200tag_enqueue_device(b200tag_detector *det, const void *device_images, size_t frame_stride_bytes, int count);
 int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_images, int count);
+/* `count` frames of ONE host allocation, `frame_stride_bytes` apart (0 = back to back), e.g. a pinned camera ring
+ * buffer: they cross PCIe in a single copy instead of one per frame. */
+int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames, size_t frame_stride_bytes, int count);
 int b200tag_finish(b200tag_detector *det);
 void *b200tag_stream(b200tag_detector *det);
 

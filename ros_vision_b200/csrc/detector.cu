@@ -552,6 +552,23 @@ int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_image
   return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
 }
 
+int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames, size_t frame_stride_bytes, int count) {
+  if (!det || !host_frames || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  const size_t stride = frame_stride_bytes ? frame_stride_bytes : det->in_bytes;
+  if (stride < det->in_bytes) return B200TAG_E_INVALID;
+  if (det->pending) {
+    if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
+  }
+  // the frames of one allocation (a camera ring buffer) cross PCIe in a single copy
+  if (stride == det->in_bytes && det->fp.in_stride == det->in_bytes) {
+    CK(cudaMemcpyAsync(det->d_in, host_frames, det->in_bytes * static_cast<size_t>(count), cudaMemcpyHostToDevice, det->stream));
+  } else {
+    CK(cudaMemcpy2DAsync(det->d_in, det->fp.in_stride, host_frames, stride, det->in_bytes, static_cast<size_t>(count),
+                         cudaMemcpyHostToDevice, det->stream));
+  }
+  return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+}
+
 int b200tag_finish(b200tag_detector *det) {
   if (!det) return B200TAG_E_INVALID;
   return finish_impl(det);

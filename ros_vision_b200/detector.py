@@ -96,6 +96,7 @@ def load_library():
     L.b200tag_detect_device.argtypes = [vp, vp, sz, i32]
     L.b200tag_enqueue_device.argtypes = [vp, vp, sz, i32]
     L.b200tag_enqueue_host.argtypes = [vp, C.POINTER(vp), i32]
+    L.b200tag_enqueue_host_block.argtypes = [vp, vp, sz, i32]
     L.b200tag_finish.argtypes = [vp]
     L.b200tag_stream.argtypes = [vp]
     L.b200tag_stream.restype = vp
@@ -257,6 +258,12 @@ class GpuDetector:
         ptrs = (C.c_void_p * len(host_ptrs))(*host_ptrs)
         self._check(self._lib.b200tag_enqueue_host(self._h, ptrs, len(host_ptrs)), "b200tag_enqueue_host")
         self.last_count = len(host_ptrs)
+
+    def EnqueueHostBlock(self, host_ptr: int, count: int, stride: int = 0) -> None:
+        """`count` frames of one host allocation (pinned ring buffer), one host->device copy."""
+        self._check(self._lib.b200tag_enqueue_host_block(self._h, C.c_void_p(host_ptr), stride, count),
+                    "b200tag_enqueue_host_block")
+        self.last_count = count
 
     def DetectDevice(self, device_ptr: int, count: int = 1, stride: int = 0, allow_overflow=False) -> int:
         rc = self._lib.b200tag_detect_device(self._h, C.c_void_p(device_ptr), stride, count)

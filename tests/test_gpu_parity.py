@@ -197,6 +197,26 @@ def test_two_detectors_interleaved(D, oracle):
     db.close()
 
 
+def test_host_block_enqueue(D, oracle):
+    """b200tag_enqueue_host_block: frames of one pinned allocation, tightly packed and with a padded stride."""
+    from ros_vision_b200 import synth
+    w, h = 640, 480
+    frames = [synth.gray_to_yuyv(synth.make_scene(w, h, 80 + i, 2, side_range=(60, 140), noise_sigma=4.0).gray).reshape(-1)
+              for i in range(3)]
+    fb = frames[0].size
+    for stride in (fb, fb + 4096):
+        buf = D.PinnedBuffer(stride * len(frames))
+        for i, f in enumerate(frames):
+            buf.array[i * stride:i * stride + fb] = f
+        det = D.GpuDetector(w, h, "yuyv", max_batch=4, keep_stages=True)
+        det.EnqueueHostBlock(buf.ptr, len(frames), 0 if stride == fb else stride)
+        det.Finish()
+        for i, f in enumerate(frames):
+            compare_all(det, oracle.detect(oracle.make_config(w, h, "yuyv", 2, 0.0), f.reshape(h, w * 2)), i, "yuyv")
+        det.close()
+        buf.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
