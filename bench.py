@@ -217,6 +217,34 @@ def reference_gpu_leg(frames, iters=300):
         return {"unavailable": repr(e)[:200]}
 
 
+def opencv_aruco_leg(frames, seconds_budget=4.0):
+    """Independent CPU datapoint: OpenCV's ArucoDetector with the AprilTag 36h11 dictionary and AprilTag
+    corner refinement on the luma plane of the same frames, OpenCV's own threading.  Not the reference and not the
+    target -- a different detector, reported for orientation only."""
+    try:
+        import cv2
+        ar = cv2.aruco
+        params = ar.DetectorParameters()
+        params.cornerRefinementMethod = ar.CORNER_REFINE_APRILTAG
+        params.aprilTagQuadDecimate = float(DECIMATE)
+        det = ar.ArucoDetector(ar.getPredefinedDictionary(ar.DICT_APRILTAG_36h11), params)
+        bpp = {"gray": 1, "yuyv": 2, "bgr": 3}[FMT]
+        grays = []
+        for f in frames[:8]:
+            a = f.reshape(H, W, bpp) if bpp > 1 else f.reshape(H, W)
+            grays.append(np.ascontiguousarray(a[:, :, 0] if FMT == "yuyv" else (a if bpp == 1 else cv2.cvtColor(a, cv2.COLOR_BGR2GRAY))))
+        det.detectMarkers(grays[0])
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds_budget:
+            det.detectMarkers(grays[n % len(grays)])
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "frames/s", "kind": f"cv2 {cv2.__version__} aruco.ArucoDetector, DICT_APRILTAG_36h11, "
+                "CORNER_REFINE_APRILTAG", "threads": cv2.getNumThreads(), "sample": f"{n} frames in {dt:.1f} s"}
+    except Exception as e:  # reporting leg only
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args):
     rank, world, local = dist_setup(args.gpus)
     if rank != 0:
@@ -444,6 +472,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps * DL,
             "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
+            "cpu_opencv_aruco": opencv_aruco_leg(frames) if (world == 1 and not args.no_cpu) else None,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},
