@@ -482,7 +482,10 @@ __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
 }
 
 // K4: unions across tile borders.  Work items per tile: its top row (TW), left column (TH),
-// right column (TH, for the up-right diagonal).  One thread per item.
+// right column (TH, for the up-right diagonal).  One thread per item collects up to three
+// neighbour pairs; inside a warp, pairs that join the same two tile-local trees (equal raw labels
+// on both sides -- on thresholded noise the same giant component shows up at every other border
+// pixel) are deduplicated with __match_any_sync, so only one lane walks the parent chains.
 constexpr int kCclMergeThreads = ((kCclTW + 2 * kCclTH + 31) / 32) * 32;
 __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   const int frame = blockIdx.z;
@@ -490,37 +493,52 @@ __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *th = p.thresh + frame * n;
   uint32_t *labels = p.labels + frame * n;
-  const int t = threadIdx.x;
-  int x, y;
-  int kind;  // 0 top row, 1 left column, 2 right column
+  const int t = threadIdx.x, lane = t & 31;
+  int x = 0, y = 0;
+  int kind = 3;  // 0 top row, 1 left column, 2 right column, 3 idle
   if (t < kCclTW) {
     kind = 0; x = x0 + t; y = y0;
   } else if (t < kCclTW + kCclTH) {
     kind = 1; x = x0; y = y0 + (t - kCclTW);
   } else if (t < kCclTW + 2 * kCclTH) {
     kind = 2; x = x0 + kCclTW - 1; y = y0 + (t - kCclTW - kCclTH);
-  } else {
-    return;
   }
-  if (x >= p.w || y >= p.h) return;
-  const uint32_t i = static_cast<uint32_t>(y * p.w + x);
-  const uint8_t v = th[i];
-  if (v == 127) return;
-  if (kind == 0) {
-    if (y == 0) return;
-    // every "up" neighbour is in another tile
-    if (th[i - p.w] == v) gunite(labels, i, i - p.w);
-    if (v == 255) {
-      if (x > 0 && th[i - p.w - 1] == 255) gunite(labels, i, i - p.w - 1);
-      if (x + 1 < p.w && th[i - p.w + 1] == 255) gunite(labels, i, i - p.w + 1);
+  uint32_t other[3];  // neighbour pixel of each candidate pair, 0xffffffff = none
+  other[0] = other[1] = other[2] = 0xffffffffu;
+  uint32_t i = 0;
+  if (kind < 3 && x < p.w && y < p.h) {
+    i = static_cast<uint32_t>(y * p.w + x);
+    const uint8_t v = th[i];
+    if (v != 127) {
+      if (kind == 0) {
+        if (y > 0) {  // every "up" neighbour is in another tile
+          if (th[i - p.w] == v) other[0] = i - p.w;
+          if (v == 255) {
+            if (x > 0 && th[i - p.w - 1] == 255) other[1] = i - p.w - 1;
+            if (x + 1 < p.w && th[i - p.w + 1] == 255) other[2] = i - p.w + 1;
+          }
+        }
+      } else if (kind == 1) {
+        if (x > 0) {
+          if (th[i - 1] == v) other[0] = i - 1;
+          // up-left lies in the left tile; rows at the tile top were handled by kind 0
+          if (v == 255 && y > y0 && th[i - p.w - 1] == 255) other[1] = i - p.w - 1;
+        }
+      } else {
+        if (v == 255 && y > y0 && x + 1 < p.w && th[i - p.w + 1] == 255) other[0] = i - p.w + 1;
+      }
     }
-  } else if (kind == 1) {
-    if (x == 0) return;
-    if (th[i - 1] == v) gunite(labels, i, i - 1);
-    // up-left lies in the left tile; rows at the tile top were handled by kind 0
-    if (v == 255 && y > y0 && th[i - p.w - 1] == 255) gunite(labels, i, i - p.w - 1);
-  } else {
-    if (v == 255 && y > y0 && x + 1 < p.w && th[i - p.w + 1] == 255) gunite(labels, i, i - p.w + 1);
+  }
+  const uint32_t mine = __ldcg(labels + i);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const bool has = other[k] != 0xffffffffu;
+    const uint32_t active = __ballot_sync(0xffffffffu, has);
+    if (!has) continue;
+    const uint32_t theirs = __ldcg(labels + other[k]);
+    const unsigned long long key = (static_cast<unsigned long long>(min(mine, theirs)) << 32) | max(mine, theirs);
+    const uint32_t group = __match_any_sync(active, key);
+    if (lane == __ffs(group) - 1 && mine != theirs) gunite(labels, mine, theirs);
   }
 }
 
