@@ -613,15 +613,12 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
                                 Counters *ctr, uint32_t *occupied) {
   uint32_t slot = hash_pair(rep0, rep1) & (p.hash_cap - 1);
   for (uint32_t probe = 0; probe < p.hash_cap; probe++) {
-    unsigned long long cur = __ldcg(keys + slot);
+    // compare-and-swap first: one L2 round trip whether the key is already there or the slot gets claimed
+    const unsigned long long cur = atomicCAS(keys + slot, kEmptyKey, key);
     if (cur == key) return slot;
-    if (cur == kEmptyKey) {
-      cur = atomicCAS(keys + slot, kEmptyKey, key);
-      if (cur == kEmptyKey) {  // we claimed it: list the slot so k_select never scans the whole table
-        occupied[atomicAdd(&ctr->num_occupied, 1u)] = slot;
-        return slot;
-      }
-      if (cur == key) return slot;
+    if (cur == kEmptyKey) {  // we claimed it: list the slot so k_select never scans the whole table
+      occupied[atomicAdd(&ctr->num_occupied, 1u)] = slot;
+      return slot;
     }
     slot = (slot + 1) & (p.hash_cap - 1);
   }
