@@ -191,6 +191,8 @@ struct DecodeShared {
   uint8_t sv[kSampleChunk];
   double lines[4][4];
   float p[4][2];
+  float e_nx[4], e_ny[4];  // per-edge normal and sample count (refine)
+  int e_ns[4];
   double gm_x[64], gm_y[64];
   int gm_v[64];  // -1 = sample outside the image
   double values[100], sharp[100];
@@ -225,8 +227,11 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
     __syncwarp();
 
     if (p.refine_edges) {  // RefineEdges, apriltag_detect.cu:405-564
-      for (int edge = 0; edge < 4; edge++) {
-        const int a = edge, b = (edge + 1) & 3;
+      // The four edges only read the unrefined corners, so they are refined side by side: lanes 0..3 own one edge
+      // each (normal, sample count, moment sums in the reference's sample order, line fit, corner), and the
+      // samples of all four edges are spread over the whole warp.
+      if (lane < 4) {
+        const int a = lane, b = (lane + 1) & 3;
         float nx = S.p[b][1] - S.p[a][1];
         float ny = -S.p[b][0] + S.p[a][0];
         const float mag = sqrtf(nx * nx + ny * ny);
@@ -235,98 +240,111 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
         if (quad.reversed_border) { nx = -nx; ny = -ny; }
         int nsamples = static_cast<int>(mag / 8);
         if (nsamples < 16) nsamples = 16;
-        double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;  // meaningful on lane 0
-        const float pax = S.p[a][0], pay = S.p[a][1], pbx = S.p[b][0], pby = S.p[b][1];
-        for (int base = 0; base < nsamples; base += kSampleChunk) {
-          const int lim = min(kSampleChunk, nsamples - base);
-          for (int j = lane; j < lim; j += 32) {
-            const int s = base + j;
-            const double alpha = (1.0 + s) / (nsamples + 1);
-            const double x0 = alpha * pax + (1 - alpha) * pbx;
-            const double y0 = alpha * pay + (1 - alpha) * pby;
-            double Mn = 0, Mcount = 0;
-            const double range = static_cast<double>(static_cast<float>(p.f)) + 1;
-            // n runs over -range, -range + 0.25, ..., range (multiples of 0.25: exact in double).  The two
-            // byte gathers of five consecutive n are issued together; the sums keep the order of n.
-            const int nt = static_cast<int>(8 * range) + 1;
-            for (int t0 = 0; t0 < nt; t0 += 5) {
-              int g1v[5], g2v[5];
-              double nv[5];
-              bool okv[5];
+        S.e_nx[lane] = nx;
+        S.e_ny[lane] = ny;
+        S.e_ns[lane] = nsamples;
+      }
+      __syncwarp();
+      const int ns0 = S.e_ns[0], ns1 = S.e_ns[1], ns2 = S.e_ns[2], ns3 = S.e_ns[3];
+      const int off1 = ns0, off2 = ns0 + ns1, off3 = ns0 + ns1 + ns2, total = off3 + ns3;
+      double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;  // lanes 0..3: sums of their edge
+      const int my_lo = lane == 0 ? 0 : (lane == 1 ? off1 : (lane == 2 ? off2 : off3));
+      const int my_hi = lane == 0 ? off1 : (lane == 1 ? off2 : (lane == 2 ? off3 : total));
+      for (int base = 0; base < total; base += kSampleChunk) {
+        const int lim = min(kSampleChunk, total - base);
+        for (int j = lane; j < lim; j += 32) {
+          const int g = base + j;
+          const int edge = (g >= off1) + (g >= off2) + (g >= off3);
+          const int s = g - (edge == 0 ? 0 : (edge == 1 ? off1 : (edge == 2 ? off2 : off3)));
+          const int nsamples = S.e_ns[edge];
+          const int a = edge, b = (edge + 1) & 3;
+          const float nx = S.e_nx[edge], ny = S.e_ny[edge];
+          const float pax = S.p[a][0], pay = S.p[a][1], pbx = S.p[b][0], pby = S.p[b][1];
+          const double alpha = (1.0 + s) / (nsamples + 1);
+          const double x0 = alpha * pax + (1 - alpha) * pbx;
+          const double y0 = alpha * pay + (1 - alpha) * pby;
+          double Mn = 0, Mcount = 0;
+          const double range = static_cast<double>(static_cast<float>(p.f)) + 1;
+          // n runs over -range, -range + 0.25, ..., range (multiples of 0.25: exact in double).  The two
+          // byte gathers of five consecutive n are issued together; the sums keep the order of n.
+          const int nt = static_cast<int>(8 * range) + 1;
+          for (int t0 = 0; t0 < nt; t0 += 5) {
+            int g1v[5], g2v[5];
+            double nv[5];
+            bool okv[5];
 #pragma unroll
-              for (int k = 0; k < 5; k++) {
-                const double n = -range + 0.25 * (t0 + k);
-                const double grange = 1;
-                const int x1 = static_cast<int>(x0 + (n + grange) * nx);
-                const int y1 = static_cast<int>(y0 + (n + grange) * ny);
-                const int x2 = static_cast<int>(x0 + (n - grange) * nx);
-                const int y2 = static_cast<int>(y0 + (n - grange) * ny);
-                const bool ok = (t0 + k < nt) && !(x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) && !(x2 < 0 || x2 >= W || y2 < 0 || y2 >= H);
-                nv[k] = n;
-                okv[k] = ok;
-                g1v[k] = ok ? im[static_cast<size_t>(y1) * W + x1] : 0;
-                g2v[k] = ok ? im[static_cast<size_t>(y2) * W + x2] : 0;
-              }
+            for (int k = 0; k < 5; k++) {
+              const double n = -range + 0.25 * (t0 + k);
+              const double grange = 1;
+              const int x1 = static_cast<int>(x0 + (n + grange) * nx);
+              const int y1 = static_cast<int>(y0 + (n + grange) * ny);
+              const int x2 = static_cast<int>(x0 + (n - grange) * nx);
+              const int y2 = static_cast<int>(y0 + (n - grange) * ny);
+              const bool ok = (t0 + k < nt) && !(x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) && !(x2 < 0 || x2 >= W || y2 < 0 || y2 >= H);
+              nv[k] = n;
+              okv[k] = ok;
+              g1v[k] = ok ? im[static_cast<size_t>(y1) * W + x1] : 0;
+              g2v[k] = ok ? im[static_cast<size_t>(y2) * W + x2] : 0;
+            }
 #pragma unroll
-              for (int k = 0; k < 5; k++) {
-                if (!okv[k] || g1v[k] < g2v[k]) continue;
-                const double weight = static_cast<double>((g2v[k] - g1v[k]) * (g2v[k] - g1v[k]));
-                Mn += weight * nv[k];
-                Mcount += weight;
-              }
-            }
-            uint8_t valid = 0;
-            double bestx = 0, besty = 0;
-            if (Mcount != 0) {
-              const double n0 = Mn / Mcount;
-              bestx = x0 + n0 * nx;
-              besty = y0 + n0 * ny;
-              undistort(&bestx, &besty, p);
-              valid = 1;
-            }
-            S.sx[j] = bestx;
-            S.sy[j] = besty;
-            S.sv[j] = valid;
-          }
-          __syncwarp();
-          if (lane == 0) {
-            for (int j = 0; j < lim; j++) {
-              if (!S.sv[j]) continue;
-              const double bx = S.sx[j], by = S.sy[j];
-              Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N++;
+            for (int k = 0; k < 5; k++) {
+              if (!okv[k] || g1v[k] < g2v[k]) continue;
+              const double weight = static_cast<double>((g2v[k] - g1v[k]) * (g2v[k] - g1v[k]));
+              Mn += weight * nv[k];
+              Mcount += weight;
             }
           }
-          __syncwarp();
+          uint8_t valid = 0;
+          double bestx = 0, besty = 0;
+          if (Mcount != 0) {
+            const double n0 = Mn / Mcount;
+            bestx = x0 + n0 * nx;
+            besty = y0 + n0 * ny;
+            undistort(&bestx, &besty, p);
+            valid = 1;
+          }
+          S.sx[j] = bestx;
+          S.sy[j] = besty;
+          S.sv[j] = valid;
         }
-        if (lane == 0) {
-          const double Ex = Mx / N, Ey = My / N;
-          const double Cxx = Mxx / N - Ex * Ex;
-          const double Cxy = Mxy / N - Ex * Ey;
-          const double Cyy = Myy / N - Ey * Ey;
-          const double normal_theta = .5 * atan2f(static_cast<float>(-2 * Cxy), static_cast<float>(Cyy - Cxx));
-          S.lines[edge][0] = Ex;
-          S.lines[edge][1] = Ey;
-          S.lines[edge][2] = cosf(static_cast<float>(normal_theta));
-          S.lines[edge][3] = sinf(static_cast<float>(normal_theta));
+        __syncwarp();
+        if (lane < 4) {  // this chunk's samples of my edge, in sample order
+          const int lo = max(base, my_lo) - base, hi = min(base + lim, my_hi) - base;
+          for (int j = lo; j < hi; j++) {
+            if (!S.sv[j]) continue;
+            const double bx = S.sx[j], by = S.sy[j];
+            Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N++;
+          }
         }
         __syncwarp();
       }
-      if (lane == 0) {
-        for (int i = 0; i < 4; i++) {
-          const double A00 = S.lines[i][3], A01 = -S.lines[(i + 1) & 3][3];
-          const double A10 = -S.lines[i][2], A11 = S.lines[(i + 1) & 3][2];
-          const double B0 = -S.lines[i][0] + S.lines[(i + 1) & 3][0];
-          const double B1 = -S.lines[i][1] + S.lines[(i + 1) & 3][1];
-          const double det = A00 * A11 - A10 * A01;
-          if (fabs(det) > 0.001) {
-            const double W00 = A11 / det, W01 = -A01 / det;
-            const double L0 = W00 * B0 + W01 * B1;
-            double px = S.lines[i][0] + L0 * A00;
-            double py = S.lines[i][1] + L0 * A10;
-            redistort(&px, &py, p);
-            S.p[(i + 1) & 3][0] = static_cast<float>(px);
-            S.p[(i + 1) & 3][1] = static_cast<float>(py);
-          }
+      if (lane < 4) {
+        const double Ex = Mx / N, Ey = My / N;
+        const double Cxx = Mxx / N - Ex * Ex;
+        const double Cxy = Mxy / N - Ex * Ey;
+        const double Cyy = Myy / N - Ey * Ey;
+        const double normal_theta = .5 * atan2f(static_cast<float>(-2 * Cxy), static_cast<float>(Cyy - Cxx));
+        S.lines[lane][0] = Ex;
+        S.lines[lane][1] = Ey;
+        S.lines[lane][2] = cosf(static_cast<float>(normal_theta));
+        S.lines[lane][3] = sinf(static_cast<float>(normal_theta));
+      }
+      __syncwarp();
+      if (lane < 4) {
+        const int i = lane;
+        const double A00 = S.lines[i][3], A01 = -S.lines[(i + 1) & 3][3];
+        const double A10 = -S.lines[i][2], A11 = S.lines[(i + 1) & 3][2];
+        const double B0 = -S.lines[i][0] + S.lines[(i + 1) & 3][0];
+        const double B1 = -S.lines[i][1] + S.lines[(i + 1) & 3][1];
+        const double det = A00 * A11 - A10 * A01;
+        if (fabs(det) > 0.001) {
+          const double W00 = A11 / det, W01 = -A01 / det;
+          const double L0 = W00 * B0 + W01 * B1;
+          double px = S.lines[i][0] + L0 * A00;
+          double py = S.lines[i][1] + L0 * A10;
+          redistort(&px, &py, p);
+          S.p[(i + 1) & 3][0] = static_cast<float>(px);
+          S.p[(i + 1) & 3][1] = static_cast<float>(py);
         }
       }
       __syncwarp();
