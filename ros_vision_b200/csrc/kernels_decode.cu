@@ -394,24 +394,24 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
     }
     for (int j = lane; j < 100; j += 32) S.values[j] = 0.0;
     __syncwarp();
-    if (lane == 0) {
-      GrayModel wm, bm;
+    if (lane < 2) {  // lane 0 fits the white model, lane 1 the black one (each sums its samples in order)
+      GrayModel m;
       for (int i = 0; i < 3; i++) {
-        for (int j = 0; j < 3; j++) { wm.A[i][j] = 0; bm.A[i][j] = 0; }
-        wm.B[i] = bm.B[i] = wm.C[i] = bm.C[i] = 0;
+        for (int j = 0; j < 3; j++) m.A[i][j] = 0;
+        m.B[i] = m.C[i] = 0;
       }
       for (int j = 0; j < 64; j++) {
         if (S.gm_v[j] < 0) continue;
         const int is_white = ((j >> 3) & 1) == 0;  // patterns alternate white, black
-        if (is_white) gm_add(&wm, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
-        else gm_add(&bm, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
+        if (is_white == (lane == 0)) gm_add(&m, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
       }
-      gm_solve(&wm);
-      gm_solve(&bm);
-      S.white = wm;
-      S.black = bm;
+      gm_solve(&m);
+      if (lane == 0) S.white = m; else S.black = m;
+    }
+    __syncwarp();
+    if (lane == 0) {
       const int reversed_border = 0;
-      S.ok = !((gm_interp(&wm, 0, 0) - gm_interp(&bm, 0, 0) < 0) != reversed_border);
+      S.ok = !((gm_interp(&S.white, 0, 0) - gm_interp(&S.black, 0, 0) < 0) != reversed_border);
     }
     __syncwarp();
     if (!S.ok) continue;
