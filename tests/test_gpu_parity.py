@@ -217,6 +217,25 @@ def test_host_block_enqueue(D, oracle):
         buf.close()
 
 
+def test_largest_coordinates(D, oracle):
+    """A 3840x2160 quad image (decimate 1): base coordinates up to 3839 exercise the 12-bit fields of the point,
+    segment and sort-key records."""
+    from ros_vision_b200 import synth
+    w, h = 3840, 2160
+    sc = synth.make_scene(w, h, 91, 6, side_range=(200, 500), noise_sigma=2.0)
+    det = D.GpuDetector(w, h, "gray", quad_decimate=1, keep_stages=True)
+    det.Detect(sc.gray)
+    assert det.FrameInfo().status == 0
+    orc = oracle.detect(oracle.make_config(w, h, "gray", 1, 0.0), sc.gray)
+    compare_front_end(det, orc, 0, "gray")
+    got = compare_detections(det, orc, 0)
+    assert len(got) >= 5
+    quads = det.FitQuads()
+    assert np.array_equal(quads["corners"], orc.corners["corners"]), "QuadCorners (bit-exact float)"
+    assert float(quads["corners"][:, :, 0].max()) > 2048  # the far side of the frame is really used
+    det.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
