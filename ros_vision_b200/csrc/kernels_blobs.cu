@@ -21,7 +21,7 @@ namespace b200tag {
 
 static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
-constexpr uint32_t kMediumCap = 768;    // blobs of 257..1024 points: 128-thread CTA, everything in shared memory
+constexpr uint32_t kMediumCap = 768;    // medium tier: 128-thread CTA, everything in shared memory
 
 // ---------------------------------------------------------------------------------------------
 // K7
@@ -232,15 +232,15 @@ __global__ void __launch_bounds__(256) k_cluster_finish(FrameParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9: blob -> quad.  Two tiers share one code path (template parameter GS = threads per blob):
-//   small blobs (<= 256 points, ~3/4 of all blobs): ONE WARP per blob, everything in shared
-//     memory, only __syncwarp between phases;
-//   large blobs: one 256-thread CTA per blob; sort / errors / peaks in shared memory up to 4096
-//     points, prefix moments in shared memory up to 1024 points, the rare bigger blob works in
-//     its own (L2-resident) segment of the global arrays.
-// Phases: bitonic angle sort -> weights + prefix moments -> windowed line-fit error -> 7-tap
-// smoothing -> peak list -> [one warp] 10 strongest peaks -> table of the <= 90 candidate side
-// fits -> [one warp] 210 corner combinations + argmin -> [4 lanes] lines and corners, quad tests.
+// K9: blob -> peak table.  Three tiers share one code path (template parameter GS = threads per blob):
+//   small  (<= kSmallBlobPoints = 192 points, most blobs): ONE WARP per blob, everything in shared memory,
+//          only __syncwarp between phases;
+//   medium (<= kMediumCap = 768 points): one 128-thread CTA per blob, everything in shared memory;
+//   large  : one 256-thread CTA per blob; sort / errors / peaks in shared memory up to kSortCap = 4096
+//          points with the prefix moments in the blob's own (L2-resident) global segment; the rare bigger
+//          blob works entirely in its segments of the global arrays.
+// Phases: extents + SelectBlobs -> angle keys + bucket sort -> weights + prefix moments -> windowed
+// line-fit error -> 7-tap smoothing -> peak list -> [one warp] 10 strongest peaks -> PeakTable for k_quads.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLargeThreads = 256;
 constexpr int kSmallWarps = 4;          // warps (= blobs in flight) per small-tier CTA
@@ -298,8 +298,8 @@ struct Mom {
 };
 
 // Prefix moments live either in global memory as b200tag_lfp records (large tiers) or, for blobs of at most
-// 1024 points, in shared memory as six separate arrays: Mxx/Myy/Mxy 64 bit, Mx/My/W 32 bit unsigned
-// (W <= 1024 * 362 and Mx, My <= W * 8192 < 2^32), 36 bytes per point instead of 48 and conflict-free.
+// 768 points, in shared memory as six separate arrays: Mxx/Myy/Mxy 64 bit, Mx/My/W 32 bit unsigned
+// (W <= 768 * 361 and Mx, My <= W * 8192 < 2^32), 36 bytes per point instead of 48 and conflict-free.
 struct LfStore {
   b200tag_lfp *aos;            // global records, or nullptr
   unsigned long long *m64;     // shared: [3][cap]
@@ -1151,10 +1151,10 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p
 }
 
 // ---- CTA tiers: one CTA per blob ----------------------------------------------------------------
-//   medium: 128 threads, blobs of 257..1024 points, everything in shared memory (3 CTAs per SM)
-//   large : 256 threads, blobs above 1024 points; sort / errors / peaks in shared memory up to 4096 points,
-//           prefix moments in the blob's own L2-resident segment
-// Both pull from the same work list and skip the blobs of the other tier.
+//   medium: 128 threads, blobs of 193..768 points, everything in shared memory (5 CTAs per SM)
+//   large : 256 threads, blobs above 768 points; sort / errors / peaks in shared memory up to 4096 points,
+//           prefix moments in the blob's own L2-resident segment (3 CTAs per SM)
+// k_select sorts the blobs into the tiers' work lists (medium from the front of large_list, large from its back).
 template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP>
 struct CtaShared {
   unsigned long long keys[KEY_CAP];
