@@ -760,17 +760,18 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   if (tid >= 32 && tid < kBpTH * 4) s_ebase[tid >> 2][tid & 3] += s_half;
   if (tid == 0) s_npts += s_half;
   __syncthreads();
-  {
-    const int tx = tid % kBpTW;
-    const unsigned long long below = (1ull << tx) - 1ull;
-    for (int ry = tid / kBpTW; ry < kBpTH; ry += kBpThreads / kBpTW) {
-      const uint32_t pix = static_cast<uint32_t>(ry * kBpTW + tx) << 3;
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        const unsigned long long e = s_emit[ry][d];
-        if ((e >> tx) & 1ull)
-          s_pts[s_ebase[ry][d] + __popcll(e & below)] = static_cast<uint16_t>(pix | (d << 1) | ((s_b2w[ry][d] >> tx) & 1ull));
-      }
+  {  // list entries: one thread per 16-bit quarter of an emission word walks its set bits (3 on average)
+    static_assert(kBpThreads == kBpTH * 4 * 4 && kBpTW == 64, "one thread per (row, direction, quarter)");
+    const int ry = tid >> 4, d = (tid >> 2) & 3, q = tid & 3;
+    const unsigned long long e = s_emit[ry][d];
+    uint32_t piece = static_cast<uint32_t>(e >> (16 * q)) & 0xffffu;
+    const uint32_t bw = static_cast<uint32_t>(s_b2w[ry][d] >> (16 * q));
+    uint32_t pos = s_ebase[ry][d] + __popcll(e & ((1ull << (16 * q)) - 1ull));
+    const uint32_t head = (static_cast<uint32_t>(ry * kBpTW + 16 * q) << 3) | (d << 1);
+    while (piece) {
+      const int b = __ffs(static_cast<int>(piece)) - 1;
+      piece &= piece - 1;
+      s_pts[pos++] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
     }
   }
   __syncthreads();
