@@ -85,7 +85,7 @@ static_assert(sizeof(Counters) == 128, "Counters layout");
 // What the fit kernels hand to k_quads for every blob with at least one peak: the (at most 10) strongest
 // peaks in position order and exactly the prefix-moment records ReadMoments (line_fit_filter.cu:745-796)
 // can touch for ranges between them -- lf[idx], lf[idx - 1] and lf[cnt - 1].
-struct PeakTable {
+struct alignas(16) PeakTable {  // 1072 bytes: a multiple of 16, moved with 16-byte accesses
   uint32_t blob, cnt, nsel, npk;
   uint32_t rep0, rep1;
   uint32_t idx[kMaxPeaks];
@@ -93,6 +93,7 @@ struct PeakTable {
   b200tag_lfp before[kMaxPeaks];  // lf[idx[k] - 1] (zero when idx[k] == 0)
   b200tag_lfp last;               // lf[cnt - 1]
 };
+static_assert(sizeof(PeakTable) % 16 == 0, "PeakTable is copied in 16-byte pieces");
 
 struct FrameParams {
   // geometry

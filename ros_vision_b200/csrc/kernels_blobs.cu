@@ -434,12 +434,12 @@ struct BlobScratch {
 };
 
 // Scratch of k_quads, one per warp.
-struct QuadScratch {
+struct alignas(16) QuadScratch {
   double seg_err[kMaxPeaks][kMaxPeaks];  // fit error of side (a -> b); kDblMax if mse > max_line_fit_mse
   double seg_nx[kMaxPeaks][kMaxPeaks], seg_ny[kMaxPeaks][kMaxPeaks];
   double lines[4][4];
   float corners[4][2];
-  PeakTable t;
+  alignas(16) PeakTable t;
 };
 
 // nested-loop (Unrank) order of the C(10,4) corner choices, line_fit_filter.cu:709-728
@@ -951,10 +951,17 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
   const PeakTable *tables = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap;
   for (uint32_t fq = blockIdx.x * kQuadWarps + (threadIdx.x >> 5); fq < nfq; fq += gridDim.x * kQuadWarps) {
     __syncwarp();
-    {  // the table into shared memory, 8 bytes per lane and trip
-      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(tables + fq);
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&S.t);
-      for (uint32_t i = lane; i < sizeof(PeakTable) / 8; i += 32) dst[i] = __ldcg(src + i);
+    {  // the table into shared memory: every lane issues all of its 16-byte loads before the first store
+      constexpr uint32_t kPieces = sizeof(PeakTable) / 16, kPer = (kPieces + 31) / 32;
+      const uint4 *src = reinterpret_cast<const uint4 *>(tables + fq);
+      uint4 *dst = reinterpret_cast<uint4 *>(&S.t);
+      uint4 v[kPer];
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; k++)
+        if (lane + 32 * k < kPieces) v[k] = __ldcg(src + lane + 32 * k);
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; k++)
+        if (lane + 32 * k < kPieces) dst[lane + 32 * k] = v[k];
     }
     __syncwarp();
     const PeakTable &T = S.t;

@@ -514,7 +514,9 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
 
 int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
   if (kt) kt->begin("decode", s);
-  k_decode<<<dim3(148, frames), 32, 0, s>>>(p);
+  // one warp per CTA; about 2400 CTAs in total (a frame has ~100 candidate quads), all 148 SMs for a single frame
+  const unsigned per_frame = static_cast<unsigned>(frames) >= 16 ? (2368u + frames - 1) / frames : 148u;
+  k_decode<<<dim3(per_frame < 8u ? 8u : per_frame, frames), 32, 0, s>>>(p);
   if (kt) kt->end(s);
   return 1;
 }

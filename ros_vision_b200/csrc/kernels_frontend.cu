@@ -317,18 +317,20 @@ __device__ __forceinline__ uint32_t sfind(uint32_t *par, uint32_t a) {
   return a;
 }
 
-__device__ __forceinline__ void sunite(uint32_t *par, uint32_t a, uint32_t b) {
+// Unites the trees of a and b (any nodes of them) and returns the root of the result as seen by this thread --
+// a valid starting point for the caller's next union on the same run.
+__device__ __forceinline__ uint32_t sunite(uint32_t *par, uint32_t a, uint32_t b) {
   while (true) {
     a = sfind(par, a);
     b = sfind(par, b);
-    if (a == b) return;
+    if (a == b) return a;
     if (a < b) {
       const uint32_t t = a;
       a = b;
       b = t;
     }
     const uint32_t old = atomicMin(&par[a], b);
-    if (old == a) return;
+    if (old == a) return b;
     a = old;
   }
 }
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
       const uint32_t run = bit_span(s, len);
       m &= ~run;
       uint32_t ov = up & (colour ? (run | (run << 1) | (run >> 1)) : run);
-      const uint32_t node = row * kCclTW + s;
+      uint32_t node = row * kCclTW + s;  // replaced by its current root after every union: later finds start there
       while (ov) {
         const int bpos = __ffs(static_cast<int>(ov)) - 1;
         const uint32_t below = ~up & ((1u << bpos) - 1u);
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
         const uint32_t above = ~up >> bpos;
         const int ulen = above ? __ffs(static_cast<int>(above)) - 1 : 32 - bpos;
         ov &= ~bit_span(bpos, ulen);
-        sunite(s_par, node, (row - 1) * kCclTW + us);
+        node = sunite(s_par, node, (row - 1) * kCclTW + us);
       }
     }
   }
