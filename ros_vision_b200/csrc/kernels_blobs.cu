@@ -506,7 +506,6 @@ struct BlobWork {
 };
 
 constexpr uint32_t kMaxBucketLoad = 24;  // fuller buckets (thin, elongated blobs) fall back to the bitonic network
-constexpr uint32_t kThetaSpan = 50265483u;  // theta = llrintf((atan2f + pi) * 8e6) < 2 * pi * 8e6 + 1
 
 // GS = threads per blob; AOS = prefix moments as records in global memory (else shared-memory arrays);
 // KEEP = also write the debug stage arrays (keep_stages) -- separate instantiations, so the production
@@ -580,6 +579,9 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     uint32_t N = 1;
     while (N < cnt) N <<= 1;
     const uint32_t B = min(N, wk.hist_cap);
+    // bucket = theta >> bk_shift: theta < 2 * pi * 8e6 + 1 < 2^26, so the B power-of-two buckets cover [0, 2^26) and
+    // three quarters of them are in use (average load <= 4/3); a shift instead of a 64-bit multiply and divide
+    const uint32_t bk_shift = 26u - (31u - static_cast<uint32_t>(__clz(static_cast<int>(B))));
     for (uint32_t i = gt; i < B; i += GS) wk.hist[i] = 0;
     if (gt == 0) S.npeaks = 0;
     gsync<GS>();
@@ -594,7 +596,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       long long ti = llrintf(theta);
       if (ti < 0) ti = 0;
       const uint32_t th = static_cast<uint32_t>(ti & 0xfffffff);
-      const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(th) * B / kThetaSpan));
+      const uint32_t bk = (th >> bk_shift);
       th_tmp[i] = th;
       rk_tmp[i] = atomicAdd(&wk.hist[bk], 1u);
     }
@@ -640,7 +642,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       gsync<GS>();
       for (uint32_t i = gt; i < cnt; i += GS) {
         const uint32_t v = raw[i], th = th_tmp[i];
-        const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(th) * B / kThetaSpan));
+        const uint32_t bk = (th >> bk_shift);
         wk.keys[wk.hist[bk] + rk_tmp[i]] = pack_sort_key(th, sp_dir(v), sp_by(v), sp_bx(v));
       }
       gsync<GS>();
@@ -657,7 +659,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
           preg[j] = 0xffffffffu;
           if (q < cnt) {
             const unsigned long long key = wk.keys[q];
-            const uint32_t bk = min(B - 1, static_cast<uint32_t>(static_cast<unsigned long long>(key_theta(key)) * B / kThetaSpan));
+            const uint32_t bk = (key_theta(key) >> bk_shift);
             const uint32_t lo = wk.hist[bk], hi = (bk + 1 < B) ? wk.hist[bk + 1] : cnt;
             uint32_t pos = lo;
 #pragma unroll 1
@@ -1168,7 +1170,8 @@ struct CtaShared {
   unsigned long long lf64[LF_CAP > 0 ? 3 * LF_CAP : 1];  // prefix moments (LfStore); bucket-sort scratch before that
   uint32_t lf32[LF_CAP > 0 ? 3 * LF_CAP : 1];
   alignas(16) float errs[KEY_CAP];  // also holds 8-byte peak keys
-  long long scan[6 * THREADS];
+  // warp totals of the prefix scan; in the large tier also the bucket counters of the angle sort (KEY_CAP words)
+  long long scan[(LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP / 2 : 6 * THREADS];
   BlobScratch scratch;
 };
 
@@ -1184,7 +1187,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(tier == 0 ? ctr->num_medium : ctr->num_large, p.blob_cap);
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
-  constexpr uint32_t kScanHist = (6u * THREADS * 2u >= 2048u) ? 2048u : ((6u * THREADS * 2u >= 1024u) ? 1024u : 512u);
+  constexpr uint32_t kScanHist = (LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP : ((6u * THREADS * 2u >= 2048u) ? 2048u : 1024u);
   uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
   uint32_t nxt = 0;
   if (tid == 0) nxt = atomicAdd(next, 1u);
