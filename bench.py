@@ -401,7 +401,7 @@ def run_ours(args):
              for _ in range(L)]
     # one pinned block holding the batch back to back, as a camera ring buffer would (the engine then moves each
     # lane's frames with a single host->device copy)
-    pinned = [D.PinnedBuffer(frame_bytes * B)]
+    pinned = [D.PinnedBuffer(frame_bytes * B, write_combined=args.wc)]
     pinned[0].array[:] = host_batch.reshape(-1)
     ptrs = [pinned[0].ptr + i * frame_bytes for i in range(B)]
     lane_ptrs = [ptrs[l * per_lane] for l in range(L)]
@@ -532,6 +532,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="detector instances (CUDA streams) used by the end-to-end leg")
     ap.add_argument("--device-lanes", type=int, default=2,
                     help="detector instances (CUDA streams) taking turns in the device-resident leg")
+    ap.add_argument("--wc", action="store_true", help="write-combined pinned frame buffer in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU / reference-GPU reporting legs (profiling runs)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config to measure; the contract line is config 2 (the default)")

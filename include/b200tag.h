@@ -241,6 +241,10 @@ int b200tag_estimate_poses(const b200tag_detection *dets, int count, double tags
 
 /* Pinned host staging memory, so b200tag_detect* can overlap H2D with compute. */
 void *b200tag_alloc_pinned(size_t bytes);
+/* Write-combined pinned memory: for buffers the CPU (or a capture driver) only ever WRITES, such as a camera ring
+ * buffer; the DMA engine reads it without snooping the CPU caches, which matters when several GPUs pull frames from
+ * the same host at once.  CPU reads from it are slow.  Free with b200tag_free_pinned. */
+void *b200tag_alloc_pinned_wc(size_t bytes);
 void b200tag_free_pinned(void *p);
 
 /* Number of this library's kernels launched per frame batch (for benchmarks' gpu_launches). */

@@ -754,6 +754,15 @@ void *b200tag_alloc_pinned(size_t bytes) {
   return p;
 }
 
+void *b200tag_alloc_pinned_wc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
 void b200tag_free_pinned(void *p) {
   if (p) cudaFreeHost(p);
 }

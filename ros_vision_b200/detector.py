@@ -111,6 +111,8 @@ def load_library():
     L.b200tag_undistort.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)] + [C.c_double] * 9
     L.b200tag_alloc_pinned.argtypes = [sz]
     L.b200tag_alloc_pinned.restype = vp
+    L.b200tag_alloc_pinned_wc.argtypes = [sz]
+    L.b200tag_alloc_pinned_wc.restype = vp
     L.b200tag_free_pinned.argtypes = [vp]
     L.b200tag_free_pinned.restype = None
     L.b200tag_kernels_per_batch.argtypes = [vp]
@@ -152,9 +154,9 @@ def estimate_poses(detections: np.ndarray, tagsize: float, fx: float, fy: float,
 class PinnedBuffer:
     """Page-locked host staging memory (numpy view), for the host->device leg of Detect."""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, write_combined: bool = False):
         self._lib = load_library()
-        self.ptr = self._lib.b200tag_alloc_pinned(nbytes)
+        self.ptr = (self._lib.b200tag_alloc_pinned_wc if write_combined else self._lib.b200tag_alloc_pinned)(nbytes)
         if not self.ptr:
             raise B200TagError("b200tag_alloc_pinned failed")
         self.nbytes = nbytes
