@@ -447,9 +447,9 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   det->in_bytes = N * bpp;
   if (cfg->format == B200TAG_FMT_GRAY8) { p.gray = det->d_in; p.gray_stride = in_stride; }
   else { p.gray = base + o_gray; p.gray_stride = N; }
-  p.quad = base + o_quad; p.quad_stride = n;
+  p.quad = base + o_quad;
   p.quad_tmp = p.blur_ksz ? base + o_quad_tmp : nullptr;
-  p.minmax_raw = base + o_mmr; p.minmax_stride = tiles * 2;
+  p.minmax_raw = base + o_mmr;
   p.minmax = base + o_mm;
   p.thresh = base + o_th;
   p.labels = reinterpret_cast<uint32_t *>(base + o_lab);

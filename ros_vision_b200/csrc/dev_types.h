@@ -123,12 +123,12 @@ struct FrameParams {
   // buffers (frame 0) and per-frame strides in elements
   const uint8_t *in;    size_t in_stride;
   uint8_t *gray;        size_t gray_stride;      // W*H (aliases `in` for GRAY8)
-  uint8_t *quad;        size_t quad_stride;      // w*h
+  uint8_t *quad;                                  // w*h
   uint8_t *quad_tmp;                              // w*h, blur scratch (same stride)
-  uint8_t *minmax_raw;  size_t minmax_stride;    // tiles*2
+  uint8_t *minmax_raw;                            // tiles*2
   uint8_t *minmax;                                // tiles*2 filtered (keep_stages)
-  uint8_t *thresh;                                // w*h (quad_stride)
-  uint32_t *labels;                               // w*h (quad_stride)
+  uint8_t *thresh;                                // w*h
+  uint32_t *labels;                               // w*h
   uint32_t *sizes;                                // w*h
   uint64_t *points;     // point_cap
   // blob-pair hash (hash_cap each): key and point count; extents are computed per blob later

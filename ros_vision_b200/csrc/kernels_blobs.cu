@@ -414,15 +414,6 @@ __device__ __forceinline__ uint32_t float_order(float f) {  // monotone float ->
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr double kDblMax = 1.7976931348623157e308;
 
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = t < v ? t : v;
-  }
-  return v;
-}
-
 // Per-blob scratch of the fit kernels (always in shared memory).
 struct BlobScratch {
   uint32_t peak_idx[kMaxPeaks];
