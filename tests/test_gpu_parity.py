@@ -236,6 +236,38 @@ def test_largest_coordinates(D, oracle):
     det.close()
 
 
+def test_random_scenes(D, oracle):
+    """Forty random frames -- sizes, formats, decimation, noise level, tag count and size all drawn at random --
+    every stage against the oracle.  Rare paths (equal angles, crowded buckets, blobs on tile corners) get their
+    chance here."""
+    from ros_vision_b200 import synth
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    for k in range(40):
+        dec = int(rng.choice([1, 2, 2, 2, 3]))
+        w = int(rng.integers(12, 60)) * 8 * dec
+        h = int(rng.integers(10, 44)) * 8 * dec
+        w, h = (w // (4 * dec)) * 4 * dec, (h // (4 * dec)) * 4 * dec
+        fmt = str(rng.choice(["gray", "yuyv", "bgr"]))
+        if fmt == "yuyv":
+            w = (w // 8) * 8
+            if (w // dec) % 4:
+                continue
+        ntags = int(rng.integers(0, 5))
+        smax = max(24.0, min(w, h) / 2.5)
+        sc = synth.make_scene(w, h, 7000 + k, ntags, side_range=(min(20.0 * dec, smax), smax),
+                              noise_sigma=float(rng.uniform(0.0, 8.0)), clutter=bool(rng.integers(0, 2)),
+                              salt_pepper=float(rng.choice([0.0, 0.0, 0.01])))
+        frame = _pack(sc.gray, fmt, np.random.default_rng(k))
+        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, 0.0), frame)
+        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, keep_stages=True)
+        det.Detect(frame)
+        compare_all(det, orc, 0, fmt)
+        det.close()
+        checked += 1
+    assert checked >= 30
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
