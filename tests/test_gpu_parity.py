@@ -268,6 +268,34 @@ def test_random_scenes(D, oracle):
     assert checked >= 30
 
 
+def test_production_variant_matches_oracle(D, oracle):
+    """keep_stages = 0 (what the node and bench.py run: the kernel variants without any debug-stage code, no cluster
+    extents pass): quads and detections against the oracle, single frames and a batch, with and without CUDA graphs."""
+    import os
+    from ros_vision_b200 import synth
+    w, h = 1280, 800
+    frames = [synth.config_frame(2, i)[0] for i in range(6)]
+    orcs = [oracle.detect(oracle.make_config(w, h, "yuyv", 2, 0.0), f) for f in frames]
+    for no_graph in ("0", "1"):
+        os.environ["B200TAG_NO_GRAPH"] = no_graph
+        try:
+            det = D.GpuDetector(w, h, "yuyv", max_batch=8)
+        finally:
+            os.environ.pop("B200TAG_NO_GRAPH", None)
+        for rounds in range(2):  # the second round replays the captured graph
+            det.DetectBatch(frames)
+            for i, orc in enumerate(orcs):
+                compare_detections(det, orc, i)
+                quads = det.FitQuads(i)
+                assert np.array_equal(quads["corners"], orc.corners["corners"]), "QuadCorners (bit-exact float)"
+                info = det.FrameInfo(i)
+                assert info.num_points == len(orc.points) and info.num_blobs == int(orc.clusters["selected"].sum())
+                assert info.num_selected_points == len(orc.spoints) and info.num_fit_quads == len(orc.fitquads)
+        det.Detect(frames[3])
+        compare_detections(det, orcs[3], 0)
+        det.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
