@@ -58,7 +58,13 @@ def select_config(cfg: int):
 
 def make_frames(n_unique=None):
     from ros_vision_b200 import synth
-    return [np.ascontiguousarray(synth.config_frame(CONFIG, i)[0]).reshape(-1) for i in range(n_unique or UNIQUE_FRAMES)]
+    out = []
+    for i in range(n_unique or UNIQUE_FRAMES):
+        frame, fmt, w, h, dec, sigma, sc = synth.config_frame(CONFIG, i)
+        if fmt != FMT:  # --format: the same scene in another pixel format (e.g. the node's bgr8 frames)
+            frame = {"gray": lambda g: g, "yuyv": synth.gray_to_yuyv, "bgr": synth.gray_to_bgr}[FMT](sc.gray)
+        out.append(np.ascontiguousarray(frame).reshape(-1))
+    return out
 
 
 def algorithmic_bytes_per_frame(points_per_frame: float) -> float:
@@ -78,6 +84,7 @@ def kernel_bytes(name: str, P: float, tiers: dict) -> float:
         "pre_yuyv_dec2": 2 * N + N + n + n / 8,
         "pre_generic": bpp * N + (N if FMT != "gray" else 0) + n + n / 8,
         "pre_bgr_dec1": 3 * N + N + n,
+        "pre_bgr_dec2": 3 * N + N + n + n / 8,
         "blur": n + n,
         "tile_minmax": n + n / 8,
         "threshold": n + n / 8 + n,
@@ -471,7 +478,7 @@ def run_ours(args):
         if t:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
             traffic_src = f"profiles/summary_{t['tag']}.md ({t['report']})"
-    fe_names = {"pre_yuyv_dec2", "pre_gray_dec2", "pre_bgr_dec1", "pre_generic", "blur", "tile_minmax", "threshold",
+    fe_names = {"pre_yuyv_dec2", "pre_gray_dec2", "pre_bgr_dec1", "pre_bgr_dec2", "pre_generic", "blur", "tile_minmax", "threshold",
                 "ccl_local", "ccl_merge", "ccl_final", "boundary", "select", "scatter"}
     fe = [k for k in kern if k["kernel"] in fe_names]
     fe_ms, fe_bytes = sum(k["ms"] for k in fe), sum(k["alg_bytes"] for k in fe)
@@ -536,8 +543,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU / reference-GPU reporting legs (profiling runs)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config to measure; the contract line is config 2 (the default)")
+    ap.add_argument("--format", default=None, choices=["gray", "yuyv", "bgr"],
+                    help="pixel format of the frames (default: the config's own; the contract line is YUYV)")
     args = ap.parse_args()
     select_config(args.config)
+    if args.format:
+        global FMT, WORKLOAD
+        if args.format != FMT:
+            WORKLOAD += f" [frames delivered as {args.format}]"
+        FMT = args.format
     if args.batch == 128 and args.config != 2:
         args.batch = BATCH
     if args.impl == "reference":

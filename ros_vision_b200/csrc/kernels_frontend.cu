@@ -100,6 +100,62 @@ __device__ __forceinline__ uint8_t luma_of(const uint8_t *in, int fmt, size_t i)
   return static_cast<uint8_t>((4211 * r + 8258 * g + 1606 * b + (1 << 13) + (16 << 14)) >> 14);
 }
 
+// K1 for BGR8 input, decimate 2 -- the node's own frames (sensor_msgs bgr8, quad_decimate 2,
+// apriltags_cuda_detector.cu:399-404) without the CPU cvtColor: one thread = one threshold tile = 8x8 input
+// pixels = 24 bytes per row, read as three 8-byte words; luma as cv::COLOR_BGR2YUV_YUYV computes it.
+__global__ void __launch_bounds__(128) k_pre_bgr_dec2(FrameParams p) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (tx >= p.tiles_x) return;
+  const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
+  const uint8_t *in = p.in + frame * p.in_stride;
+  uint8_t *gray = p.gray + frame * N;
+  uint8_t *quad = p.quad + frame * n;
+  uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    uint2 v[4][3];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const size_t row = static_cast<size_t>(ty) * 8 + half * 4 + r;
+      const uint2 *src = reinterpret_cast<const uint2 *>(in + (row * p.W + static_cast<size_t>(tx) * 8) * 3);
+      v[r][0] = __ldcs(src);
+      v[r][1] = __ldcs(src + 1);
+      v[r][2] = __ldcs(src + 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const size_t row = static_cast<size_t>(ty) * 8 + half * 4 + r;
+      const uint32_t wds[6] = {v[r][0].x, v[r][0].y, v[r][1].x, v[r][1].y, v[r][2].x, v[r][2].y};
+      uint32_t out[2] = {0, 0};
+#pragma unroll
+      for (int px = 0; px < 8; px++) {
+        const int byte = px * 3;
+        const uint32_t bb = (wds[byte >> 2] >> ((byte & 3) * 8)) & 0xff;
+        const uint32_t gg = (wds[(byte + 1) >> 2] >> (((byte + 1) & 3) * 8)) & 0xff;
+        const uint32_t rr = (wds[(byte + 2) >> 2] >> (((byte + 2) & 3) * 8)) & 0xff;
+        const uint32_t y = (4211u * rr + 8258u * gg + 1606u * bb + (1u << 13) + (16u << 14)) >> 14;
+        out[px >> 2] |= y << (8 * (px & 3));
+      }
+      *reinterpret_cast<uint2 *>(gray + row * p.W + static_cast<size_t>(tx) * 8) = make_uint2(out[0], out[1]);
+      if ((r & 1) == 0) {
+        const uint32_t d = __byte_perm(out[0], out[1], 0x6420);
+        const size_t qrow = static_cast<size_t>(ty) * 4 + half * 2 + (r >> 1);
+        *reinterpret_cast<uint32_t *>(quad + qrow * p.w + static_cast<size_t>(tx) * 4) = d;
+        mn = __vminu4(mn, d);
+        mx = __vmaxu4(mx, d);
+      }
+    }
+  }
+  mn = __vminu4(mn, mn >> 16);
+  mn = __vminu4(mn, mn >> 8);
+  mx = __vmaxu4(mx, mx >> 16);
+  mx = __vmaxu4(mx, mx >> 8);
+  uint8_t *mm = p.minmax_raw + (frame * static_cast<size_t>(p.tiles_x) * p.tiles_y + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+  *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn & 0xff, mx & 0xff);
+}
+
 // K1 generic: any format, any integer decimation.  One thread = one threshold tile
 // (4f x 4f full-res pixels).  `dst_quad` is quad_tmp when a blur follows.
 __global__ void __launch_bounds__(128) k_pre_generic(FrameParams p, int write_minmax) {
@@ -863,6 +919,11 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   if (p.fmt == B200TAG_FMT_YUYV && p.f == 2 && !p.blur_ksz) {
     if (kt) kt->begin("pre_yuyv_dec2", s);
     k_pre_yuyv_dec2<<<tgrid, 128, 0, s>>>(p);
+    if (kt) kt->end(s);
+    launches++;
+  } else if (p.fmt == B200TAG_FMT_BGR8 && p.f == 2 && !p.blur_ksz && (reinterpret_cast<uintptr_t>(p.in) | p.in_stride) % 8 == 0) {
+    if (kt) kt->begin("pre_bgr_dec2", s);
+    k_pre_bgr_dec2<<<tgrid, 128, 0, s>>>(p);
     if (kt) kt->end(s);
     launches++;
   } else if (p.fmt == B200TAG_FMT_GRAY8 && p.f == 2 && !p.blur_ksz && (reinterpret_cast<uintptr_t>(p.in) | p.in_stride) % 8 == 0) {
