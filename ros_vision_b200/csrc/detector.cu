@@ -483,7 +483,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
     return true;
   };
   if (!ck(cudaStreamCreateWithFlags(&det->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(B200TAG_E_CUDA);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     if (!ck(cudaStreamCreateWithFlags(&det->side.s[i], cudaStreamNonBlocking), "cudaStreamCreate(side)")) return fail(B200TAG_E_CUDA);
     if (!ck(cudaEventCreateWithFlags(&det->side.join[i], cudaEventDisableTiming), "cudaEventCreate")) return fail(B200TAG_E_CUDA);
   }
@@ -519,7 +519,7 @@ void b200tag_destroy(b200tag_detector *det) {
     drop_graphs(det);
     cudaStreamDestroy(det->stream);
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     if (det->side.s[i]) cudaStreamDestroy(det->side.s[i]);
     if (det->side.join[i]) cudaEventDestroy(det->side.join[i]);
   }

@@ -75,7 +75,9 @@ struct Counters {  // one per frame, zeroed before each frame
   uint32_t num_selected_blobs;  // candidates that also pass SelectBlobs' extent / polarity tests
   uint32_t num_medium;          // candidates of the medium tier (front of large_list)
   uint32_t num_large;           // candidates of the large tier (back of large_list)
-  uint32_t pad[15];
+  uint32_t num_huge;            // candidates above the large tier's shared-memory capacity (back of small_list)
+  uint32_t next_huge;
+  uint32_t pad[13];
 };
 __host__ __device__ inline uint32_t alloc_clusters(unsigned long long a) { return static_cast<uint32_t>(a >> 40); }
 __host__ __device__ inline uint32_t alloc_blobs(unsigned long long a) { return static_cast<uint32_t>(a >> 20) & 0xfffffu; }

@@ -46,8 +46,8 @@ struct KernelTimer {
 // Side streams + events that let the three independent blob-tier kernels run concurrently (fork after the
 // scatter, join before the quad search).  Owned by the detector; null = everything on the main stream.
 struct SideStreams {
-  cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
 };
 
 // Each returns the number of kernels it launched.

@@ -22,6 +22,7 @@ namespace b200tag {
 static inline unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
 constexpr uint32_t kMediumCap = 768;    // medium tier: 128-thread CTA, everything in shared memory
+constexpr uint32_t kSortCap = 4096;     // large tier: points sorted / filtered in shared memory
 
 // ---------------------------------------------------------------------------------------------
 // K7
@@ -50,9 +51,9 @@ __device__ __forceinline__ bool select_blob(const FrameParams &p, uint32_t count
 // (apriltag_gpu.cu:536-541) are applied here; the extent and polarity tests need the blob's
 // points and run at the top of the fit kernels.
 __global__ void __launch_bounds__(256) k_select(FrameParams p) {
-  __shared__ uint32_t s_warp[8][5];  // per-warp totals: occupied, candidates, small, points, medium
+  __shared__ uint32_t s_warp[8][6];  // per-warp totals: occupied, candidates, small, points, medium, huge
   __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_pbase, s_mbase, s_lbase;
+  __shared__ uint32_t s_pbase, s_mbase, s_lbase, s_hbase;
   const int frame = blockIdx.y;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
   Counters *ctr = p.counters + frame;
@@ -87,10 +88,12 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
     }
     const bool small = sel && rec.count <= kSmallBlobPoints;
     const bool medium = sel && !small && rec.count <= kMediumCap;
+    const bool huge = sel && rec.count > kSortCap;
     const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
     const uint32_t sel_mask = __ballot_sync(0xffffffffu, sel);
     const uint32_t small_mask = __ballot_sync(0xffffffffu, small);
     const uint32_t medium_mask = __ballot_sync(0xffffffffu, medium);
+    const uint32_t huge_mask = __ballot_sync(0xffffffffu, huge);
     uint32_t incl = sel ? rec.count : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -104,28 +107,31 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       s_warp[warp][2] = __popc(small_mask);
       s_warp[warp][3] = warp_pts;
       s_warp[warp][4] = __popc(medium_mask);
+      s_warp[warp][5] = __popc(huge_mask);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
       for (int w = 0; w < 8; w++) {
-        const uint32_t a0 = s_warp[w][0], a1 = s_warp[w][1], a2 = s_warp[w][2], a3 = s_warp[w][3], a4 = s_warp[w][4];
-        s_warp[w][0] = t0; s_warp[w][1] = t1; s_warp[w][2] = t2; s_warp[w][3] = t3; s_warp[w][4] = t4;  // exclusive prefixes
-        t0 += a0; t1 += a1; t2 += a2; t3 += a3; t4 += a4;
+        const uint32_t a0 = s_warp[w][0], a1 = s_warp[w][1], a2 = s_warp[w][2], a3 = s_warp[w][3], a4 = s_warp[w][4], a5 = s_warp[w][5];
+        s_warp[w][0] = t0; s_warp[w][1] = t1; s_warp[w][2] = t2; s_warp[w][3] = t3; s_warp[w][4] = t4; s_warp[w][5] = t5;  // exclusive prefixes
+        t0 += a0; t1 += a1; t2 += a2; t3 += a3; t4 += a4; t5 += a5;
       }
       unsigned long long base = 0;
-      uint32_t pb = 0, mb = 0, lb = 0;
+      uint32_t pb = 0, mb = 0, lb = 0, hb = 0;
       if (t0) {
         const unsigned long long add = (static_cast<unsigned long long>(t0) << 40) | (static_cast<unsigned long long>(t1) << 20) | t2;
         base = atomicAdd(&ctr->alloc, add);
         if (t3) pb = atomicAdd(&ctr->num_seg_points, t3);
         if (t4) mb = atomicAdd(&ctr->num_medium, t4);
-        if (t1 - t2 - t4) lb = atomicAdd(&ctr->num_large, t1 - t2 - t4);
+        if (t1 - t2 - t4 - t5) lb = atomicAdd(&ctr->num_large, t1 - t2 - t4 - t5);
+        if (t5) hb = atomicAdd(&ctr->num_huge, t5);
       }
       s_base = base;
       s_pbase = pb;
       s_mbase = mb;
       s_lbase = lb;
+      s_hbase = hb;
     }
     __syncthreads();
     const unsigned long long base = s_base;
@@ -137,8 +143,11 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
       const uint32_t bw = s_warp[warp][1] + __popc(sel_mask & ((1u << lane) - 1u));    // rank among this CTA's blobs
       const uint32_t sw = s_warp[warp][2] + __popc(small_mask & ((1u << lane) - 1u));  // ... among its small blobs
       const uint32_t mw = s_warp[warp][4] + __popc(medium_mask & ((1u << lane) - 1u)); // ... among its medium blobs
-      // the CTA tiers share one array: medium blobs fill it from the front, large blobs from the back
-      const uint32_t cta_pos = medium ? s_mbase + mw : p.blob_cap - 1u - (s_lbase + (bw - sw - mw));
+      const uint32_t hw = s_warp[warp][5] + __popc(huge_mask & ((1u << lane) - 1u));   // ... among its huge blobs
+      // two arrays, four lists: small blobs fill small_list from the front, huge ones from its back;
+      // medium blobs fill large_list from the front, large ones from its back
+      const uint32_t cta_pos = medium ? s_mbase + mw
+                             : (huge ? p.blob_cap - 1u - (s_hbase + hw) : p.blob_cap - 1u - (s_lbase + (bw - sw - mw - hw)));
       const uint32_t b = bbase + bw;
       const uint32_t off = s_pbase + s_warp[warp][3] + incl - rec.count;
       if (b < p.blob_cap && static_cast<uint64_t>(off) + rec.count <= p.point_cap) {
@@ -146,6 +155,7 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
         blobs[b] = rec;
         seg_off = off;
         if (small) small_list[sbase + sw] = b;
+        else if (huge) small_list[cta_pos] = b;
         else large_list[cta_pos] = b;
       } else {
         atomicOr(&ctr->status, B200TAG_ST_BLOBS_OVERFLOW);
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
         if (small) {
           if (sbase + sw < p.blob_cap) small_list[sbase + sw] = 0xffffffffu;
         } else if (cta_pos < p.blob_cap) {
-          large_list[cta_pos] = 0xffffffffu;
+          (huge ? small_list : large_list)[cta_pos] = 0xffffffffu;
         }
       }
     }
@@ -244,7 +254,6 @@ __global__ void __launch_bounds__(256) k_cluster_finish(FrameParams p) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kLargeThreads = 256;
 constexpr int kSmallWarps = 4;          // warps (= blobs in flight) per small-tier CTA
-constexpr uint32_t kSortCap = 4096;     // large tier: points sorted / filtered in shared memory
 
 template <int GS>
 __device__ __forceinline__ void gsync() {
@@ -417,8 +426,8 @@ constexpr double kDblMax = 1.7976931348623157e308;
 // Per-blob scratch of the fit kernels (always in shared memory).
 struct BlobScratch {
   uint32_t peak_idx[kMaxPeaks];
-  uint32_t red_u[8][4];  // per-warp partial extents (CTA tiers)
-  int red_i[8][3];
+  uint32_t red_u[16][4];  // per-warp partial extents (CTA tiers, up to 512 threads)
+  int red_i[16][3];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
   uint32_t cur;      // blob being processed
@@ -1175,11 +1184,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   const int tid = threadIdx.x;
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t *list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t nlist = min(tier == 0 ? ctr->num_medium : ctr->num_large, p.blob_cap);
+  // tier 0: medium (front of large_list), 1: large (back of large_list), 2: huge (back of small_list)
+  const uint32_t *list = (tier == 2 ? p.small_list : p.large_list) + static_cast<size_t>(frame) * p.blob_cap;
+  const uint32_t nlist = min(tier == 0 ? ctr->num_medium : (tier == 1 ? ctr->num_large : ctr->num_huge), p.blob_cap);
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
   constexpr uint32_t kScanHist = (LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP : ((6u * THREADS * 2u >= 2048u) ? 2048u : 1024u);
-  uint32_t *next = tier == 0 ? &ctr->next_medium : &ctr->next_large;
+  uint32_t *next = tier == 0 ? &ctr->next_medium : (tier == 1 ? &ctr->next_large : &ctr->next_huge);
   uint32_t nxt = 0;
   if (tid == 0) nxt = atomicAdd(next, 1u);
   while (true) {
@@ -1230,7 +1240,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
 #define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
-#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, 0xffffffffu, 3, KEEP>
+#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, kSortCap, 3, KEEP>
+// huge: 512 threads, blobs above 4096 points (clutter, image-spanning edges); keys / errors / peaks in shared memory up
+// to 8192 points (one CTA per SM), beyond that in place in the global arrays
+constexpr int kHugeThreads = 512;
+constexpr uint32_t kHugeCap = 8192;
+using HugeShared = CtaShared<kHugeThreads, kHugeCap, 0>;
+#define K_FIT_HUGE(KEEP) k_fit_cta<kHugeThreads, kHugeCap, 0, kSortCap + 1, 0xffffffffu, 1, KEEP>
 
 void launch_blobs_init(cudaStream_t s) {
   static bool dev_ready[64] = {false};
@@ -1243,6 +1259,8 @@ void launch_blobs_init(cudaStream_t s) {
     cudaFuncSetAttribute(K_FIT_MEDIUM(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(MediumShared)));
     cudaFuncSetAttribute(K_FIT_LARGE(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
     cudaFuncSetAttribute(K_FIT_LARGE(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
+    cudaFuncSetAttribute(K_FIT_HUGE(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HugeShared)));
+    cudaFuncSetAttribute(K_FIT_HUGE(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HugeShared)));
     k_init_combos<<<1, 1, 0, s>>>();
     dev_ready[dev] = true;
   }
@@ -1255,7 +1273,7 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (kt) kt->begin("scatter", s);
   k_scatter<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
-  int launches = 5;
+  int launches = 6;
   if (p.clusters) {  // debug stage only (keep_stages)
     k_cluster_extents<<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
     k_cluster_finish<<<dim3(16, frames), 256, 0, s>>>(p);
@@ -1264,13 +1282,21 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   // The three tiers are independent and each is latency bound at modest occupancy: with side streams they run
   // concurrently (largest blobs first), so their tails overlap; the per-kernel timing mode runs them serially.
   // Resident capacity per SM: 5 small-tier CTAs (4 warps = 4 blobs each), 5 medium-tier CTAs, 3 large-tier CTAs.
-  const bool fork = side && side->s[0] && side->s[1];
-  cudaStream_t s_large = fork ? side->s[0] : s, s_medium = fork ? side->s[1] : s;
+  const bool fork = side && side->s[0] && side->s[1] && side->s[2];
+  cudaStream_t s_large = fork ? side->s[0] : s, s_medium = fork ? side->s[1] : s, s_huge = fork ? side->s[2] : s;
   if (fork) {
     cudaEventRecord(side->fork, s);
     cudaStreamWaitEvent(s_large, side->fork, 0);
     cudaStreamWaitEvent(s_medium, side->fork, 0);
+    cudaStreamWaitEvent(s_huge, side->fork, 0);
   }
+  if (kt) kt->begin("fit_huge", s);
+  {
+    const dim3 g(max(1u, min(148u, cdivu(592u, frames))), frames);
+    if (p.keep_stages) K_FIT_HUGE(true)<<<g, kHugeThreads, sizeof(HugeShared), s_huge>>>(p, 2);
+    else K_FIT_HUGE(false)<<<g, kHugeThreads, sizeof(HugeShared), s_huge>>>(p, 2);
+  }
+  if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
   {
     const dim3 g(max(3u, min(444u, cdivu(1776u, frames))), frames);
@@ -1295,8 +1321,10 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   if (fork) {
     cudaEventRecord(side->join[0], s_large);
     cudaEventRecord(side->join[1], s_medium);
+    cudaEventRecord(side->join[2], s_huge);
     cudaStreamWaitEvent(s, side->join[0], 0);
     cudaStreamWaitEvent(s, side->join[1], 0);
+    cudaStreamWaitEvent(s, side->join[2], 0);
   }
   if (kt) kt->begin("quads", s);
   k_quads<<<dim3(max(2u, min(592u, cdivu(2368u, frames))), frames), kQuadWarps * 32, 0, s>>>(p);
