@@ -118,7 +118,7 @@ typedef struct b200tag_frame_info {
 /* Stage selectors for b200tag_copy_stage: the reference's Copy*To debug accessors
  * (apriltag_gpu.h:98-183), generalised. */
 enum {
-  B200TAG_STAGE_GRAY = 0,        /* uint8[W*H]                      CopyGrayTo */
+  B200TAG_STAGE_GRAY = 0,        /* uint8[W*H]                      CopyGrayTo (GRAY8 detectors: host / JPEG frames only) */
   B200TAG_STAGE_QUAD_IMAGE = 1,  /* uint8[w*h]                      CopyDecimatedTo */
   B200TAG_STAGE_THRESHOLD = 2,   /* uint8[w*h]                      CopyThresholdedTo */
   B200TAG_STAGE_LABELS = 3,      /* uint32[w*h]                     CopyUnionMarkersTo */
@@ -201,6 +201,16 @@ int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_image
 /* `count` frames of ONE host allocation, `frame_stride_bytes` apart (0 = back to back), e.g. a pinned camera ring
  * buffer: they cross PCIe in a single copy instead of one per frame. */
 int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames, size_t frame_stride_bytes, int count);
+/* Camera wire format (reference: camera_publisher.cpp:198,336 decodes the cameras' MJPG stream
+ * to bgr8 with OpenCV on the CPU, apriltags_cuda_detector.cu:399-401 then converts bgr8 -> YUYV).  `count` baseline
+ * JPEG bitstreams in host memory, each width x height of a detector created for B200TAG_FMT_GRAY8: nvJPEG decodes the
+ * luminance planes on the detector's stream into its input staging buffer and the detection pipeline runs behind it.
+ * enqueue + b200tag_finish, or the synchronous b200tag_detect_mjpg.  B200TAG_E_INVALID for a bitstream nvJPEG cannot
+ * parse or of the wrong size.  nvJPEG (libnvjpeg.so.12 of the CUDA toolkit) is loaded on first use;
+ * b200tag_mjpg_backend names the nvJPEG backend in use ("" before the first call). */
+int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count);
+int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count);
+const char *b200tag_mjpg_backend(const b200tag_detector *det);
 int b200tag_finish(b200tag_detector *det);
 void *b200tag_stream(b200tag_detector *det);
 

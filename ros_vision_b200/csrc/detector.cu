@@ -3,6 +3,8 @@
 // (reference: src/apriltags_cuda/src/apriltag_gpu.cu:111-220,725-1166) without any of its seven
 // mid-frame host synchronisations: every data-dependent size stays in device counters.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h>
 
 #include <algorithm>
 #include <cmath>
@@ -10,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200tag.h"
@@ -21,6 +24,23 @@ int upload_family();
 }
 
 using namespace b200tag;
+
+// nvJPEG, bound at first use (b200tag_enqueue_mjpg): the library is part of the CUDA toolkit, but a detector that is
+// never handed JPEG frames should not need it.
+struct MjpgDecoder {
+  void *lib = nullptr;
+  nvjpegHandle_t handle = nullptr;
+  nvjpegJpegState_t state = nullptr;
+  int backend = -1;       // nvjpegBackend_t the handle was created with
+  int batch = 0;          // batch size of the last nvjpegDecodeBatchedInitialize
+  decltype(&nvjpegCreateEx) create = nullptr;
+  decltype(&nvjpegDestroy) destroy = nullptr;
+  decltype(&nvjpegJpegStateCreate) state_create = nullptr;
+  decltype(&nvjpegJpegStateDestroy) state_destroy = nullptr;
+  decltype(&nvjpegGetImageInfo) image_info = nullptr;
+  decltype(&nvjpegDecodeBatchedInitialize) batched_init = nullptr;
+  decltype(&nvjpegDecodeBatched) batched = nullptr;
+};
 
 struct b200tag_detector {
   b200tag_config cfg;
@@ -50,10 +70,13 @@ struct b200tag_detector {
   std::vector<std::vector<b200tag_quad>> quads;
   std::vector<bool> quads_valid;
   int last_count = 0;
+  const uint8_t *last_images = nullptr;  // input of the last enqueue (d_in for host / JPEG frames)
+  size_t last_stride = 0;
   bool pending = false;
   int kernels_per_batch = 0;
   std::string err;
   KernelTimer timer;
+  MjpgDecoder mjpg;
 };
 
 namespace b200tag {
@@ -270,6 +293,8 @@ int record_sequence(b200tag_detector *det, const void *device_images, size_t str
 // graph and replayed: one graph launch instead of 15 stream operations per batch (what matters for the
 // single-frame latency path, where the kernels are short).
 int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt) {
+  det->last_images = static_cast<const uint8_t *>(device_images);
+  det->last_stride = stride ? stride : det->in_bytes;
   int launches = 0;
   bool done = false;
   if (!kt && det->use_graphs) {
@@ -524,6 +549,9 @@ void b200tag_destroy(b200tag_detector *det) {
     if (det->side.join[i]) cudaEventDestroy(det->side.join[i]);
   }
   if (det->side.fork) cudaEventDestroy(det->side.fork);
+  if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
+  if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
+  if (det->mjpg.lib) dlclose(det->mjpg.lib);
   if (det->arena) cudaFree(det->arena);
   if (det->h_counters) cudaFreeHost(det->h_counters);
   if (det->h_dets) cudaFreeHost(det->h_dets);
@@ -567,6 +595,132 @@ int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames
                          cudaMemcpyHostToDevice, det->stream));
   }
   return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+}
+
+// Camera wire format: the cameras deliver MJPG (system_config.json "format": "MJPG"), which
+// the reference's camera node has OpenCV decode to bgr8 on the CPU (camera_publisher.cpp:198,336) before the detector
+// node converts bgr8 -> YUYV -> gray.  Here the JPEG bitstreams cross PCIe as they are (about a tenth of the YUYV
+// bytes), nvJPEG decodes their luminance plane straight into the detector's input staging buffer on the detector's
+// stream, and the gray pipeline runs behind it.
+static int mjpg_open(b200tag_detector *det) {
+  MjpgDecoder &m = det->mjpg;
+  if (m.handle) return 0;
+  if (!m.lib) {
+    for (const char *name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) {
+      m.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (m.lib) break;
+    }
+    if (!m.lib) {
+      det->err = std::string("nvJPEG not found: ") + dlerror();
+      return B200TAG_E_INVALID;
+    }
+    bool ok = true;
+    auto bind = [&](auto &fn, const char *sym) {
+      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(m.lib, sym));
+      ok = ok && fn != nullptr;
+    };
+    bind(m.create, "nvjpegCreateEx");
+    bind(m.destroy, "nvjpegDestroy");
+    bind(m.state_create, "nvjpegJpegStateCreate");
+    bind(m.state_destroy, "nvjpegJpegStateDestroy");
+    bind(m.image_info, "nvjpegGetImageInfo");
+    bind(m.batched_init, "nvjpegDecodeBatchedInitialize");
+    bind(m.batched, "nvjpegDecodeBatched");
+    if (!ok) {
+      det->err = "nvJPEG library lacks the batched-decode entry points";
+      dlclose(m.lib);
+      m.lib = nullptr;
+      return B200TAG_E_INVALID;
+    }
+  }
+  // B200TAG_NVJPEG_BACKEND=hardware|gpu|hybrid|default picks one backend; otherwise the first that can be created, in
+  // the order GPU Huffman decode, default.  (The fixed-function engine is opt-in: it wants pinned input buffers.)
+  std::vector<int> order = {NVJPEG_BACKEND_GPU_HYBRID, NVJPEG_BACKEND_DEFAULT};
+  if (const char *e = getenv("B200TAG_NVJPEG_BACKEND")) {
+    const std::string v(e);
+    if (v == "hardware") order = {NVJPEG_BACKEND_HARDWARE};
+    else if (v == "gpu") order = {NVJPEG_BACKEND_GPU_HYBRID};
+    else if (v == "hybrid") order = {NVJPEG_BACKEND_HYBRID};
+    else if (v == "default") order = {NVJPEG_BACKEND_DEFAULT};
+  }
+  for (int b : order) {
+    if (m.create(static_cast<nvjpegBackend_t>(b), nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &m.handle) == NVJPEG_STATUS_SUCCESS) {
+      m.backend = b;
+      break;
+    }
+    m.handle = nullptr;
+  }
+  if (!m.handle) {
+    det->err = "nvjpegCreateEx failed for every requested backend";
+    return B200TAG_E_CUDA;
+  }
+  if (m.state_create(m.handle, &m.state) != NVJPEG_STATUS_SUCCESS) {
+    m.destroy(m.handle);
+    m.handle = nullptr;
+    det->err = "nvjpegJpegStateCreate failed";
+    return B200TAG_E_CUDA;
+  }
+  m.batch = 0;
+  return 0;
+}
+
+int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
+  if (!det || !jpegs || !sizes || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  if (det->cfg.format != B200TAG_FMT_GRAY8) {
+    det->err = "b200tag_enqueue_mjpg needs a detector created for B200TAG_FMT_GRAY8 (the JPEG luminance plane is the image)";
+    return B200TAG_E_INVALID;
+  }
+  if (det->pending) {
+    if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
+  }
+  if (int rc = mjpg_open(det)) return rc;
+  MjpgDecoder &m = det->mjpg;
+  std::vector<nvjpegImage_t> dst(count);
+  for (int f = 0; f < count; f++) {
+    if (!jpegs[f] || sizes[f] == 0) return B200TAG_E_INVALID;
+    int ncomp = 0, w[NVJPEG_MAX_COMPONENT] = {0}, h[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    if (m.image_info(m.handle, jpegs[f], sizes[f], &ncomp, &ss, w, h) != NVJPEG_STATUS_SUCCESS) {
+      det->err = "frame " + std::to_string(f) + ": not a JPEG bitstream nvJPEG can parse";
+      return B200TAG_E_INVALID;
+    }
+    if (w[0] != det->cfg.width || h[0] != det->cfg.height) {
+      det->err = "frame " + std::to_string(f) + ": JPEG is " + std::to_string(w[0]) + "x" + std::to_string(h[0]) +
+                 ", detector was created for " + std::to_string(det->cfg.width) + "x" + std::to_string(det->cfg.height);
+      return B200TAG_E_INVALID;
+    }
+    memset(&dst[f], 0, sizeof(nvjpegImage_t));
+    dst[f].channel[0] = det->d_in + static_cast<size_t>(f) * det->fp.in_stride;
+    dst[f].pitch[0] = static_cast<size_t>(det->cfg.width);
+  }
+  if (m.batch != count) {
+    if (m.batched_init(m.handle, m.state, count, 1, NVJPEG_OUTPUT_Y) != NVJPEG_STATUS_SUCCESS) {
+      det->err = "nvjpegDecodeBatchedInitialize failed";
+      return B200TAG_E_CUDA;
+    }
+    m.batch = count;
+  }
+  const nvjpegStatus_t st = m.batched(m.handle, m.state, jpegs, sizes, dst.data(), det->stream);
+  if (st != NVJPEG_STATUS_SUCCESS) {
+    det->err = "nvjpegDecodeBatched failed with status " + std::to_string(static_cast<int>(st));
+    return st == NVJPEG_STATUS_BAD_JPEG || st == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? B200TAG_E_INVALID : B200TAG_E_CUDA;
+  }
+  return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+}
+
+int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
+  if (int rc = b200tag_enqueue_mjpg(det, jpegs, sizes, count)) return rc;
+  return finish_impl(det);
+}
+
+const char *b200tag_mjpg_backend(const b200tag_detector *det) {
+  if (!det || !det->mjpg.handle) return "";
+  switch (det->mjpg.backend) {
+    case NVJPEG_BACKEND_HARDWARE: return "hardware";
+    case NVJPEG_BACKEND_GPU_HYBRID: return "gpu";
+    case NVJPEG_BACKEND_HYBRID: return "hybrid";
+    default: return "default";
+  }
 }
 
 int b200tag_finish(b200tag_detector *det) {
@@ -646,7 +800,12 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
   const uint32_t nsel = std::min(c.num_seg_points, p.point_cap);  // segments of all candidate blobs
   switch (stage) {
     case B200TAG_STAGE_GRAY:
-      if (det->cfg.format == B200TAG_FMT_GRAY8) return B200TAG_E_INVALID;  // the gray image is the caller's input
+      if (det->cfg.format == B200TAG_FMT_GRAY8) {
+        // the gray image is the input itself: available while it sits in the detector's own staging buffer
+        // (host frames, decoded JPEG luminance), not for caller-owned device frames
+        if (det->last_images != det->d_in) return B200TAG_E_INVALID;
+        src = det->d_in + f * det->last_stride; bytes = N; break;
+      }
       src = p.gray + f * N; bytes = N; break;
     case B200TAG_STAGE_QUAD_IMAGE: src = p.quad + f * n; bytes = n; break;
     case B200TAG_STAGE_THRESHOLD: src = p.thresh + f * n; bytes = n; break;

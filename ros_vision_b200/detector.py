@@ -97,6 +97,10 @@ def load_library():
     L.b200tag_enqueue_device.argtypes = [vp, vp, sz, i32]
     L.b200tag_enqueue_host.argtypes = [vp, C.POINTER(vp), i32]
     L.b200tag_enqueue_host_block.argtypes = [vp, vp, sz, i32]
+    L.b200tag_enqueue_mjpg.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32]
+    L.b200tag_detect_mjpg.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32]
+    L.b200tag_mjpg_backend.argtypes = [vp]
+    L.b200tag_mjpg_backend.restype = C.c_char_p
     L.b200tag_finish.argtypes = [vp]
     L.b200tag_stream.argtypes = [vp]
     L.b200tag_stream.restype = vp
@@ -266,6 +270,25 @@ class GpuDetector:
         self._check(self._lib.b200tag_enqueue_host_block(self._h, C.c_void_p(host_ptr), stride, count),
                     "b200tag_enqueue_host_block")
         self.last_count = count
+
+    def EnqueueMjpg(self, jpegs) -> None:
+        """Camera wire format: `jpegs` = JPEG bitstreams (bytes / uint8 arrays) of width x height; nvJPEG decodes their
+        luminance planes on the detector's stream and the gray pipeline runs behind it (detector created with fmt="gray")."""
+        arrs = [np.frombuffer(j, dtype=np.uint8) if isinstance(j, (bytes, bytearray, memoryview)) else np.ascontiguousarray(j, dtype=np.uint8)
+                for j in jpegs]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        sizes = (C.c_size_t * len(arrs))(*[a.size for a in arrs])
+        self._mjpg_keep = (arrs, ptrs, sizes)  # the bitstreams stay alive until Finish
+        self._check(self._lib.b200tag_enqueue_mjpg(self._h, ptrs, sizes, len(arrs)), "b200tag_enqueue_mjpg")
+        self.last_count = len(arrs)
+
+    def DetectMjpg(self, jpegs, allow_overflow=False) -> int:
+        self.EnqueueMjpg(jpegs)
+        return self.Finish(allow_overflow)
+
+    @property
+    def mjpg_backend(self) -> str:
+        return (self._lib.b200tag_mjpg_backend(self._h) or b"").decode()
 
     def DetectDevice(self, device_ptr: int, count: int = 1, stride: int = 0, allow_overflow=False) -> int:
         rc = self._lib.b200tag_detect_device(self._h, C.c_void_p(device_ptr), stride, count)
