@@ -202,15 +202,23 @@ int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_image
  * buffer: they cross PCIe in a single copy instead of one per frame. */
 int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames, size_t frame_stride_bytes, int count);
 /* Camera wire format (reference: camera_publisher.cpp:198,336 decodes the cameras' MJPG stream
- * to bgr8 with OpenCV on the CPU, apriltags_cuda_detector.cu:399-401 then converts bgr8 -> YUYV).  `count` baseline
- * JPEG bitstreams in host memory, each width x height of a detector created for B200TAG_FMT_GRAY8: nvJPEG decodes the
- * luminance planes on the detector's stream into its input staging buffer and the detection pipeline runs behind it.
- * enqueue + b200tag_finish, or the synchronous b200tag_detect_mjpg.  B200TAG_E_INVALID for a bitstream nvJPEG cannot
- * parse or of the wrong size.  nvJPEG (libnvjpeg.so.12 of the CUDA toolkit) is loaded on first use;
- * b200tag_mjpg_backend names the nvJPEG backend in use ("" before the first call). */
+ * to bgr8 with OpenCV on the CPU, apriltags_cuda_detector.cu:399-401 then converts bgr8 -> YUYV).  `count` JPEG
+ * bitstreams in host memory, each width x height of a detector created for B200TAG_FMT_GRAY8: their luminance planes
+ * are decoded on the detector's stream into its input staging buffer and the detection pipeline runs behind that.
+ * Baseline JPEG (8-bit, Huffman, one interleaved scan, gray or YCbCr with full-resolution luminance, with or without
+ * DHT segments / restart markers -- what UVC cameras send) goes through the detector's own decode kernel
+ * (csrc/kernels_jpeg.cu); other JPEG kinds (progressive, ...) through nvJPEG (libnvjpeg.so.12 of the CUDA toolkit,
+ * loaded on first use).  enqueue + b200tag_finish, or the synchronous b200tag_detect_mjpg.  B200TAG_E_INVALID for a
+ * bitstream that cannot be parsed or is of the wrong size.  b200tag_mjpg_backend names the decoder of the last batch
+ * ("native", or nvJPEG's "gpu" / "hardware" / "hybrid" / "default"; "" before the first call).
+ * b200tag_jpeg_probe (host only) parses the headers: info = {width, height, blocks per MCU, luminance blocks per MCU
+ * horizontally, vertically, restart interval, offset of the entropy-coded data, MCUs}, `dht_out` the Huffman tables in
+ * use (per table: present flag, 16 counts, values; tables K.3-K.6 of ITU-T T.81 when the stream has none); returns 1
+ * for a JPEG the native kernel does not handle. */
 int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count);
 int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count);
 const char *b200tag_mjpg_backend(const b200tag_detector *det);
+int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_t *dht_out, size_t dht_cap, size_t *dht_len);
 int b200tag_finish(b200tag_detector *det);
 void *b200tag_stream(b200tag_detector *det);
 

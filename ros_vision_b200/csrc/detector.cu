@@ -17,6 +17,7 @@
 
 #include "../../include/b200tag.h"
 #include "dev_types.h"
+#include "jpeg.h"
 #include "kernels.h"
 
 namespace b200tag {
@@ -40,6 +41,16 @@ struct MjpgDecoder {
   decltype(&nvjpegGetImageInfo) image_info = nullptr;
   decltype(&nvjpegDecodeBatchedInitialize) batched_init = nullptr;
   decltype(&nvjpegDecodeBatched) batched = nullptr;
+};
+
+// The detector's own JPEG luminance decoder (kernels_jpeg.cu): one pinned host block and its device twin hold, per
+// batch, the frame descriptors, the Huffman table sets and the entropy-coded segments; one copy moves all of it.
+struct NativeJpeg {
+  uint8_t *h_block = nullptr;  // pinned
+  uint8_t *d_block = nullptr;
+  size_t cap = 0;
+  std::vector<JpegParsed> parsed;
+  bool last_native = false;    // the last MJPG batch went through this decoder (else nvJPEG)
 };
 
 struct b200tag_detector {
@@ -77,6 +88,7 @@ struct b200tag_detector {
   std::string err;
   KernelTimer timer;
   MjpgDecoder mjpg;
+  NativeJpeg jpeg;
 };
 
 namespace b200tag {
@@ -549,6 +561,8 @@ void b200tag_destroy(b200tag_detector *det) {
     if (det->side.join[i]) cudaEventDestroy(det->side.join[i]);
   }
   if (det->side.fork) cudaEventDestroy(det->side.fork);
+  if (det->jpeg.h_block) cudaFreeHost(det->jpeg.h_block);
+  if (det->jpeg.d_block) cudaFree(det->jpeg.d_block);
   if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
   if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
@@ -664,6 +678,75 @@ static int mjpg_open(b200tag_detector *det) {
   return 0;
 }
 
+// The detector's own decoder.  Returns 0 when the batch was enqueued, 1 when some frame is a valid JPEG of a kind the
+// kernel does not handle (progressive, 12-bit, ...: the caller falls back to nvJPEG), or a negative error.
+static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
+  NativeJpeg &J = det->jpeg;
+  J.parsed.resize(count);
+  std::vector<int> set_of(count, 0);
+  std::vector<int> set_owner;  // frame whose tables define each distinct set
+  size_t bytes = 0;
+  for (int f = 0; f < count; f++) {
+    if (!jpegs[f] || sizes[f] == 0) return B200TAG_E_INVALID;
+    std::string why;
+    const int rc = jpeg_parse(jpegs[f], sizes[f], &J.parsed[f], &why);
+    if (rc == kJpegUnsupported) return 1;
+    if (rc != kJpegOk) {
+      det->err = "frame " + std::to_string(f) + ": not a JPEG bitstream this decoder can parse (" + why + ")";
+      return B200TAG_E_INVALID;
+    }
+    const JpegFrame &fr = J.parsed[f].frame;
+    if (fr.width != det->cfg.width || fr.height != det->cfg.height) {
+      det->err = "frame " + std::to_string(f) + ": JPEG is " + std::to_string(fr.width) + "x" + std::to_string(fr.height) +
+                 ", detector was created for " + std::to_string(det->cfg.width) + "x" + std::to_string(det->cfg.height);
+      return B200TAG_E_INVALID;
+    }
+    int set = -1;
+    for (size_t k = 0; k < set_owner.size(); k++)
+      if (J.parsed[set_owner[k]].dht == J.parsed[f].dht) set = static_cast<int>(k);
+    if (set < 0) {
+      if (set_owner.size() >= 255) return 1;
+      set = static_cast<int>(set_owner.size());
+      set_owner.push_back(f);
+    }
+    set_of[f] = set;
+    bytes += (sizes[f] - J.parsed[f].scan_begin + 15) & ~static_cast<size_t>(15);
+  }
+  const size_t frames_bytes = (sizeof(JpegFrame) * count + 15) & ~static_cast<size_t>(15);
+  const size_t tables_bytes = sizeof(JpegTables) * set_owner.size();
+  const size_t total = frames_bytes + tables_bytes + bytes + 64;
+  if (total > 0xffffffffull) return 1;
+  if (total > J.cap) {
+    CK(cudaStreamSynchronize(det->stream));
+    if (J.h_block) cudaFreeHost(J.h_block);
+    if (J.d_block) cudaFree(J.d_block);
+    J.h_block = J.d_block = nullptr;
+    J.cap = 0;
+    const size_t want = total + total / 2;
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&J.h_block), want, cudaHostAllocDefault));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_block), want));
+    J.cap = want;
+  }
+  JpegFrame *hf = reinterpret_cast<JpegFrame *>(J.h_block);
+  JpegTables *ht = reinterpret_cast<JpegTables *>(J.h_block + frames_bytes);
+  size_t off = frames_bytes + tables_bytes;
+  for (size_t k = 0; k < set_owner.size(); k++) ht[k] = J.parsed[set_owner[k]].tables;
+  for (int f = 0; f < count; f++) {
+    const size_t n = sizes[f] - J.parsed[f].scan_begin;
+    memcpy(J.h_block + off, jpegs[f] + J.parsed[f].scan_begin, n);
+    hf[f] = J.parsed[f].frame;
+    hf[f].data_off = static_cast<uint32_t>(off);
+    hf[f].data_len = static_cast<uint32_t>(n);
+    hf[f].tables = static_cast<uint8_t>(set_of[f]);
+    off += (n + 15) & ~static_cast<size_t>(15);
+  }
+  CK(cudaMemcpyAsync(J.d_block, J.h_block, off, cudaMemcpyHostToDevice, det->stream));
+  launch_jpeg_luma(J.d_block, reinterpret_cast<const JpegFrame *>(J.d_block),
+                   reinterpret_cast<const JpegTables *>(J.d_block + frames_bytes), det->d_in, det->fp.in_stride, count, det->stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
   if (!det || !jpegs || !sizes || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
   if (det->cfg.format != B200TAG_FMT_GRAY8) {
@@ -673,6 +756,17 @@ int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, con
   if (det->pending) {
     if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
   }
+  // B200TAG_MJPG_DECODER=nvjpeg sends everything through nvJPEG (the comparison arm of tools/bench_mjpg.py)
+  const char *which = getenv("B200TAG_MJPG_DECODER");
+  if (!(which && std::string(which) == "nvjpeg")) {
+    const int rc = mjpg_native(det, jpegs, sizes, count);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      det->jpeg.last_native = true;
+      return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+    }
+  }
+  det->jpeg.last_native = false;
   if (int rc = mjpg_open(det)) return rc;
   MjpgDecoder &m = det->mjpg;
   std::vector<nvjpegImage_t> dst(count);
@@ -714,6 +808,7 @@ int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, cons
 }
 
 const char *b200tag_mjpg_backend(const b200tag_detector *det) {
+  if (det && det->jpeg.last_native) return "native";
   if (!det || !det->mjpg.handle) return "";
   switch (det->mjpg.backend) {
     case NVJPEG_BACKEND_HARDWARE: return "hardware";
@@ -721,6 +816,22 @@ const char *b200tag_mjpg_backend(const b200tag_detector *det) {
     case NVJPEG_BACKEND_HYBRID: return "hybrid";
     default: return "default";
   }
+}
+
+int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_t *dht_out, size_t dht_cap, size_t *dht_len) {
+  JpegParsed P;
+  std::string why;
+  const int rc = jpeg_parse(jpeg, size, &P, &why);
+  if (rc != kJpegOk) return rc == kJpegUnsupported ? 1 : B200TAG_E_INVALID;
+  if (info) {
+    const JpegFrame &f = P.frame;
+    const int32_t v[8] = {f.width, f.height, f.nblocks, f.hmax, f.vmax, f.restart_interval, static_cast<int32_t>(P.scan_begin),
+                          f.mcus_x * f.mcus_y};
+    memcpy(info, v, sizeof(v));
+  }
+  if (dht_len) *dht_len = P.dht.size();
+  if (dht_out && dht_cap >= P.dht.size()) memcpy(dht_out, P.dht.data(), P.dht.size());
+  return 0;
 }
 
 int b200tag_finish(b200tag_detector *det) {
