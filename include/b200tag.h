@@ -219,6 +219,14 @@ int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, con
 int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count);
 const char *b200tag_mjpg_backend(const b200tag_detector *det);
 int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_t *dht_out, size_t dht_cap, size_t *dht_len);
+/* How many of the first `count` frames of the last MJPG batch the parallel decode kernels handled (the rest -- streams
+ * with restart markers, or whose synchronisation was not proven within the fixed number of rounds -- went through the
+ * sequential warp-per-frame kernel).  Synchronises the stream. */
+int b200tag_mjpg_parallel_frames(b200tag_detector *det, int count);
+/* Test hook: host model of the parallel JPEG decode kernels (same entropy-decoding core and arithmetic, threads replaced
+ * by loops), so the scheme can be checked without a GPU.  Not on any detection path.  0 = plane written to `out`;
+ * 1 = a stream the parallel path does not take (restart markers, non-baseline); `rounds` = synchronisation rounds. */
+int b200tag_debug_jpeg_model(const uint8_t *jpeg, size_t size, uint8_t *out, size_t out_cap, int *rounds);
 int b200tag_finish(b200tag_detector *det);
 void *b200tag_stream(b200tag_detector *det);
 

@@ -18,6 +18,7 @@
 #include "../../include/b200tag.h"
 #include "dev_types.h"
 #include "jpeg.h"
+#include "jpeg_core.h"
 #include "kernels.h"
 
 namespace b200tag {
@@ -49,8 +50,15 @@ struct NativeJpeg {
   uint8_t *h_block = nullptr;  // pinned
   uint8_t *d_block = nullptr;
   size_t cap = 0;
+  uint8_t *d_ws = nullptr;     // workspace of the parallel kernels, sized with `cap`
+  int16_t *d_coef = nullptr;   // coefficient buffer (fixed size, all zero between batches)
+  size_t coef_stride = 0;
+  bool init = false;
   std::vector<JpegParsed> parsed;
   bool last_native = false;    // the last MJPG batch went through this decoder (else nvJPEG)
+  int launches = 0;            // kernels of the last decode
+  const uint32_t *d_proven = nullptr;  // per frame of the last batch: decoded by the parallel kernels
+  bool last_parallel = false;
 };
 
 struct b200tag_detector {
@@ -563,6 +571,8 @@ void b200tag_destroy(b200tag_detector *det) {
   if (det->side.fork) cudaEventDestroy(det->side.fork);
   if (det->jpeg.h_block) cudaFreeHost(det->jpeg.h_block);
   if (det->jpeg.d_block) cudaFree(det->jpeg.d_block);
+  if (det->jpeg.d_ws) cudaFree(det->jpeg.d_ws);
+  if (det->jpeg.d_coef) cudaFree(det->jpeg.d_coef);
   if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
   if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
@@ -713,24 +723,46 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     bytes += (sizes[f] - J.parsed[f].scan_begin + 15) & ~static_cast<size_t>(15);
   }
   const size_t frames_bytes = (sizeof(JpegFrame) * count + 15) & ~static_cast<size_t>(15);
-  const size_t tables_bytes = sizeof(JpegTables) * set_owner.size();
+  const size_t tables_bytes = (sizeof(JpegTables) * set_owner.size() + 15) & ~static_cast<size_t>(15);
   const size_t total = frames_bytes + tables_bytes + bytes + 64;
-  if (total > 0xffffffffull) return 1;
+  if (total > 0x7fffffffull) return 1;
+  const size_t B = static_cast<size_t>(det->cfg.max_batch);
+  auto ws_layout = [&](size_t cap, size_t *chunks, size_t *subs) {
+    *chunks = cap / kJpegChunk + B + 16;
+    *subs = cap / (kJpegSubBits / 8) + B + 16;
+  };
+  if (!J.init) {
+    float cosv[64];
+    jpeg_cos_table(cosv);
+    launch_jpeg_init(cosv);
+    J.coef_stride = static_cast<size_t>((det->cfg.width + 31) / 32 * 32) * static_cast<size_t>((det->cfg.height + 31) / 32 * 32);
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_coef), J.coef_stride * B * sizeof(int16_t)));
+    CK(cudaMemsetAsync(J.d_coef, 0, J.coef_stride * B * sizeof(int16_t), det->stream));
+    J.init = true;
+  }
   if (total > J.cap) {
     CK(cudaStreamSynchronize(det->stream));
     if (J.h_block) cudaFreeHost(J.h_block);
     if (J.d_block) cudaFree(J.d_block);
-    J.h_block = J.d_block = nullptr;
+    if (J.d_ws) cudaFree(J.d_ws);
+    J.h_block = J.d_block = J.d_ws = nullptr;
     J.cap = 0;
-    const size_t want = total + total / 2;
+    const size_t want = (total + total / 2 + 4095) & ~static_cast<size_t>(4095);
+    size_t chunks, subs;
+    ws_layout(want, &chunks, &subs);
     CK(cudaHostAlloc(reinterpret_cast<void **>(&J.h_block), want, cudaHostAllocDefault));
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_block), want));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 8 + (chunks + subs) * 4 + B * (kJpegSyncRounds + 2) * 4 + 256));
     J.cap = want;
   }
   JpegFrame *hf = reinterpret_cast<JpegFrame *>(J.h_block);
   JpegTables *ht = reinterpret_cast<JpegTables *>(J.h_block + frames_bytes);
   size_t off = frames_bytes + tables_bytes;
   for (size_t k = 0; k < set_owner.size(); k++) ht[k] = J.parsed[set_owner[k]].tables;
+  JpegBatch jb;
+  memset(&jb, 0, sizeof(jb));
+  uint32_t chunk_off = 0, sub_off = 0;
+  bool any_parallel = false;
   for (int f = 0; f < count; f++) {
     const size_t n = sizes[f] - J.parsed[f].scan_begin;
     memcpy(J.h_block + off, jpegs[f] + J.parsed[f].scan_begin, n);
@@ -738,11 +770,44 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     hf[f].data_off = static_cast<uint32_t>(off);
     hf[f].data_len = static_cast<uint32_t>(n);
     hf[f].tables = static_cast<uint8_t>(set_of[f]);
+    hf[f].chunk_off = chunk_off;
+    hf[f].sub_off = sub_off;
+    const uint32_t nch = static_cast<uint32_t>((n + kJpegChunk - 1) / kJpegChunk);
+    const uint32_t nsub = static_cast<uint32_t>((n * 8 + kJpegSubBits - 1) / kJpegSubBits) + 1;
+    chunk_off += nch;
+    sub_off += nsub;
+    jb.max_chunks = std::max(jb.max_chunks, nch);
+    jb.max_subs = std::max(jb.max_subs, nsub);
+    jb.max_luma_blocks = std::max<uint32_t>(jb.max_luma_blocks, static_cast<uint32_t>(hf[f].mcus_x) * hf[f].mcus_y * hf[f].hmax * hf[f].vmax);
+    any_parallel = any_parallel || hf[f].restart_interval == 0;
+    if (static_cast<size_t>(hf[f].mcus_x) * hf[f].mcus_y * hf[f].hmax * hf[f].vmax * 64 > J.coef_stride) return 1;
     off += (n + 15) & ~static_cast<size_t>(15);
   }
+  size_t chunks, subs;
+  ws_layout(J.cap, &chunks, &subs);
+  uint8_t *w = J.d_ws;
+  jb.raw = J.d_block;
+  jb.clean = w; w += J.cap;
+  jb.sync = reinterpret_cast<unsigned long long *>(w); w += subs * 8;
+  jb.chunk_cnt = reinterpret_cast<uint32_t *>(w); w += chunks * 4;
+  jb.nblk = reinterpret_cast<uint32_t *>(w); w += subs * 4;
+  jb.changed = reinterpret_cast<uint32_t *>(w); w += B * kJpegSyncRounds * 4;
+  jb.proven = reinterpret_cast<uint32_t *>(w); w += B * 4;
+  jb.clean_len = reinterpret_cast<uint32_t *>(w);
+  jb.frames = reinterpret_cast<const JpegFrame *>(J.d_block);
+  jb.tables = reinterpret_cast<const JpegTables *>(J.d_block + frames_bytes);
+  jb.coef = J.d_coef;
+  jb.coef_stride = J.coef_stride;
+  jb.out = det->d_in;
+  jb.out_stride = det->fp.in_stride;
+  jb.count = count;
   CK(cudaMemcpyAsync(J.d_block, J.h_block, off, cudaMemcpyHostToDevice, det->stream));
-  launch_jpeg_luma(J.d_block, reinterpret_cast<const JpegFrame *>(J.d_block),
-                   reinterpret_cast<const JpegTables *>(J.d_block + frames_bytes), det->d_in, det->fp.in_stride, count, det->stream);
+  // B200TAG_MJPG_DECODER=sequential keeps every frame on the warp-per-frame kernel (tests / comparison)
+  const char *which = getenv("B200TAG_MJPG_DECODER");
+  if (which && std::string(which) == "sequential") any_parallel = false;
+  J.launches = launch_jpeg_decode(jb, any_parallel, det->stream);
+  J.d_proven = jb.proven;
+  J.last_parallel = any_parallel;
   CK(cudaGetLastError());
   return 0;
 }
@@ -832,6 +897,21 @@ int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_
   if (dht_len) *dht_len = P.dht.size();
   if (dht_out && dht_cap >= P.dht.size()) memcpy(dht_out, P.dht.data(), P.dht.size());
   return 0;
+}
+
+int b200tag_mjpg_parallel_frames(b200tag_detector *det, int count) {
+  if (!det || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  if (!det->jpeg.last_native || !det->jpeg.last_parallel) return 0;
+  std::vector<uint32_t> h(count);
+  CK(cudaStreamSynchronize(det->stream));
+  CK(cudaMemcpy(h.data(), det->jpeg.d_proven, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (uint32_t v : h) n += v ? 1 : 0;
+  return n;
+}
+
+int b200tag_debug_jpeg_model(const uint8_t *jpeg, size_t size, uint8_t *out, size_t out_cap, int *rounds) {
+  return jpeg_model_decode(jpeg, size, out, out_cap, rounds);
 }
 
 int b200tag_finish(b200tag_detector *det) {

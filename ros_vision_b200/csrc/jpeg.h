@@ -41,6 +41,29 @@ struct JpegFrame {
   uint8_t blk_by[kJpegMaxBlocksPerMcu];
   uint8_t comp_dc[4], comp_ac[4];          // Huffman table selectors per component
   uint16_t quant[64];                      // luminance quantisation table, natural (row-major) order
+  uint32_t chunk_off;                      // first unstuffing chunk / first subsequence of this frame in the batch arrays
+  uint32_t sub_off;
+};
+
+// Device workspace of one batch for the parallel decoder (kernels_jpeg.cu)
+struct JpegSyncState;
+struct JpegBatch {
+  const uint8_t *raw;         // descriptors, tables and entropy-coded segments as uploaded
+  uint8_t *clean;             // unstuffed segments, at the same offsets as in `raw`
+  const JpegFrame *frames;
+  const JpegTables *tables;
+  uint32_t *chunk_cnt;        // per 64-byte raw chunk: bytes kept, then their exclusive prefix
+  uint32_t *clean_len;        // per frame: unstuffed bytes
+  unsigned long long *sync;   // per subsequence: JpegSyncState at its start
+  uint32_t *nblk;             // per subsequence: blocks completed in it, then their exclusive prefix
+  uint32_t *changed;          // [frame][round]: some state changed in that round
+  uint32_t *proven;           // per frame: the parallel decode reached its fixed point
+  int16_t *coef;              // [frame][luminance block][64], zigzag order; all zero between batches
+  size_t coef_stride;         // int16 per frame
+  uint8_t *out;
+  size_t out_stride;
+  int count;
+  uint32_t max_chunks, max_subs, max_luma_blocks;  // largest per-frame counts in the batch (grid sizes)
 };
 
 // Host side ---------------------------------------------------------------------------------------------------------
@@ -56,5 +79,14 @@ struct JpegParsed {
 // Parses the headers of one JPEG (markers up to SOS).  kJpegUnsupported: a valid JPEG this decoder does not handle
 // (progressive, arithmetic, 12-bit, non-interleaved scans, subsampled luminance, table ids above 1).
 int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *why);
+
+// cos((2x+1) u pi / 16) * C(u) / 2 as floats, [x][u]: the one table both the kernels and the host model use
+void jpeg_cos_table(float out[64]);
+
+// Host model of the parallel decoder (same core, same arithmetic, threads replaced by loops) -- a test hook that lets
+// the scheme be checked without a GPU; nothing on the detection path calls it.  Returns 0, 1 = stream kind the
+// parallel path does not take (restart markers, non-baseline), negative = malformed.  rounds = synchronisation rounds
+// until the proving round (Jacobi order, an upper bound for the kernels' in-place order).
+int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_cap, int *rounds);
 
 }  // namespace b200tag

@@ -1,0 +1,143 @@
+// Entropy-decoding core of the JPEG luminance decoder, shared by the CUDA kernels (kernels_jpeg.cu) and by the host
+// model of the parallel scheme (jpeg_host.cc, a test hook that mirrors the kernels thread by thread).
+//
+// Parallel Huffman decoding by self-synchronisation (Klein & Wiseman 2003; Weissenberger & Schmidt 2018 for JPEG on
+// GPUs): the unstuffed scan is cut into subsequences of kJpegSubBits bits.  The decoder state at a subsequence
+// boundary is (bit position of the first codeword that starts in the subsequence, block index inside the MCU, zigzag
+// index inside the block).  f_i maps the state at the start of subsequence i to the state at the start of i + 1 by
+// decoding.  Thread i iterates  s[i+1] <- f_i(s[i])  starting from the guess "a block starts at my first bit"; because
+// Huffman decoders that start in different states fall into step after a few codewords, the iteration reaches its
+// fixed point -- which, s[0] being known, is the true decoding -- after a few rounds instead of after n.  A round in
+// which nothing changes proves the fixed point.
+#pragma once
+#include <cstdint>
+
+#include "jpeg.h"
+
+#if defined(__CUDACC__)
+#define JPEG_HD __host__ __device__ __forceinline__
+#else
+#define JPEG_HD inline
+#endif
+
+namespace b200tag {
+
+constexpr uint32_t kJpegSubBits = 1024;  // bits per subsequence (128 bytes of unstuffed data)
+constexpr int kJpegSyncRounds = 8;       // rounds launched; a frame that is not proven by then is decoded sequentially
+constexpr uint32_t kJpegChunk = 64;      // raw bytes per thread of the unstuffing passes
+
+struct JpegSyncState {
+  uint32_t pos;  // bit offset of the next codeword in the unstuffed scan
+  uint32_t cz;   // block index within the MCU | zigzag index << 8 (0 = a DC codeword is next)
+};
+
+// 32 bits of the big-endian bit stream starting at bit `pos`; `words` is 4-byte aligned
+JPEG_HD uint32_t jpeg_peek32(const uint32_t *words, uint32_t pos) {
+  const uint32_t i = pos >> 5, sh = pos & 31u;
+  uint32_t w0 = words[i], w1 = words[i + 1];
+#if defined(__CUDA_ARCH__)
+  w0 = __byte_perm(w0, 0, 0x0123);
+  w1 = __byte_perm(w1, 0, 0x0123);
+  return __funnelshift_l(w1, w0, sh);
+#else
+  w0 = __builtin_bswap32(w0);
+  w1 = __builtin_bswap32(w1);
+  return sh ? (w0 << sh) | (w1 >> (32u - sh)) : w0;
+#endif
+}
+
+// F.2.2.3 DECODE on the 16 leading bits of `peek`; returns the symbol, *len = code length
+JPEG_HD uint32_t jpeg_lookup(const JpegHuff &h, uint32_t peek, uint32_t *len) {
+  const uint32_t p16 = peek >> 16;
+  const uint32_t e = h.fast[p16 >> (16 - kJpegFastBits)];
+  if (e) {
+    *len = e >> 8;
+    return e & 0xffu;
+  }
+  uint32_t l = kJpegFastBits + 1;
+  while (l <= 16 && static_cast<int32_t>(p16 >> (16 - l)) > h.maxcode[l]) l++;
+  if (l > 16) {  // not a codeword of this table
+    *len = 16;
+    return 0;
+  }
+  *len = l;
+  return h.vals[(h.valoff[l] + static_cast<int32_t>(p16 >> (16 - l))) & 0xff];
+}
+
+// F.2.2.1 RECEIVE + EXTEND: the s bits that follow the `len`-bit codeword in `peek`
+JPEG_HD int jpeg_value(uint32_t peek, uint32_t len, uint32_t s) {
+  if (s == 0) return 0;
+  const int v = static_cast<int>((peek << len) >> (32u - s));
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+// Decodes codewords from state `s` until one ends at or beyond bit `limit` (or the data ends at `end_bits`); returns
+// the number of blocks completed.  sink.dc(c, diff), sink.ac(c, z, v) and sink.block_end(c) see every coefficient.
+template <class Sink>
+JPEG_HD uint32_t jpeg_decode_span(const uint32_t *words, uint32_t end_bits, uint32_t limit, const JpegFrame &F,
+                                  const JpegTables &T, JpegSyncState &s, Sink &sink) {
+  uint32_t pos = s.pos, c = s.cz & 0xffu, z = s.cz >> 8, blocks = 0;
+  const uint32_t nblocks = F.nblocks;
+  while (pos < limit && pos < end_bits) {
+    const uint32_t peek = jpeg_peek32(words, pos);
+    const uint32_t comp = F.blk_comp[c];
+    uint32_t len;
+    if (z == 0) {
+      uint32_t t = jpeg_lookup(T.dc[F.comp_dc[comp]], peek, &len) & 15u;
+      t = t > 11u ? 11u : t;
+      sink.dc(c, jpeg_value(peek, len, t));
+      pos += len + t;
+      z = 1;
+    } else {
+      const uint32_t rs = jpeg_lookup(T.ac[F.comp_ac[comp]], peek, &len);
+      const uint32_t run = rs >> 4;
+      uint32_t sz = rs & 15u;
+      if (sz == 0) {
+        pos += len;
+        z = run == 15u ? z + 16u : 64u;  // ZRL : EOB
+      } else {
+        sz = sz > 10u ? 10u : sz;
+        z += run;
+        if (z <= 63u) sink.ac(c, z, jpeg_value(peek, len, sz));
+        pos += len + sz;
+        z++;
+      }
+    }
+    if (z >= 64u) {
+      sink.block_end(c);
+      z = 0;
+      blocks++;
+      if (++c == nblocks) c = 0;
+    }
+  }
+  s.pos = pos;
+  s.cz = c | (z << 8);
+  return blocks;
+}
+
+struct JpegNullSink {
+  JPEG_HD void dc(uint32_t, int) {}
+  JPEG_HD void ac(uint32_t, uint32_t, int) {}
+  JPEG_HD void block_end(uint32_t) {}
+};
+
+// Writes the luminance coefficients (zigzag order, DC as the difference to the previous luminance block) of the blocks
+// it sees, numbered from `block` (count of all blocks of all components before the span).
+struct JpegCoefSink {
+  int16_t *coef;       // [luminance block][64]
+  uint32_t mcu;        // MCU of the block being decoded
+  uint32_t nmcu;
+  uint32_t luma_per_mcu;
+  uint32_t nblocks;
+  JPEG_HD void dc(uint32_t c, int v) {
+    if (c < luma_per_mcu && mcu < nmcu) coef[(static_cast<size_t>(mcu) * luma_per_mcu + c) * 64] = static_cast<int16_t>(v);
+  }
+  JPEG_HD void ac(uint32_t c, uint32_t z, int v) {
+    if (c < luma_per_mcu && mcu < nmcu) coef[(static_cast<size_t>(mcu) * luma_per_mcu + c) * 64 + z] = static_cast<int16_t>(v);
+  }
+  JPEG_HD void block_end(uint32_t c) {
+    if (c + 1 == nblocks) mcu++;
+  }
+};
+
+}  // namespace b200tag

@@ -2,7 +2,10 @@
 // A few hundred header bytes per frame; the entropy-coded data is not touched here.
 #include "jpeg.h"
 
+#include <cmath>
 #include <cstring>
+
+#include "jpeg_core.h"
 
 namespace b200tag {
 namespace {
@@ -218,6 +221,7 @@ int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *wh
   f.vmax = static_cast<uint8_t>(vmax);
   f.mcus_x = static_cast<uint16_t>((width + 8 * hmax - 1) / (8 * hmax));
   f.mcus_y = static_cast<uint16_t>((height + 8 * vmax - 1) / (8 * vmax));
+  if (restart > 0xffff) return fail(kJpegMalformed, "bad DRI");
   f.restart_interval = static_cast<uint16_t>(restart);
   memcpy(f.quant, quant[tq[0]], sizeof(f.quant));
   for (int i = 0; i < 64; i++)
@@ -238,6 +242,100 @@ int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *wh
     if (!ac[i].present) memset(&out->tables.ac[i], 0, sizeof(JpegHuff));
   }
   return kJpegOk;
+}
+
+void jpeg_cos_table(float out[64]) {
+  for (int x = 0; x < 8; x++)
+    for (int u = 0; u < 8; u++)
+      out[x * 8 + u] = static_cast<float>(std::cos((2 * x + 1) * u * 3.14159265358979323846 / 16.0) * (u == 0 ? std::sqrt(0.5) : 1.0) * 0.5);
+}
+
+int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_cap, int *rounds) {
+  JpegParsed P;
+  std::string why;
+  const int rc = jpeg_parse(jpeg, len, &P, &why);
+  if (rc == kJpegUnsupported) return 1;
+  if (rc != kJpegOk) return -1;
+  const JpegFrame &F = P.frame;
+  if (F.restart_interval) return 1;
+  if (out_cap < static_cast<size_t>(F.width) * F.height) return -1;
+  // unstuffing passes (k_jpeg_unstuff_*): FF 00 -> FF
+  std::vector<uint8_t> clean;
+  for (size_t i = P.scan_begin; i < len; i++) {
+    if (jpeg[i] == 0 && i > P.scan_begin && jpeg[i - 1] == 0xff) continue;
+    clean.push_back(jpeg[i]);
+  }
+  const uint32_t end_bits = static_cast<uint32_t>(clean.size()) * 8u;
+  clean.resize(((clean.size() + 3) & ~size_t(3)) + 16, 0);
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(clean.data());
+  const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  // synchronisation rounds (k_jpeg_sync)
+  std::vector<JpegSyncState> s(nsub ? nsub : 1, JpegSyncState{0, 0}), next;
+  std::vector<uint32_t> nblk(nsub ? nsub : 1, 0);
+  JpegNullSink none;
+  int used = 0;
+  bool proven = nsub <= 1;
+  for (int r = 0; r < 64 && !proven; r++) {
+    next = s;
+    bool changed = false;
+    for (uint32_t i = 0; i + 1 < nsub; i++) {
+      JpegSyncState st = (r == 0 || i == 0) ? JpegSyncState{i * kJpegSubBits, 0} : s[i];
+      nblk[i] = jpeg_decode_span(words, end_bits, (i + 1) * kJpegSubBits, F, P.tables, st, none);
+      if (r == 0 || st.pos != s[i + 1].pos || st.cz != s[i + 1].cz) {
+        next[i + 1] = st;
+        changed = true;
+      }
+    }
+    s.swap(next);
+    used = r + 1;
+    if (!changed) proven = true;
+  }
+  if (rounds) *rounds = used;
+  if (!proven) return -2;
+  // block numbering (k_jpeg_blockscan) and coefficient pass (k_jpeg_write)
+  const uint32_t luma_per_mcu = static_cast<uint32_t>(F.hmax) * F.vmax, nmcu = static_cast<uint32_t>(F.mcus_x) * F.mcus_y;
+  std::vector<int16_t> coef(static_cast<size_t>(nmcu) * luma_per_mcu * 64, 0);
+  uint32_t base = 0;
+  for (uint32_t i = 0; i < nsub; i++) {
+    JpegSyncState st = i == 0 ? JpegSyncState{0, 0} : s[i];
+    JpegCoefSink sink{coef.data(), base / F.nblocks, nmcu, luma_per_mcu, F.nblocks};
+    const uint32_t done = jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, P.tables, st, sink);
+    base += i + 1 == nsub ? done : nblk[i];
+  }
+  // DC prediction (k_jpeg_dcscan) and inverse DCT (k_jpeg_idct)
+  float cosv[64];
+  jpeg_cos_table(cosv);
+  int pred = 0;
+  for (uint32_t lb = 0; lb < nmcu * luma_per_mcu; lb++) {
+    int16_t *zz = &coef[static_cast<size_t>(lb) * 64];
+    pred += zz[0];
+    float nat[64], tmp[64];
+    bool any_ac = false;
+    for (int k = 0; k < 64; k++) {
+      const int v = k == 0 ? pred : zz[k];
+      any_ac = any_ac || (k > 0 && v != 0);
+      nat[kZigzag[k]] = static_cast<float>(v) * static_cast<float>(F.quant[kZigzag[k]]);
+    }
+    const uint32_t mcu = lb / luma_per_mcu, j = lb % luma_per_mcu;
+    const int bx0 = static_cast<int>((mcu % F.mcus_x) * F.hmax + F.blk_bx[j]) * 8;
+    const int by0 = static_cast<int>((mcu / F.mcus_x) * F.vmax + F.blk_by[j]) * 8;
+    for (int y = 0; y < 8; y++)
+      for (int u = 0; u < 8; u++) {
+        float acc = 0.0f;
+        for (int v = 0; v < 8; v++) acc += cosv[y * 8 + v] * nat[v * 8 + u];
+        tmp[y * 8 + u] = acc;
+      }
+    for (int y = 0; y < 8; y++)
+      for (int x = 0; x < 8; x++) {
+        float acc = 0.0f;
+        for (int u = 0; u < 8; u++) acc += cosv[x * 8 + u] * tmp[y * 8 + u];
+        float v = any_ac ? acc + 128.0f : nat[0] * 0.125f + 128.0f;
+        const int pv = static_cast<int>(std::nearbyintf(v));
+        const int px = bx0 + x, py = by0 + y;
+        if (px < F.width && py < F.height) out[static_cast<size_t>(py) * F.width + px] = static_cast<uint8_t>(pv < 0 ? 0 : (pv > 255 ? 255 : pv));
+      }
+  }
+  return 0;
 }
 
 }  // namespace b200tag

@@ -57,11 +57,11 @@ int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer 
 void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s);
 void launch_blobs_init(cudaStream_t s);
 
-// JPEG luminance planes of `count` frames (jpeg.h) into `out`, frames `out_stride` bytes apart: one warp per frame.
-struct JpegFrame;
-struct JpegTables;
-void launch_jpeg_luma(const uint8_t *bits, const JpegFrame *frames, const JpegTables *tables, uint8_t *out, size_t out_stride,
-                      int count, cudaStream_t s);
+// JPEG luminance planes of a batch (jpeg.h): the parallel kernels for streams without restart markers, the sequential
+// warp-per-frame kernel for the rest.  Returns the number of kernels launched.
+struct JpegBatch;
+void launch_jpeg_init(const float cosv[64]);
+int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s);
 
 }  // namespace b200tag
 

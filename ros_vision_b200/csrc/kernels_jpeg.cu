@@ -13,6 +13,7 @@
 #include <cstdint>
 
 #include "jpeg.h"
+#include "jpeg_core.h"
 #include "kernels.h"
 
 namespace b200tag {
@@ -24,6 +25,8 @@ constexpr int kRingWords = kRingBytes / 4;
 __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+__constant__ float c_cosv[64];  // jpeg_cos_table(): cos((2x+1) u pi / 16) * C(u) / 2, [x][u]
 
 struct Shared {
   JpegTables tab;
@@ -123,9 +126,10 @@ __device__ __forceinline__ int receive_extend(BitReader &r, uint32_t s) {
 
 __global__ void __launch_bounds__(32) k_jpeg_luma(const uint8_t *__restrict__ bits, const JpegFrame *__restrict__ frames,
                                                   const JpegTables *__restrict__ tables, uint8_t *__restrict__ out,
-                                                  size_t out_stride) {
+                                                  size_t out_stride, const uint32_t *__restrict__ proven) {
   __shared__ Shared S;
   const int lane = threadIdx.x;
+  if (proven && proven[blockIdx.x]) return;  // the parallel kernels decoded this frame
   static_assert(sizeof(JpegFrame) % 4 == 0 && sizeof(JpegTables) % 4 == 0, "copied as words");
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + blockIdx.x);
@@ -141,8 +145,7 @@ __global__ void __launch_bounds__(32) k_jpeg_luma(const uint8_t *__restrict__ bi
     for (int i = lane; i < 64; i += 32) {
       S.quant[i] = static_cast<float>(F->quant[i]);
       S.zigzag[i] = c_zigzag[i];
-      const int x = i >> 3, u = i & 7;
-      S.cosv[i] = cospif(static_cast<float>((2 * x + 1) * u) * 0.0625f) * (u == 0 ? 0.70710678118654752f : 1.0f) * 0.5f;
+      S.cosv[i] = c_cosv[i];
     }
   }
   const int width = F->width, height = F->height;
@@ -272,11 +275,297 @@ __global__ void __launch_bounds__(32) k_jpeg_luma(const uint8_t *__restrict__ bi
   }
 }
 
+
+// ---- parallel path (streams without restart markers): unstuff -> synchronise -> coefficients -> DC -> IDCT -------------
+
+// exclusive scan over a 1024-thread CTA; returns the prefix of `v`, *total = CTA sum
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();  // warp_sums may still be read from a previous call
+  if (lane == 31) warp_sums[wi] = incl;
+  __syncthreads();
+  if (wi == 0) {
+    uint32_t w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  *total = warp_sums[31];
+  return incl - v + (wi ? warp_sums[wi - 1] : 0u);
+}
+
+// T.81 B.1.1.5: inside the entropy-coded segment FF 00 stands for the byte FF.  Pass 1 counts the bytes each 64-byte
+// chunk keeps, pass 2 turns the counts into offsets, pass 3 moves the bytes.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_jpeg_unstuff(JpegBatch B) {
+  const JpegFrame *F = B.frames + blockIdx.y;
+  if (F->restart_interval) return;
+  const uint32_t len = F->data_len, nch = (len + kJpegChunk - 1) / kJpegChunk;
+  const uint32_t ch = blockIdx.x * 256 + threadIdx.x;
+  if (ch >= nch) return;
+  const uint8_t *src = B.raw + F->data_off + static_cast<size_t>(ch) * kJpegChunk;
+  const uint32_t n = min(kJpegChunk, len - ch * kJpegChunk);
+  uint32_t prev = ch ? src[-1] : 0u;
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) v[i] = reinterpret_cast<const uint4 *>(src)[i];  // data_off is 16-byte aligned
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
+  uint8_t *dst = nullptr;
+  if (SCATTER) dst = B.clean + F->data_off + B.chunk_cnt[F->chunk_off + ch];
+  uint32_t kept = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t b = (w[i] >> (8 * j)) & 0xffu;
+      const bool keep = (4u * i + j < n) && !(b == 0u && prev == 0xffu);
+      if (keep) {
+        if (SCATTER) dst[kept] = static_cast<uint8_t>(b);
+        kept++;
+      }
+      prev = b;
+    }
+  }
+  if (!SCATTER) B.chunk_cnt[F->chunk_off + ch] = kept;
+}
+
+__global__ void __launch_bounds__(1024) k_jpeg_unstuff_scan(JpegBatch B) {
+  __shared__ uint32_t warp_sums[32];
+  const JpegFrame *F = B.frames + blockIdx.x;
+  if (F->restart_interval) return;
+  const uint32_t nch = (F->data_len + kJpegChunk - 1) / kJpegChunk;
+  uint32_t *cnt = B.chunk_cnt + F->chunk_off;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nch; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nch ? cnt[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(v, warp_sums, &total);
+    if (i < nch) cnt[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) B.clean_len[blockIdx.x] = carry;
+  // a zero tail so that the last codewords can be peeked as whole words
+  if (threadIdx.x < 16) B.clean[F->data_off + carry + threadIdx.x] = 0;
+}
+
+constexpr int kSyncThreads = 128;  // consecutive subsequences per CTA
+constexpr int kSyncLocalIters = 48;
+
+// One synchronisation round: every CTA iterates s[i+1] <- f_i(s[i]) on its 128 subsequences to the local fixed point
+// (a thread decodes again only when its input state changed), then publishes the states that differ from the stored
+// ones.  A round that publishes nothing proves the fixed point.
+__global__ void __launch_bounds__(kSyncThreads) k_jpeg_sync(JpegBatch B, int round) {
+  __shared__ JpegTables T;
+  __shared__ JpegFrame F;
+  __shared__ unsigned long long st[kSyncThreads + 1];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.frames + f);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&F);
+    for (uint32_t i = tid; i < sizeof(JpegFrame) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (F.restart_interval) return;
+  uint32_t *changed = B.changed + static_cast<size_t>(f) * kJpegSyncRounds;
+  if (round >= 2 && changed[round - 1] == 0) return;  // proven by an earlier round
+  const uint32_t end_bits = B.clean_len[f] * 8u;
+  const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  const uint32_t first = blockIdx.x * kSyncThreads;
+  if (first + 1 >= nsub) return;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.tables + F.tables);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+    for (uint32_t i = tid; i < sizeof(JpegTables) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  const uint32_t i = first + tid;
+  const bool active = i + 1 < nsub;  // the last subsequence has no successor
+  unsigned long long *sync = B.sync + F.sub_off;
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(B.clean + F.data_off);
+  auto pack = [](const JpegSyncState &s) { return static_cast<unsigned long long>(s.pos) | (static_cast<unsigned long long>(s.cz) << 32); };
+  // states at the start of my subsequence (st[tid]) and of the next CTA's first one (st[128])
+  if (i < nsub) st[tid] = (round == 0 || i == 0) ? static_cast<unsigned long long>(i) * kJpegSubBits : sync[i];
+  if (tid == kSyncThreads - 1) st[kSyncThreads] = 0xffffffffffffffffull;
+  __syncthreads();
+  unsigned long long last_in = 0xffffffffffffffffull, out = 0;
+  uint32_t nb = 0;
+  JpegNullSink none;
+  for (int it = 0; it < kSyncLocalIters; it++) {
+    const unsigned long long in = active ? st[tid] : 0ull;
+    if (active && in != last_in) {
+      JpegSyncState s{static_cast<uint32_t>(in), static_cast<uint32_t>(in >> 32)};
+      nb = jpeg_decode_span(words, end_bits, (i + 1) * kJpegSubBits, F, T, s, none);
+      out = pack(s);
+      last_in = in;
+    }
+    __syncthreads();
+    const bool ch = active && st[tid + 1] != out;
+    if (ch) st[tid + 1] = out;
+    if (!__syncthreads_or(ch)) break;
+  }
+  if (active) {
+    B.nblk[F.sub_off + i] = nb;
+    // (after kSyncLocalIters without a local fixed point `out` may be stale; the next round continues from it)
+    if (round == 0 || sync[i + 1] != out) {
+      sync[i + 1] = out;
+      changed[round] = 1;
+    }
+  }
+}
+
+// Per frame: is the fixed point proven, and the number of blocks before each subsequence.
+__global__ void __launch_bounds__(1024) k_jpeg_blockscan(JpegBatch B) {
+  __shared__ uint32_t warp_sums[32];
+  const int f = blockIdx.x;
+  const JpegFrame *F = B.frames + f;
+  const bool ok = F->restart_interval == 0 && B.changed[static_cast<size_t>(f) * kJpegSyncRounds + kJpegSyncRounds - 1] == 0;
+  if (threadIdx.x == 0) B.proven[f] = ok ? 1u : 0u;
+  if (!ok) return;
+  const uint32_t end_bits = B.clean_len[f] * 8u;
+  const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  uint32_t *nblk = B.nblk + F->sub_off;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nsub; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i + 1 < nsub ? nblk[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(v, warp_sums, &total);
+    if (i < nsub) nblk[i] = carry + ex;
+    carry += total;
+  }
+}
+
+// Every subsequence again, this time keeping the luminance coefficients.
+__global__ void __launch_bounds__(kSyncThreads) k_jpeg_write(JpegBatch B) {
+  __shared__ JpegTables T;
+  __shared__ JpegFrame F;
+  const int f = blockIdx.y, tid = threadIdx.x;
+  if (!B.proven[f]) return;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.frames + f);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&F);
+    for (uint32_t i = tid; i < sizeof(JpegFrame) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t end_bits = B.clean_len[f] * 8u;
+  const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  if (blockIdx.x * kSyncThreads >= nsub) return;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.tables + F.tables);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+    for (uint32_t i = tid; i < sizeof(JpegTables) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * kSyncThreads + tid;
+  if (i >= nsub) return;
+  const unsigned long long in = i == 0 ? 0ull : B.sync[F.sub_off + i];
+  JpegSyncState s{static_cast<uint32_t>(in), static_cast<uint32_t>(in >> 32)};
+  JpegCoefSink sink{B.coef + static_cast<size_t>(f) * B.coef_stride, B.nblk[F.sub_off + i] / F.nblocks,
+                    static_cast<uint32_t>(F.mcus_x) * F.mcus_y, static_cast<uint32_t>(F.hmax) * F.vmax, F.nblocks};
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(B.clean + F.data_off);
+  jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, T, s, sink);
+}
+
+// F.2.1.3.1: DC coefficients are coded as differences to the previous block of the component -> running sum over the
+// luminance blocks in stream order.
+__global__ void __launch_bounds__(1024) k_jpeg_dcscan(JpegBatch B) {
+  __shared__ uint32_t warp_sums[32];
+  const int f = blockIdx.x;
+  if (!B.proven[f]) return;
+  const JpegFrame *F = B.frames + f;
+  const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * F->hmax * F->vmax;
+  int16_t *coef = B.coef + static_cast<size_t>(f) * B.coef_stride;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nlb; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nlb ? static_cast<uint32_t>(static_cast<int>(coef[static_cast<size_t>(i) * 64])) : 0u;  // wraps like int
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(v, warp_sums, &total);
+    if (i < nlb) coef[static_cast<size_t>(i) * 64] = static_cast<int16_t>(static_cast<int>(carry + ex + v));
+    carry += total;
+  }
+}
+
+// Dequantisation + A.3.3 inverse DCT + level shift, 64 threads per block, four blocks per CTA; the coefficient buffer
+// is handed back all zero.
+__global__ void __launch_bounds__(256) k_jpeg_idct(JpegBatch B) {
+  __shared__ float nat[4][64], tmp[4][64];
+  __shared__ uint32_t any_ac[4][2];
+  const int f = blockIdx.y;
+  if (!B.proven[f]) return;
+  const JpegFrame *F = B.frames + f;
+  const uint32_t luma_per_mcu = static_cast<uint32_t>(F->hmax) * F->vmax;
+  const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * luma_per_mcu;
+  const int q = threadIdx.x >> 6, o = threadIdx.x & 63;
+  const uint32_t lb = blockIdx.x * 4 + q;
+  const bool live = lb < nlb;
+  int v = 0;
+  if (live) {
+    int16_t *c = B.coef + static_cast<size_t>(f) * B.coef_stride + static_cast<size_t>(lb) * 64 + o;
+    v = *c;
+    if (v) *c = 0;
+    const int n = c_zigzag[o];
+    nat[q][n] = static_cast<float>(v) * static_cast<float>(F->quant[n]);
+  }
+  const uint32_t acm = __ballot_sync(0xffffffffu, o > 0 && v != 0);
+  if ((threadIdx.x & 31) == 0) any_ac[q][(threadIdx.x >> 5) & 1] = acm;
+  __syncthreads();
+  const bool ac = (any_ac[q][0] | any_ac[q][1]) != 0;
+  {
+    const int y = o >> 3, u = o & 7;
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += c_cosv[y * 8 + k] * nat[q][k * 8 + u];
+    tmp[q][o] = s;
+  }
+  __syncthreads();
+  if (!live) return;
+  const int y = o >> 3, x = o & 7;
+  float s = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) s += c_cosv[x * 8 + u] * tmp[q][y * 8 + u];
+  const float val = ac ? s + 128.0f : nat[q][0] * 0.125f + 128.0f;
+  const int pv = min(255, max(0, __float2int_rn(val)));
+  const uint32_t mcu = lb / luma_per_mcu, j = lb % luma_per_mcu;
+  const int px = static_cast<int>((mcu % F->mcus_x) * F->hmax + F->blk_bx[j]) * 8 + x;
+  const int py = static_cast<int>((mcu / F->mcus_x) * F->vmax + F->blk_by[j]) * 8 + y;
+  if (px < F->width && py < F->height) B.out[static_cast<size_t>(f) * B.out_stride + static_cast<size_t>(py) * F->width + px] = static_cast<uint8_t>(pv);
+}
+
 }  // namespace
 
-void launch_jpeg_luma(const uint8_t *bits, const JpegFrame *frames, const JpegTables *tables, uint8_t *out, size_t out_stride,
-                      int count, cudaStream_t s) {
-  k_jpeg_luma<<<count, 32, 0, s>>>(bits, frames, tables, out, out_stride);
+void launch_jpeg_init(const float cosv[64]) { cudaMemcpyToSymbol(c_cosv, cosv, 64 * sizeof(float)); }
+
+// Returns the number of kernels launched.  Frames with restart markers, and frames whose parallel decode did not reach
+// its fixed point within kJpegSyncRounds rounds, are decoded by the sequential warp-per-frame kernel at the end.
+int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s) {
+  int launches = 0;
+  if (any_parallel) {
+    cudaMemsetAsync(B.changed, 0, sizeof(uint32_t) * kJpegSyncRounds * B.count, s);
+    const dim3 gch((B.max_chunks + 255) / 256, B.count);
+    k_jpeg_unstuff<false><<<gch, 256, 0, s>>>(B);
+    k_jpeg_unstuff_scan<<<B.count, 1024, 0, s>>>(B);
+    k_jpeg_unstuff<true><<<gch, 256, 0, s>>>(B);
+    const dim3 gsub((B.max_subs + kSyncThreads - 1) / kSyncThreads, B.count);
+    for (int r = 0; r < kJpegSyncRounds; r++) k_jpeg_sync<<<gsub, kSyncThreads, 0, s>>>(B, r);
+    k_jpeg_blockscan<<<B.count, 1024, 0, s>>>(B);
+    k_jpeg_write<<<gsub, kSyncThreads, 0, s>>>(B);
+    k_jpeg_dcscan<<<B.count, 1024, 0, s>>>(B);
+    k_jpeg_idct<<<dim3((B.max_luma_blocks + 3) / 4, B.count), 256, 0, s>>>(B);
+    launches += 7 + kJpegSyncRounds;
+  }
+  k_jpeg_luma<<<B.count, 32, 0, s>>>(B.raw, B.frames, B.tables, B.out, B.out_stride, any_parallel ? B.proven : nullptr);
+  return launches + 1;
 }
 
 }  // namespace b200tag

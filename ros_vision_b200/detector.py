@@ -100,6 +100,9 @@ def load_library():
     L.b200tag_enqueue_mjpg.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32]
     L.b200tag_detect_mjpg.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32]
     L.b200tag_mjpg_backend.argtypes = [vp]
+    L.b200tag_mjpg_parallel_frames.argtypes = [vp, i32]
+    L.b200tag_debug_jpeg_model.argtypes = [vp, sz, vp, sz, C.POINTER(i32)]
+    L.b200tag_jpeg_probe.argtypes = [vp, sz, C.POINTER(C.c_int32), vp, sz, C.POINTER(sz)]
     L.b200tag_mjpg_backend.restype = C.c_char_p
     L.b200tag_finish.argtypes = [vp]
     L.b200tag_stream.argtypes = [vp]
@@ -139,6 +142,18 @@ def default_config(width: int, height: int, fmt: str = "yuyv") -> Config:
     if rc:
         raise B200TagError("b200tag_default_config failed")
     return cfg
+
+
+def jpeg_model_decode(jpeg: bytes, width: int, height: int):
+    """Test hook: the host model of the parallel JPEG decode kernels -> (luminance plane, synchronisation rounds)."""
+    lib = load_library()
+    buf = np.frombuffer(jpeg, dtype=np.uint8)
+    out = np.zeros((height, width), dtype=np.uint8)
+    rounds = C.c_int32(0)
+    rc = lib.b200tag_debug_jpeg_model(buf.ctypes.data_as(C.c_void_p), buf.size, out.ctypes.data_as(C.c_void_p), out.size, C.byref(rounds))
+    if rc:
+        raise ValueError(f"b200tag_debug_jpeg_model: {rc}")
+    return out, rounds.value
 
 
 def estimate_poses(detections: np.ndarray, tagsize: float, fx: float, fy: float, cx: float, cy: float) -> np.ndarray:
@@ -285,6 +300,10 @@ class GpuDetector:
     def DetectMjpg(self, jpegs, allow_overflow=False) -> int:
         self.EnqueueMjpg(jpegs)
         return self.Finish(allow_overflow)
+
+    def MjpgParallelFrames(self) -> int:
+        """Frames of the last MJPG batch decoded by the parallel kernels (the rest took the sequential kernel)."""
+        return int(self._lib.b200tag_mjpg_parallel_frames(self._h, self.last_count))
 
     @property
     def mjpg_backend(self) -> str:

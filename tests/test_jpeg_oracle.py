@@ -62,7 +62,6 @@ def test_host_parser_agrees_with_oracle(cases, pyjpeg):
     from ros_vision_b200 import build, detector
     build.build_native()
     lib = detector.load_library()
-    lib.b200tag_jpeg_probe.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _, streams = cases
     for name, jpg in streams.items():
         rc, info, dht = _probe(lib, jpg)
@@ -81,3 +80,22 @@ def test_host_parser_agrees_with_oracle(cases, pyjpeg):
     assert _probe(lib, prog.tobytes())[0] == 1
     assert _probe(lib, b"\x12" * 64)[0] < 0
     assert _probe(lib, streams["422"][:200])[0] < 0
+
+
+def test_parallel_scheme_host_model(cases, pyjpeg):
+    """The self-synchronising parallel decode (subsequences, fixed-point rounds, block numbering, DC scan, float IDCT) as
+    the kernels do it, run by the host model: within 1 level of the oracle on every stream without restart markers."""
+    from ros_vision_b200 import build, detector
+    build.build_native()
+    sc, streams = cases
+    h, w = sc.gray.shape
+    for name, jpg in streams.items():
+        if "rst" in name:
+            with pytest.raises(ValueError, match="1"):
+                detector.jpeg_model_decode(jpg, w, h)
+            continue
+        got, rounds = detector.jpeg_model_decode(jpg, w, h)
+        ref = pyjpeg.decode_luma(jpg)
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-4, name
+        assert 1 <= rounds <= 40, (name, rounds)
