@@ -752,13 +752,18 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     ws_layout(want, &chunks, &subs);
     CK(cudaHostAlloc(reinterpret_cast<void **>(&J.h_block), want, cudaHostAllocDefault));
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_block), want));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 8 + (chunks + subs) * 4 + B * (kJpegSyncRounds + 2) * 4 + 256));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 16 + (chunks + subs) * 4 + B * (kJpegSyncRounds + 2) * 4 + 256));
     J.cap = want;
   }
   JpegFrame *hf = reinterpret_cast<JpegFrame *>(J.h_block);
   JpegTables *ht = reinterpret_cast<JpegTables *>(J.h_block + frames_bytes);
   size_t off = frames_bytes + tables_bytes;
-  for (size_t k = 0; k < set_owner.size(); k++) ht[k] = J.parsed[set_owner[k]].tables;
+  for (size_t k = 0; k < set_owner.size(); k++) {
+    if (!jpeg_build_tables(J.parsed[set_owner[k]].dht, &ht[k])) {
+      det->err = "frame " + std::to_string(set_owner[k]) + ": invalid Huffman table";
+      return B200TAG_E_INVALID;
+    }
+  }
   JpegBatch jb;
   memset(&jb, 0, sizeof(jb));
   uint32_t chunk_off = 0, sub_off = 0;
@@ -789,6 +794,7 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
   jb.raw = J.d_block;
   jb.clean = w; w += J.cap;
   jb.sync = reinterpret_cast<unsigned long long *>(w); w += subs * 8;
+  jb.sync_in = reinterpret_cast<unsigned long long *>(w); w += subs * 8;
   jb.chunk_cnt = reinterpret_cast<uint32_t *>(w); w += chunks * 4;
   jb.nblk = reinterpret_cast<uint32_t *>(w); w += subs * 4;
   jb.changed = reinterpret_cast<uint32_t *>(w); w += B * kJpegSyncRounds * 4;

@@ -55,6 +55,7 @@ struct JpegBatch {
   uint32_t *chunk_cnt;        // per 64-byte raw chunk: bytes kept, then their exclusive prefix
   uint32_t *clean_len;        // per frame: unstuffed bytes
   unsigned long long *sync;   // per subsequence: JpegSyncState at its start
+  unsigned long long *sync_in; // per subsequence: the start state its published successor state was decoded from
   uint32_t *nblk;             // per subsequence: blocks completed in it, then their exclusive prefix
   uint32_t *changed;          // [frame][round]: some state changed in that round
   uint32_t *proven;           // per frame: the parallel decode reached its fixed point
@@ -73,12 +74,13 @@ struct JpegParsed {
   JpegFrame frame;              // data_off / tables still to be filled by the caller
   size_t scan_begin = 0;        // first byte of the entropy-coded segment within the file
   std::vector<uint8_t> dht;     // canonical form of the four tables in use (counts + values), to find identical sets
-  JpegTables tables;
 };
 
 // Parses the headers of one JPEG (markers up to SOS).  kJpegUnsupported: a valid JPEG this decoder does not handle
 // (progressive, arithmetic, 12-bit, non-interleaved scans, subsampled luminance, table ids above 1).
 int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *why);
+// Decoder form of the tables in JpegParsed::dht (once per distinct set of a batch); false: not a valid prefix code
+bool jpeg_build_tables(const std::vector<uint8_t> &dht, JpegTables *out);
 
 // cos((2x+1) u pi / 16) * C(u) / 2 as floats, [x][u]: the one table both the kernels and the host model use
 void jpeg_cos_table(float out[64]);

@@ -235,13 +235,28 @@ int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *wh
       out->dht.insert(out->dht.end(), t->counts, t->counts + 16);
       out->dht.insert(out->dht.end(), t->vals.begin(), t->vals.end());
     }
-  for (int i = 0; i < 2; i++) {
-    if (dc[i].present && !build_huff(dc[i], &out->tables.dc[i])) return fail(kJpegMalformed, "invalid Huffman table");
-    if (ac[i].present && !build_huff(ac[i], &out->tables.ac[i])) return fail(kJpegMalformed, "invalid Huffman table");
-    if (!dc[i].present) memset(&out->tables.dc[i], 0, sizeof(JpegHuff));
-    if (!ac[i].present) memset(&out->tables.ac[i], 0, sizeof(JpegHuff));
-  }
   return kJpegOk;
+}
+
+bool jpeg_build_tables(const std::vector<uint8_t> &dht, JpegTables *out) {
+  memset(out, 0, sizeof(*out));
+  size_t o = 0;
+  for (int i = 0; i < 2; i++)
+    for (int kind = 0; kind < 2; kind++) {  // order of jpeg_parse: dc[i], ac[i]
+      if (o >= dht.size()) return false;
+      if (!dht[o++]) continue;
+      if (o + 16 > dht.size()) return false;
+      RawTable t;
+      memcpy(t.counts, dht.data() + o, 16);
+      size_t total = 0;
+      for (int l = 0; l < 16; l++) total += t.counts[l];
+      o += 16;
+      if (total > 256 || o + total > dht.size()) return false;
+      t.vals.assign(dht.begin() + o, dht.begin() + o + total);
+      o += total;
+      if (!build_huff(t, kind ? &out->ac[i] : &out->dc[i])) return false;
+    }
+  return true;
 }
 
 void jpeg_cos_table(float out[64]) {
@@ -258,6 +273,8 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   if (rc != kJpegOk) return -1;
   const JpegFrame &F = P.frame;
   if (F.restart_interval) return 1;
+  JpegTables tables;
+  if (!jpeg_build_tables(P.dht, &tables)) return -1;
   if (out_cap < static_cast<size_t>(F.width) * F.height) return -1;
   // unstuffing passes (k_jpeg_unstuff_*): FF 00 -> FF
   std::vector<uint8_t> clean;
@@ -280,7 +297,7 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
     bool changed = false;
     for (uint32_t i = 0; i + 1 < nsub; i++) {
       JpegSyncState st = (r == 0 || i == 0) ? JpegSyncState{i * kJpegSubBits, 0} : s[i];
-      nblk[i] = jpeg_decode_span(words, end_bits, (i + 1) * kJpegSubBits, F, P.tables, st, none);
+      nblk[i] = jpeg_decode_span(words, end_bits, (i + 1) * kJpegSubBits, F, tables, st, none);
       if (r == 0 || st.pos != s[i + 1].pos || st.cz != s[i + 1].cz) {
         next[i + 1] = st;
         changed = true;
@@ -299,7 +316,7 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   for (uint32_t i = 0; i < nsub; i++) {
     JpegSyncState st = i == 0 ? JpegSyncState{0, 0} : s[i];
     JpegCoefSink sink{coef.data(), base / F.nblocks, nmcu, luma_per_mcu, F.nblocks};
-    const uint32_t done = jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, P.tables, st, sink);
+    const uint32_t done = jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, tables, st, sink);
     base += i + 1 == nsub ? done : nblk[i];
   }
   // DC prediction (k_jpeg_dcscan) and inverse DCT (k_jpeg_idct)

@@ -397,8 +397,15 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_sync(JpegBatch B, int rou
   if (i < nsub) st[tid] = (round == 0 || i == 0) ? static_cast<unsigned long long>(i) * kJpegSubBits : sync[i];
   if (tid == kSyncThreads - 1) st[kSyncThreads] = 0xffffffffffffffffull;
   __syncthreads();
+  // what this subsequence was last decoded from, and what came out (kept across rounds: a launch whose input did not
+  // change has nothing to decode)
   unsigned long long last_in = 0xffffffffffffffffull, out = 0;
   uint32_t nb = 0;
+  if (active && round > 0) {
+    last_in = B.sync_in[F.sub_off + i];
+    out = sync[i + 1];
+    nb = B.nblk[F.sub_off + i];
+  }
   JpegNullSink none;
   for (int it = 0; it < kSyncLocalIters; it++) {
     const unsigned long long in = active ? st[tid] : 0ull;
@@ -415,6 +422,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_sync(JpegBatch B, int rou
   }
   if (active) {
     B.nblk[F.sub_off + i] = nb;
+    B.sync_in[F.sub_off + i] = last_in;
     // (after kSyncLocalIters without a local fixed point `out` may be stale; the next round continues from it)
     if (round == 0 || sync[i + 1] != out) {
       sync[i + 1] = out;
@@ -496,50 +504,91 @@ __global__ void __launch_bounds__(1024) k_jpeg_dcscan(JpegBatch B) {
   }
 }
 
-// Dequantisation + A.3.3 inverse DCT + level shift, 64 threads per block, four blocks per CTA; the coefficient buffer
-// is handed back all zero.
-__global__ void __launch_bounds__(256) k_jpeg_idct(JpegBatch B) {
-  __shared__ float nat[4][64], tmp[4][64];
-  __shared__ uint32_t any_ac[4][2];
+// Dequantisation + A.3.3 inverse DCT + level shift: 8 threads per block (a column each, then a row each), 32 blocks per
+// CTA; the sums run in the same order as in the sequential kernel, so both give the same bits.  The coefficient
+// buffer is handed back all zero.
+constexpr int kIdctBlocks = 32;   // blocks per CTA
+constexpr int kIdctStride = 72;   // floats per block in shared memory (72 mod 32 = 8: four blocks of a warp on distinct banks)
+__global__ void __launch_bounds__(kIdctBlocks * 8) k_jpeg_idct(JpegBatch B) {
+  __shared__ __align__(16) float nat[kIdctBlocks * kIdctStride];
+  __shared__ __align__(16) float tmp[kIdctBlocks * kIdctStride];
+  __shared__ float quant[64];
+  __shared__ uint8_t zz[64];
   const int f = blockIdx.y;
   if (!B.proven[f]) return;
   const JpegFrame *F = B.frames + f;
   const uint32_t luma_per_mcu = static_cast<uint32_t>(F->hmax) * F->vmax;
   const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * luma_per_mcu;
-  const int q = threadIdx.x >> 6, o = threadIdx.x & 63;
-  const uint32_t lb = blockIdx.x * 4 + q;
-  const bool live = lb < nlb;
-  int v = 0;
-  if (live) {
-    int16_t *c = B.coef + static_cast<size_t>(f) * B.coef_stride + static_cast<size_t>(lb) * 64 + o;
-    v = *c;
-    if (v) *c = 0;
-    const int n = c_zigzag[o];
-    nat[q][n] = static_cast<float>(v) * static_cast<float>(F->quant[n]);
+  if (threadIdx.x < 64) {
+    quant[threadIdx.x] = static_cast<float>(F->quant[threadIdx.x]);
+    zz[threadIdx.x] = c_zigzag[threadIdx.x];
   }
-  const uint32_t acm = __ballot_sync(0xffffffffu, o > 0 && v != 0);
-  if ((threadIdx.x & 31) == 0) any_ac[q][(threadIdx.x >> 5) & 1] = acm;
   __syncthreads();
-  const bool ac = (any_ac[q][0] | any_ac[q][1]) != 0;
+  const int q = threadIdx.x >> 3, j = threadIdx.x & 7, lane = threadIdx.x & 31;
+  const uint32_t lb = blockIdx.x * kIdctBlocks + q;
+  const bool live = lb < nlb;
+  float *mine = nat + q * kIdctStride;
+  bool nz_ac = false;
   {
-    const int y = o >> 3, u = o & 7;
-    float s = 0.0f;
+    // coefficients j*8 .. j*8+7 of the block (zigzag order): one 16-byte load, scattered to natural order
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    uint4 *src = reinterpret_cast<uint4 *>(B.coef + static_cast<size_t>(f) * B.coef_stride + static_cast<size_t>(lb) * 64) + j;
+    if (live) {
+      raw = *src;
+      if (raw.x | raw.y | raw.z | raw.w) *src = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int k = 0; k < 8; k++) s += c_cosv[y * 8 + k] * nat[q][k * 8 + u];
-    tmp[q][o] = s;
+    for (int i = 0; i < 8; i++) {
+      const int v = static_cast<int16_t>((w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+      const int k = j * 8 + i, n = zz[k];
+      mine[n] = static_cast<float>(v) * quant[n];
+      nz_ac = nz_ac || (k > 0 && v != 0);
+    }
+  }
+  const uint32_t acm = __ballot_sync(0xffffffffu, nz_ac);
+  const bool ac = ((acm >> (lane & ~7)) & 0xffu) != 0;
+  __syncthreads();
+  {  // column u = j: tmp[y][u] = sum_v c[y][v] nat[v][u]
+    float in[8];
+#pragma unroll
+    for (int v = 0; v < 8; v++) in[v] = mine[v * 8 + j];
+    float *t = tmp + q * kIdctStride;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      float s = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 8; v++) s += c_cosv[y * 8 + v] * in[v];
+      t[y * 8 + j] = s;
+    }
   }
   __syncthreads();
   if (!live) return;
-  const int y = o >> 3, x = o & 7;
-  float s = 0.0f;
+  // row y = j: out[y][x] = sum_u c[x][u] tmp[y][u]
+  const float4 r0 = *reinterpret_cast<const float4 *>(tmp + q * kIdctStride + j * 8);
+  const float4 r1 = *reinterpret_cast<const float4 *>(tmp + q * kIdctStride + j * 8 + 4);
+  const float in[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const float flat = mine[0] * 0.125f + 128.0f;
+  uint32_t px8[2] = {0, 0};
 #pragma unroll
-  for (int u = 0; u < 8; u++) s += c_cosv[x * 8 + u] * tmp[q][y * 8 + u];
-  const float val = ac ? s + 128.0f : nat[q][0] * 0.125f + 128.0f;
-  const int pv = min(255, max(0, __float2int_rn(val)));
-  const uint32_t mcu = lb / luma_per_mcu, j = lb % luma_per_mcu;
-  const int px = static_cast<int>((mcu % F->mcus_x) * F->hmax + F->blk_bx[j]) * 8 + x;
-  const int py = static_cast<int>((mcu / F->mcus_x) * F->vmax + F->blk_by[j]) * 8 + y;
-  if (px < F->width && py < F->height) B.out[static_cast<size_t>(f) * B.out_stride + static_cast<size_t>(py) * F->width + px] = static_cast<uint8_t>(pv);
+  for (int x = 0; x < 8; x++) {
+    float s = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += c_cosv[x * 8 + u] * in[u];
+    const float val = ac ? s + 128.0f : flat;
+    const uint32_t pv = static_cast<uint32_t>(min(255, max(0, __float2int_rn(val))));
+    px8[x >> 2] |= pv << (8 * (x & 3));
+  }
+  const uint32_t mcu = lb / luma_per_mcu, jb = lb % luma_per_mcu;
+  const int px = static_cast<int>((mcu % F->mcus_x) * F->hmax + F->blk_bx[jb]) * 8;
+  const int py = static_cast<int>((mcu / F->mcus_x) * F->vmax + F->blk_by[jb]) * 8 + j;
+  if (py >= F->height) return;
+  uint8_t *row = B.out + static_cast<size_t>(f) * B.out_stride + static_cast<size_t>(py) * F->width + px;
+  if (px + 8 <= F->width && (reinterpret_cast<uintptr_t>(row) & 7u) == 0) {
+    *reinterpret_cast<uint2 *>(row) = make_uint2(px8[0], px8[1]);
+  } else {
+    for (int x = 0; x < 8 && px + x < F->width; x++) row[x] = static_cast<uint8_t>((px8[x >> 2] >> (8 * (x & 3))) & 0xffu);
+  }
 }
 
 }  // namespace
@@ -561,7 +610,7 @@ int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s) {
     k_jpeg_blockscan<<<B.count, 1024, 0, s>>>(B);
     k_jpeg_write<<<gsub, kSyncThreads, 0, s>>>(B);
     k_jpeg_dcscan<<<B.count, 1024, 0, s>>>(B);
-    k_jpeg_idct<<<dim3((B.max_luma_blocks + 3) / 4, B.count), 256, 0, s>>>(B);
+    k_jpeg_idct<<<dim3((B.max_luma_blocks + kIdctBlocks - 1) / kIdctBlocks, B.count), kIdctBlocks * 8, 0, s>>>(B);
     launches += 7 + kJpegSyncRounds;
   }
   k_jpeg_luma<<<B.count, 32, 0, s>>>(B.raw, B.frames, B.tables, B.out, B.out_stride, any_parallel ? B.proven : nullptr);

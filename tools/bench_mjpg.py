@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """End-to-end throughput of the camera wire format: config-2 scenes as 4:2:2 JPEG bitstreams
-in host memory -> b200tag_enqueue_mjpg (nvJPEG luminance decode + detection) -> detections on the host.  Informational:
-the headline bench (bench.py) stays on raw YUYV frames.  Usage: python tools/bench_mjpg.py [--batch 128] [--steps 20]
-[--lanes 2] [--quality 90]; B200TAG_NVJPEG_BACKEND=hardware|gpu|hybrid|default selects the nvJPEG backend."""
+in host memory -> b200tag_enqueue_mjpg (luminance decode + detection on one stream) -> detections on the host.
+Informational: the headline bench (bench.py) stays on raw YUYV frames.  Usage: python tools/bench_mjpg.py [--batch 128]
+[--steps 20] [--lanes 2] [--quality 75] [--decoder native|sequential|nvjpeg]; with --decoder nvjpeg,
+B200TAG_NVJPEG_BACKEND=hardware|gpu|hybrid|default selects the nvJPEG backend."""
 import argparse
 import json
 import os
@@ -23,9 +24,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lanes", type=int, default=2)
-    ap.add_argument("--quality", type=int, default=90)
+    ap.add_argument("--quality", type=int, default=75)
     ap.add_argument("--unique", type=int, default=16)
+    ap.add_argument("--decoder", default="native", choices=["native", "sequential", "nvjpeg"],
+                    help="native: the engine's parallel decode kernels; sequential: its warp-per-frame kernel; nvjpeg: the library")
     a = ap.parse_args()
+    if a.decoder != "native":
+        os.environ["B200TAG_MJPG_DECODER"] = a.decoder
     D.load_library()
     w, h = 1280, 800
     jpgs, ntags = [], 0
@@ -59,7 +64,8 @@ def main():
     print(json.dumps({"metric": "mjpg_frames_per_second_end_to_end", "value": a.batch * a.steps / dt, "unit": "frames/s",
                       "ms_per_step": 1e3 * dt / a.steps, "batch": a.batch, "lanes": a.lanes, "steps": a.steps,
                       "jpeg_bytes_per_frame": int(np.mean([len(j) for j in jpgs])), "quality": a.quality,
-                      "nvjpeg_backend": dets[0].mjpg_backend, "tags_found": found, "tags_present": ntags}))
+                      "decoder": a.decoder if a.decoder != "nvjpeg" else "nvjpeg/" + dets[0].mjpg_backend,
+                      "parallel_frames_last_batch": dets[0].MjpgParallelFrames(), "tags_found": found, "tags_present": ntags}))
     for d in dets:
         d.close()
 
