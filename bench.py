@@ -274,6 +274,54 @@ def opencv_aruco_leg(frames, seconds_budget=4.0):
         return {"unavailable": repr(e)[:200]}
 
 
+def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
+    """Informational: the same config-2 scenes as 4:2:2 JPEG bitstreams in host memory ->
+    b200tag_enqueue_mjpg (hand-written JPEG luminance decode kernels + detection) -> detections on the host; wall clock
+    around `steps` 128-frame batches on two detectors.  None when OpenCV (the test encoder) is missing."""
+    try:
+        import cv2
+    except ImportError:
+        return None
+    from ros_vision_b200 import detector as D, synth
+    jpgs, present = [], 0
+    for i in range(UNIQUE_FRAMES):
+        _, _, w, h, dec, sigma, sc = synth.config_frame(2, i)
+        bgr = synth.gray_to_bgr(sc.gray, np.random.default_rng(i))
+        ok, buf = cv2.imencode(".jpg", bgr, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                              cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422])
+        if not ok:
+            return None
+        jpgs.append(buf.tobytes())
+        present += len(sc.tags)
+    batch = [jpgs[i % len(jpgs)] for i in range(BATCH)]
+    dets = [D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, max_batch=BATCH, device=local) for _ in range(2)]
+    for _ in range(3):
+        for d in dets:
+            d.EnqueueMjpg(batch)
+        for d in dets:
+            d.Finish()
+    found = sum(len(dets[0].Detections(f)) for f in range(len(jpgs)))
+    parallel = dets[0].MjpgParallelFrames()
+    t0 = time.perf_counter()
+    pending = []
+    for it in range(steps):
+        d = dets[it % 2]
+        if len(pending) == 2:
+            pending.pop(0).Finish()
+        d.EnqueueMjpg(batch)
+        pending.append(d)
+    for d in pending:
+        d.Finish()
+    dt = time.perf_counter() - t0
+    out = {"value": BATCH * steps / dt, "unit": "frames/s", "what": "JPEG bytes in host memory -> detections on the host",
+           "jpeg_bytes_per_frame": int(np.mean([len(j) for j in jpgs])), "quality": quality, "sampling": "4:2:2",
+           "h2d_bytes_per_step": int(sum(len(j) for j in batch)), "frames_per_step": BATCH, "steps": steps,
+           "decoder": dets[0].mjpg_backend, "frames_decoded_by_parallel_kernels": parallel, "tags_found": found, "tags_present": present}
+    for d in dets:
+        d.close()
+    return out
+
+
 def run_reference(args):
     rank, world, local = dist_setup(args.gpus)
     if rank != 0:
@@ -515,6 +563,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps * DL,
             "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
             "cpu_opencv_aruco": opencv_aruco_leg(frames) if (world == 1 and not args.no_cpu) else None,
+            "e2e_mjpg": mjpg_leg(local) if (world == 1 and not args.no_cpu and CONFIG == 2 and FMT == "yuyv") else None,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},

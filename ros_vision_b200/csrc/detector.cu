@@ -52,6 +52,7 @@ struct NativeJpeg {
   size_t cap = 0;
   uint8_t *d_ws = nullptr;     // workspace of the parallel kernels, sized with `cap`
   int16_t *d_coef = nullptr;   // coefficient buffer (fixed size, all zero between batches)
+  uint32_t *d_rst = nullptr;   // restart-interval starts, one slot per 8x8 block of a frame
   size_t coef_stride = 0;
   bool init = false;
   std::vector<JpegParsed> parsed;
@@ -573,6 +574,7 @@ void b200tag_destroy(b200tag_detector *det) {
   if (det->jpeg.d_block) cudaFree(det->jpeg.d_block);
   if (det->jpeg.d_ws) cudaFree(det->jpeg.d_ws);
   if (det->jpeg.d_coef) cudaFree(det->jpeg.d_coef);
+  if (det->jpeg.d_rst) cudaFree(det->jpeg.d_rst);
   if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
   if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
@@ -738,6 +740,7 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     J.coef_stride = static_cast<size_t>((det->cfg.width + 31) / 32 * 32) * static_cast<size_t>((det->cfg.height + 31) / 32 * 32);
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_coef), J.coef_stride * B * sizeof(int16_t)));
     CK(cudaMemsetAsync(J.d_coef, 0, J.coef_stride * B * sizeof(int16_t), det->stream));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_rst), J.coef_stride / 64 * B * sizeof(uint32_t)));
     J.init = true;
   }
   if (total > J.cap) {
@@ -752,7 +755,7 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     ws_layout(want, &chunks, &subs);
     CK(cudaHostAlloc(reinterpret_cast<void **>(&J.h_block), want, cudaHostAllocDefault));
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_block), want));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 16 + (chunks + subs) * 4 + B * (kJpegSyncRounds + 2) * 4 + 256));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 16 + (2 * chunks + subs) * 4 + B * (kJpegSyncRounds + 3) * 4 + 256));
     J.cap = want;
   }
   JpegFrame *hf = reinterpret_cast<JpegFrame *>(J.h_block);
@@ -784,7 +787,11 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     jb.max_chunks = std::max(jb.max_chunks, nch);
     jb.max_subs = std::max(jb.max_subs, nsub);
     jb.max_luma_blocks = std::max<uint32_t>(jb.max_luma_blocks, static_cast<uint32_t>(hf[f].mcus_x) * hf[f].mcus_y * hf[f].hmax * hf[f].vmax);
-    any_parallel = any_parallel || hf[f].restart_interval == 0;
+    any_parallel = true;
+    if (hf[f].restart_interval) {
+      const uint32_t nmcu = static_cast<uint32_t>(hf[f].mcus_x) * hf[f].mcus_y;
+      jb.max_intervals = std::max(jb.max_intervals, (nmcu + hf[f].restart_interval - 1) / hf[f].restart_interval);
+    }
     if (static_cast<size_t>(hf[f].mcus_x) * hf[f].mcus_y * hf[f].hmax * hf[f].vmax * 64 > J.coef_stride) return 1;
     off += (n + 15) & ~static_cast<size_t>(15);
   }
@@ -796,10 +803,14 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
   jb.sync = reinterpret_cast<unsigned long long *>(w); w += subs * 8;
   jb.sync_in = reinterpret_cast<unsigned long long *>(w); w += subs * 8;
   jb.chunk_cnt = reinterpret_cast<uint32_t *>(w); w += chunks * 4;
+  jb.chunk_rst = reinterpret_cast<uint32_t *>(w); w += chunks * 4;
   jb.nblk = reinterpret_cast<uint32_t *>(w); w += subs * 4;
   jb.changed = reinterpret_cast<uint32_t *>(w); w += B * kJpegSyncRounds * 4;
   jb.proven = reinterpret_cast<uint32_t *>(w); w += B * 4;
-  jb.clean_len = reinterpret_cast<uint32_t *>(w);
+  jb.clean_len = reinterpret_cast<uint32_t *>(w); w += B * 4;
+  jb.nrst = reinterpret_cast<uint32_t *>(w);
+  jb.rst_pos = J.d_rst;
+  jb.rst_stride = static_cast<uint32_t>(J.coef_stride / 64);
   jb.frames = reinterpret_cast<const JpegFrame *>(J.d_block);
   jb.tables = reinterpret_cast<const JpegTables *>(J.d_block + frames_bytes);
   jb.coef = J.d_coef;

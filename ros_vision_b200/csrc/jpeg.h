@@ -54,6 +54,11 @@ struct JpegBatch {
   const JpegTables *tables;
   uint32_t *chunk_cnt;        // per 64-byte raw chunk: bytes kept, then their exclusive prefix
   uint32_t *clean_len;        // per frame: unstuffed bytes
+  uint32_t *chunk_rst;        // per chunk: RSTn markers ending in it, then their exclusive prefix
+  uint32_t *nrst;             // per frame: RSTn markers found
+  uint32_t *rst_pos;          // [frame][rst_stride]: unstuffed byte offset at which the interval after each marker starts
+  uint32_t rst_stride;
+  uint32_t max_intervals;     // largest number of restart intervals of a frame in the batch
   unsigned long long *sync;   // per subsequence: JpegSyncState at its start
   unsigned long long *sync_in; // per subsequence: the start state its published successor state was decoded from
   uint32_t *nblk;             // per subsequence: blocks completed in it, then their exclusive prefix

@@ -71,14 +71,14 @@ JPEG_HD int jpeg_value(uint32_t peek, uint32_t len, uint32_t s) {
   return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
 }
 
-// Decodes codewords from state `s` until one ends at or beyond bit `limit` (or the data ends at `end_bits`); returns
-// the number of blocks completed.  sink.dc(c, diff), sink.ac(c, z, v) and sink.block_end(c) see every coefficient.
+// Decodes codewords from state `s` until one ends at or beyond bit `limit`, the data ends at `end_bits`, or
+// `max_blocks` blocks are complete; returns the number of blocks completed.  sink.dc(c, diff), sink.ac(c, z, v) and sink.block_end(c) see every coefficient.
 template <class Sink>
 JPEG_HD uint32_t jpeg_decode_span(const uint32_t *words, uint32_t end_bits, uint32_t limit, const JpegFrame &F,
-                                  const JpegTables &T, JpegSyncState &s, Sink &sink) {
+                                  const JpegTables &T, JpegSyncState &s, Sink &sink, uint32_t max_blocks = 0xffffffffu) {
   uint32_t pos = s.pos, c = s.cz & 0xffu, z = s.cz >> 8, blocks = 0;
   const uint32_t nblocks = F.nblocks;
-  while (pos < limit && pos < end_bits) {
+  while (pos < limit && pos < end_bits && blocks < max_blocks) {
     const uint32_t peek = jpeg_peek32(words, pos);
     const uint32_t comp = F.blk_comp[c];
     uint32_t len;
@@ -138,6 +138,21 @@ struct JpegCoefSink {
   JPEG_HD void block_end(uint32_t c) {
     if (c + 1 == nblocks) mcu++;
   }
+};
+
+// The same for one restart interval decoded from its start by a single thread: DC prediction (F.2.1.3.1) is a running
+// sum inside the interval, so the absolute value is written straight away.
+struct JpegIntervalSink {
+  JpegCoefSink to;
+  int pred;
+  JPEG_HD void dc(uint32_t c, int v) {
+    if (c < to.luma_per_mcu) {
+      pred += v;
+      to.dc(c, pred);
+    }
+  }
+  JPEG_HD void ac(uint32_t c, uint32_t z, int v) { to.ac(c, z, v); }
+  JPEG_HD void block_end(uint32_t c) { to.block_end(c); }
 };
 
 }  // namespace b200tag

@@ -2,6 +2,7 @@
 // A few hundred header bytes per frame; the entropy-coded data is not touched here.
 #include "jpeg.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -272,27 +273,45 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   if (rc == kJpegUnsupported) return 1;
   if (rc != kJpegOk) return -1;
   const JpegFrame &F = P.frame;
-  if (F.restart_interval) return 1;
   JpegTables tables;
   if (!jpeg_build_tables(P.dht, &tables)) return -1;
   if (out_cap < static_cast<size_t>(F.width) * F.height) return -1;
-  // unstuffing passes (k_jpeg_unstuff_*): FF 00 -> FF
+  // unstuffing passes (k_jpeg_unstuff_*): FF 00 -> FF, RSTn markers out (their positions = interval starts)
   std::vector<uint8_t> clean;
+  std::vector<uint32_t> rst;
   for (size_t i = P.scan_begin; i < len; i++) {
-    if (jpeg[i] == 0 && i > P.scan_begin && jpeg[i - 1] == 0xff) continue;
-    clean.push_back(jpeg[i]);
+    const uint8_t b = jpeg[i], prev = i > P.scan_begin ? jpeg[i - 1] : 0, nb = i + 1 < len ? jpeg[i + 1] : 0;
+    if (b == 0 && prev == 0xff) continue;
+    if (b == 0xff && nb >= 0xd0 && nb <= 0xd7) continue;
+    if (prev == 0xff && b >= 0xd0 && b <= 0xd7) {
+      rst.push_back(static_cast<uint32_t>(clean.size()));
+      continue;
+    }
+    clean.push_back(b);
   }
   const uint32_t end_bits = static_cast<uint32_t>(clean.size()) * 8u;
   clean.resize(((clean.size() + 3) & ~size_t(3)) + 16, 0);
   const uint32_t *words = reinterpret_cast<const uint32_t *>(clean.data());
-  const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  const uint32_t luma_per_mcu = static_cast<uint32_t>(F.hmax) * F.vmax, nmcu = static_cast<uint32_t>(F.mcus_x) * F.mcus_y;
+  std::vector<int16_t> coef(static_cast<size_t>(nmcu) * luma_per_mcu * 64, 0);
+  const uint32_t nsub = F.restart_interval ? 0 : (end_bits + kJpegSubBits - 1) / kJpegSubBits;
+  if (F.restart_interval) {  // k_jpeg_write_rst: one "thread" per restart interval
+    const uint32_t ri = F.restart_interval, nint = (nmcu + ri - 1) / ri;
+    if (rst.size() + 1 != nint) return -2;
+    for (uint32_t k = 0; k < nint; k++) {
+      JpegSyncState st{k ? rst[k - 1] * 8u : 0u, 0u};
+      JpegIntervalSink sink{{coef.data(), k * ri, nmcu, luma_per_mcu, F.nblocks}, 0};
+      jpeg_decode_span(words, end_bits, k + 1 < nint ? rst[k] * 8u : end_bits, F, tables, st, sink, std::min(ri, nmcu - k * ri) * F.nblocks);
+    }
+    if (rounds) *rounds = 0;
+  }
   // synchronisation rounds (k_jpeg_sync)
   std::vector<JpegSyncState> s(nsub ? nsub : 1, JpegSyncState{0, 0}), next;
   std::vector<uint32_t> nblk(nsub ? nsub : 1, 0);
   JpegNullSink none;
   int used = 0;
   bool proven = nsub <= 1;
-  for (int r = 0; r < 64 && !proven; r++) {
+  for (int r = 0; r < 64 && !proven && !F.restart_interval; r++) {
     next = s;
     bool changed = false;
     for (uint32_t i = 0; i + 1 < nsub; i++) {
@@ -307,11 +326,9 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
     used = r + 1;
     if (!changed) proven = true;
   }
-  if (rounds) *rounds = used;
+  if (rounds && !F.restart_interval) *rounds = used;
   if (!proven) return -2;
   // block numbering (k_jpeg_blockscan) and coefficient pass (k_jpeg_write)
-  const uint32_t luma_per_mcu = static_cast<uint32_t>(F.hmax) * F.vmax, nmcu = static_cast<uint32_t>(F.mcus_x) * F.mcus_y;
-  std::vector<int16_t> coef(static_cast<size_t>(nmcu) * luma_per_mcu * 64, 0);
   uint32_t base = 0;
   for (uint32_t i = 0; i < nsub; i++) {
     JpegSyncState st = i == 0 ? JpegSyncState{0, 0} : s[i];
@@ -325,7 +342,7 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   int pred = 0;
   for (uint32_t lb = 0; lb < nmcu * luma_per_mcu; lb++) {
     int16_t *zz = &coef[static_cast<size_t>(lb) * 64];
-    pred += zz[0];
+    pred = F.restart_interval ? zz[0] : pred + zz[0];
     float nat[64], tmp[64];
     bool any_ac = false;
     for (int k = 0; k < 64; k++) {

@@ -304,59 +304,82 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *war
   return incl - v + (wi ? warp_sums[wi - 1] : 0u);
 }
 
-// T.81 B.1.1.5: inside the entropy-coded segment FF 00 stands for the byte FF.  Pass 1 counts the bytes each 64-byte
-// chunk keeps, pass 2 turns the counts into offsets, pass 3 moves the bytes.
+// T.81 B.1.1.5: inside the entropy-coded segment FF 00 stands for the byte FF; FF D0..D7 are the RSTn markers between
+// restart intervals (E.1.4), which are taken out and remembered as interval starts.  Pass 1 counts the bytes each
+// 64-byte chunk keeps (and the markers that end in it), pass 2 turns the counts into offsets, pass 3 moves the bytes.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_jpeg_unstuff(JpegBatch B) {
   const JpegFrame *F = B.frames + blockIdx.y;
-  if (F->restart_interval) return;
   const uint32_t len = F->data_len, nch = (len + kJpegChunk - 1) / kJpegChunk;
   const uint32_t ch = blockIdx.x * 256 + threadIdx.x;
   if (ch >= nch) return;
   const uint8_t *src = B.raw + F->data_off + static_cast<size_t>(ch) * kJpegChunk;
   const uint32_t n = min(kJpegChunk, len - ch * kJpegChunk);
   uint32_t prev = ch ? src[-1] : 0u;
+  const uint32_t after = ch * kJpegChunk + n < len ? src[n] : 0u;  // first byte of the next chunk
   uint4 v[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) v[i] = reinterpret_cast<const uint4 *>(src)[i];  // data_off is 16-byte aligned
   const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
   uint8_t *dst = nullptr;
-  if (SCATTER) dst = B.clean + F->data_off + B.chunk_cnt[F->chunk_off + ch];
-  uint32_t kept = 0;
+  uint32_t *rst = nullptr;
+  uint32_t base = 0, rst_room = 0;
+  if (SCATTER) {
+    base = B.chunk_cnt[F->chunk_off + ch];
+    dst = B.clean + F->data_off + base;
+    const uint32_t r0 = B.chunk_rst[F->chunk_off + ch];
+    rst = B.rst_pos + static_cast<size_t>(blockIdx.y) * B.rst_stride + r0;
+    rst_room = r0 < B.rst_stride ? B.rst_stride - r0 : 0u;
+  }
+  uint32_t kept = 0, markers = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
+      const uint32_t k = 4u * i + j;
       const uint32_t b = (w[i] >> (8 * j)) & 0xffu;
-      const bool keep = (4u * i + j < n) && !(b == 0u && prev == 0xffu);
-      if (keep) {
+      const uint32_t nb = k + 1 < n ? ((k + 1) & 3u ? (w[i] >> (8 * (j + 1))) & 0xffu : (w[(i + 1) & 15] & 0xffu)) : after;
+      const bool in = k < n;
+      const bool marker2 = in && prev == 0xffu && b >= 0xd0u && b <= 0xd7u;  // second byte of an RSTn
+      const bool marker1 = in && b == 0xffu && nb >= 0xd0u && nb <= 0xd7u;   // first byte of an RSTn
+      const bool stuffed = in && b == 0u && prev == 0xffu;
+      if (in && !marker1 && !marker2 && !stuffed) {
         if (SCATTER) dst[kept] = static_cast<uint8_t>(b);
         kept++;
       }
-      prev = b;
+      if (marker2) {
+        if (SCATTER && markers < rst_room) rst[markers] = base + kept;
+        markers++;
+      }
+      if (in) prev = b;
     }
   }
-  if (!SCATTER) B.chunk_cnt[F->chunk_off + ch] = kept;
+  if (!SCATTER) {
+    B.chunk_cnt[F->chunk_off + ch] = kept;
+    B.chunk_rst[F->chunk_off + ch] = markers;
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_jpeg_unstuff_scan(JpegBatch B) {
   __shared__ uint32_t warp_sums[32];
   const JpegFrame *F = B.frames + blockIdx.x;
-  if (F->restart_interval) return;
   const uint32_t nch = (F->data_len + kJpegChunk - 1) / kJpegChunk;
-  uint32_t *cnt = B.chunk_cnt + F->chunk_off;
-  uint32_t carry = 0;
+  uint32_t *cnt = B.chunk_cnt + F->chunk_off, *rst = B.chunk_rst + F->chunk_off;
+  uint32_t carry = 0, carry_rst = 0;
   for (uint32_t base = 0; base < nch; base += 1024) {
     const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nch ? cnt[i] : 0u;
     uint32_t total;
-    const uint32_t ex = cta_exclusive_scan(v, warp_sums, &total);
+    const uint32_t ex = cta_exclusive_scan(i < nch ? cnt[i] : 0u, warp_sums, &total);
     if (i < nch) cnt[i] = carry + ex;
     carry += total;
+    const uint32_t exr = cta_exclusive_scan(i < nch ? rst[i] : 0u, warp_sums, &total);
+    if (i < nch) rst[i] = carry_rst + exr;
+    carry_rst += total;
   }
-  if (threadIdx.x == 0) B.clean_len[blockIdx.x] = carry;
-  // a zero tail so that the last codewords can be peeked as whole words
-  if (threadIdx.x < 16) B.clean[F->data_off + carry + threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    B.clean_len[blockIdx.x] = carry;
+    B.nrst[blockIdx.x] = carry_rst;
+  }
 }
 
 constexpr int kSyncThreads = 128;  // consecutive subsequences per CTA
@@ -436,9 +459,16 @@ __global__ void __launch_bounds__(1024) k_jpeg_blockscan(JpegBatch B) {
   __shared__ uint32_t warp_sums[32];
   const int f = blockIdx.x;
   const JpegFrame *F = B.frames + f;
-  const bool ok = F->restart_interval == 0 && B.changed[static_cast<size_t>(f) * kJpegSyncRounds + kJpegSyncRounds - 1] == 0;
+  bool ok;
+  if (F->restart_interval) {  // every interval is decoded from its own start: all that is needed is the right number of markers
+    const uint32_t nmcu = static_cast<uint32_t>(F->mcus_x) * F->mcus_y;
+    const uint32_t nint = (nmcu + F->restart_interval - 1) / F->restart_interval;
+    ok = B.nrst[f] + 1 == nint && B.nrst[f] <= B.rst_stride;
+  } else {
+    ok = B.changed[static_cast<size_t>(f) * kJpegSyncRounds + kJpegSyncRounds - 1] == 0;
+  }
   if (threadIdx.x == 0) B.proven[f] = ok ? 1u : 0u;
-  if (!ok) return;
+  if (!ok || F->restart_interval) return;
   const uint32_t end_bits = B.clean_len[f] * 8u;
   const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
   uint32_t *nblk = B.nblk + F->sub_off;
@@ -465,6 +495,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_write(JpegBatch B) {
     for (uint32_t i = tid; i < sizeof(JpegFrame) / 4; i += kSyncThreads) dst[i] = src[i];
   }
   __syncthreads();
+  if (F.restart_interval) return;  // k_jpeg_write_rst
   const uint32_t end_bits = B.clean_len[f] * 8u;
   const uint32_t nsub = (end_bits + kJpegSubBits - 1) / kJpegSubBits;
   if (blockIdx.x * kSyncThreads >= nsub) return;
@@ -484,6 +515,40 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_write(JpegBatch B) {
   jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, T, s, sink);
 }
 
+// Streams with restart markers: an interval starts on a byte boundary with zero predictors (E.1.4), so one thread per
+// interval decodes it from its own start -- no synchronisation rounds, absolute DC values written directly.
+__global__ void __launch_bounds__(kSyncThreads) k_jpeg_write_rst(JpegBatch B) {
+  __shared__ JpegTables T;
+  __shared__ JpegFrame F;
+  const int f = blockIdx.y, tid = threadIdx.x;
+  if (!B.proven[f]) return;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.frames + f);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&F);
+    for (uint32_t i = tid; i < sizeof(JpegFrame) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (!F.restart_interval) return;
+  const uint32_t nmcu = static_cast<uint32_t>(F.mcus_x) * F.mcus_y, ri = F.restart_interval;
+  const uint32_t nint = (nmcu + ri - 1) / ri;
+  if (blockIdx.x * kSyncThreads >= nint) return;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(B.tables + F.tables);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+    for (uint32_t i = tid; i < sizeof(JpegTables) / 4; i += kSyncThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t k = blockIdx.x * kSyncThreads + tid;
+  if (k >= nint) return;
+  const uint32_t *rst = B.rst_pos + static_cast<size_t>(f) * B.rst_stride;
+  const uint32_t end_bits = B.clean_len[f] * 8u;
+  JpegSyncState s{k ? rst[k - 1] * 8u : 0u, 0u};
+  const uint32_t limit = k + 1 < nint ? rst[k] * 8u : end_bits;
+  JpegIntervalSink sink{{B.coef + static_cast<size_t>(f) * B.coef_stride, k * ri, nmcu, static_cast<uint32_t>(F.hmax) * F.vmax, F.nblocks}, 0};
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(B.clean + F.data_off);
+  jpeg_decode_span(words, end_bits, limit, F, T, s, sink, min(ri, nmcu - k * ri) * F.nblocks);
+}
+
 // F.2.1.3.1: DC coefficients are coded as differences to the previous block of the component -> running sum over the
 // luminance blocks in stream order.
 __global__ void __launch_bounds__(1024) k_jpeg_dcscan(JpegBatch B) {
@@ -491,6 +556,7 @@ __global__ void __launch_bounds__(1024) k_jpeg_dcscan(JpegBatch B) {
   const int f = blockIdx.x;
   if (!B.proven[f]) return;
   const JpegFrame *F = B.frames + f;
+  if (F->restart_interval) return;  // k_jpeg_write_rst wrote absolute values
   const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * F->hmax * F->vmax;
   int16_t *coef = B.coef + static_cast<size_t>(f) * B.coef_stride;
   uint32_t carry = 0;
@@ -595,8 +661,9 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) k_jpeg_idct(JpegBatch B) {
 
 void launch_jpeg_init(const float cosv[64]) { cudaMemcpyToSymbol(c_cosv, cosv, 64 * sizeof(float)); }
 
-// Returns the number of kernels launched.  Frames with restart markers, and frames whose parallel decode did not reach
-// its fixed point within kJpegSyncRounds rounds, are decoded by the sequential warp-per-frame kernel at the end.
+// Returns the number of kernels launched.  Frames whose parallel decode did not reach its fixed point within
+// kJpegSyncRounds rounds (or whose restart markers do not add up) are decoded by the sequential warp-per-frame kernel
+// at the end.
 int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s) {
   int launches = 0;
   if (any_parallel) {
@@ -609,6 +676,10 @@ int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s) {
     for (int r = 0; r < kJpegSyncRounds; r++) k_jpeg_sync<<<gsub, kSyncThreads, 0, s>>>(B, r);
     k_jpeg_blockscan<<<B.count, 1024, 0, s>>>(B);
     k_jpeg_write<<<gsub, kSyncThreads, 0, s>>>(B);
+    if (B.max_intervals) {
+      k_jpeg_write_rst<<<dim3((B.max_intervals + kSyncThreads - 1) / kSyncThreads, B.count), kSyncThreads, 0, s>>>(B);
+      launches++;
+    }
     k_jpeg_dcscan<<<B.count, 1024, 0, s>>>(B);
     k_jpeg_idct<<<dim3((B.max_luma_blocks + kIdctBlocks - 1) / kIdctBlocks, B.count), kIdctBlocks * 8, 0, s>>>(B);
     launches += 7 + kJpegSyncRounds;

@@ -100,9 +100,9 @@ def test_native_decoder_every_baseline_variant(D, monkeypatch):
     det = D.GpuDetector(w, h, "gray", quad_decimate=2, keep_stages=True, max_batch=len(names))
     det.DetectMjpg([streams[n] for n in names])
     assert det.mjpg_backend == "native"
-    # streams without restart markers take the parallel kernels (a frame whose synchronisation is not proven within the
-    # fixed number of rounds would fall back to the sequential kernel: none of these does)
-    assert det.MjpgParallelFrames() == sum("rst" not in n for n in names)
+    # every stream takes the parallel kernels (a frame whose synchronisation is not proven within the fixed number of
+    # rounds, or whose restart markers do not add up, would fall back to the sequential kernel: none of these does)
+    assert det.MjpgParallelFrames() == len(names)
     planes = [det.CopyGrayTo(f).reshape(h, w).copy() for f in range(len(names))]
     monkeypatch.setenv("B200TAG_MJPG_DECODER", "sequential")
     det.DetectMjpg([streams[n] for n in names])
@@ -113,8 +113,7 @@ def test_native_decoder_every_baseline_variant(D, monkeypatch):
         ref = pyjpeg.decode_luma(streams[name])
         got = planes[f]
         assert np.array_equal(got, det.CopyGrayTo(f).reshape(h, w)), name   # parallel and sequential kernels: same bits
-        if "rst" not in name:
-            assert np.array_equal(got, D.jpeg_model_decode(streams[name], w, h)[0]), name   # and the host model
+        assert np.array_equal(got, D.jpeg_model_decode(streams[name], w, h)[0]), name   # and the host model
         diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1, (name, diff.max())
         exact += int((diff == 0).mean() > 0.999)   # float vs double IDCT: ties at .5 are the only differences

@@ -84,18 +84,15 @@ def test_host_parser_agrees_with_oracle(cases, pyjpeg):
 
 def test_parallel_scheme_host_model(cases, pyjpeg):
     """The self-synchronising parallel decode (subsequences, fixed-point rounds, block numbering, DC scan, float IDCT) as
-    the kernels do it, run by the host model: within 1 level of the oracle on every stream without restart markers."""
+    the kernels do it, run by the host model (restart-marker streams: one interval per thread instead): within 1 level
+    of the oracle on every stream."""
     from ros_vision_b200 import build, detector
     build.build_native()
     sc, streams = cases
     h, w = sc.gray.shape
     for name, jpg in streams.items():
-        if "rst" in name:
-            with pytest.raises(ValueError, match="1"):
-                detector.jpeg_model_decode(jpg, w, h)
-            continue
         got, rounds = detector.jpeg_model_decode(jpg, w, h)
         ref = pyjpeg.decode_luma(jpg)
         diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-4, name
-        assert 1 <= rounds <= 40, (name, rounds)
+        assert (rounds == 0) if "rst" in name else (1 <= rounds <= 40), (name, rounds)   # restart intervals need no rounds
