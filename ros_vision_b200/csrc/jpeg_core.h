@@ -22,7 +22,7 @@
 
 namespace b200tag {
 
-constexpr uint32_t kJpegSubBits = 1024;  // bits per subsequence (128 bytes of unstuffed data)
+constexpr uint32_t kJpegSubBits = 512;   // bits per subsequence (64 bytes of unstuffed data)
 constexpr int kJpegSyncRounds = 8;       // rounds launched; a frame that is not proven by then is decoded sequentially
 constexpr uint32_t kJpegChunk = 64;      // raw bytes per thread of the unstuffing passes
 
