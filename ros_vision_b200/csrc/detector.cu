@@ -53,6 +53,7 @@ struct NativeJpeg {
   uint8_t *d_ws = nullptr;     // workspace of the parallel kernels, sized with `cap`
   int16_t *d_coef = nullptr;   // coefficient buffer (fixed size, all zero between batches)
   uint32_t *d_rst = nullptr;   // restart-interval starts, one slot per 8x8 block of a frame
+  int16_t *d_dcs = nullptr;    // DC values, one per 8x8 block of a frame
   size_t coef_stride = 0;
   bool init = false;
   std::vector<JpegParsed> parsed;
@@ -575,6 +576,7 @@ void b200tag_destroy(b200tag_detector *det) {
   if (det->jpeg.d_ws) cudaFree(det->jpeg.d_ws);
   if (det->jpeg.d_coef) cudaFree(det->jpeg.d_coef);
   if (det->jpeg.d_rst) cudaFree(det->jpeg.d_rst);
+  if (det->jpeg.d_dcs) cudaFree(det->jpeg.d_dcs);
   if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
   if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
@@ -734,13 +736,12 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     *subs = cap / (kJpegSubBits / 8) + B + 16;
   };
   if (!J.init) {
-    float cosv[64];
-    jpeg_cos_table(cosv);
-    launch_jpeg_init(cosv);
     J.coef_stride = static_cast<size_t>((det->cfg.width + 31) / 32 * 32) * static_cast<size_t>((det->cfg.height + 31) / 32 * 32);
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_coef), J.coef_stride * B * sizeof(int16_t)));
     CK(cudaMemsetAsync(J.d_coef, 0, J.coef_stride * B * sizeof(int16_t), det->stream));
     CK(cudaMalloc(reinterpret_cast<void **>(&J.d_rst), J.coef_stride / 64 * B * sizeof(uint32_t)));
+    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_dcs), J.coef_stride / 64 * B * sizeof(int16_t)));
+    CK(cudaMemsetAsync(J.d_dcs, 0, J.coef_stride / 64 * B * sizeof(int16_t), det->stream));
     J.init = true;
   }
   if (total > J.cap) {
@@ -815,6 +816,7 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
   jb.tables = reinterpret_cast<const JpegTables *>(J.d_block + frames_bytes);
   jb.coef = J.d_coef;
   jb.coef_stride = J.coef_stride;
+  jb.dcs = J.d_dcs;
   jb.out = det->d_in;
   jb.out_stride = det->fp.in_stride;
   jb.count = count;

@@ -66,6 +66,7 @@ struct JpegBatch {
   uint32_t *proven;           // per frame: the parallel decode reached its fixed point
   int16_t *coef;              // [frame][luminance block][64], zigzag order; all zero between batches
   size_t coef_stride;         // int16 per frame
+  int16_t *dcs;               // [frame][luminance block]: DC differences, then DC values (coef_stride / 64 per frame)
   uint8_t *out;
   size_t out_stride;
   int count;
@@ -86,9 +87,6 @@ struct JpegParsed {
 int jpeg_parse(const uint8_t *data, size_t len, JpegParsed *out, std::string *why);
 // Decoder form of the tables in JpegParsed::dht (once per distinct set of a batch); false: not a valid prefix code
 bool jpeg_build_tables(const std::vector<uint8_t> &dht, JpegTables *out);
-
-// cos((2x+1) u pi / 16) * C(u) / 2 as floats, [x][u]: the one table both the kernels and the host model use
-void jpeg_cos_table(float out[64]);
 
 // Host model of the parallel decoder (same core, same arithmetic, threads replaced by loops) -- a test hook that lets
 // the scheme be checked without a GPU; nothing on the detection path calls it.  Returns 0, 1 = stream kind the

@@ -115,6 +115,25 @@ JPEG_HD uint32_t jpeg_decode_span(const uint32_t *words, uint32_t end_bits, uint
   return blocks;
 }
 
+// 8-point inverse DCT of T.81 A.3.3, x[n] = sum_k C(k)/2 X[k] cos((2n+1) k pi / 16), by the even/odd split (22
+// multiplications and 28 additions instead of 64 + 56).  One function for the kernels and the host model: the same
+// operations in the same order, no contraction into FMAs (the library is built with -fmad=false / -ffp-contract=off).
+JPEG_HD void jpeg_idct8(const float X[8], float x[8]) {
+  constexpr float d1 = 0.49039264f, d2 = 0.46193977f, d3 = 0.41573481f, d4 = 0.35355339f, d5 = 0.27778512f, d6 = 0.19134172f,
+                  d7 = 0.09754516f;  // cos(j pi / 16) / 2
+  const float ee0 = (X[0] + X[4]) * d4, ee1 = (X[0] - X[4]) * d4;
+  const float eo0 = X[2] * d2 + X[6] * d6, eo1 = X[2] * d6 - X[6] * d2;
+  const float e0 = ee0 + eo0, e1 = ee1 + eo1, e2 = ee1 - eo1, e3 = ee0 - eo0;
+  const float o0 = X[1] * d1 + X[3] * d3 + X[5] * d5 + X[7] * d7;
+  const float o1 = X[1] * d3 - X[3] * d7 - X[5] * d1 - X[7] * d5;
+  const float o2 = X[1] * d5 - X[3] * d1 + X[5] * d7 + X[7] * d3;
+  const float o3 = X[1] * d7 - X[3] * d5 + X[5] * d3 - X[7] * d1;
+  x[0] = e0 + o0; x[7] = e0 - o0;
+  x[1] = e1 + o1; x[6] = e1 - o1;
+  x[2] = e2 + o2; x[5] = e2 - o2;
+  x[3] = e3 + o3; x[4] = e3 - o3;
+}
+
 struct JpegNullSink {
   JPEG_HD void dc(uint32_t, int) {}
   JPEG_HD void ac(uint32_t, uint32_t, int) {}
@@ -124,13 +143,14 @@ struct JpegNullSink {
 // Writes the luminance coefficients (zigzag order, DC as the difference to the previous luminance block) of the blocks
 // it sees, numbered from `block` (count of all blocks of all components before the span).
 struct JpegCoefSink {
-  int16_t *coef;       // [luminance block][64]
+  int16_t *coef;       // [luminance block][64]; entry 0 of a block is not used ...
+  int16_t *dcs;        // ... the DC values have an array of their own, [luminance block]
   uint32_t mcu;        // MCU of the block being decoded
   uint32_t nmcu;
   uint32_t luma_per_mcu;
   uint32_t nblocks;
   JPEG_HD void dc(uint32_t c, int v) {
-    if (c < luma_per_mcu && mcu < nmcu) coef[(static_cast<size_t>(mcu) * luma_per_mcu + c) * 64] = static_cast<int16_t>(v);
+    if (c < luma_per_mcu && mcu < nmcu) dcs[static_cast<size_t>(mcu) * luma_per_mcu + c] = static_cast<int16_t>(v);
   }
   JPEG_HD void ac(uint32_t c, uint32_t z, int v) {
     if (c < luma_per_mcu && mcu < nmcu) coef[(static_cast<size_t>(mcu) * luma_per_mcu + c) * 64 + z] = static_cast<int16_t>(v);

@@ -260,12 +260,6 @@ bool jpeg_build_tables(const std::vector<uint8_t> &dht, JpegTables *out) {
   return true;
 }
 
-void jpeg_cos_table(float out[64]) {
-  for (int x = 0; x < 8; x++)
-    for (int u = 0; u < 8; u++)
-      out[x * 8 + u] = static_cast<float>(std::cos((2 * x + 1) * u * 3.14159265358979323846 / 16.0) * (u == 0 ? std::sqrt(0.5) : 1.0) * 0.5);
-}
-
 int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_cap, int *rounds) {
   JpegParsed P;
   std::string why;
@@ -293,14 +287,14 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   clean.resize(((clean.size() + 3) & ~size_t(3)) + 16, 0);
   const uint32_t *words = reinterpret_cast<const uint32_t *>(clean.data());
   const uint32_t luma_per_mcu = static_cast<uint32_t>(F.hmax) * F.vmax, nmcu = static_cast<uint32_t>(F.mcus_x) * F.mcus_y;
-  std::vector<int16_t> coef(static_cast<size_t>(nmcu) * luma_per_mcu * 64, 0);
+  std::vector<int16_t> coef(static_cast<size_t>(nmcu) * luma_per_mcu * 64, 0), dcs(static_cast<size_t>(nmcu) * luma_per_mcu, 0);
   const uint32_t nsub = F.restart_interval ? 0 : (end_bits + kJpegSubBits - 1) / kJpegSubBits;
   if (F.restart_interval) {  // k_jpeg_write_rst: one "thread" per restart interval
     const uint32_t ri = F.restart_interval, nint = (nmcu + ri - 1) / ri;
     if (rst.size() + 1 != nint) return -2;
     for (uint32_t k = 0; k < nint; k++) {
       JpegSyncState st{k ? rst[k - 1] * 8u : 0u, 0u};
-      JpegIntervalSink sink{{coef.data(), k * ri, nmcu, luma_per_mcu, F.nblocks}, 0};
+      JpegIntervalSink sink{{coef.data(), dcs.data(), k * ri, nmcu, luma_per_mcu, F.nblocks}, 0};
       jpeg_decode_span(words, end_bits, k + 1 < nint ? rst[k] * 8u : end_bits, F, tables, st, sink, std::min(ri, nmcu - k * ri) * F.nblocks);
     }
     if (rounds) *rounds = 0;
@@ -332,17 +326,15 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   uint32_t base = 0;
   for (uint32_t i = 0; i < nsub; i++) {
     JpegSyncState st = i == 0 ? JpegSyncState{0, 0} : s[i];
-    JpegCoefSink sink{coef.data(), base / F.nblocks, nmcu, luma_per_mcu, F.nblocks};
+    JpegCoefSink sink{coef.data(), dcs.data(), base / F.nblocks, nmcu, luma_per_mcu, F.nblocks};
     const uint32_t done = jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, tables, st, sink);
     base += i + 1 == nsub ? done : nblk[i];
   }
   // DC prediction (k_jpeg_dcscan) and inverse DCT (k_jpeg_idct)
-  float cosv[64];
-  jpeg_cos_table(cosv);
   int pred = 0;
   for (uint32_t lb = 0; lb < nmcu * luma_per_mcu; lb++) {
     int16_t *zz = &coef[static_cast<size_t>(lb) * 64];
-    pred = F.restart_interval ? zz[0] : pred + zz[0];
+    pred = F.restart_interval ? dcs[lb] : pred + dcs[lb];
     float nat[64], tmp[64];
     bool any_ac = false;
     for (int k = 0; k < 64; k++) {
@@ -353,21 +345,22 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
     const uint32_t mcu = lb / luma_per_mcu, j = lb % luma_per_mcu;
     const int bx0 = static_cast<int>((mcu % F.mcus_x) * F.hmax + F.blk_bx[j]) * 8;
     const int by0 = static_cast<int>((mcu / F.mcus_x) * F.vmax + F.blk_by[j]) * 8;
-    for (int y = 0; y < 8; y++)
-      for (int u = 0; u < 8; u++) {
-        float acc = 0.0f;
-        for (int v = 0; v < 8; v++) acc += cosv[y * 8 + v] * nat[v * 8 + u];
-        tmp[y * 8 + u] = acc;
-      }
-    for (int y = 0; y < 8; y++)
+    for (int u = 0; u < 8; u++) {  // columns, then rows (k_jpeg_idct)
+      float in[8], o[8];
+      for (int v = 0; v < 8; v++) in[v] = nat[v * 8 + u];
+      jpeg_idct8(in, o);
+      for (int y = 0; y < 8; y++) tmp[y * 8 + u] = o[y];
+    }
+    for (int y = 0; y < 8; y++) {
+      float o[8];
+      jpeg_idct8(tmp + y * 8, o);
       for (int x = 0; x < 8; x++) {
-        float acc = 0.0f;
-        for (int u = 0; u < 8; u++) acc += cosv[x * 8 + u] * tmp[y * 8 + u];
-        float v = any_ac ? acc + 128.0f : nat[0] * 0.125f + 128.0f;
+        float v = any_ac ? o[x] + 128.0f : nat[0] * 0.125f + 128.0f;
         const int pv = static_cast<int>(std::nearbyintf(v));
         const int px = bx0 + x, py = by0 + y;
         if (px < F.width && py < F.height) out[static_cast<size_t>(py) * F.width + px] = static_cast<uint8_t>(pv < 0 ? 0 : (pv > 255 ? 255 : pv));
       }
+    }
   }
   return 0;
 }

@@ -60,7 +60,6 @@ void launch_blobs_init(cudaStream_t s);
 // JPEG luminance planes of a batch (jpeg.h): the parallel kernels for streams without restart markers, the sequential
 // warp-per-frame kernel for the rest.  Returns the number of kernels launched.
 struct JpegBatch;
-void launch_jpeg_init(const float cosv[64]);
 int launch_jpeg_decode(const JpegBatch &B, bool any_parallel, cudaStream_t s);
 
 }  // namespace b200tag

@@ -26,15 +26,12 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-__constant__ float c_cosv[64];  // jpeg_cos_table(): cos((2x+1) u pi / 16) * C(u) / 2, [x][u]
-
 struct Shared {
   JpegTables tab;
   JpegFrame frame;
   uint32_t ring[kRingWords];
   float coef[64];  // dequantised coefficients of the current block, natural order
   float tmp[64];
-  float cosv[64];  // cos((2x+1) u pi / 16) * C(u) / 2, [x][u]
   float quant[64];
   uint8_t zigzag[64];
 };
@@ -145,7 +142,6 @@ __global__ void __launch_bounds__(32) k_jpeg_luma(const uint8_t *__restrict__ bi
     for (int i = lane; i < 64; i += 32) {
       S.quant[i] = static_cast<float>(F->quant[i]);
       S.zigzag[i] = c_zigzag[i];
-      S.cosv[i] = c_cosv[i];
     }
   }
   const int width = F->width, height = F->height;
@@ -247,25 +243,29 @@ __global__ void __launch_bounds__(32) k_jpeg_luma(const uint8_t *__restrict__ bi
         }
         continue;
       }
-      // A.3.3 inverse DCT, separable: columns (tmp[y][u] = sum_v c[y][v] coef[v][u]) then rows
+      // A.3.3 inverse DCT, separable: lanes 0..7 take a column each, then a row each (jpeg_idct8, shared with the
+      // parallel kernels and the host model)
+      if (lane < 8) {
+        float in[8], o[8];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int o = lane + 32 * h, y = o >> 3, u = o & 7;
-        float s = 0.0f;
+        for (int v = 0; v < 8; v++) in[v] = S.coef[v * 8 + lane];
+        jpeg_idct8(in, o);
 #pragma unroll
-        for (int v = 0; v < 8; v++) s += S.cosv[y * 8 + v] * S.coef[v * 8 + u];
-        S.tmp[o] = s;
+        for (int y = 0; y < 8; y++) S.tmp[y * 8 + lane] = o[y];
       }
       __syncwarp();
+      if (lane < 8) {
+        float in[8], o[8];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int o = lane + 32 * h, y = o >> 3, x = o & 7;
-        float s = 0.0f;
+        for (int u = 0; u < 8; u++) in[u] = S.tmp[lane * 8 + u];
+        jpeg_idct8(in, o);
+        const int py = by0 + lane;
 #pragma unroll
-        for (int u = 0; u < 8; u++) s += S.cosv[x * 8 + u] * S.tmp[y * 8 + u];
-        const int pv = min(255, max(0, __float2int_rn(s + 128.0f)));
-        const int px = bx0 + x, py = by0 + y;
-        if (px < width && py < height) img[static_cast<size_t>(py) * width + px] = static_cast<uint8_t>(pv);
+        for (int x = 0; x < 8; x++) {
+          const int pv = min(255, max(0, __float2int_rn(o[x] + 128.0f)));
+          const int px = bx0 + x;
+          if (px < width && py < height) img[static_cast<size_t>(py) * width + px] = static_cast<uint8_t>(pv);
+        }
       }
     }
     if (++mx == mcus_x) {
@@ -309,27 +309,35 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *war
 // 64-byte chunk keeps (and the markers that end in it), pass 2 turns the counts into offsets, pass 3 moves the bytes.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_jpeg_unstuff(JpegBatch B) {
+  // pass 3 stages the CTA's output (its 256 chunks are consecutive, so is what they keep) in shared memory and writes
+  // it out as whole words; +4: the staging area starts at the destination's offset within its first word
+  __shared__ __align__(16) uint8_t stage[SCATTER ? 256 * kJpegChunk + 4 : 4];
   const JpegFrame *F = B.frames + blockIdx.y;
   const uint32_t len = F->data_len, nch = (len + kJpegChunk - 1) / kJpegChunk;
-  const uint32_t ch = blockIdx.x * 256 + threadIdx.x;
-  if (ch >= nch) return;
+  const uint32_t ch0 = blockIdx.x * 256, ch = ch0 + threadIdx.x;
+  if (ch0 >= nch) return;
+  const bool have = ch < nch;
   const uint8_t *src = B.raw + F->data_off + static_cast<size_t>(ch) * kJpegChunk;
-  const uint32_t n = min(kJpegChunk, len - ch * kJpegChunk);
-  uint32_t prev = ch ? src[-1] : 0u;
-  const uint32_t after = ch * kJpegChunk + n < len ? src[n] : 0u;  // first byte of the next chunk
+  const uint32_t n = have ? min(kJpegChunk, len - ch * kJpegChunk) : 0u;
+  uint32_t prev = (have && ch) ? src[-1] : 0u;
+  const uint32_t after = (have && ch * kJpegChunk + n < len) ? src[n] : 0u;  // first byte of the next chunk
   uint4 v[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) v[i] = reinterpret_cast<const uint4 *>(src)[i];  // data_off is 16-byte aligned
+  for (int i = 0; i < 4; i++) v[i] = have ? reinterpret_cast<const uint4 *>(src)[i] : make_uint4(0, 0, 0, 0);  // data_off is 16-byte aligned
   const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
   uint8_t *dst = nullptr;
   uint32_t *rst = nullptr;
-  uint32_t base = 0, rst_room = 0;
+  uint32_t base = 0, rst_room = 0, cta_base = 0, shift = 0;
   if (SCATTER) {
-    base = B.chunk_cnt[F->chunk_off + ch];
-    dst = B.clean + F->data_off + base;
-    const uint32_t r0 = B.chunk_rst[F->chunk_off + ch];
-    rst = B.rst_pos + static_cast<size_t>(blockIdx.y) * B.rst_stride + r0;
-    rst_room = r0 < B.rst_stride ? B.rst_stride - r0 : 0u;
+    cta_base = B.chunk_cnt[F->chunk_off + ch0];
+    shift = (F->data_off + cta_base) & 3u;
+    if (have) {
+      base = B.chunk_cnt[F->chunk_off + ch];
+      dst = stage + shift + (base - cta_base);
+      const uint32_t r0 = B.chunk_rst[F->chunk_off + ch];
+      rst = B.rst_pos + static_cast<size_t>(blockIdx.y) * B.rst_stride + r0;
+      rst_room = r0 < B.rst_stride ? B.rst_stride - r0 : 0u;
+    }
   }
   uint32_t kept = 0, markers = 0;
 #pragma unroll
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(256) k_jpeg_unstuff(JpegBatch B) {
     for (int j = 0; j < 4; j++) {
       const uint32_t k = 4u * i + j;
       const uint32_t b = (w[i] >> (8 * j)) & 0xffu;
-      const uint32_t nb = k + 1 < n ? ((k + 1) & 3u ? (w[i] >> (8 * (j + 1))) & 0xffu : (w[(i + 1) & 15] & 0xffu)) : after;
+      const uint32_t nb = k + 1 < n ? (j < 3 ? (w[i] >> (8 * ((j + 1) & 3))) & 0xffu : (w[(i + 1) & 15] & 0xffu)) : after;
       const bool in = k < n;
       const bool marker2 = in && prev == 0xffu && b >= 0xd0u && b <= 0xd7u;  // second byte of an RSTn
       const bool marker1 = in && b == 0xffu && nb >= 0xd0u && nb <= 0xd7u;   // first byte of an RSTn
@@ -355,8 +363,27 @@ __global__ void __launch_bounds__(256) k_jpeg_unstuff(JpegBatch B) {
     }
   }
   if (!SCATTER) {
-    B.chunk_cnt[F->chunk_off + ch] = kept;
-    B.chunk_rst[F->chunk_off + ch] = markers;
+    if (have) {
+      B.chunk_cnt[F->chunk_off + ch] = kept;
+      B.chunk_rst[F->chunk_off + ch] = markers;
+    }
+    return;
+  }
+  // total kept by the CTA = (offset of the chunk after its last one, or the frame's unstuffed length) - cta_base
+  __shared__ uint32_t s_total;
+  const uint32_t last = min(nch, ch0 + 256u) - 1u;
+  if (ch == last) s_total = base + kept - cta_base;
+  __syncthreads();
+  const uint32_t total = s_total;
+  uint8_t *out = B.clean + F->data_off + cta_base - shift;  // word aligned; stage[i] <-> out[i]
+  const uint32_t lo = shift, hi = shift + total;            // valid bytes of the staging area
+  const uint32_t w_lo = (lo + 3u) / 4u, w_hi = hi / 4u;     // whole words inside [lo, hi)
+  for (uint32_t i = w_lo + threadIdx.x; i < w_hi; i += 256) reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(stage)[i];
+  if (threadIdx.x < 4) {  // the partial words at both ends, byte by byte
+    const uint32_t i = lo + threadIdx.x;
+    if (i < min(hi, w_lo * 4u)) out[i] = stage[i];
+    const uint32_t t = max(w_hi * 4u, w_lo * 4u) + threadIdx.x;
+    if (t < hi && t >= lo) out[t] = stage[t];
   }
 }
 
@@ -509,7 +536,8 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_write(JpegBatch B) {
   if (i >= nsub) return;
   const unsigned long long in = i == 0 ? 0ull : B.sync[F.sub_off + i];
   JpegSyncState s{static_cast<uint32_t>(in), static_cast<uint32_t>(in >> 32)};
-  JpegCoefSink sink{B.coef + static_cast<size_t>(f) * B.coef_stride, B.nblk[F.sub_off + i] / F.nblocks,
+  JpegCoefSink sink{B.coef + static_cast<size_t>(f) * B.coef_stride, B.dcs + static_cast<size_t>(f) * (B.coef_stride / 64),
+                    B.nblk[F.sub_off + i] / F.nblocks,
                     static_cast<uint32_t>(F.mcus_x) * F.mcus_y, static_cast<uint32_t>(F.hmax) * F.vmax, F.nblocks};
   const uint32_t *words = reinterpret_cast<const uint32_t *>(B.clean + F.data_off);
   jpeg_decode_span(words, end_bits, i + 1 == nsub ? 0xffffffffu : (i + 1) * kJpegSubBits, F, T, s, sink);
@@ -544,7 +572,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_jpeg_write_rst(JpegBatch B) {
   const uint32_t end_bits = B.clean_len[f] * 8u;
   JpegSyncState s{k ? rst[k - 1] * 8u : 0u, 0u};
   const uint32_t limit = k + 1 < nint ? rst[k] * 8u : end_bits;
-  JpegIntervalSink sink{{B.coef + static_cast<size_t>(f) * B.coef_stride, k * ri, nmcu, static_cast<uint32_t>(F.hmax) * F.vmax, F.nblocks}, 0};
+  JpegIntervalSink sink{{B.coef + static_cast<size_t>(f) * B.coef_stride, B.dcs + static_cast<size_t>(f) * (B.coef_stride / 64), k * ri, nmcu, static_cast<uint32_t>(F.hmax) * F.vmax, F.nblocks}, 0};
   const uint32_t *words = reinterpret_cast<const uint32_t *>(B.clean + F.data_off);
   jpeg_decode_span(words, end_bits, limit, F, T, s, sink, min(ri, nmcu - k * ri) * F.nblocks);
 }
@@ -558,21 +586,21 @@ __global__ void __launch_bounds__(1024) k_jpeg_dcscan(JpegBatch B) {
   const JpegFrame *F = B.frames + f;
   if (F->restart_interval) return;  // k_jpeg_write_rst wrote absolute values
   const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * F->hmax * F->vmax;
-  int16_t *coef = B.coef + static_cast<size_t>(f) * B.coef_stride;
+  int16_t *dcs = B.dcs + static_cast<size_t>(f) * (B.coef_stride / 64);
   uint32_t carry = 0;
   for (uint32_t base = 0; base < nlb; base += 1024) {
     const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nlb ? static_cast<uint32_t>(static_cast<int>(coef[static_cast<size_t>(i) * 64])) : 0u;  // wraps like int
+    const uint32_t v = i < nlb ? static_cast<uint32_t>(static_cast<int>(dcs[i])) : 0u;  // wraps like int
     uint32_t total;
     const uint32_t ex = cta_exclusive_scan(v, warp_sums, &total);
-    if (i < nlb) coef[static_cast<size_t>(i) * 64] = static_cast<int16_t>(static_cast<int>(carry + ex + v));
+    if (i < nlb) dcs[i] = static_cast<int16_t>(static_cast<int>(carry + ex + v));
     carry += total;
   }
 }
 
 // Dequantisation + A.3.3 inverse DCT + level shift: 8 threads per block (a column each, then a row each), 32 blocks per
-// CTA; the sums run in the same order as in the sequential kernel, so both give the same bits.  The coefficient
-// buffer is handed back all zero.
+// CTA; jpeg_idct8 is shared with the sequential kernel and the host model, so all three give the same bits.  The
+// coefficient buffer is handed back all zero.
 constexpr int kIdctBlocks = 32;   // blocks per CTA
 constexpr int kIdctStride = 72;   // floats per block in shared memory (72 mod 32 = 8: four blocks of a warp on distinct banks)
 __global__ void __launch_bounds__(kIdctBlocks * 8) k_jpeg_idct(JpegBatch B) {
@@ -581,27 +609,46 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) k_jpeg_idct(JpegBatch B) {
   __shared__ float quant[64];
   __shared__ uint8_t zz[64];
   const int f = blockIdx.y;
-  if (!B.proven[f]) return;
   const JpegFrame *F = B.frames + f;
-  const uint32_t luma_per_mcu = static_cast<uint32_t>(F->hmax) * F->vmax;
-  const uint32_t nlb = static_cast<uint32_t>(F->mcus_x) * F->mcus_y * luma_per_mcu;
+  const int q = threadIdx.x >> 3, j = threadIdx.x & 7, lane = threadIdx.x & 31;
+  const uint32_t lb = blockIdx.x * kIdctBlocks + q;
+  // every global load of the CTA is issued before the first use of any of them (a CTA lives for a few microseconds:
+  // dependent round trips to L2 / HBM would dominate it)
+  uint4 *src = reinterpret_cast<uint4 *>(B.coef + static_cast<size_t>(f) * B.coef_stride + static_cast<size_t>(lb) * 64) + j;
+  int16_t *dc = B.dcs + static_cast<size_t>(f) * (B.coef_stride / 64) + lb;
+  uint4 raw = make_uint4(0, 0, 0, 0);
+  uint32_t dcv = 0;
+  const bool in_buffer = lb < B.max_luma_blocks;  // inside the frame's slice of the coefficient buffer
+  if (in_buffer) {
+    raw = *src;
+    if (j == 0) dcv = static_cast<uint16_t>(*dc);  // the DC value lives in its own array (and is cleared like the rest)
+  }
+  const uint32_t proven = B.proven[f];
+  const uint32_t hmax = F->hmax, vmax = F->vmax, mcus_x = F->mcus_x, mcus_y = F->mcus_y;
+  const int width = F->width, height = F->height;
+  float qv = 0.0f;
+  if (threadIdx.x < 64) qv = static_cast<float>(F->quant[threadIdx.x]);
+  if (!proven) return;
+  const uint32_t luma_per_mcu = hmax * vmax;
+  const uint32_t nlb = mcus_x * mcus_y * luma_per_mcu;
   if (threadIdx.x < 64) {
-    quant[threadIdx.x] = static_cast<float>(F->quant[threadIdx.x]);
+    quant[threadIdx.x] = qv;
     zz[threadIdx.x] = c_zigzag[threadIdx.x];
   }
   __syncthreads();
-  const int q = threadIdx.x >> 3, j = threadIdx.x & 7, lane = threadIdx.x & 31;
-  const uint32_t lb = blockIdx.x * kIdctBlocks + q;
   const bool live = lb < nlb;
   float *mine = nat + q * kIdctStride;
   bool nz_ac = false;
   {
     // coefficients j*8 .. j*8+7 of the block (zigzag order): one 16-byte load, scattered to natural order
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    uint4 *src = reinterpret_cast<uint4 *>(B.coef + static_cast<size_t>(f) * B.coef_stride + static_cast<size_t>(lb) * 64) + j;
     if (live) {
-      raw = *src;
       if (raw.x | raw.y | raw.z | raw.w) *src = make_uint4(0, 0, 0, 0);
+      if (j == 0) {
+        raw.x = (raw.x & 0xffff0000u) | dcv;
+        if (dcv) *dc = 0;
+      }
+    } else {
+      raw = make_uint4(0, 0, 0, 0);
     }
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -615,51 +662,44 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) k_jpeg_idct(JpegBatch B) {
   const uint32_t acm = __ballot_sync(0xffffffffu, nz_ac);
   const bool ac = ((acm >> (lane & ~7)) & 0xffu) != 0;
   __syncthreads();
-  {  // column u = j: tmp[y][u] = sum_v c[y][v] nat[v][u]
-    float in[8];
+  {  // column u = j
+    float in[8], o[8];
 #pragma unroll
     for (int v = 0; v < 8; v++) in[v] = mine[v * 8 + j];
+    jpeg_idct8(in, o);
     float *t = tmp + q * kIdctStride;
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      float s = 0.0f;
-#pragma unroll
-      for (int v = 0; v < 8; v++) s += c_cosv[y * 8 + v] * in[v];
-      t[y * 8 + j] = s;
-    }
+    for (int y = 0; y < 8; y++) t[y * 8 + j] = o[y];
   }
   __syncthreads();
   if (!live) return;
-  // row y = j: out[y][x] = sum_u c[x][u] tmp[y][u]
+  // row y = j
   const float4 r0 = *reinterpret_cast<const float4 *>(tmp + q * kIdctStride + j * 8);
   const float4 r1 = *reinterpret_cast<const float4 *>(tmp + q * kIdctStride + j * 8 + 4);
   const float in[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  float o[8];
+  jpeg_idct8(in, o);
   const float flat = mine[0] * 0.125f + 128.0f;
   uint32_t px8[2] = {0, 0};
 #pragma unroll
   for (int x = 0; x < 8; x++) {
-    float s = 0.0f;
-#pragma unroll
-    for (int u = 0; u < 8; u++) s += c_cosv[x * 8 + u] * in[u];
-    const float val = ac ? s + 128.0f : flat;
+    const float val = ac ? o[x] + 128.0f : flat;
     const uint32_t pv = static_cast<uint32_t>(min(255, max(0, __float2int_rn(val))));
     px8[x >> 2] |= pv << (8 * (x & 3));
   }
   const uint32_t mcu = lb / luma_per_mcu, jb = lb % luma_per_mcu;
-  const int px = static_cast<int>((mcu % F->mcus_x) * F->hmax + F->blk_bx[jb]) * 8;
-  const int py = static_cast<int>((mcu / F->mcus_x) * F->vmax + F->blk_by[jb]) * 8 + j;
-  if (py >= F->height) return;
-  uint8_t *row = B.out + static_cast<size_t>(f) * B.out_stride + static_cast<size_t>(py) * F->width + px;
-  if (px + 8 <= F->width && (reinterpret_cast<uintptr_t>(row) & 7u) == 0) {
+  const int px = static_cast<int>((mcu % mcus_x) * hmax + F->blk_bx[jb]) * 8;
+  const int py = static_cast<int>((mcu / mcus_x) * vmax + F->blk_by[jb]) * 8 + j;
+  if (py >= height) return;
+  uint8_t *row = B.out + static_cast<size_t>(f) * B.out_stride + static_cast<size_t>(py) * width + px;
+  if (px + 8 <= width && (reinterpret_cast<uintptr_t>(row) & 7u) == 0) {
     *reinterpret_cast<uint2 *>(row) = make_uint2(px8[0], px8[1]);
   } else {
-    for (int x = 0; x < 8 && px + x < F->width; x++) row[x] = static_cast<uint8_t>((px8[x >> 2] >> (8 * (x & 3))) & 0xffu);
+    for (int x = 0; x < 8 && px + x < width; x++) row[x] = static_cast<uint8_t>((px8[x >> 2] >> (8 * (x & 3))) & 0xffu);
   }
 }
 
 }  // namespace
-
-void launch_jpeg_init(const float cosv[64]) { cudaMemcpyToSymbol(c_cosv, cosv, 64 * sizeof(float)); }
 
 // Returns the number of kernels launched.  Frames whose parallel decode did not reach its fixed point within
 // kJpegSyncRounds rounds (or whose restart markers do not add up) are decoded by the sequential warp-per-frame kernel
