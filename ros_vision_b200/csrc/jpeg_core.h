@@ -73,41 +73,66 @@ JPEG_HD int jpeg_value(uint32_t peek, uint32_t len, uint32_t s) {
 
 // Decodes codewords from state `s` until one ends at or beyond bit `limit`, the data ends at `end_bits`, or
 // `max_blocks` blocks are complete; returns the number of blocks completed.  sink.dc(c, diff), sink.ac(c, z, v) and sink.block_end(c) see every coefficient.
+JPEG_HD uint32_t min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// big-endian word `i` of the bit stream
+JPEG_HD uint32_t jpeg_word(const uint32_t *words, uint32_t i) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(words[i], 0, 0x0123);
+#else
+  return __builtin_bswap32(words[i]);
+#endif
+}
+
 template <class Sink>
 JPEG_HD uint32_t jpeg_decode_span(const uint32_t *words, uint32_t end_bits, uint32_t limit, const JpegFrame &F,
                                   const JpegTables &T, JpegSyncState &s, Sink &sink, uint32_t max_blocks = 0xffffffffu) {
   uint32_t pos = s.pos, c = s.cz & 0xffu, z = s.cz >> 8, blocks = 0;
   const uint32_t nblocks = F.nblocks;
+  // bit buffer: the next `nbits` (> 32 before every codeword) bits of the stream, left aligned; a codeword and its
+  // value bits (<= 27) are taken from the top half, one word is fetched per 32 bits consumed
+  uint32_t wi = (pos >> 5) + 2;
+  unsigned long long acc = ((static_cast<unsigned long long>(jpeg_word(words, wi - 2)) << 32) | jpeg_word(words, wi - 1)) << (pos & 31u);
+  int nbits = 64 - static_cast<int>(pos & 31u);
+  // Huffman tables of the current block's component (they change at block ends only)
+  const JpegHuff *hdc = &T.dc[F.comp_dc[F.blk_comp[c]]], *hac = &T.ac[F.comp_ac[F.blk_comp[c]]];
   while (pos < limit && pos < end_bits && blocks < max_blocks) {
-    const uint32_t peek = jpeg_peek32(words, pos);
-    const uint32_t comp = F.blk_comp[c];
-    uint32_t len;
-    if (z == 0) {
-      uint32_t t = jpeg_lookup(T.dc[F.comp_dc[comp]], peek, &len) & 15u;
-      t = t > 11u ? 11u : t;
-      sink.dc(c, jpeg_value(peek, len, t));
-      pos += len + t;
-      z = 1;
-    } else {
-      const uint32_t rs = jpeg_lookup(T.ac[F.comp_ac[comp]], peek, &len);
-      const uint32_t run = rs >> 4;
-      uint32_t sz = rs & 15u;
-      if (sz == 0) {
-        pos += len;
-        z = run == 15u ? z + 16u : 64u;  // ZRL : EOB
-      } else {
-        sz = sz > 10u ? 10u : sz;
-        z += run;
-        if (z <= 63u) sink.ac(c, z, jpeg_value(peek, len, sz));
-        pos += len + sz;
-        z++;
-      }
+    if (nbits <= 32) {
+      acc |= static_cast<unsigned long long>(jpeg_word(words, wi++)) << (32 - nbits);
+      nbits += 32;
     }
+    const uint32_t peek = static_cast<uint32_t>(acc >> 32);
+    // one code path for DC and AC codewords (the lanes of a warp are at different places of their blocks): F.2.2.1 /
+    // F.2.2.2 differ in the table, in the run and in what the decoded value is
+    const bool is_dc = z == 0;
+    uint32_t len;
+    const uint32_t rs = jpeg_lookup(is_dc ? *hdc : *hac, peek, &len);
+    const uint32_t run = is_dc ? 0u : rs >> 4;
+    uint32_t sz = rs & 15u;
+    sz = min_u32(sz, is_dc ? 11u : 10u);
+    const int v = jpeg_value(peek, len, sz);
+    const uint32_t used = len + sz;
+    if (is_dc) {
+      sink.dc(c, v);
+      z = 1;
+    } else if (sz == 0) {
+      z = run == 15u ? z + 16u : 64u;  // ZRL : EOB
+    } else {
+      z += run;
+      if (z <= 63u) sink.ac(c, z, v);
+      z++;
+    }
+    pos += used;
+    acc <<= used;
+    nbits -= static_cast<int>(used);
     if (z >= 64u) {
       sink.block_end(c);
       z = 0;
       blocks++;
       if (++c == nblocks) c = 0;
+      const uint32_t comp = F.blk_comp[c];
+      hdc = &T.dc[F.comp_dc[comp]];
+      hac = &T.ac[F.comp_ac[comp]];
     }
   }
   s.pos = pos;
