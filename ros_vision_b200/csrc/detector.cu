@@ -466,8 +466,8 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_occ = plan.take(HB * 4);
   const size_t o_blobs = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(b200tag_blob) * B);
   const size_t o_segp = plan.take(static_cast<size_t>(p.point_cap) * 4 * B);
-  const size_t o_small = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
-  const size_t o_large = plan.take(static_cast<size_t>(p.blob_cap) * 4 * B);
+  const size_t o_small = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(WorkItem) * B);
+  const size_t o_large = plan.take(static_cast<size_t>(p.blob_cap) * sizeof(WorkItem) * B);
   const size_t o_clusters = p.cluster_cap ? plan.take(static_cast<size_t>(p.cluster_cap) * sizeof(b200tag_blob) * B) : 0;
   const size_t o_seg = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
   const size_t o_lfp = plan.take(static_cast<size_t>(p.point_cap) * sizeof(b200tag_lfp) * B);
@@ -509,8 +509,8 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.seg_pts = reinterpret_cast<uint32_t *>(base + o_segp);
   p.occupied = reinterpret_cast<uint32_t *>(base + o_occ);
   p.blobs = reinterpret_cast<b200tag_blob *>(base + o_blobs);
-  p.small_list = reinterpret_cast<uint32_t *>(base + o_small);
-  p.large_list = reinterpret_cast<uint32_t *>(base + o_large);
+  p.small_list = reinterpret_cast<WorkItem *>(base + o_small);
+  p.large_list = reinterpret_cast<WorkItem *>(base + o_large);
   p.clusters = p.cluster_cap ? reinterpret_cast<b200tag_blob *>(base + o_clusters) : nullptr;
   p.seg_keys = reinterpret_cast<uint64_t *>(base + o_seg);
   p.lfp = reinterpret_cast<b200tag_lfp *>(base + o_lfp);

@@ -97,6 +97,12 @@ struct alignas(16) PeakTable {  // 1072 bytes: a multiple of 16, moved with 16-b
 };
 static_assert(sizeof(PeakTable) % 16 == 0, "PeakTable is copied in 16-byte pieces");
 
+// One entry of the fit kernels' work lists: everything a kernel needs to start loading the blob's points, so that the
+// blob record itself is off the critical path.  blob = 0xffffffff marks a slot whose blob did not fit the buffers.
+struct alignas(16) WorkItem {
+  uint32_t blob, offset, count, pad;
+};
+
 struct FrameParams {
   // geometry
   int32_t W, H;        // full resolution
@@ -141,8 +147,8 @@ struct FrameParams {
   uint32_t *occupied;   // hash_cap: slots claimed this frame, in claim order
   b200tag_blob *blobs;  // blob_cap
   uint32_t *seg_pts;    // point_cap: segment points (27 bit) of candidate blobs, unsorted
-  uint32_t *small_list; // blob_cap: indices of blobs fitted by one warp
-  uint32_t *large_list; // blob_cap: indices of blobs fitted by one CTA
+  WorkItem *small_list; // blob_cap: blobs fitted by one warp (front), by a 512-thread CTA (back)
+  WorkItem *large_list; // blob_cap: blobs fitted by a 128-thread CTA (front), by a 256-thread CTA (back)
   b200tag_blob *clusters;  // cluster_cap (keep_stages)
   uint64_t *seg_keys;   // point_cap
   b200tag_lfp *lfp;     // point_cap

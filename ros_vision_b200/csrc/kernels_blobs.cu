@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  uint32_t *small_list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
-  uint32_t *large_list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
+  WorkItem *small_list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
+  WorkItem *large_list = p.large_list + static_cast<size_t>(frame) * p.blob_cap;
   b200tag_blob *clusters = p.clusters ? p.clusters + static_cast<size_t>(frame) * p.cluster_cap : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nocc = min(ctr->num_occupied, p.hash_cap);
@@ -154,16 +154,18 @@ __global__ void __launch_bounds__(256) k_select(FrameParams p) {
         rec.offset = off;
         blobs[b] = rec;
         seg_off = off;
-        if (small) small_list[sbase + sw] = b;
-        else if (huge) small_list[cta_pos] = b;
-        else large_list[cta_pos] = b;
+        const WorkItem item{b, off, rec.count, 0u};
+        if (small) small_list[sbase + sw] = item;
+        else if (huge) small_list[cta_pos] = item;
+        else large_list[cta_pos] = item;
       } else {
         atomicOr(&ctr->status, B200TAG_ST_BLOBS_OVERFLOW);
         // keep the work lists dense: an overflowing blob still occupies its list slot, flagged invalid
+        const WorkItem none{0xffffffffu, 0u, 0u, 0u};
         if (small) {
-          if (sbase + sw < p.blob_cap) small_list[sbase + sw] = 0xffffffffu;
+          if (sbase + sw < p.blob_cap) small_list[sbase + sw] = none;
         } else if (cta_pos < p.blob_cap) {
-          (huge ? small_list : large_list)[cta_pos] = 0xffffffffu;
+          (huge ? small_list : large_list)[cta_pos] = none;
         }
       }
     }
@@ -430,7 +432,7 @@ struct BlobScratch {
   int red_i[16][3];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
-  uint32_t cur;      // blob being processed
+  uint32_t cur;      // work-list position being processed
 };
 
 // Scratch of k_quads, one per warp.
@@ -511,11 +513,10 @@ constexpr uint32_t kMaxBucketLoad = 24;  // fuller buckets (thin, elongated blob
 // KEEP = also write the debug stage arrays (keep_stages) -- separate instantiations, so the production
 // kernels carry no debug code in their instruction stream.
 template <int GS, bool AOS, bool KEEP>
-__device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, const b200tag_blob &blob,
+__device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, uint32_t cnt, uint32_t off,
                                              b200tag_blob *blob_rec, const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
-  const uint32_t cnt = blob.count, off = blob.offset;
   const size_t pbase = static_cast<size_t>(frame) * p.point_cap + off;
   const int lane = threadIdx.x & 31;
   const bool first_warp = gt < 32;
@@ -899,7 +900,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     if (fq < p.blob_cap) {
       PeakTable *t = p.peak_tables + static_cast<size_t>(frame) * p.blob_cap + fq;
       if (lane == 0) {
-        t->blob = b; t->cnt = cnt; t->nsel = nm; t->npk = npk; t->rep0 = blob.rep0; t->rep1 = blob.rep1;
+        t->blob = b; t->cnt = cnt; t->nsel = nm; t->npk = npk; t->rep0 = blob_rec->rep0; t->rep1 = blob_rec->rep1;
         t->last = lf_load<AOS>(wk.lf, cnt - 1);
       }
       if (lane < static_cast<int>(nm)) {
@@ -1133,7 +1134,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p
   const int lane = threadIdx.x & 31;
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
-  const uint32_t *list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
+  const WorkItem *list = p.small_list + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(alloc_small(ctr->alloc), p.blob_cap);
   BlobWork wk;
   wk.keys = S.keys;
@@ -1152,10 +1153,10 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p
     const uint32_t li = __shfl_sync(0xffffffffu, nxt, 0);
     if (li >= nlist) break;
     if (lane == 0) nxt = atomicAdd(&ctr->next_small, 1u);  // the next item's round trip overlaps this blob
-    const uint32_t b = list[li];
+    const WorkItem item = list[li];
+    const uint32_t b = item.blob, off = item.offset, cnt = item.count;
     if (b >= p.blob_cap) continue;  // overflow marker
-    const b200tag_blob blob = blobs[b];
-    fit_one_blob<32, false, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, nullptr, lane);
+    fit_one_blob<32, false, KEEP>(p, frame, ctr, b, cnt, off, blobs + b, wk, S.scratch, nullptr, lane);
   }
 }
 
@@ -1185,7 +1186,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   Counters *ctr = p.counters + frame;
   b200tag_blob *blobs = p.blobs + static_cast<size_t>(frame) * p.blob_cap;
   // tier 0: medium (front of large_list), 1: large (back of large_list), 2: huge (back of small_list)
-  const uint32_t *list = (tier == 2 ? p.small_list : p.large_list) + static_cast<size_t>(frame) * p.blob_cap;
+  const WorkItem *list = (tier == 2 ? p.small_list : p.large_list) + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(tier == 0 ? ctr->num_medium : (tier == 1 ? ctr->num_large : ctr->num_huge), p.blob_cap);
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
   constexpr uint32_t kScanHist = (LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP : ((6u * THREADS * 2u >= 2048u) ? 2048u : 1024u);
@@ -1199,40 +1200,40 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
     const uint32_t li = S.scratch.cur;
     if (li >= nlist) break;
     if (tid == 0) nxt = atomicAdd(next, 1u);  // the next item's round trip overlaps this blob
-    const uint32_t b = list[tier == 0 ? li : p.blob_cap - 1u - li];
+    const WorkItem item = list[tier == 0 ? li : p.blob_cap - 1u - li];
+    const uint32_t b = item.blob, blob_off = item.offset, blob_cnt = item.count;
     if (b >= p.blob_cap) continue;  // overflow marker
-    const b200tag_blob blob = blobs[b];
-    if (blob.count < MIN_CNT || blob.count > MAX_CNT) continue;  // (cannot happen: k_select sorts blobs into tiers)
-    const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob.offset;
+    if (blob_cnt < MIN_CNT || blob_cnt > MAX_CNT) continue;  // (cannot happen: k_select sorts blobs into tiers)
+    const size_t pbase = static_cast<size_t>(frame) * p.point_cap + blob_off;
     BlobWork wk;
     // branches that the tier's size limits rule out are not compiled (each one is a full copy of the fit code)
     constexpr bool kHasSmemLf = LF_CAP > 0;
     constexpr bool kHasGlobalLf = MAX_CNT > LF_CAP;
     constexpr bool kHasInPlace = MAX_CNT > KEY_CAP;
-    if (kHasSmemLf && blob.count <= LF_CAP) {  // everything in shared memory
+    if (kHasSmemLf && blob_cnt <= LF_CAP) {  // everything in shared memory
       wk.keys = S.keys; wk.errs = S.errs;
       wk.lf.aos = nullptr; wk.lf.m64 = S.lf64; wk.lf.m32 = S.lf32; wk.lf.cap = LF_CAP;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
       wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = next_pow2(LF_CAP > 0 ? LF_CAP : 1); wk.tmp = wk.hist + next_pow2(LF_CAP > 0 ? LF_CAP : 1);
-      fit_one_blob<THREADS, false, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
-    } else if (kHasGlobalLf && KEY_CAP > LF_CAP && blob.count <= KEY_CAP) {  // prefix moments in the blob's global segment
+      fit_one_blob<THREADS, false, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
+    } else if (kHasGlobalLf && KEY_CAP > LF_CAP && blob_cnt <= KEY_CAP) {  // prefix moments in the blob's global segment
       wk.keys = S.keys; wk.errs = S.errs;
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.filt = reinterpret_cast<double *>(S.keys);
       wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
       wk.keys_in_place = false;
       wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
     } else if (kHasInPlace) {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
-      wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob.offset / 2);
+      wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob_off / 2);
       wk.keys_in_place = true;
       wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob, blobs + b, wk, S.scratch, S.scan, tid);
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
     }
   }
 }
