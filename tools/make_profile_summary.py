@@ -30,7 +30,7 @@ fit_cta_seen = collections.defaultdict(int)
 for r, n, t in zip(rows, names, times):
     key = alias.get(n)
     if n == "k_fit_cta":
-        key = "fit_medium" if "(128, 1, 1)" in r[7] else "fit_large"
+        key = "fit_medium" if "(128, 1, 1)" in r[7] else ("fit_huge" if "(512, 1, 1)" in r[7] else "fit_large")
     if key: per[key].append(t)
 ncu_ms = {}
 for k, v in per.items():
@@ -71,7 +71,7 @@ for rep in reps:
         name = re.sub(r"\(.*", "", g("Kernel Name")).replace("void ", "")
         block = g("launch__block_size")
         key = alias.get(name.split("<")[0], name)
-        if name.startswith("k_fit_cta"): key = "fit_medium" if block == "128" else "fit_large"
+        if name.startswith("k_fit_cta"): key = "fit_medium" if block == "128" else ("fit_huge" if block == "512" else "fit_large")
         rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
         traffic[key] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "report": os.path.basename(rep)}
         st = []
