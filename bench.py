@@ -319,6 +319,14 @@ def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
            "decoder": dets[0].mjpg_backend, "frames_decoded_by_parallel_kernels": parallel, "tags_found": found, "tags_present": present}
     for d in dets:
         d.close()
+    # the reference's way for this step, timed beside it: OpenCV (libjpeg-turbo) decodes each frame to bgr8 on a host
+    # core (cv::VideoCapture with CAP_PROP_CONVERT_RGB, camera_publisher.cpp:198,336); bounded to about two seconds
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 2.0:
+        cv2.imdecode(np.frombuffer(jpgs[n % len(jpgs)], np.uint8), cv2.IMREAD_COLOR)
+        n += 1
+    out["cpu_opencv_decode_only"] = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "threads": 1,
+                                     "what": "cv2.imdecode to bgr8 alone (no detection), one host thread"}
     return out
 
 
