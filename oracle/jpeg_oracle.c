@@ -1,13 +1,14 @@
 /* TEST INFRASTRUCTURE -- CPU restatement of baseline JPEG decoding, luminance plane only.
  *
  * The reference has no JPEG code of its own: its camera node asks OpenCV (cv::VideoCapture with CAP_PROP_CONVERT_RGB,
- * src/usb_camera/src/camera_publisher.cpp:198,336) to decode the cameras' MJPG stream, i.e. libjpeg(-turbo) inside
- * OpenCV -- a third-party dependency that is not vendored in the reference tree.  This file restates the published
+ * src/usb_camera/src/camera_publisher.cpp:198,336) to decode the cameras' MJPG stream, i.e. the libjpeg-turbo bundled
+ * with OpenCV, which the reference pins at 4.9.0 (src/external/CMakeLists.txt:27-35, fetched at build time) -- a
+ * third-party dependency that is not vendored in the reference tree.  This file restates the published
  * algorithm, ITU-T T.81 (baseline sequential DCT, Huffman coding): marker parsing (B.2), Huffman table generation
  * (Annex C), decoding of DC / AC coefficients (F.2.2), dequantisation and the inverse DCT (A.3.3), level shift (A.3.1).
  * JPEG decoders are only required to agree within the accuracy bounds of T.83, not bit for bit; the oracle is pinned
- * against libjpeg-turbo as shipped in this image's OpenCV (tests/test_jpeg_oracle.py: within 1 grey level on every
- * pixel of every test stream).  Straightforward on purpose: bit-by-bit canonical Huffman decoding, the IDCT as the
+ * against the libjpeg-turbo in this image's OpenCV (4.13.0 / libjpeg-turbo 3.1.2; tests/test_jpeg_oracle.py: within
+ * 1 grey level on every pixel of every test stream).  Straightforward on purpose: bit-by-bit canonical Huffman decoding, the IDCT as the
  * double-precision double sum of A.3.3.  Only tests/, smoke() and bench.py's CPU legs may use anything in oracle/. */
 #include <math.h>
 #include <stdint.h>
