@@ -1027,11 +1027,10 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
       fqo->err = best;
     }
     if (lane < 4) {
-      uint32_t i0 = 0, i1 = 0;
+      uint32_t i0 = 0;
       Mom mo;
       if (valid) {
         i0 = T.idx[d_combos[bi][lane]];
-        i1 = T.idx[d_combos[bi][(lane + 1) & 3]];
         mo = table_moments(T, d_combos[bi][lane], d_combos[bi][(lane + 1) & 3]);  // line_fit_filter.cu:1188-1191
         double err, mse;
         fit_line(mo, S.lines[lane], S.lines[lane] + 2, &err, &mse);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) k_pre_bgr_dec1(FrameParams p) {
 // are filtered, the rest copied), rows first then columns.  One CTA = 64x32 output pixels: the
 // input tile with its halo is staged in shared memory, the row pass writes a second shared tile
 // (all rows the column pass needs), the column pass writes the result.
-constexpr int kBlurTW = 64, kBlurTH = 32, kBlurMaxR = 15;
+constexpr int kBlurTW = 64, kBlurTH = 32;  // (the host caps the filter radius at 15: detector.cu blur_kernel)
 __global__ void __launch_bounds__(256) k_blur(FrameParams p) {
   extern __shared__ uint8_t s_blur[];
   const int ksz = p.blur_ksz, r = ksz >> 1;
