@@ -274,10 +274,10 @@ def opencv_aruco_leg(frames, seconds_budget=4.0):
         return {"unavailable": repr(e)[:200]}
 
 
-def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
+def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
     """Informational: the same config-2 scenes as 4:2:2 JPEG bitstreams in host memory ->
     b200tag_enqueue_mjpg (hand-written JPEG luminance decode kernels + detection) -> detections on the host; wall clock
-    around `steps` 128-frame batches on two detectors.  None when OpenCV (the test encoder) is missing."""
+    around `steps` 128-frame batches on three detectors.  None when OpenCV (the test encoder) is missing."""
     try:
         import cv2
     except ImportError:
@@ -294,7 +294,8 @@ def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
         jpgs.append(buf.tobytes())
         present += len(sc.tags)
     batch = [jpgs[i % len(jpgs)] for i in range(BATCH)]
-    dets = [D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, max_batch=BATCH, device=local) for _ in range(2)]
+    lanes = 3  # detectors (streams) in flight
+    dets = [D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, max_batch=BATCH, device=local) for _ in range(lanes)]
     for _ in range(3):
         for d in dets:
             d.EnqueueMjpg(batch)
@@ -305,8 +306,8 @@ def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
     t0 = time.perf_counter()
     pending = []
     for it in range(steps):
-        d = dets[it % 2]
-        if len(pending) == 2:
+        d = dets[it % lanes]
+        if len(pending) == lanes:
             pending.pop(0).Finish()
         d.EnqueueMjpg(batch)
         pending.append(d)
@@ -315,7 +316,7 @@ def mjpg_leg(local: int, steps: int = 12, quality: int = 75):
     dt = time.perf_counter() - t0
     out = {"value": BATCH * steps / dt, "unit": "frames/s", "what": "JPEG bytes in host memory -> detections on the host",
            "jpeg_bytes_per_frame": int(np.mean([len(j) for j in jpgs])), "quality": quality, "sampling": "4:2:2",
-           "h2d_bytes_per_step": int(sum(len(j) for j in batch)), "frames_per_step": BATCH, "steps": steps,
+           "h2d_bytes_per_step": int(sum(len(j) for j in batch)), "frames_per_step": BATCH, "steps": steps, "lanes": lanes,
            "decoder": dets[0].mjpg_backend, "frames_decoded_by_parallel_kernels": parallel, "tags_found": found, "tags_present": present}
     for d in dets:
         d.close()

@@ -2,7 +2,7 @@
 """End-to-end throughput of the camera wire format: config-2 scenes as 4:2:2 JPEG bitstreams
 in host memory -> b200tag_enqueue_mjpg (luminance decode + detection on one stream) -> detections on the host.
 Informational: the headline bench (bench.py) stays on raw YUYV frames.  Usage: python tools/bench_mjpg.py [--batch 128]
-[--steps 20] [--lanes 2] [--quality 75] [--decoder native|sequential|nvjpeg]; with --decoder nvjpeg,
+[--steps 20] [--lanes 3] [--quality 75] [--decoder native|sequential|nvjpeg]; with --decoder nvjpeg,
 B200TAG_NVJPEG_BACKEND=hardware|gpu|hybrid|default selects the nvJPEG backend."""
 import argparse
 import json
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=3)
     ap.add_argument("--quality", type=int, default=75)
     ap.add_argument("--unique", type=int, default=16)
     ap.add_argument("--decoder", default="native", choices=["native", "sequential", "nvjpeg"],
