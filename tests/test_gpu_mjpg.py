@@ -123,6 +123,24 @@ def test_native_decoder_every_baseline_variant(D, monkeypatch):
     det.close()
 
 
+def test_native_decoder_partial_blocks_at_the_edges(D, monkeypatch):
+    """A frame size that is a multiple of neither 8 nor 16 (the detector itself needs multiples of 4 at quad_decimate 1):
+    clipped blocks, pixel rows that are not 8-byte aligned."""
+    from oracle import pyjpeg
+    monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)
+    w, h = 364, 252
+    sc, streams = make_cases(w=w, h=h, seed=8)
+    names = ["gray", "444", "422", "420", "411", "422_rst7", "420_optimised"]
+    det = D.GpuDetector(w, h, "gray", quad_decimate=1, keep_stages=True, max_batch=len(names))
+    det.DetectMjpg([streams[n] for n in names], allow_overflow=True)
+    assert det.MjpgParallelFrames() == len(names)
+    for f, name in enumerate(names):
+        got = det.CopyGrayTo(f).reshape(h, w)
+        assert np.abs(got.astype(np.int32) - pyjpeg.decode_luma(streams[name]).astype(np.int32)).max() <= 1, name
+        assert np.array_equal(got, D.jpeg_model_decode(streams[name], w, h)[0]), name
+    det.close()
+
+
 def test_non_baseline_streams_go_through_nvjpeg(D, monkeypatch):
     from ros_vision_b200 import synth
     monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)

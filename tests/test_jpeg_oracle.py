@@ -96,3 +96,17 @@ def test_parallel_scheme_host_model(cases, pyjpeg):
         diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-4, name
         assert (rounds == 0) if "rst" in name else (1 <= rounds <= 40), (name, rounds)   # restart intervals need no rounds
+
+
+def test_frame_size_not_a_multiple_of_the_block(pyjpeg):
+    """Partial blocks / MCUs at the right and bottom edges (T.81 A.2.4), for oracle and host model alike."""
+    from ros_vision_b200 import build, detector
+    build.build_native()
+    sc, streams = make_cases(w=362, h=251, seed=8)
+    for name in ("gray", "444", "422", "420", "411", "422_rst7", "420_optimised"):
+        jpg = streams[name]
+        ref = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_GRAYSCALE)
+        got = pyjpeg.decode_luma(jpg)
+        assert got.shape == (251, 362) and np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1, name
+        model, _ = detector.jpeg_model_decode(jpg, 362, 251)
+        assert np.abs(model.astype(np.int32) - got.astype(np.int32)).max() <= 1, name
