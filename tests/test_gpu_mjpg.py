@@ -141,6 +141,26 @@ def test_native_decoder_partial_blocks_at_the_edges(D, monkeypatch):
     det.close()
 
 
+def test_native_decoder_at_the_largest_baseline_size(D, monkeypatch):
+    """BASELINE config 5's frame size (3840x2160, 100 tags + clutter) as one 4:2:0 JPEG: 130 k blocks, 20 k subsequences."""
+    from oracle import pyjpeg
+    from ros_vision_b200 import synth
+    monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)
+    _, _, w, h, dec, sigma, sc = synth.config_frame(5, 0)
+    ok, buf = cv2.imencode(".jpg", synth.gray_to_bgr(sc.gray, np.random.default_rng(5)), [cv2.IMWRITE_JPEG_QUALITY, 85])
+    jpg = buf.tobytes()
+    det = D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, keep_stages=True)
+    det.DetectMjpg([jpg], allow_overflow=True)
+    assert det.MjpgParallelFrames() == 1
+    got = det.CopyGrayTo(0).reshape(h, w)
+    ref = pyjpeg.decode_luma(jpg)
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-4
+    found = {int(i) for i in det.Detections(0)["id"]}
+    assert len(found & {int(t.tag_id) for t in sc.tags}) >= 0.9 * len(sc.tags)
+    det.close()
+
+
 def test_non_baseline_streams_go_through_nvjpeg(D, monkeypatch):
     from ros_vision_b200 import synth
     monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)
