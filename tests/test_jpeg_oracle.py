@@ -110,3 +110,36 @@ def test_frame_size_not_a_multiple_of_the_block(pyjpeg):
         assert got.shape == (251, 362) and np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1, name
         model, _ = detector.jpeg_model_decode(jpg, 362, 251)
         assert np.abs(model.astype(np.int32) - got.astype(np.int32)).max() <= 1, name
+
+
+def test_corrupt_streams_do_not_crash_parser_or_model(cases):
+    """Bit errors, truncation and garbage: the header parser and the host model of the decode kernels (the same
+    entropy-decoding core the kernels compile) return -- a plane, or an error code -- and never read out of bounds."""
+    import ctypes as C
+    from ros_vision_b200 import build, detector
+    build.build_native()
+    lib = detector.load_library()
+    sc, streams = cases
+    h, w = sc.gray.shape
+    rng = np.random.default_rng(123)
+    out = np.zeros((h, w), np.uint8)
+    rounds = C.c_int32(0)
+    outcomes = {"decoded": 0, "rejected": 0}
+    for name in ("422", "420_optimised", "422_rst7", "gray_no_dht"):
+        base = bytearray(streams[name])
+        for trial in range(60):
+            bad = bytearray(base)
+            kind = trial % 3
+            if kind == 0:      # bit errors in the entropy-coded data
+                for i in rng.integers(700, len(bad) - 2, size=int(rng.integers(1, 50))):
+                    bad[i] = int(rng.integers(0, 256))
+            elif kind == 1:    # truncation
+                del bad[int(rng.integers(100, len(bad))):]
+            else:              # errors in the headers
+                for i in rng.integers(2, 650, size=int(rng.integers(1, 6))):
+                    bad[i] = int(rng.integers(0, 256))
+            buf = np.frombuffer(bytes(bad), np.uint8)
+            rc = lib.b200tag_debug_jpeg_model(buf.ctypes.data_as(C.c_void_p), buf.size, out.ctypes.data_as(C.c_void_p), out.size, C.byref(rounds))
+            assert rc in (0, 1, -1, -2), rc
+            outcomes["decoded" if rc == 0 else "rejected"] += 1
+    assert outcomes["decoded"] > 40 and outcomes["rejected"] > 20, outcomes
