@@ -1,13 +1,19 @@
 // Baseline-JPEG luminance decoder on the GPU (camera wire format).  The reference leaves MJPG
 // decoding to OpenCV on the CPU (src/usb_camera/src/camera_publisher.cpp:198,336) and then converts bgr8 -> YUYV ->
-// gray; the detector only ever looks at luminance, so this kernel decodes exactly that plane, straight into the
-// detector's input staging buffer.
+// gray; the detector only ever looks at luminance, so these kernels decode exactly that plane, straight into the
+// detector's input staging buffer.  Chrominance blocks are parsed and dropped.
 //
-// Huffman-coded data is sequential within a restart interval (ITU-T T.81 F.2.2), so the parallelism is across frames:
-// one warp per frame.  All 32 lanes run the entropy decoder redundantly on identical state (same instructions, same
-// data: no divergence, no cost over a single thread), which keeps every branch warp-uniform and lets the lanes split
-// the data-parallel parts: byte unstuffing into a shared-memory ring (ballot / popc compaction), the 8x8 inverse DCT
-// (two coefficients per lane) and the pixel stores.  Chrominance blocks are parsed and dropped.
+// Two paths:
+//  * parallel (every well-formed stream): unstuffing (k_jpeg_unstuff*), then the Huffman-coded scan is decoded by one
+//    thread per 512-bit subsequence -- streams without restart markers by self-synchronisation (k_jpeg_sync rounds to
+//    a proven fixed point, k_jpeg_blockscan, k_jpeg_write; see jpeg_core.h), streams with restart markers one thread
+//    per restart interval (k_jpeg_write_rst) --, DC prediction as a scan (k_jpeg_dcscan), and the inverse DCT with
+//    eight threads per block (k_jpeg_idct);
+//  * sequential (k_jpeg_luma, the fallback for frames the parallel path could not prove): one warp per frame.  All 32
+//    lanes run the entropy decoder redundantly on identical state (same instructions, same data: no divergence, no
+//    cost over a single thread), which keeps every branch warp-uniform and lets the lanes split the data-parallel
+//    parts: byte unstuffing into a shared-memory ring (ballot / popc compaction), the inverse DCT and the pixel stores.
+// Both paths, and the host model in jpeg_host.cc, share jpeg_idct8 and produce identical planes.
 #include <cuda_runtime.h>
 
 #include <cstdint>
