@@ -66,6 +66,10 @@ class GpuDetector {
 
   // Detects april tags in the provided image (host pointer, YUYV 4:2:2 unless constructed otherwise).
   void Detect(const uint8_t *image);
+  // Extension (camera wire format): the same for one JPEG bitstream of a camera frame -- what the cameras send before
+  // the reference's camera node decodes it with OpenCV (camera_publisher.cpp:198,336).  The luminance plane is decoded
+  // on the GPU; the detector must have been constructed with pixel format B200TAG_FMT_GRAY8.
+  void DetectMjpg(const uint8_t *jpeg, size_t size);
 
   const std::vector<QuadCorners> &FitQuads() const;
   const zarray_t *Detections() const { return detections_; }
@@ -98,6 +102,7 @@ class GpuDetector {
  private:
   void Init(size_t width, size_t height, apriltag_detector_t *td, CameraMatrix cam, DistCoeffs dist, int fmt);
   void ClearDetections();
+  void Collect(int rc);  // result of a b200tag_detect* call -> detections_ (DecodeTags, apriltag_detect.cu:626-662)
 
   const size_t width_;
   const size_t height_;

@@ -87,8 +87,15 @@ void GpuDetector::ReinitializeDetections() {  // apriltag_gpu.cu:202-220
   zarray_ensure_capacity(detections_, static_cast<int>(kMaxBlobs));
 }
 
-void GpuDetector::Detect(const uint8_t *image) {
-  const int rc = b200tag_detect(handle_, image);
+void GpuDetector::Detect(const uint8_t *image) { Collect(b200tag_detect(handle_, image)); }
+
+void GpuDetector::DetectMjpg(const uint8_t *jpeg, size_t size) {
+  const uint8_t *jpegs[1] = {jpeg};
+  const size_t sizes[1] = {size};
+  Collect(b200tag_detect_mjpg(handle_, jpegs, sizes, 1));
+}
+
+void GpuDetector::Collect(int rc) {
   if (rc != 0 && rc != B200TAG_E_OVERFLOW) Fatal(b200tag_error_string(rc), b200tag_last_error(handle_));
   if (rc == B200TAG_E_OVERFLOW) std::fprintf(stderr, "GpuDetector: %s\n", b200tag_last_error(handle_));
   // DecodeTags (apriltag_detect.cu:626-632): previous detections are destroyed first

@@ -1,6 +1,6 @@
 // C++ mirror of the reference's src/apriltags_cuda/test/gpu_detector_test.cu (GpuDetectsAprilTag,
 // GpuNoAprilTagDetections) against the header-compatible GpuDetector class, without gtest / OpenCV:
-//   gpu_detector_test <gray.raw> <width> <height> <expected_count> [expected_id]
+//   gpu_detector_test <gray.raw> <width> <height> <expected_count> [expected_id [frame.jpg]]
 // The raw file is the luma plane of a golden fixture; it is packed to YUYV like the test's cvtColor.
 #include <cstdio>
 #include <cstdlib>
@@ -59,6 +59,25 @@ int main(int argc, char **argv) {
     if (zarray_size(detector.Detections()) != expected) rc = 5;
     detector.ReinitializeDetections();
     if (zarray_size(detector.Detections()) != 0) rc = 6;
+  }
+  if (argc > 6) {  // the same frame as a JPEG bitstream (camera wire format) through DetectMjpg
+    std::vector<uint8_t> jpg;
+    FILE *jf = std::fopen(argv[6], "rb");
+    if (!jf) return 3;
+    uint8_t buf[4096];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), jf)) > 0) jpg.insert(jpg.end(), buf, buf + n);
+    std::fclose(jf);
+    frc971::apriltag::GpuDetector detector(width, height, td, cam, dist, B200TAG_FMT_GRAY8);
+    detector.DetectMjpg(jpg.data(), jpg.size());
+    const zarray_t *detections = detector.Detections();
+    std::printf("mjpg detections=%d\n", zarray_size(detections));
+    if (zarray_size(detections) != expected) rc = 8;
+    for (int i = 0; i < zarray_size(detections); i++) {
+      apriltag_detection_t *det;
+      zarray_get(detections, i, &det);
+      if (det->id != std::atoi(argv[5])) rc = 8;
+    }
   }
   apriltag_detector_destroy(td);
   tag36h11_destroy(tf);

@@ -23,6 +23,7 @@ def test_class_library_exports_reference_api(built):
     for want in ["frc971::apriltag::GpuDetector::GpuDetector(unsigned long, unsigned long, apriltag_detector*, "
                  "frc971::apriltag::CameraMatrix, frc971::apriltag::DistCoeffs)",
                  "frc971::apriltag::GpuDetector::Detect(unsigned char const*)",
+                 "frc971::apriltag::GpuDetector::DetectMjpg(unsigned char const*, unsigned long)",
                  "frc971::apriltag::GpuDetector::FitQuads() const",
                  "frc971::apriltag::GpuDetector::ReinitializeDetections()",
                  "frc971::apriltag::GpuDetector::CopyGrayTo(unsigned char*) const",
@@ -45,6 +46,18 @@ def test_gpu_detector_test_cc(built, tmp_path, name, count, tag_id):
     raw = tmp_path / "gray.raw"
     raw.write_bytes(img.tobytes())
     args = [exe, str(raw), str(meta["width"]), str(meta["height"]), str(count)] + ([str(tag_id)] if tag_id is not None else [])
+    mjpg = False
+    if tag_id is not None:  # the same frame as a JPEG bitstream through GpuDetector::DetectMjpg
+        try:
+            import cv2
+            ok, buf = cv2.imencode(".jpg", img.reshape(meta["height"], meta["width"]), [cv2.IMWRITE_JPEG_QUALITY, 95])
+            (tmp_path / "frame.jpg").write_bytes(buf.tobytes())
+            args.append(str(tmp_path / "frame.jpg"))
+            mjpg = True
+        except ImportError:
+            pass
     r = subprocess.run(args, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert f"detections={count}" in r.stdout
+    if mjpg:
+        assert f"mjpg detections={count}" in r.stdout
