@@ -305,7 +305,7 @@ int jpeg_model_decode(const uint8_t *jpeg, size_t len, uint8_t *out, size_t out_
   JpegNullSink none;
   int used = 0;
   bool proven = nsub <= 1;
-  for (int r = 0; r < 64 && !proven && !F.restart_interval; r++) {
+  for (int r = 0; r < 4096 && !proven && !F.restart_interval; r++) {
     next = s;
     bool changed = false;
     for (uint32_t i = 0; i + 1 < nsub; i++) {

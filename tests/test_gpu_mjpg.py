@@ -161,6 +161,50 @@ def test_native_decoder_at_the_largest_baseline_size(D, monkeypatch):
     det.close()
 
 
+def test_mjpg_random_streams(D, monkeypatch):
+    """Random scenes, sizes, qualities, samplings, restart intervals and Huffman optimisation, in random batches: every
+    plane within 1 level of the JPEG oracle and identical to the host model, every frame on the parallel kernels.
+    B200TAG_SWEEP_SEED / B200TAG_SWEEP_COUNT run a longer sweep with other draws."""
+    import os
+    from oracle import pyjpeg
+    from ros_vision_b200 import synth
+    monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)
+    seed, count = int(os.environ.get("B200TAG_SWEEP_SEED", "11")), int(os.environ.get("B200TAG_SWEEP_COUNT", "12"))
+    rng = np.random.default_rng(seed)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    samplings = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+                 cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    done = 0
+    while done < count:
+        w, h = int(rng.integers(12, 80)) * 8, int(rng.integers(10, 60)) * 8
+        n = int(rng.integers(1, 6))
+        det = D.GpuDetector(w, h, "gray", quad_decimate=2, keep_stages=True, max_batch=n)
+        jpgs = []
+        for i in range(n):
+            sc = synth.make_scene(w, h, int(rng.integers(1, 1 << 30)), int(rng.integers(0, 4)), side_range=(24.0, max(30.0, min(w, h) / 2.5)),
+                                  noise_sigma=float(rng.uniform(0, 8)), clutter=bool(rng.integers(0, 2)))
+            colour = bool(rng.integers(0, 4))
+            img = synth.gray_to_bgr(sc.gray, np.random.default_rng(i)) if colour else sc.gray
+            params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 101))]
+            if colour:
+                params += [S, int(rng.choice(samplings))]
+            if rng.integers(0, 3) == 0:
+                params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 200))]
+            if rng.integers(0, 3) == 0:
+                params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+            ok, buf = cv2.imencode(".jpg", img, params)
+            assert ok
+            jpgs.append(buf.tobytes())
+        det.DetectMjpg(jpgs, allow_overflow=True)
+        assert det.MjpgParallelFrames() == n
+        for f, jpg in enumerate(jpgs):
+            got = det.CopyGrayTo(f).reshape(h, w)
+            assert np.abs(got.astype(np.int32) - pyjpeg.decode_luma(jpg).astype(np.int32)).max() <= 1
+            assert np.array_equal(got, D.jpeg_model_decode(jpg, w, h)[0])
+        det.close()
+        done += n
+
+
 def test_non_baseline_streams_go_through_nvjpeg(D, monkeypatch):
     from ros_vision_b200 import synth
     monkeypatch.delenv("B200TAG_MJPG_DECODER", raising=False)
