@@ -274,6 +274,14 @@ def opencv_aruco_leg(frames, seconds_budget=4.0):
         return {"unavailable": repr(e)[:200]}
 
 
+def safe_leg(fn, *a):
+    """Informational legs must never cost the bench line: a failure is reported in place of their result."""
+    try:
+        return fn(*a)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
     """Informational: the same config-2 scenes as 4:2:2 JPEG bitstreams in host memory ->
     b200tag_enqueue_mjpg (hand-written JPEG luminance decode kernels + detection) -> detections on the host; wall clock
@@ -570,9 +578,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps * DL,
-            "roofline": roof, "cpu_baseline": cb, "reference_gpu": reference_gpu_leg(frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
-            "cpu_opencv_aruco": opencv_aruco_leg(frames) if (world == 1 and not args.no_cpu) else None,
-            "e2e_mjpg": mjpg_leg(local) if (world == 1 and not args.no_cpu and CONFIG == 2 and FMT == "yuyv") else None,
+            "roofline": roof, "cpu_baseline": cb, "reference_gpu": safe_leg(reference_gpu_leg, frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
+            "cpu_opencv_aruco": safe_leg(opencv_aruco_leg, frames) if (world == 1 and not args.no_cpu) else None,
+            "e2e_mjpg": safe_leg(mjpg_leg, local) if (world == 1 and not args.no_cpu and CONFIG == 2 and FMT == "yuyv") else None,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},

@@ -14,4 +14,5 @@ cb = d.get("cpu_baseline")
 if cb: print("  cpu", round(cb["value"], 1), cb["unit"], cb["cores"], "threads")
 print("  clocks", d.get("clocks"))
 mj = d.get("e2e_mjpg")
-if mj: print(f"  e2e_mjpg {mj['value']:.0f} frames/s  ({mj['jpeg_bytes_per_frame']} B/frame, q{mj['quality']}, decoder {mj['decoder']}, parallel {mj['frames_decoded_by_parallel_kernels']}/{mj['frames_per_step']}, tags {mj['tags_found']}/{mj['tags_present']})")
+if mj and "error" in mj: print("  e2e_mjpg failed:", mj["error"])
+elif mj: print(f"  e2e_mjpg {mj['value']:.0f} frames/s  ({mj['jpeg_bytes_per_frame']} B/frame, q{mj['quality']}, decoder {mj['decoder']}, parallel {mj['frames_decoded_by_parallel_kernels']}/{mj['frames_per_step']}, tags {mj['tags_found']}/{mj['tags_present']})")
