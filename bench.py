@@ -74,29 +74,35 @@ def algorithmic_bytes_per_frame(points_per_frame: float) -> float:
     return bpp * N + (N if FMT != "gray" else 0) + (n if (DECIMATE > 1 or SIGMA != 0) else 0) + n + 4 * n + 8.0 * points_per_frame
 
 
-# per-kernel algorithmic bytes per frame ("Per-kernel algorithmic bytes"; the kernels of
-# the new engine move 8-byte point records and 4-byte segment points)
+# per-kernel algorithmic bytes per frame ("Per-kernel algorithmic bytes", for the kernels as
+# they are fused here; DESIGN.md section 2 lists them).  Per-blob kernels (fit_*, quads, decode) are latency / issue
+# bound: their only compulsory HBM traffic is the 4-byte segment point each of them reads once.
+FRONT_END = ("pre_yuyv_dec2", "pre_gray_dec2", "pre_bgr_dec1", "pre_bgr_dec2", "pre_generic", "blur", "tile_minmax",
+             "ccl_local", "ccl_merge", "ccl_handoff", "ccl_final", "boundary", "select", "scatter")
+
+
 def kernel_bytes(name: str, P: float, tiers: dict) -> float:
     N, n = W * H, (W // DECIMATE) * (H // DECIMATE)
     Pseg = tiers["small"] + tiers["medium"] + tiers["large"]
     bpp = {"gray": 1, "yuyv": 2, "bgr": 3}[FMT]
     table = {
         "pre_yuyv_dec2": 2 * N + N + n + n / 8,
+        "pre_gray_dec2": N / 2 + n + n / 8,
         "pre_generic": bpp * N + (N if FMT != "gray" else 0) + n + n / 8,
         "pre_bgr_dec1": 3 * N + N + n,
         "pre_bgr_dec2": 3 * N + N + n + n / 8,
         "blur": n + n,
         "tile_minmax": n + n / 8,
-        "threshold": n + n / 8 + n,
-        "ccl_local": n + 4 * n + 4 * n,
-        "ccl_merge": 0.0,
-        "ccl_final": 4 * n + 4 * n + 4 * n,
-        "boundary": n + 4 * n + 4 * n + 8 * P,
+        "ccl_local": n + n / 8 + n + 4 * n + 4 * n,   # quad image + raw tile min/max in; thresholded, labels, sizes out
+        "ccl_merge": 0.0,                             # tile borders only
+        "ccl_handoff": 0.0,                           # border-touching tile roots only
+        "ccl_final": 4 * n + 4 * n,                   # label words in, label words out
+        "boundary": 4 * n + 8 * P,                    # label words in, point records out
         "select": 0.0,
         "scatter": 8 * P + 4 * Pseg,
-        "fit_small": 4 * tiers["small"],   # reads its blobs' segment points once; everything else stays in shared memory
+        "fit_small": 4 * tiers["small"],
         "fit_medium": 4 * tiers["medium"],
-        "fit_large": 4 * tiers["large"] + 2 * 48 * tiers["large"],  # + prefix moments written and read in its (L2-resident) segment
+        "fit_large": 4 * tiers["large"],
         "decode": 0.0,
     }
     return table.get(name, 0.0)
@@ -282,17 +288,21 @@ def safe_leg(fn, *a):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
-    """Informational: the same config-2 scenes as 4:2:2 JPEG bitstreams in host memory ->
+def mjpg_leg(local: int, rank: int = 0, world: int = 1, steps: int = 18, quality: int = 75):
+    """SURVEY section 8 row f2, at every N: the same config-2 scenes as 4:2:2 JPEG bitstreams in host memory ->
     b200tag_enqueue_mjpg (hand-written JPEG luminance decode kernels + detection) -> detections on the host; wall clock
-    around `steps` 128-frame batches on three detectors.  None when OpenCV (the test encoder) is missing."""
+    around `steps` 128-frame batches on three detectors per GPU, barrier on both sides, max over ranks.  It moves 1/18 of
+    the raw-YUYV bytes over PCIe, so it shows what the box does when the host->device link is not the limit.
+    None when OpenCV (the test encoder) is missing."""
     try:
         import cv2
     except ImportError:
         return None
+    import torch
+    import torch.distributed as dist
     from ros_vision_b200 import detector as D, synth
     jpgs, present = [], 0
-    for i in range(UNIQUE_FRAMES):
+    for i in range(16):
         _, _, w, h, dec, sigma, sc = synth.config_frame(2, i)
         bgr = synth.gray_to_bgr(sc.gray, np.random.default_rng(i))
         ok, buf = cv2.imencode(".jpg", bgr, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
@@ -301,9 +311,10 @@ def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
             return None
         jpgs.append(buf.tobytes())
         present += len(sc.tags)
-    batch = [jpgs[i % len(jpgs)] for i in range(BATCH)]
+    nb = 128
+    batch = [jpgs[(i + 3 * rank) % len(jpgs)] for i in range(nb)]
     lanes = 3  # detectors (streams) in flight
-    dets = [D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, max_batch=BATCH, device=local) for _ in range(lanes)]
+    dets = [D.GpuDetector(w, h, "gray", quad_decimate=dec, quad_sigma=sigma, max_batch=nb, device=local) for _ in range(lanes)]
     for _ in range(3):
         for d in dets:
             d.EnqueueMjpg(batch)
@@ -311,6 +322,9 @@ def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
             d.Finish()
     found = sum(len(dets[0].Detections(f)) for f in range(len(jpgs)))
     parallel = dets[0].MjpgParallelFrames()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     pending = []
     for it in range(steps):
@@ -321,21 +335,28 @@ def mjpg_leg(local: int, steps: int = 18, quality: int = 75):
         pending.append(d)
     for d in pending:
         d.Finish()
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    out = {"value": BATCH * steps / dt, "unit": "frames/s", "what": "JPEG bytes in host memory -> detections on the host",
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"value": nb * steps * world / dt, "unit": "frames/s", "what": "JPEG bytes in host memory -> detections on the host",
            "jpeg_bytes_per_frame": int(np.mean([len(j) for j in jpgs])), "quality": quality, "sampling": "4:2:2",
-           "h2d_bytes_per_step": int(sum(len(j) for j in batch)), "frames_per_step": BATCH, "steps": steps, "lanes": lanes,
-           "decoder": dets[0].mjpg_backend, "frames_decoded_by_parallel_kernels": parallel, "tags_found": found, "tags_present": present}
+           "h2d_bytes_per_step": int(sum(len(j) for j in batch)), "frames_per_step_per_gpu": nb, "steps": steps, "lanes": lanes,
+           "n_gpus": world, "decoder": dets[0].mjpg_backend, "frames_decoded_by_parallel_kernels": parallel,
+           "tags_found": found, "tags_present": present}
     for d in dets:
         d.close()
-    # the reference's way for this step, timed beside it: OpenCV (libjpeg-turbo) decodes each frame to bgr8 on a host
-    # core (cv::VideoCapture with CAP_PROP_CONVERT_RGB, camera_publisher.cpp:198,336); bounded to about two seconds
-    t0, n = time.perf_counter(), 0
-    while time.perf_counter() - t0 < 2.0:
-        cv2.imdecode(np.frombuffer(jpgs[n % len(jpgs)], np.uint8), cv2.IMREAD_COLOR)
-        n += 1
-    out["cpu_opencv_decode_only"] = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "threads": 1,
-                                     "what": "cv2.imdecode to bgr8 alone (no detection), one host thread"}
+    if rank == 0 and world == 1:
+        # the reference's way for this step, timed beside it: OpenCV (libjpeg-turbo) decodes each frame to bgr8 on a host
+        # core (cv::VideoCapture with CAP_PROP_CONVERT_RGB, camera_publisher.cpp:198,336); bounded to about two seconds
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            cv2.imdecode(np.frombuffer(jpgs[n % len(jpgs)], np.uint8), cv2.IMREAD_COLOR)
+            n += 1
+        out["cpu_opencv_decode_only"] = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "threads": 1,
+                                         "what": "cv2.imdecode to bgr8 alone (no detection), one host thread"}
     return out
 
 
@@ -382,6 +403,169 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+class Timing:
+    """barrier + synchronize on both sides, CUDA events on the detectors' own streams, max over lanes and ranks."""
+
+    def __init__(self, torch, dist, world, local):
+        self.torch, self.dist, self.world, self.local = torch, dist, world, local
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def device_resident_leg(T: Timing, D, rank, frames, B, DL, steps, warmup, clocks=None):
+    """`DL` detectors, one CUDA stream each, take turns on batches that already sit in HBM: while the host collects
+    lane k's results (the only host work between two batches) lane k+1's kernels keep the GPU busy.  One step = one
+    batch per lane.  Returns the first detector (kept open, warm) and the device batch for the profiling leg."""
+    torch, local = T.torch, T.local
+    host_batch = np.stack([frames[(i + rank * 3) % len(frames)] for i in range(B)])
+    dev_batch = torch.from_numpy(host_batch).cuda()
+    dlanes = [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=B, device=local) for _ in range(DL)]
+    dbatches = [dev_batch] + [dev_batch.clone() for _ in range(DL - 1)]
+    dstreams = [torch.cuda.ExternalStream(d.stream, device=torch.device("cuda", local)) for d in dlanes]
+    for d, b in zip(dlanes, dbatches):
+        for _ in range(max(3, warmup)):
+            d.DetectDevice(b.data_ptr(), B)
+    det = dlanes[0]
+    infos = [det.FrameInfo(f) for f in range(B)]
+    assert all(i.status == 0 for i in infos), "device buffer overflow during warm-up"
+    e0 = torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]   # lane 0, after each of its batches
+    e_end = [torch.cuda.Event(enable_timing=True) for _ in dlanes]
+    T.barrier()
+    ctx = clocks if clocks is not None else _Null()
+    with ctx:
+        e0.record(dstreams[0])
+        for s_ in range(steps):
+            for li, (d, b) in enumerate(zip(dlanes, dbatches)):
+                d.EnqueueDevice(b.data_ptr(), B)  # this lane's previous results are collected here
+                if li == 0:
+                    marks[s_].record(dstreams[0])
+        for d, st, ev in zip(dlanes, dstreams, e_end):
+            d.Finish()
+            ev.record(st)
+        T.barrier()
+    ms = T.max_ranks(max(e0.elapsed_time(ev) for ev in e_end))
+    # per-step spread: lane 0's batch-to-batch intervals (its stream is busy back to back in steady state)
+    gaps = [marks[k - 1].elapsed_time(marks[k]) for k in range(1, steps)]
+    for d in dlanes[1:]:
+        d.close()
+    return det, dev_batch, host_batch, ms, gaps, infos
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def end_to_end_leg(T: Timing, D, host_batch, frame_bytes, B, L, steps, expect_dets_of, wc=False, clocks=None):
+    """`L` detectors (one CUDA stream each) take turns, so lane k's host->device copy overlaps lane k-1's kernels;
+    every frame crosses PCIe inside the timed region (one cudaMemcpyAsync per lane batch from one pinned block, as a
+    camera ring buffer would be) and its detections are collected on the host before the lane is reused."""
+    torch, local = T.torch, T.local
+    per_lane = B // L
+    lanes = [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=per_lane, device=local) for _ in range(L)]
+    pinned = D.PinnedBuffer(frame_bytes * B, write_combined=wc)
+    pinned.array[:] = host_batch.reshape(-1)
+    lane_ptrs = [pinned.ptr + l * per_lane * frame_bytes for l in range(L)]
+    for _ in range(3):
+        for l, ld in enumerate(lanes):
+            ld.EnqueueHostBlock(lane_ptrs[l], per_lane)
+    for ld in lanes:
+        ld.Finish()
+    T.barrier()
+    ctx = clocks if clocks is not None else _Null()
+    with ctx:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for l, ld in enumerate(lanes):
+                ld.EnqueueHostBlock(lane_ptrs[l], per_lane)   # waits for + collects this lane's previous batch first
+        ndets = 0
+        for ld in lanes:
+            ld.Finish()
+            ndets += sum(len(ld.Detections(f)) for f in range(per_lane))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    dt = T.max_ranks(dt)
+    if expect_dets_of is not None:
+        assert ndets == sum(len(expect_dets_of.Detections(f)) for f in range(per_lane * L)), "end-to-end path lost detections"
+    for ld in lanes:
+        ld.close()
+    return per_lane * L * steps * T.world / dt, per_lane * L, ndets, pinned
+
+
+def latency_leg(D, local, pinned, frame_bytes, nframes, iters):
+    """One frame at a time: pinned host frame in, detections on the host out (GpuDetector::Detect as the node calls it)."""
+    det1 = D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=1, device=local)
+    lat = []
+    for i in range(iters + 10):
+        t0 = time.perf_counter()
+        det1.DetectPointers([pinned.ptr + (i % nframes) * frame_bytes])
+        lat.append((time.perf_counter() - t0) * 1e3)
+    det1.close()
+    lat = np.sort(np.array(lat[10:]))
+    return float(lat[len(lat) // 2]), float(lat[int(len(lat) * 0.99)])
+
+
+def extra_config_leg(T: Timing, D, rank, cfg, steps):
+    """BASELINE configs 4 and 5 at N GPUs (reference scaling model: one detector per camera,
+    launch_vision.py:231-310).  config 4: camera stream s -> GPU s, one detector + CUDA stream per camera stream;
+    config 5: the 4K clutter scene, batch 16 per GPU.  Same engine, same legs, fewer steps."""
+    saved = (W, H, FMT, DECIMATE, SIGMA, WORKLOAD, UNIQUE_FRAMES, BATCH, CONFIG)
+    select_config(cfg)
+    try:
+        # config 4: every rank renders ITS camera stream (seeds 4000 + 1000 * stream + frame); config 5: frames 16*gpu ...
+        frames = []
+        from ros_vision_b200 import synth
+        for i in range(UNIQUE_FRAMES):
+            idx = (1000 * rank + i) if cfg == 4 else (16 * rank + i)
+            frames.append(np.ascontiguousarray(synth.config_frame(cfg, idx)[0]).reshape(-1))
+        B = BATCH
+        det, dev_batch, host_batch, ms, gaps, infos = device_resident_leg(T, D, rank, frames, B, 2, steps, 3)
+        value = B * 2 * steps * T.world / (ms * 1e-3)
+        ndet = sum(len(det.Detections(f)) for f in range(B))
+        e2e, per_step, _, pinned = end_to_end_leg(T, D, host_batch, frames[0].size, B, 2, steps, det)
+        p50, p99 = latency_leg(D, T.local, pinned, frames[0].size, B, 60)
+        p50, p99 = T.max_ranks(p50), T.max_ranks(p99)
+        pinned.close()
+        det.close()
+        P = float(np.mean([i.num_points for i in infos]))
+        return {"workload": WORKLOAD, "frames_per_batch": B, "streams_per_gpu": 2, "steps": steps, "value": value, "unit": "frames/s",
+                "e2e": e2e, "p50_latency_ms": p50, "p99_latency_ms": p99, "latency_note": "max over ranks of each rank's p50 / p99",
+                "h2d_bytes_per_frame": int(frames[0].size), "points_per_frame": P, "detections_per_batch": ndet, "n_gpus": T.world,
+                "whole_path_hbm_frac": algorithmic_bytes_per_frame(P) * value / T.world / 1e9 / PEAK[0]}
+    finally:
+        globals().update(dict(zip(("W", "H", "FMT", "DECIMATE", "SIGMA", "WORKLOAD", "UNIQUE_FRAMES", "BATCH", "CONFIG"), saved)))
+
+
+PEAK = [6650.0, "fallback (B200_PROFILING.md)"]
+
+
+def load_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        PEAK[0], PEAK[1] = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -395,27 +579,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D.load_library()
+    load_peak()
+    peak, peak_src = PEAK
+    T = Timing(torch, dist, world, local)
     frames = make_frames()
     frame_bytes = frames[0].size
     B = args.batch
+    DL = max(1, args.device_lanes)
+    clocks = ClockSampler(local)
 
-    det = D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=B, device=local)
-    # inputs resident in HBM: B frames, rank-dependent rotation of the pool so ranks do not share frames
-    host_batch = np.stack([frames[(i + rank * 3) % len(frames)] for i in range(B)])
-    dev_batch = torch.from_numpy(host_batch).cuda()
-    stream = torch.cuda.ExternalStream(det.stream, device=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # --- device-resident throughput ---------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        det.DetectDevice(dev_batch.data_ptr(), B)
+    # --- device-resident throughput (the line's `value`) ------------------------------------------
+    det, dev_batch, host_batch, ms, gaps, infos = device_resident_leg(T, D, rank, frames, B, DL, args.steps, args.warmup, clocks)
+    value = B * DL * args.steps * world / (ms * 1e-3)
     ndet_per_batch = sum(len(det.Detections(f)) for f in range(B))
-    infos = [det.FrameInfo(f) for f in range(B)]
-    assert all(i.status == 0 for i in infos), "device buffer overflow during warm-up"
     P = float(np.mean([i.num_points for i in infos]))
     Psel = float(np.mean([i.num_selected_points for i in infos]))
     nblobs = float(np.mean([i.num_blobs for i in infos]))
@@ -429,142 +605,78 @@ def run_ours(args):
         tiers["large"] += float(cnts[cnts > MEDIUM_CAP].sum()) / nd
     launches_per_step = det.kernels_per_batch()
 
-    # `device_lanes` detectors, one CUDA stream each, take turns on resident batches: while the host collects lane k's
-    # results (the only host work between two batches) lane k+1's kernels keep the GPU busy, and the latency-bound tail
-    # of one batch overlaps the bandwidth-bound front end of the next.  One "step" = one batch per lane.
-    DL = max(1, args.device_lanes)
-    dlanes = [det] + [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=B, device=local)
-                      for _ in range(DL - 1)]
-    dbatches = [dev_batch] + [dev_batch.clone() for _ in range(DL - 1)]
-    dstreams = [torch.cuda.ExternalStream(d.stream, device=torch.device("cuda", local)) for d in dlanes]
-    for d, b in zip(dlanes[1:], dbatches[1:]):
-        for _ in range(3):
-            d.DetectDevice(b.data_ptr(), B)
-    e0 = torch.cuda.Event(enable_timing=True)
-    e_end = [torch.cuda.Event(enable_timing=True) for _ in dlanes]
-    barrier()
-    with ClockSampler(local) as clocks:
-        e0.record(dstreams[0])
-        for _ in range(args.steps):
-            for d, b in zip(dlanes, dbatches):
-                d.EnqueueDevice(b.data_ptr(), B)  # this lane's previous results are collected here
-        for d, st, ev in zip(dlanes, dstreams, e_end):
-            d.Finish()
-            ev.record(st)
-        barrier()
-    ms = max(e0.elapsed_time(ev) for ev in e_end)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_frames = B * DL * args.steps * world
-    value = total_frames / (ms * 1e-3)
-    for d in dlanes[1:]:
-        d.close()
-    del dbatches
-
-    # --- end to end: pinned host frames -> detections on the host -------------------------------
-    # `lanes` detectors (one CUDA stream each) take turns, so lane k's host->device copies overlap
-    # lane k-1's kernels; every frame still crosses PCIe inside the timed region and its detections
-    # are collected on the host (Finish) before the lane is reused.
+    # --- end to end: pinned host frames -> detections on the host (the line's `e2e`) --------------
     L = max(1, args.lanes)
-    per_lane = B // L
-    lanes = [D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=per_lane, device=local)
-             for _ in range(L)]
-    # one pinned block holding the batch back to back, as a camera ring buffer would (the engine then moves each
-    # lane's frames with a single host->device copy)
-    pinned = [D.PinnedBuffer(frame_bytes * B, write_combined=args.wc)]
-    pinned[0].array[:] = host_batch.reshape(-1)
-    ptrs = [pinned[0].ptr + i * frame_bytes for i in range(B)]
-    lane_ptrs = [ptrs[l * per_lane] for l in range(L)]
+    e2e_value, e2e_frames_per_step, _, pinned = end_to_end_leg(T, D, host_batch, frame_bytes, B, L, args.steps, det, args.wc, clocks)
+    d2h = 128 * e2e_frames_per_step + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
 
-    def e2e_step():
-        n = 0
-        for l, ld in enumerate(lanes):
-            ld.EnqueueHostBlock(lane_ptrs[l], per_lane)   # waits for + collects this lane's previous batch first
-        return n
+    # --- single-frame latency ----------------------------------------------------------------------
+    p50, p99 = latency_leg(D, local, pinned, frame_bytes, B, args.latency_iters)
+    pinned.close()
 
-    for _ in range(3):
-        e2e_step()
-    for ld in lanes:
-        ld.Finish()
-    barrier()
-    with clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        e2e_dets = 0
-        for ld in lanes:
-            ld.Finish()
-            e2e_dets += sum(len(ld.Detections(f)) for f in range(per_lane))
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_frames = per_lane * L * args.steps * world
-    e2e_value = e2e_frames / e2e_s
-    assert e2e_dets == sum(len(det.Detections(f)) for f in range(per_lane * L)), "end-to-end path lost detections"
-    d2h = 128 * per_lane * L + 168 * ndet_per_batch  # counters + detection records written to pinned host memory
-    for ld in lanes:
-        ld.close()
-
-    # --- single-frame latency (host frame in, detections out) -----------------------------------
-    det1 = D.GpuDetector(W, H, FMT, quad_decimate=DECIMATE, quad_sigma=SIGMA, max_batch=1, device=local)
-    lat = []
-    for i in range(args.latency_iters + 10):
-        t0 = time.perf_counter()
-        det1.DetectPointers([ptrs[i % B]])
-        lat.append((time.perf_counter() - t0) * 1e3)
-    lat = np.sort(np.array(lat[10:]))
-    p50, p99 = float(lat[len(lat) // 2]), float(lat[int(len(lat) * 0.99)])
-    det1.close()
-
-    # --- per-kernel times and the roofline of the dominant kernel --------------------------------
-    prof = det.ProfileDevice(dev_batch.data_ptr(), B, iters=3)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # --- per-kernel times (CUDA events around each launch, kernels serialised on the detector's stream) ----
+    prof = det.ProfileDevice(dev_batch.data_ptr(), B, iters=5)
     kern = []
     for name, kms in prof:
         by = kernel_bytes(name, P, tiers) * B
-        kern.append({"kernel": name, "ms": kms, "alg_bytes": by, "gbs": (by / (kms * 1e-3) / 1e9) if kms > 0 else None})
+        kern.append({"kernel": name, "ms": kms, "alg_bytes": by, "gbs": (by / (kms * 1e-3) / 1e9) if kms > 0 else None,
+                     "frac": (by / (kms * 1e-3) / 1e9 / peak) if kms > 0 else None})
     step_kernel_ms = sum(k["ms"] for k in kern)
-    dom = max(kern, key=lambda k: k["ms"])
-    # DRAM bytes per launch of the dominant kernel from its committed `ncu --set full` capture (profiles/traffic.json,
-    # written by tools/make_profile_summary.py); null when that kernel has no capture yet
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and B == BATCH:
-        t = json.load(open(tpath)).get(dom["kernel"])
-        if t:
-            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
-            traffic_src = f"profiles/summary_{t['tag']}.md ({t['report']})"
-    fe_names = {"pre_yuyv_dec2", "pre_gray_dec2", "pre_bgr_dec1", "pre_bgr_dec2", "pre_generic", "blur", "tile_minmax", "threshold",
-                "ccl_local", "ccl_merge", "ccl_final", "boundary", "select", "scatter"}
-    fe = [k for k in kern if k["kernel"] in fe_names]
+    fe = [k for k in kern if k["kernel"] in FRONT_END]
     fe_ms, fe_bytes = sum(k["ms"] for k in fe), sum(k["alg_bytes"] for k in fe)
+    # The headline kernel is the SLOWEST FRONT-END kernel (the front end is what the HBM roofline is about; the
+    # per-blob kernels are latency / issue bound and are reported with their issue-slot utilisation instead).
+    dom = max(fe, key=lambda k: k["ms"])
+    ncu = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        ncu = json.load(open(tpath))
+    t = ncu.get(dom["kernel"]) if B == BATCH else None
+    traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) if t else None
+    traffic_src = f"profiles/summary_{t['tag']}.md ({t['report']})" if t else None
+    for k in kern:
+        e = ncu.get(k["kernel"])
+        if e and "issue_active_pct" in e:
+            k["ncu_issue_active_pct"] = e["issue_active_pct"]
+            k["ncu_dram_bytes"] = e["dram_read_bytes"] + e["dram_write_bytes"]
+    b_frame = algorithmic_bytes_per_frame(P)
     roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": (dom["gbs"] / peak) if dom["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src,
+            "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
             "alg_bytes_per_launch": dom["alg_bytes"], "peak_source": peak_src,
             "share_of_step": dom["ms"] / step_kernel_ms if step_kernel_ms else None,
-            "whole_path": {"alg_bytes_per_frame": algorithmic_bytes_per_frame(P),
-                           "achieved": algorithmic_bytes_per_frame(P) * B * DL / (ms / args.steps * 1e-3) / 1e9,
-                           "frac": algorithmic_bytes_per_frame(P) * B * DL / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "selection": "slowest front-end kernel by CUDA-event time (per-blob kernels are not HBM bound)",
+            "whole_path": {"alg_bytes_per_frame": b_frame,
+                           "achieved": b_frame * B * DL / (ms / args.steps * 1e-3) / 1e9,
+                           "frac": b_frame * B * DL / (ms / args.steps * 1e-3) / 1e9 / peak},
             "front_end": {"kernels": [k["kernel"] for k in fe], "ms": fe_ms, "alg_bytes": fe_bytes,
                           "achieved": fe_bytes / (fe_ms * 1e-3) / 1e9 if fe_ms else None,
-                          "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peak if fe_ms else None},
+                          "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peak if fe_ms else None,
+                          "compulsory": {"alg_bytes": b_frame * B, "what": "B_frame of SURVEY 8(d): every array once",
+                                         "frac": b_frame * B / (fe_ms * 1e-3) / 1e9 / peak if fe_ms else None}},
             "note": "per-kernel times are CUDA events around each launch with the kernels serialised on one stream; in the "
-                    "timed run the three fit kernels overlap on side streams.  The per-blob kernels (fit_*, quads, decode) are "
-                    "latency / instruction-issue bound, not bandwidth bound (profiles/summary_*.md): their HBM fraction is "
-                    "reported for completeness.",
+                    "timed run the fit kernels overlap on side streams.  fit_*, quads and decode are latency / issue bound: "
+                    "their alg_bytes is the 4-byte segment point they read, ncu_issue_active_pct (profiles/traffic.json) is "
+                    "the figure that describes them.",
             "kernels": kern}
+    det.close()
+    del dev_batch
+
+    # --- the other multi-GPU BASELINE configs and the MJPG input path, at this N -------------------
+    extra = {}
+    if not args.no_extra and CONFIG == 2 and FMT == "yuyv":
+        for cfg in (4, 5):
+            try:
+                extra[f"config{cfg}"] = extra_config_leg(T, D, rank, cfg, max(3, args.steps // 8))
+            except Exception as e:  # noqa: BLE001 -- reporting legs never cost the contract line (all ranks fail alike or not at all)
+                extra[f"config{cfg}"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            extra["e2e_mjpg"] = mjpg_leg(local, rank, world)
+        except Exception as e:  # noqa: BLE001
+            extra["e2e_mjpg"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
-        cb = cpu_baseline(frames) if (world == 1 and not args.no_cpu) else None  # rank 0 at N=1 only
+        solo = world == 1 and not args.no_cpu
+        g = np.array(gaps) if gaps else np.array([ms / args.steps])
         line = {
             "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -574,21 +686,23 @@ def run_ours(args):
                        "l2": f"inputs ({frame_bytes * B / 1e6:.0f} MB/step/GPU) and intermediates exceed the 126 MB L2; no explicit flush",
                        "sharding": "frames by rank, no collective",
                        "cpu_affinity": (f"rank 0 on {len(numa_cpus)} cores next to its GPU (NVML ideal CPU set)" if numa_cpus else "unchanged")},
+            "step_stats": {"what": "rank 0, stream 0: interval between consecutive batches of one lane (one step), ms",
+                           "min": float(g.min()), "median": float(np.median(g)), "max": float(g.max()), "n": int(g.size)},
             "p50_latency_ms": p50, "p99_latency_ms": p99,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * per_lane * L,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * e2e_frames_per_step,
                     "d2h_bytes_per_step": d2h, "lanes": L},
             "gpu_launches": launches_per_step * args.steps * DL,
-            "roofline": roof, "cpu_baseline": cb, "reference_gpu": safe_leg(reference_gpu_leg, frames) if (world == 1 and not args.no_cpu and CONFIG in (2, 4)) else None,
-            "cpu_opencv_aruco": safe_leg(opencv_aruco_leg, frames) if (world == 1 and not args.no_cpu) else None,
-            "e2e_mjpg": safe_leg(mjpg_leg, local) if (world == 1 and not args.no_cpu and CONFIG == 2 and FMT == "yuyv") else None,
+            "roofline": roof,
+            "cpu_baseline": safe_leg(cpu_baseline, frames) if solo else None,
+            "reference_gpu": safe_leg(reference_gpu_leg, frames) if (solo and CONFIG in (2, 4)) else None,
+            "cpu_opencv_aruco": safe_leg(opencv_aruco_leg, frames) if solo else None,
+            "e2e_mjpg": extra.pop("e2e_mjpg", None),
+            "extra": extra,
             "clocks": clocks.summary(),
             "stats": {"points_per_frame": P, "selected_points_per_frame": Psel, "blobs_per_frame": nblobs, "candidate_points_by_tier": tiers,
                       "detections_per_batch": ndet_per_batch},
         }
         print(json.dumps(line))
-    for pb in pinned:
-        pb.close()
-    det.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -607,6 +721,7 @@ def main():
                     help="detector instances (CUDA streams) taking turns in the device-resident leg")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned frame buffer in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU / reference-GPU reporting legs (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 4 / config 5 / MJPG legs (profiling runs)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config to measure; the contract line is config 2 (the default)")
     ap.add_argument("--format", default=None, choices=["gray", "yuyv", "bgr"],

@@ -4,7 +4,15 @@
 // mid-frame host synchronisations: every data-dependent size stays in device counters.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+// nvJPEG is optional: it only serves JPEG kinds the detector's own decode kernels do not take (progressive, 12-bit,
+// arithmetic coding) and the comparison arm of tools/bench_mjpg.py.  Without its header the library builds all the
+// same and such streams are refused with B200TAG_E_INVALID.
+#if defined(__has_include)
+#if __has_include(<nvjpeg.h>) && !defined(B200TAG_NO_NVJPEG)
 #include <nvjpeg.h>
+#define B200TAG_HAVE_NVJPEG 1
+#endif
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +37,7 @@ using namespace b200tag;
 
 // nvJPEG, bound at first use (b200tag_enqueue_mjpg): the library is part of the CUDA toolkit, but a detector that is
 // never handed JPEG frames should not need it.
+#ifdef B200TAG_HAVE_NVJPEG
 struct MjpgDecoder {
   void *lib = nullptr;
   nvjpegHandle_t handle = nullptr;
@@ -43,6 +52,13 @@ struct MjpgDecoder {
   decltype(&nvjpegDecodeBatchedInitialize) batched_init = nullptr;
   decltype(&nvjpegDecodeBatched) batched = nullptr;
 };
+#else
+struct MjpgDecoder {
+  void *lib = nullptr;
+  void *handle = nullptr;
+  int backend = -1;
+};
+#endif
 
 // The detector's own JPEG luminance decoder (kernels_jpeg.cu): one pinned host block and its device twin hold, per
 // batch, the frame descriptors, the Huffman table sets and the entropy-coded segments; one copy moves all of it.
@@ -126,6 +142,22 @@ thread_local std::string g_create_error;
   } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The current CUDA device is per host thread.  Every entry point that touches CUDA runs on the detector's own
+// device and puts the caller's back on exit, so a detector can be driven from any thread (a ROS executor) and
+// detectors on different GPUs can live in one process.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (dev >= 0 && prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 struct ArenaPlan {
   size_t off = 0;
@@ -420,16 +452,16 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
     b200tag_destroy(det);
     return rc;
   };
-  if (cfg->device >= 0) {
-    if (cudaSetDevice(cfg->device) != cudaSuccess) {
-      det->err = "cudaSetDevice failed";
-      return fail(B200TAG_E_NO_DEVICE);
-    }
+  if (cfg->device >= ndev) {
+    det->err = "device ordinal out of range";
+    return fail(B200TAG_E_NO_DEVICE);
   }
-  if (cudaGetDevice(&det->device) != cudaSuccess) {
+  if (cfg->device >= 0) det->device = cfg->device;
+  else if (cudaGetDevice(&det->device) != cudaSuccess) {
     det->err = "cudaGetDevice failed";
     return fail(B200TAG_E_NO_DEVICE);
   }
+  DeviceGuard on_device(det->device);  // the caller's current device is left as it was
   build_params(det);
   FrameParams &p = det->fp;
   const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
@@ -457,6 +489,9 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   const size_t o_th = plan.take(n * B);
   const size_t o_lab = plan.take(n * 4 * B);
   const size_t o_sz = plan.take(n * 4 * B);
+  const size_t ccl_tiles = ccl_tiles_per_frame(p.w, p.h);
+  const size_t o_troots = plan.take(ccl_tiles * ccl_root_cap() * 4 * B);
+  const size_t o_tnroots = plan.take(ccl_tiles * 4 * B);
   const size_t o_pts = plan.take(static_cast<size_t>(p.point_cap) * 8 * B);
   const size_t HB = static_cast<size_t>(hc) * B;
   const size_t o_hkey = plan.take(HB * 8);
@@ -501,6 +536,8 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   p.thresh = base + o_th;
   p.labels = reinterpret_cast<uint32_t *>(base + o_lab);
   p.sizes = reinterpret_cast<uint32_t *>(base + o_sz);
+  p.tile_roots = reinterpret_cast<uint32_t *>(base + o_troots);
+  p.tile_nroots = reinterpret_cast<uint32_t *>(base + o_tnroots);
   p.points = reinterpret_cast<uint64_t *>(base + o_pts);
   p.h_key = reinterpret_cast<unsigned long long *>(base + o_hkey);
   p.h_count = reinterpret_cast<uint32_t *>(base + o_hcnt);
@@ -561,6 +598,7 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
 
 void b200tag_destroy(b200tag_detector *det) {
   if (!det) return;
+  DeviceGuard on_device(det->device);
   if (det->stream) {
     cudaStreamSynchronize(det->stream);
     drop_graphs(det);
@@ -577,9 +615,11 @@ void b200tag_destroy(b200tag_detector *det) {
   if (det->jpeg.d_coef) cudaFree(det->jpeg.d_coef);
   if (det->jpeg.d_rst) cudaFree(det->jpeg.d_rst);
   if (det->jpeg.d_dcs) cudaFree(det->jpeg.d_dcs);
+#ifdef B200TAG_HAVE_NVJPEG
   if (det->mjpg.state) det->mjpg.state_destroy(det->mjpg.state);
   if (det->mjpg.handle) det->mjpg.destroy(det->mjpg.handle);
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
+#endif
   if (det->arena) cudaFree(det->arena);
   if (det->h_counters) cudaFreeHost(det->h_counters);
   if (det->h_dets) cudaFreeHost(det->h_dets);
@@ -588,6 +628,7 @@ void b200tag_destroy(b200tag_detector *det) {
 
 int b200tag_enqueue_device(b200tag_detector *det, const void *device_images, size_t stride, int count) {
   if (!det || !device_images || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   if (det->pending) {
     if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
   }
@@ -596,6 +637,7 @@ int b200tag_enqueue_device(b200tag_detector *det, const void *device_images, siz
 
 int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_images, int count) {
   if (!det || !host_images || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   if (det->pending) {
     if (int rc = finish_impl(det)) if (rc != B200TAG_E_OVERFLOW) return rc;
   }
@@ -610,6 +652,7 @@ int b200tag_enqueue_host(b200tag_detector *det, const uint8_t *const *host_image
 
 int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames, size_t frame_stride_bytes, int count) {
   if (!det || !host_frames || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   const size_t stride = frame_stride_bytes ? frame_stride_bytes : det->in_bytes;
   if (stride < det->in_bytes) return B200TAG_E_INVALID;
   if (det->pending) {
@@ -630,6 +673,7 @@ int b200tag_enqueue_host_block(b200tag_detector *det, const uint8_t *host_frames
 // node converts bgr8 -> YUYV -> gray.  Here the JPEG bitstreams cross PCIe as they are (about a tenth of the YUYV
 // bytes), nvJPEG decodes their luminance plane straight into the detector's input staging buffer on the detector's
 // stream, and the gray pipeline runs behind it.
+#ifdef B200TAG_HAVE_NVJPEG
 static int mjpg_open(b200tag_detector *det) {
   MjpgDecoder &m = det->mjpg;
   if (m.handle) return 0;
@@ -691,6 +735,7 @@ static int mjpg_open(b200tag_detector *det) {
   m.batch = 0;
   return 0;
 }
+#endif
 
 // The detector's own decoder.  Returns 0 when the batch was enqueued, 1 when some frame is a valid JPEG of a kind the
 // kernel does not handle (progressive, 12-bit, ...: the caller falls back to nvJPEG), or a negative error.
@@ -735,28 +780,45 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     *chunks = cap / kJpegChunk + B + 16;
     *subs = cap / (kJpegSubBits / 8) + B + 16;
   };
-  if (!J.init) {
-    J.coef_stride = static_cast<size_t>((det->cfg.width + 31) / 32 * 32) * static_cast<size_t>((det->cfg.height + 31) / 32 * 32);
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_coef), J.coef_stride * B * sizeof(int16_t)));
-    CK(cudaMemsetAsync(J.d_coef, 0, J.coef_stride * B * sizeof(int16_t), det->stream));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_rst), J.coef_stride / 64 * B * sizeof(uint32_t)));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_dcs), J.coef_stride / 64 * B * sizeof(int16_t)));
-    CK(cudaMemsetAsync(J.d_dcs, 0, J.coef_stride / 64 * B * sizeof(int16_t), det->stream));
+  if (!J.init) {  // fixed-size buffers: allocated together, committed only when all three exist
+    const size_t stride = static_cast<size_t>((det->cfg.width + 31) / 32 * 32) * static_cast<size_t>((det->cfg.height + 31) / 32 * 32);
+    int16_t *coef = nullptr, *dcs = nullptr;
+    uint32_t *rst = nullptr;
+    const cudaError_t e1 = cudaMalloc(reinterpret_cast<void **>(&coef), stride * B * sizeof(int16_t));
+    const cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(reinterpret_cast<void **>(&rst), stride / 64 * B * sizeof(uint32_t)) : e1;
+    const cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc(reinterpret_cast<void **>(&dcs), stride / 64 * B * sizeof(int16_t)) : e2;
+    if (e3 != cudaSuccess) {
+      cudaFree(coef); cudaFree(rst); cudaFree(dcs);
+      cudaGetLastError();
+      det->err = std::string("allocating the JPEG coefficient buffers failed: ") + cudaGetErrorString(e3);
+      return B200TAG_E_NOMEM;
+    }
+    J.coef_stride = stride; J.d_coef = coef; J.d_rst = rst; J.d_dcs = dcs;
     J.init = true;
+    CK(cudaMemsetAsync(J.d_coef, 0, J.coef_stride * B * sizeof(int16_t), det->stream));
+    CK(cudaMemsetAsync(J.d_dcs, 0, J.coef_stride / 64 * B * sizeof(int16_t), det->stream));
   }
-  if (total > J.cap) {
+  if (total > J.cap) {  // per-batch buffers grow together: the old set is released only once the new one exists
     CK(cudaStreamSynchronize(det->stream));
-    if (J.h_block) cudaFreeHost(J.h_block);
-    if (J.d_block) cudaFree(J.d_block);
-    if (J.d_ws) cudaFree(J.d_ws);
-    J.h_block = J.d_block = J.d_ws = nullptr;
-    J.cap = 0;
     const size_t want = (total + total / 2 + 4095) & ~static_cast<size_t>(4095);
     size_t chunks, subs;
     ws_layout(want, &chunks, &subs);
-    CK(cudaHostAlloc(reinterpret_cast<void **>(&J.h_block), want, cudaHostAllocDefault));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_block), want));
-    CK(cudaMalloc(reinterpret_cast<void **>(&J.d_ws), want + subs * 16 + (2 * chunks + subs) * 4 + B * (kJpegSyncRounds + 3) * 4 + 256));
+    uint8_t *h_block = nullptr, *d_block = nullptr, *d_ws = nullptr;
+    const cudaError_t e1 = cudaHostAlloc(reinterpret_cast<void **>(&h_block), want, cudaHostAllocDefault);
+    const cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(reinterpret_cast<void **>(&d_block), want) : e1;
+    const cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc(reinterpret_cast<void **>(&d_ws), want + subs * 16 + (2 * chunks + subs) * 4 +
+                                                                                              B * (kJpegSyncRounds + 3) * 4 + 256) : e2;
+    if (e3 != cudaSuccess) {
+      if (h_block) cudaFreeHost(h_block);
+      cudaFree(d_block); cudaFree(d_ws);
+      cudaGetLastError();
+      det->err = std::string("allocating the JPEG batch buffers failed: ") + cudaGetErrorString(e3);
+      return B200TAG_E_NOMEM;
+    }
+    if (J.h_block) cudaFreeHost(J.h_block);
+    if (J.d_block) cudaFree(J.d_block);
+    if (J.d_ws) cudaFree(J.d_ws);
+    J.h_block = h_block; J.d_block = d_block; J.d_ws = d_ws;
     J.cap = want;
   }
   JpegFrame *hf = reinterpret_cast<JpegFrame *>(J.h_block);
@@ -833,6 +895,7 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
 
 int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
   if (!det || !jpegs || !sizes || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   if (det->cfg.format != B200TAG_FMT_GRAY8) {
     det->err = "b200tag_enqueue_mjpg needs a detector created for B200TAG_FMT_GRAY8 (the JPEG luminance plane is the image)";
     return B200TAG_E_INVALID;
@@ -851,6 +914,7 @@ int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, con
     }
   }
   det->jpeg.last_native = false;
+#ifdef B200TAG_HAVE_NVJPEG
   if (int rc = mjpg_open(det)) return rc;
   MjpgDecoder &m = det->mjpg;
   std::vector<nvjpegImage_t> dst(count);
@@ -884,6 +948,10 @@ int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, con
     return st == NVJPEG_STATUS_BAD_JPEG || st == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? B200TAG_E_INVALID : B200TAG_E_CUDA;
   }
   return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+#else
+  det->err = "this JPEG kind (progressive / 12-bit / arithmetic) needs nvJPEG, which this build was compiled without";
+  return B200TAG_E_INVALID;
+#endif
 }
 
 int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
@@ -894,12 +962,16 @@ int b200tag_detect_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, cons
 const char *b200tag_mjpg_backend(const b200tag_detector *det) {
   if (det && det->jpeg.last_native) return "native";
   if (!det || !det->mjpg.handle) return "";
+#ifdef B200TAG_HAVE_NVJPEG
   switch (det->mjpg.backend) {
     case NVJPEG_BACKEND_HARDWARE: return "hardware";
     case NVJPEG_BACKEND_GPU_HYBRID: return "gpu";
     case NVJPEG_BACKEND_HYBRID: return "hybrid";
     default: return "default";
   }
+#else
+  return "";
+#endif
 }
 
 int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_t *dht_out, size_t dht_cap, size_t *dht_len) {
@@ -920,6 +992,7 @@ int b200tag_jpeg_probe(const uint8_t *jpeg, size_t size, int32_t info[8], uint8_
 
 int b200tag_mjpg_parallel_frames(b200tag_detector *det, int count) {
   if (!det || count < 1 || count > det->cfg.max_batch) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   if (!det->jpeg.last_native || !det->jpeg.last_parallel) return 0;
   std::vector<uint32_t> h(count);
   CK(cudaStreamSynchronize(det->stream));
@@ -935,6 +1008,7 @@ int b200tag_debug_jpeg_model(const uint8_t *jpeg, size_t size, uint8_t *out, siz
 
 int b200tag_finish(b200tag_detector *det) {
   if (!det) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   return finish_impl(det);
 }
 
@@ -980,6 +1054,7 @@ const b200tag_quad *b200tag_quads(const b200tag_detector *cdet, int frame, int *
   if (count) *count = 0;
   b200tag_detector *det = const_cast<b200tag_detector *>(cdet);
   if (!det || frame < 0 || frame >= det->last_count || det->pending) return nullptr;
+  DeviceGuard on_device(det->device);
   if (!det->quads_valid[frame]) {
     const uint32_t nq = std::min(det->h_counters[frame].num_quads, det->fp.quad_cap);
     det->quads[frame].resize(nq);
@@ -999,6 +1074,7 @@ const b200tag_quad *b200tag_quads(const b200tag_detector *cdet, int frame, int *
 
 int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, size_t cap, size_t *out_bytes) {
   if (!det || frame < 0 || frame >= det->last_count || det->pending) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   const FrameParams &p = det->fp;
   const Counters &c = det->h_counters[frame];
   const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
@@ -1019,7 +1095,16 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
       src = p.gray + f * N; bytes = N; break;
     case B200TAG_STAGE_QUAD_IMAGE: src = p.quad + f * n; bytes = n; break;
     case B200TAG_STAGE_THRESHOLD: src = p.thresh + f * n; bytes = n; break;
-    case B200TAG_STAGE_LABELS: src = p.labels + f * n; bytes = n * 4; break;
+    case B200TAG_STAGE_LABELS: {  // label words carry colour / size flags in their top bits (dev_types.h): strip them
+      bytes = n * 4;
+      if (out_bytes) *out_bytes = bytes;
+      if (!dst) return 0;
+      if (cap < bytes) return B200TAG_E_INVALID;
+      CK(cudaMemcpy(dst, p.labels + f * n, bytes, cudaMemcpyDeviceToHost));
+      uint32_t *o = static_cast<uint32_t *>(dst);
+      for (size_t i = 0; i < n; i++) o[i] &= 0x0fffffffu;
+      return 0;
+    }
     case B200TAG_STAGE_SIZES: src = p.sizes + f * n; bytes = n * 4; break;
     case B200TAG_STAGE_MINMAX:
       if (!p.keep_stages) return B200TAG_E_INVALID;
@@ -1072,6 +1157,7 @@ int b200tag_copy_stage(b200tag_detector *det, int frame, int stage, void *dst, s
 
 int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, double cy) {
   if (!det) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   drop_graphs(det);  // the parameters are baked into the captured launches
   det->cfg.fx = det->fp.fx = fx; det->cfg.cx = det->fp.cx = cx;
   det->cfg.fy = det->fp.fy = fy; det->cfg.cy = det->fp.cy = cy;
@@ -1080,6 +1166,7 @@ int b200tag_set_camera(b200tag_detector *det, double fx, double cx, double fy, d
 
 int b200tag_set_distortion(b200tag_detector *det, double k1, double k2, double p1, double p2, double k3) {
   if (!det) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   drop_graphs(det);
   det->cfg.k1 = det->fp.k1 = k1; det->cfg.k2 = det->fp.k2 = k2; det->cfg.p1 = det->fp.p1 = p1;
   det->cfg.p2 = det->fp.p2 = p2; det->cfg.k3 = det->fp.k3 = k3;
@@ -1160,6 +1247,7 @@ int b200tag_kernels_per_batch(const b200tag_detector *det) { return det ? det->k
 int b200tag_profile_device(b200tag_detector *det, const void *device_images, size_t stride, int count, int iters,
                            const char **names, float *ms, int cap, int *n_out) {
   if (!det || !device_images || count < 1 || count > det->cfg.max_batch || iters < 1) return B200TAG_E_INVALID;
+  DeviceGuard on_device(det->device);
   if (det->pending) finish_impl(det);
   std::vector<double> acc;
   for (int it = 0; it < iters; it++) {

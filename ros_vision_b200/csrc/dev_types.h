@@ -136,8 +136,10 @@ struct FrameParams {
   uint8_t *minmax_raw;                            // tiles*2
   uint8_t *minmax;                                // tiles*2 filtered (keep_stages)
   uint8_t *thresh;                                // w*h
-  uint32_t *labels;                               // w*h
+  uint32_t *labels;                               // w*h label words: [27:0] label | [28] component >= 25 px | [30:29] colour
   uint32_t *sizes;                                // w*h
+  uint32_t *tile_roots;   // per CCL tile: tile roots that touch the tile border (k_ccl_local -> k_ccl_handoff)
+  uint32_t *tile_nroots;  // per CCL tile: entries in use
   uint64_t *points;     // point_cap
   // blob-pair hash (hash_cap each): key and point count; extents are computed per blob later
   unsigned long long *h_key;

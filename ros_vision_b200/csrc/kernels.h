@@ -54,6 +54,8 @@ struct SideStreams {
 int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side);
 int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);
+size_t ccl_tiles_per_frame(int w, int h);  // CCL tiles of one frame and the capacity of a tile's root list
+size_t ccl_root_cap();
 void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s);
 void launch_blobs_init(cudaStream_t s);
 

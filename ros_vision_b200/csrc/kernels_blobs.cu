@@ -14,6 +14,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "dev_types.h"
 #include "kernels.h"
 
@@ -1155,6 +1157,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p
     const WorkItem item = list[li];
     const uint32_t b = item.blob, off = item.offset, cnt = item.count;
     if (b >= p.blob_cap) continue;  // overflow marker
+    // On a blob-list overflow (frame flagged B200TAG_ST_BLOBS_OVERFLOW) the huge tier's entries, which fill this
+    // list from its back, can reach into the range read here; this tier's buffers hold kSmallBlobPoints points.
+    if (cnt > kSmallBlobPoints) continue;
     fit_one_blob<32, false, KEEP>(p, frame, ctr, b, cnt, off, blobs + b, wk, S.scratch, nullptr, lane);
   }
 }
@@ -1250,6 +1255,8 @@ using HugeShared = CtaShared<kHugeThreads, kHugeCap, 0>;
 
 void launch_blobs_init(cudaStream_t s) {
   static bool dev_ready[64] = {false};
+  static std::mutex mu;  // detectors may be created from several threads
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !dev_ready[dev]) {

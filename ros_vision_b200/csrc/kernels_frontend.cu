@@ -299,64 +299,21 @@ __global__ void __launch_bounds__(128) k_tile_minmax(FrameParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: 3x3 dilation of the tile min/max (edge tiles skip missing neighbours) + threshold.
-// One thread per tile: 9 cached uchar2 reads, 4 x 4-byte pixel loads, 4 x 4-byte stores.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_threshold(FrameParams p) {
-  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ty = blockIdx.y;
-  const int frame = blockIdx.z;
-  if (tx >= p.tiles_x) return;
-  const size_t n = static_cast<size_t>(p.w) * p.h;
-  const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
-  const uchar2 *raw = reinterpret_cast<const uchar2 *>(p.minmax_raw + frame * tiles * 2);
-  int mn = 255, mx = 0;
-#pragma unroll
-  for (int j = -1; j <= 1; j++) {
-    const int ry = ty + j;
-    if (ry < 0 || ry >= p.tiles_y) continue;
-#pragma unroll
-    for (int i = -1; i <= 1; i++) {
-      const int rx = tx + i;
-      if (rx < 0 || rx >= p.tiles_x) continue;
-      const uchar2 m = raw[static_cast<size_t>(ry) * p.tiles_x + rx];
-      mn = min(mn, static_cast<int>(m.x));
-      mx = max(mx, static_cast<int>(m.y));
-    }
-  }
-  if (p.keep_stages) {
-    uint8_t *mm = p.minmax + (frame * tiles + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
-    *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn, mx);
-  }
-  const uint8_t *quad = p.quad + frame * n;
-  uint8_t *th = p.thresh + frame * n;
-  const bool flat = (mx - mn) < p.min_white_black_diff;
-  const int thr = mn + (mx - mn) / 2;
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const size_t off = (static_cast<size_t>(ty) * 4 + r) * p.w + static_cast<size_t>(tx) * 4;
-    const uint32_t d = *reinterpret_cast<const uint32_t *>(quad + off);
-    uint32_t o = 0x7f7f7f7fu;
-    if (!flat) {
-      o = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (static_cast<int>((d >> (8 * k)) & 0xff) > thr) o |= 0xffu << (8 * k);
-    }
-    *reinterpret_cast<uint32_t *>(th + off) = o;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Connected components.  255 is 8-connected, 0 is 4-connected, 127 joins nothing.
 // Label of a component = its smallest pixel index (roots are kept minimal by atomicMin
 // links), size[root] = pixel count.
+//
+// A label word carries its pixel's colour class in bits [30:29] from the moment it is written (0 black,
+// 1 white, 2 gray): both ends of every union have the same colour, so the bits ride through find / atomicMin
+// unchanged, and the later kernels read labels only -- never the thresholded image or, per pixel, the sizes.
+// k_ccl_final adds bit 28 = "component has at least 25 pixels".  [27:0] is the label proper.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCclTW = 32;  // tile width: one 32-bit run mask per row and colour
 constexpr int kCclTH = 64;  // tile height
 constexpr int kCclThreads = 128;
 constexpr int kCclWarps = kCclThreads / 32;
 static_assert(kCclThreads == 2 * kCclTH, "one thread per (row, colour)");
+static_assert(kCclThreads == (kCclTW / 4) * (kCclTH / 4), "one thread per 4x4 threshold tile of the CCL tile");
 
 // Find with path halving.  Parent links only ever move to an ancestor (a smaller index of the same
 // component), so the plain stores are safe next to the atomicMin links of concurrent unions.  On
@@ -396,42 +353,110 @@ __device__ __forceinline__ uint32_t bit_span(int lo, int len) {
   return (len >= 32 ? ~0u : ((1u << len) - 1u)) << lo;
 }
 
-// K3: one CTA labels a 32x64 tile entirely in shared memory, working on RUNS instead of pixels.
-// A row of the tile is two 32-bit masks (white, black).  The union-find nodes are the first
-// pixels of the horizontal runs; one thread per (row, colour) walks the runs of its mask with
-// ffs/clz and unites each with the runs it touches in the row above (white: 8-connected, i.e.
-// the run dilated by one pixel; black: 4-connected).  A second walk compresses every run start
-// to its root and adds the run length to the root's pixel count.  Only the final write-out is
-// per pixel: label = global index of the root of the pixel's run, 16-byte stores.
+constexpr uint32_t kLabelMask = 0x0fffffffu;   // [27:0] label
+constexpr uint32_t kLabelBig = 1u << 28;       // component has >= kMinBlobPixels pixels (set by k_ccl_final)
+constexpr int kColourShift = 29;               // [30:29] 0 black, 1 white, 2 gray
+constexpr uint32_t kColourGray = 2u << kColourShift;
+// tile roots that touch their tile's border (the only ones a cross-tile merge can dethrone): at most one per border pixel
+constexpr uint32_t kCclRootCap = 2 * kCclTW + 2 * kCclTH;
+
+// K2+K3: adaptive threshold (threshold.cu:84-147) fused with the tile-local labelling
+// (labeling_allegretti_2019_BKE.cu:114-300).  One CTA = a 32x64 tile of the quad image = 8x16 threshold tiles.
+//   (T) thread = one 4x4 threshold tile: 3x3 dilation of the raw tile min/max (edge tiles skip missing
+//       neighbours), threshold value into shared memory;
+//   (A) thread = 4 pixels of a row (one 4-byte load): byte-wise compare (__vcmpgtu4) gives the thresholded word,
+//       stored as is; its white / black nibbles are OR-reduced over the 8 lanes of the row into the two 32-bit run
+//       masks of the row -- the labelling never reads the thresholded image back;
+//   (B) union-find on RUNS: nodes are the first pixels of the horizontal runs; one thread per (row, colour) walks
+//       the runs of its mask with ffs/clz and unites each with the runs it touches in the row above (white:
+//       8-connected, i.e. the run dilated by one pixel; black: 4-connected);
+//   (C) a second walk compresses every run start to its root and adds the run length to the root's pixel count
+//       (upper half of the counter: how many of the runs touch the tile border);
+//   (D) write-out per pixel, 16-byte stores: label = global index of the root of the pixel's run | colour, sizes =
+//       count at tile roots, 0 elsewhere; tile roots that touch the border go to the tile's root list, from which
+//       k_ccl_handoff moves the counts of merged-away roots to the final roots.
 __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   __shared__ uint32_t s_mask[2][kCclTH];  // [0] black, [1] white
   __shared__ uint32_t s_par[kCclTH * kCclTW];
   __shared__ uint32_t s_cnt[kCclTH * kCclTW];
+  __shared__ uint16_t s_thr[kCclTH / 4][kCclTW / 4];  // threshold of the 4x4 tile; 0xffff = flat (all 127)
+  __shared__ uint32_t s_roots[kCclRootCap];
+  __shared__ uint32_t s_nroots;
 
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
-  const uint8_t *th = p.thresh + frame * n;
+  const uint8_t *quad = p.quad + frame * n;
+  uint8_t *th = p.thresh + frame * n;
   uint32_t *labels = p.labels + frame * n;
   uint32_t *sizes = p.sizes + frame * n;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
 
-  // (A) run masks: lane = column, rows strided over the warps (all of a warp's row loads are issued
-  //     before the first ballot); pixels outside the image count as 127 (join nothing)
-  {
-    constexpr int kRows = kCclTH / kCclWarps;
-    uint32_t a[kRows];
+  {  // (T)
+    const int tlx = tid & 7, tly = tid >> 3;
+    const int tx = (x0 >> 2) + tlx, ty = (y0 >> 2) + tly;
+    uint32_t enc = 0xffffu;
+    if (tx < p.tiles_x && ty < p.tiles_y) {
+      const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
+      const uchar2 *raw = reinterpret_cast<const uchar2 *>(p.minmax_raw + frame * tiles * 2);
+      int mn = 255, mx = 0;
 #pragma unroll
-    for (int k = 0; k < kRows; k++) {
-      const int gy = y0 + warp + k * kCclWarps;
-      a[k] = 127;
-      if (gy < p.h && x0 + lane < p.w) a[k] = th[static_cast<size_t>(gy) * p.w + x0 + lane];
+      for (int j = -1; j <= 1; j++) {
+        const int ry = ty + j;
+        if (ry < 0 || ry >= p.tiles_y) continue;
+#pragma unroll
+        for (int i = -1; i <= 1; i++) {
+          const int rx = tx + i;
+          if (rx < 0 || rx >= p.tiles_x) continue;
+          const uchar2 m = __ldg(raw + static_cast<size_t>(ry) * p.tiles_x + rx);
+          mn = min(mn, static_cast<int>(m.x));
+          mx = max(mx, static_cast<int>(m.y));
+        }
+      }
+      if (p.keep_stages) {
+        uint8_t *mm = p.minmax + (frame * tiles + static_cast<size_t>(ty) * p.tiles_x + tx) * 2;
+        *reinterpret_cast<uchar2 *>(mm) = make_uchar2(mn, mx);
+      }
+      if ((mx - mn) >= p.min_white_black_diff) enc = static_cast<uint32_t>(mn + (mx - mn) / 2);
+    }
+    s_thr[tly][tlx] = static_cast<uint16_t>(enc);
+    if (tid == 0) s_nroots = 0;
+  }
+  __syncthreads();
+
+  // (A) thresholded pixels + run masks: 8 lanes per row, 4 rows per warp, 16 rows per pass; all four pixel loads
+  //     of a thread are issued before the first use.  Pixels outside the image join nothing.
+  {
+    constexpr int kPasses = kCclTH / (kCclThreads / 8);
+    const int xq = tid & 7, rsub = tid >> 3;
+    const int gx = x0 + 4 * xq;
+    const uint32_t row_lanes = 0xffu << (lane & 24);
+    uint32_t d[kPasses];
+#pragma unroll
+    for (int k = 0; k < kPasses; k++) {
+      const int gy = y0 + rsub + k * (kCclThreads / 8);
+      d[k] = 0;
+      if (gy < p.h && gx < p.w) d[k] = __ldg(reinterpret_cast<const uint32_t *>(quad + static_cast<size_t>(gy) * p.w + gx));
     }
 #pragma unroll
-    for (int k = 0; k < kRows; k++) {
-      const int r = warp + k * kCclWarps;
-      const uint32_t wm = __ballot_sync(0xffffffffu, a[k] == 255), bm = __ballot_sync(0xffffffffu, a[k] == 0);
-      if (lane == 0) {
+    for (int k = 0; k < kPasses; k++) {
+      const int r = rsub + k * (kCclThreads / 8);
+      const int gy = y0 + r;
+      const bool inside = gy < p.h && gx < p.w;
+      const uint32_t t = s_thr[r >> 2][xq];
+      uint32_t wn = 0, bn = 0;
+      if (inside) {
+        uint32_t o = 0x7f7f7f7fu;
+        if (t != 0xffffu) {
+          o = __vcmpgtu4(d[k], t * 0x01010101u);  // 0xff where v > thresh (threshold.cu:138-142)
+          wn = ((o & 0x01010101u) * 0x01020408u) >> 24;  // one bit per byte, byte 0 -> bit 0
+          bn = wn ^ 0xfu;
+        }
+        *reinterpret_cast<uint32_t *>(th + static_cast<size_t>(gy) * p.w + gx) = o;
+      }
+      const uint32_t wm = __reduce_or_sync(row_lanes, wn << (4 * xq));
+      const uint32_t bm = __reduce_or_sync(row_lanes, bn << (4 * xq));
+      if (xq == 0) {
         s_mask[1][r] = wm;
         s_mask[0][r] = bm;
       }
@@ -470,9 +495,10 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   }
   __syncthreads();
 
-  // (C) compress run starts to their roots, per-root pixel counts
+  // (C) compress run starts to their roots, per-root pixel counts (low half) and border-touching runs (high half)
   {
     uint32_t m = mine;
+    const bool edge_row = row == 0 || row == kCclTH - 1;
     while (m) {
       const int s = __ffs(static_cast<int>(m)) - 1;
       const uint32_t inv = ~(m >> s);
@@ -481,13 +507,13 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
       const uint32_t node = row * kCclTW + s;
       const uint32_t root = sfind(s_par, node);
       if (root != node) s_par[node] = root;
-      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len));
+      const uint32_t touches = (edge_row || s == 0 || s + len == kCclTW) ? 0x10000u : 0u;
+      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len) | touches);
     }
   }
   __syncthreads();
 
-  // (D) write out, 4 pixels (16 bytes of labels) per thread: label = global index of the root of
-  //     the pixel's run; sizes = count at local roots, 0 elsewhere
+  // (D) write out, 4 pixels (16 bytes of labels) per thread
   for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
     const int r = i / (kCclTW / 4), xq = (i % (kCclTW / 4)) * 4;
     const int gy = y0 + r, gx = x0 + xq;
@@ -498,27 +524,40 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int x = xq + k;
-      lab[k] = static_cast<uint32_t>(g + k);
+      lab[k] = static_cast<uint32_t>(g + k) | kColourGray;
       sz[k] = 0;
       const bool isw = (wm >> x) & 1u, isb = (bm >> x) & 1u;
       if (isw || isb) {
         const uint32_t below = ~(isw ? wm : bm) & ((1u << x) - 1u);
         const int s = below ? 32 - __clz(static_cast<int>(below)) : 0;
         const uint32_t root = s_par[r * kCclTW + s];
-        lab[k] = static_cast<uint32_t>((y0 + (root / kCclTW)) * p.w + x0 + (root % kCclTW));
-        if (root == static_cast<uint32_t>(r * kCclTW + x)) sz[k] = s_cnt[root];
+        lab[k] = static_cast<uint32_t>((y0 + (root / kCclTW)) * p.w + x0 + (root % kCclTW)) | (isw ? 1u << kColourShift : 0u);
+        if (root == static_cast<uint32_t>(r * kCclTW + x)) {
+          const uint32_t c = s_cnt[root];
+          sz[k] = c & 0xffffu;
+          if (c >> 16) s_roots[atomicAdd(&s_nroots, 1u)] = static_cast<uint32_t>(g + k);
+        }
       }
     }
     *reinterpret_cast<uint4 *>(labels + g) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
     *reinterpret_cast<uint4 *>(sizes + g) = make_uint4(sz[0], sz[1], sz[2], sz[3]);
   }
+  __syncthreads();
+  {
+    const uint32_t nr = s_nroots;
+    const size_t tile = (static_cast<size_t>(frame) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    uint32_t *list = p.tile_roots + tile * kCclRootCap;
+    for (uint32_t i = tid; i < nr; i += kCclThreads) list[i] = s_roots[i];
+    if (tid == 0) p.tile_nroots[tile] = nr;
+  }
 }
 
+// Global find on label words: the index is [27:0], the colour bits travel along (equal at both ends of a link).
 __device__ __forceinline__ uint32_t gfind(const uint32_t *par, uint32_t a) {
-  uint32_t q = __ldcg(par + a);
+  uint32_t q = __ldcg(par + (a & kLabelMask));
   while (q != a) {
     a = q;
-    q = __ldcg(par + a);
+    q = __ldcg(par + (a & kLabelMask));
   }
   return a;
 }
@@ -533,7 +572,7 @@ __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
       a = b;
       b = t;
     }
-    const uint32_t old = atomicMin(par + a, b);
+    const uint32_t old = atomicMin(par + (a & kLabelMask), b);
     if (old == a) return;
     a = old;
   }
@@ -541,15 +580,14 @@ __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
 
 // K4: unions across tile borders.  Work items per tile: its top row (TW), left column (TH),
 // right column (TH, for the up-right diagonal).  One thread per item collects up to three
-// neighbour pairs; inside a warp, pairs that join the same two tile-local trees (equal raw labels
-// on both sides -- on thresholded noise the same giant component shows up at every other border
-// pixel) are deduplicated with __match_any_sync, so only one lane walks the parent chains.
+// neighbour pairs (colour from the label words themselves); inside a warp, pairs that join the same two
+// tile-local trees (equal raw labels on both sides -- on thresholded noise the same giant component shows up at
+// every other border pixel) are deduplicated with __match_any_sync, so only one lane walks the parent chains.
 constexpr int kCclMergeThreads = ((kCclTW + 2 * kCclTH + 31) / 32) * 32;
 __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
-  const uint8_t *th = p.thresh + frame * n;
   uint32_t *labels = p.labels + frame * n;
   const int t = threadIdx.x, lane = t & 31;
   int x = 0, y = 0;
@@ -564,75 +602,92 @@ __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   uint32_t other[3];  // neighbour pixel of each candidate pair, 0xffffffff = none
   other[0] = other[1] = other[2] = 0xffffffffu;
   uint32_t i = 0;
-  if (kind < 3 && x < p.w && y < p.h) {
-    i = static_cast<uint32_t>(y * p.w + x);
-    const uint8_t v = th[i];
-    if (v != 127) {
-      if (kind == 0) {
-        if (y > 0) {  // every "up" neighbour is in another tile
-          if (th[i - p.w] == v) other[0] = i - p.w;
-          if (v == 255) {
-            if (x > 0 && th[i - p.w - 1] == 255) other[1] = i - p.w - 1;
-            if (x + 1 < p.w && th[i - p.w + 1] == 255) other[2] = i - p.w + 1;
-          }
+  const bool live = kind < 3 && x < p.w && y < p.h;
+  if (live) i = static_cast<uint32_t>(y * p.w + x);
+  const uint32_t mine = __ldcg(labels + i);
+  const uint32_t colour = mine >> kColourShift;  // 0 black, 1 white, 2 gray
+  if (live && colour != 2) {
+    if (kind == 0) {
+      if (y > 0) {  // every "up" neighbour is in another tile
+        other[0] = i - p.w;
+        if (colour == 1) {
+          if (x > 0) other[1] = i - p.w - 1;
+          if (x + 1 < p.w) other[2] = i - p.w + 1;
         }
-      } else if (kind == 1) {
-        if (x > 0) {
-          if (th[i - 1] == v) other[0] = i - 1;
-          // up-left lies in the left tile; rows at the tile top were handled by kind 0
-          if (v == 255 && y > y0 && th[i - p.w - 1] == 255) other[1] = i - p.w - 1;
-        }
-      } else {
-        if (v == 255 && y > y0 && x + 1 < p.w && th[i - p.w + 1] == 255) other[0] = i - p.w + 1;
       }
+    } else if (kind == 1) {
+      if (x > 0) {
+        other[0] = i - 1;
+        // up-left lies in the left tile; rows at the tile top were handled by kind 0
+        if (colour == 1 && y > y0) other[1] = i - p.w - 1;
+      }
+    } else {
+      if (colour == 1 && y > y0 && x + 1 < p.w) other[0] = i - p.w + 1;
     }
   }
-  const uint32_t mine = __ldcg(labels + i);
+  uint32_t theirs[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) theirs[k] = other[k] != 0xffffffffu ? __ldcg(labels + other[k]) : 0xffffffffu;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    const bool has = other[k] != 0xffffffffu;
+    const bool has = other[k] != 0xffffffffu && (theirs[k] >> kColourShift) == colour;
     const uint32_t active = __ballot_sync(0xffffffffu, has);
     if (!has) continue;
-    const uint32_t theirs = __ldcg(labels + other[k]);
-    const unsigned long long key = (static_cast<unsigned long long>(min(mine, theirs)) << 32) | max(mine, theirs);
+    const unsigned long long key = (static_cast<unsigned long long>(min(mine, theirs[k])) << 32) | max(mine, theirs[k]);
     const uint32_t group = __match_any_sync(active, key);
-    if (lane == __ffs(group) - 1 && mine != theirs) gunite(labels, mine, theirs);
+    if (lane == __ffs(group) - 1 && mine != theirs[k]) gunite(labels, mine, theirs[k]);
   }
 }
 
-// K5: every pixel jumps to its root; tile-local roots that were merged away hand their
-// pixel count to the final root.  4 pixels (16 bytes of labels) per thread.
+// K4b: tile roots that a cross-tile merge dethroned hand their pixel count to the final root.  Only roots whose
+// tile-local component touches the tile border can be affected, and k_ccl_local listed exactly those: one warp
+// per tile walks its list (the reference scans every pixel for this, labeling_allegretti_2019_BKE.cu:340-462).
+__global__ void __launch_bounds__(256) k_ccl_handoff(FrameParams p, uint32_t tiles_per_frame) {
+  const int frame = blockIdx.y;
+  const size_t n = static_cast<size_t>(p.w) * p.h;
+  const uint32_t *labels = p.labels + frame * n;
+  uint32_t *sizes = p.sizes + frame * n;
+  const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= tiles_per_frame) return;
+  const size_t t = static_cast<size_t>(frame) * tiles_per_frame + tile;
+  const uint32_t nr = p.tile_nroots[t];
+  const uint32_t *list = p.tile_roots + t * kCclRootCap;
+  for (uint32_t e = threadIdx.x & 31; e < nr; e += 32) {
+    const uint32_t self = list[e];
+    const uint32_t me = __ldcg(labels + self);
+    if ((me & kLabelMask) == self) continue;  // still a root
+    const uint32_t root = gfind(labels, me) & kLabelMask;
+    atomicAdd(sizes + root, sizes[self]);
+    sizes[self] = 0;
+  }
+}
+
+// K5: every pixel jumps to its root and learns whether its component is large enough to bound a blob
+// (sizes are final after k_ccl_handoff).  4 pixels (16 bytes of labels) per thread; 16 bytes in, 16 bytes out.
 __global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
   const int frame = blockIdx.y;
   const size_t n = static_cast<size_t>(p.w) * p.h;
   uint32_t *labels = p.labels + frame * n;
-  uint32_t *sizes = p.sizes + frame * n;
+  const uint32_t *sizes = p.sizes + frame * n;
   const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
   const uint4 l = __ldcg(reinterpret_cast<const uint4 *>(labels + i4));
-  const uint4 s = __ldcg(reinterpret_cast<const uint4 *>(sizes + i4));
   uint32_t lab[4] = {l.x, l.y, l.z, l.w};
-  const uint32_t sz[4] = {s.x, s.y, s.z, s.w};
   // neighbouring pixels mostly alternate between two tile roots (a white and a black component): chase each once
-  uint32_t m_lab0 = 0xffffffffu, m_root0 = 0, m_lab1 = 0xffffffffu, m_root1 = 0;
+  uint32_t m_lab0 = 0xffffffffu, m_out0 = 0, m_lab1 = 0xffffffffu, m_out1 = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const uint32_t self = static_cast<uint32_t>(i4 + k);
-    if (lab[k] != self || sz[k] != 0) {  // 127-pixels (own index, size 0) need nothing
-      uint32_t root;
-      if (lab[k] == m_lab0) root = m_root0;
-      else if (lab[k] == m_lab1) root = m_root1;
-      else {
-        root = gfind(labels, lab[k]);
-        m_lab1 = m_lab0; m_root1 = m_root0;
-        m_lab0 = lab[k]; m_root0 = root;
-      }
-      lab[k] = root;
-      if (sz[k] != 0 && root != self) {
-        atomicAdd(sizes + root, sz[k]);
-        sizes[self] = 0;
-      }
+    if ((lab[k] >> kColourShift) == 2) continue;  // 127-pixels: own index, never large enough
+    uint32_t out;
+    if (lab[k] == m_lab0) out = m_out0;
+    else if (lab[k] == m_lab1) out = m_out1;
+    else {
+      const uint32_t root = gfind(labels, lab[k]);
+      out = root | (__ldg(sizes + (root & kLabelMask)) >= kMinBlobPixels ? kLabelBig : 0u);
+      m_lab1 = m_lab0; m_out1 = m_out0;
+      m_lab0 = lab[k]; m_out0 = out;
     }
+    lab[k] = out;
   }
   *reinterpret_cast<uint4 *>(labels + i4) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
 }
@@ -684,7 +739,7 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
   return kInvalidSlot;
 }
 
-// staged cell: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
+// staged cell = label word: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
 __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
   __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
@@ -699,9 +754,7 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kBpTW, y0 = blockIdx.y * kBpTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
-  const uint8_t *th = p.thresh + frame * n;
   const uint32_t *labels = p.labels + frame * n;
-  const uint32_t *sizes = p.sizes + frame * n;
   Counters *ctr = p.counters + frame;
   uint64_t *points = p.points + static_cast<size_t>(frame) * p.point_cap;
   const size_t hoff = static_cast<size_t>(frame) * p.hash_cap;
@@ -714,33 +767,22 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
     s_lkey[i] = kEmptyKey;
     s_lcnt[i] = 0;
   }
-  {  // halo tile: all of a thread's pixel and label loads are issued before the dependent size gathers
+  {  // halo tile: the label words already are the cells (k_ccl_final); outside the image = gray
     constexpr int kCells = (kBpTH + 1) * (kBpTW + 2);
     constexpr int kPer = (kCells + kBpThreads - 1) / kBpThreads;
-    uint32_t v[kPer], lab[kPer];
+    uint32_t cell[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
       const int i = tid + k * kBpThreads;
       const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
       const int gx = x0 - 1 + c, gy = y0 + r;
-      v[k] = 127;
-      lab[k] = 0;
-      if (i < kCells && gx >= 0 && gx < p.w && gy < p.h) {
-        const size_t g = static_cast<size_t>(gy) * p.w + gx;
-        v[k] = th[g];
-        lab[k] = labels[g];
-      }
+      cell[k] = kColourGray;
+      if (i < kCells && gx >= 0 && gx < p.w && gy < p.h) cell[k] = __ldg(labels + static_cast<size_t>(gy) * p.w + gx);
     }
-    uint32_t sz[kPer];
-#pragma unroll
-    for (int k = 0; k < kPer; k++) sz[k] = v[k] != 127 ? __ldg(sizes + lab[k]) : 0u;
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
       const int i = tid + k * kBpThreads;
-      if (i >= kCells) continue;
-      uint32_t cell = 2u << 29;
-      if (v[k] != 127) cell = lab[k] | ((sz[k] >= kMinBlobPixels ? 1u : 0u) << 28) | ((v[k] ? 1u : 0u) << 29);
-      (&s_cell[0][0])[i] = cell;
+      if (i < kCells) (&s_cell[0][0])[i] = cell[k];
     }
   }
   __syncthreads();
@@ -960,11 +1002,6 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
       launches++;
     }
   }
-  if (kt) kt->begin("threshold", s);
-  k_threshold<<<tgrid, 128, 0, s>>>(p);
-  if (kt) kt->end(s);
-  launches++;
-
   const dim3 cgrid(cdiv(p.w, kCclTW), cdiv(p.h, kCclTH), frames);
   if (kt) kt->begin("ccl_local", s);
   k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
@@ -972,10 +1009,13 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   if (kt) kt->begin("ccl_merge", s);
   k_ccl_merge<<<cgrid, kCclMergeThreads, 0, s>>>(p);
   if (kt) kt->end(s);
+  if (kt) kt->begin("ccl_handoff", s);
+  k_ccl_handoff<<<dim3(cdiv(cgrid.x * cgrid.y, 8), frames), 256, 0, s>>>(p, cgrid.x * cgrid.y);
+  if (kt) kt->end(s);
   if (kt) kt->begin("ccl_final", s);
   k_ccl_final<<<dim3(cdiv(static_cast<unsigned>((static_cast<size_t>(p.w) * p.h + 3) / 4), 256), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
-  launches += 3;
+  launches += 4;
 
   if (kt) kt->begin("boundary", s);
   k_boundary<<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, kBpTH), frames), kBpThreads, 0, s>>>(p);
@@ -983,6 +1023,9 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   launches++;
   return launches;
 }
+
+size_t ccl_tiles_per_frame(int w, int h) { return static_cast<size_t>(cdiv(w, kCclTW)) * cdiv(h, kCclTH); }
+size_t ccl_root_cap() { return kCclRootCap; }
 
 void launch_hash_clear(const FrameParams &p, int frames, cudaStream_t s) {
   k_hash_clear<<<296, 256, 0, s>>>(p, frames);

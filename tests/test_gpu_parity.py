@@ -157,6 +157,34 @@ def test_overflow_is_reported_not_fatal(D):
     det.close()
 
 
+def test_blob_overflow_with_huge_blobs(D, oracle):
+    """Blob-list overflow on a frame that has blobs of more than 4096 points next to many small ones: the huge
+    tier's work-list entries (filled from the back of the small tier's list) may then reach into the range the
+    warp-per-blob tier reads; it must skip them instead of fitting 4096+ points into its 192-point buffers."""
+    w, h = 1600, 1200
+    img = np.full((h, w), 200, np.uint8)
+    img[100:1100, 60:760] = 20      # two rectangles with a perimeter of 3400 px: about 6800 boundary points each
+    img[100:1100, 840:1540] = 20
+    for k in range(40):             # 40 small squares inside them: about 100 boundary points each
+        rect, j = divmod(k, 20)
+        y, x = 150 + 220 * (j // 5), (60 if rect == 0 else 840) + 60 + 120 * (j % 5)
+        img[y:y + 14, x:x + 14] = 230
+    for max_blobs in (4, 8, 16):
+        det = D.GpuDetector(w, h, "gray", quad_decimate=1, max_blobs=max_blobs)
+        with pytest.raises(D.B200TagError):
+            det.Detect(img)
+        assert det.FrameInfo().status & D.ST_BLOBS_OVERFLOW
+        det.close()
+    orc = oracle.detect(oracle.make_config(w, h, "gray", 1, 0.0), img)
+    cnt = orc.clusters["count"]
+    assert (cnt > 4096).sum() >= 2 and (cnt <= 192).sum() >= 20, "the scene must exercise both ends of the work list"
+    det = D.GpuDetector(w, h, "gray", quad_decimate=1, keep_stages=True)
+    det.Detect(img)
+    assert det.FrameInfo().status == 0
+    compare_all(det, orc, 0, "gray")
+    det.close()
+
+
 def test_other_decimation_factors(D, oracle):
     """quad_decimate 3 and 4 (the reference supports only 2): every stage against the oracle."""
     from ros_vision_b200 import synth
