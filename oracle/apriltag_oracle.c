@@ -14,7 +14,8 @@
 #include <string.h>
 
 #include "cuda_math_emul.h"
-#include "tag36h11_codes.h"
+#include "oracle_internal.h"
+#include "tag_families.h"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -23,6 +24,23 @@
 float orc_emul_atan2f(float y, float x) { return orc_cuda_atan2f(y, x); }
 float orc_emul_hypotf(float a, float b) { return orc_cuda_hypotf(a, b); }
 uint64_t orc_tag36h11_code(int id) { return orc_tag36h11_codes[id]; }
+
+/* Built-in families (libapriltag tagXXhYY_create(), apriltag_utils.cu:10-27): AprilTag 3 layouts, normal border. */
+static const orc_family k_families[ORC_NUM_FAMILIES] = {
+    {"tag36h11", orc_tag36h11_NBITS, orc_tag36h11_NCODES, orc_tag36h11_WIDTH_AT_BORDER, orc_tag36h11_TOTAL_WIDTH, 0,
+     orc_tag36h11_MIN_HAMMING, orc_tag36h11_codes, orc_tag36h11_bit_x, orc_tag36h11_bit_y},
+    {"tag25h9", orc_tag25h9_NBITS, orc_tag25h9_NCODES, orc_tag25h9_WIDTH_AT_BORDER, orc_tag25h9_TOTAL_WIDTH, 0,
+     orc_tag25h9_MIN_HAMMING, orc_tag25h9_codes, orc_tag25h9_bit_x, orc_tag25h9_bit_y},
+    {"tag16h5", orc_tag16h5_NBITS, orc_tag16h5_NCODES, orc_tag16h5_WIDTH_AT_BORDER, orc_tag16h5_TOTAL_WIDTH, 0,
+     orc_tag16h5_MIN_HAMMING, orc_tag16h5_codes, orc_tag16h5_bit_x, orc_tag16h5_bit_y},
+};
+const orc_family *orc_family_get(int index) { return (index >= 0 && index < ORC_NUM_FAMILIES) ? &k_families[index] : NULL; }
+int orc_family_index(const char *name) {
+  for (int i = 0; i < ORC_NUM_FAMILIES; i++)
+    if (strcmp(name, k_families[i].name) == 0) return i;
+  return -1;
+}
+static uint32_t family_mask_of(const orc_config *c) { return c->family_mask ? c->family_mask : 1u; }
 
 void orc_default_config(orc_config *c, int width, int height, int format) {
   memset(c, 0, sizeof(*c));
@@ -42,6 +60,7 @@ void orc_default_config(orc_config *c, int width, int height, int format) {
   c->min_white_black_diff = 5;
   c->fx = 1.0; c->fy = 1.0; c->cx = 0.0; c->cy = 0.0;
   c->max_stage = ORC_STAGE_DECODE;
+  c->family_mask = 1; /* tag36h11, the family the node configures (apriltags_cuda_detector.hpp:213) */
 }
 
 /* ------------------------------------------------------------------------- */
@@ -51,7 +70,7 @@ void orc_default_config(orc_config *c, int width, int height, int format) {
 /* threshold.cu:16-40 (YUYV: gray[i] = in[2i]).  BGR follows the luma OpenCV's
  * COLOR_BGR2YUV_YUYV produces, which is what the node feeds the detector
  * (apriltags_cuda_detector.cu:399-404). */
-static void to_gray(const orc_config *c, const uint8_t *in, uint8_t *gray) {
+void orc_i_to_gray(const orc_config *c, const uint8_t *in, uint8_t *gray) {
   const size_t N = (size_t)c->width * c->height;
   if (c->format == ORC_FMT_GRAY8) {
     memcpy(gray, in, N);
@@ -66,7 +85,7 @@ static void to_gray(const orc_config *c, const uint8_t *in, uint8_t *gray) {
 }
 
 /* threshold.cu:27-31: point subsample. */
-static void decimate(const uint8_t *gray, int W, int f, uint8_t *out, int w, int h) {
+void orc_i_decimate(const uint8_t *gray, int W, int f, uint8_t *out, int w, int h) {
   for (int y = 0; y < h; y++)
     for (int x = 0; x < w; x++) out[(size_t)y * w + x] = gray[(size_t)(y * f) * W + x * f];
 }
@@ -101,7 +120,7 @@ static int blur_kernel(float quad_sigma, uint8_t *k) {
   return ksz;
 }
 
-static void gaussian_blur(uint8_t *im, int w, int h, float quad_sigma) {
+void orc_i_gaussian_blur(uint8_t *im, int w, int h, float quad_sigma) {
   uint8_t k[32];
   const int ksz = blur_kernel(quad_sigma, k);
   if (!ksz) return;
@@ -136,7 +155,7 @@ static void gaussian_blur(uint8_t *im, int w, int h, float quad_sigma) {
 /* ------------------------------------------------------------------------- */
 /* Stage 2: adaptive threshold   threshold.cu:60-147                          */
 /* ------------------------------------------------------------------------- */
-static void threshold(const uint8_t *im, int w, int h, int min_white_black_diff, uint8_t *minmax_out,
+void orc_i_threshold(const uint8_t *im, int w, int h, int min_white_black_diff, uint8_t *minmax_out,
                       uint8_t *out) {
   const int tw = w / 4, th = h / 4;
   uint8_t *mm = (uint8_t *)malloc((size_t)tw * th * 2);
@@ -306,12 +325,16 @@ static float extents_dot(const orc_cluster *e) { /* line_fit_filter.h:51-58 */
   return (float)d;
 }
 
-static int min_tag_width(const orc_config *c) { /* apriltag_gpu.cu:169-181 */
-  int m = orc_tag36h11_WIDTH_AT_BORDER;
+int orc_i_min_tag_width(const orc_config *c) { /* apriltag_gpu.cu:169-181: min over the families */
+  int m = 1000000;
+  for (int f = 0; f < ORC_NUM_FAMILIES; f++)
+    if ((family_mask_of(c) >> f) & 1u)
+      if (k_families[f].width_at_border < m) m = k_families[f].width_at_border;
   m = (int)((float)m / (float)c->quad_decimate);
   if (m < 3) m = 3;
   return m;
 }
+static int min_tag_width(const orc_config *c) { return orc_i_min_tag_width(c); }
 
 static void clusters_and_filter(const orc_config *c, orc_result *r) {
   const int np = r->num_points;
@@ -883,7 +906,9 @@ int orc_homography_compute(const double c[4][4], double Hout[9]) {
   return 0;
 }
 
-static void h_project(const double *H, double x, double y, double *ox, double *oy) {
+void orc_i_h_project(const double *H, double x, double y, double *ox, double *oy);
+static void h_project(const double *H, double x, double y, double *ox, double *oy) { orc_i_h_project(H, x, y, ox, oy); }
+void orc_i_h_project(const double *H, double x, double y, double *ox, double *oy) {
   const double xx = H[0] * x + H[1] * y + H[2];
   const double yy = H[3] * x + H[4] * y + H[5];
   const double zz = H[6] * x + H[7] * y + H[8];
@@ -936,32 +961,46 @@ static double value_for_pixel(const uint8_t *im, int W, int H, double px, double
          im[(size_t)y2 * W + x1] * (1 - x) * y + im[(size_t)y2 * W + x2] * x * y;
 }
 
-static uint64_t rotate90_36(uint64_t w) { return ((w << 9) | (w >> 27)) & ((1ULL << 36) - 1); }
+/* rotate90 (libapriltag apriltag.c): the codeword of the tag turned by 90 degrees */
+static uint64_t rotate90(uint64_t w, int nbits) {
+  int p = nbits;
+  uint64_t l = 0;
+  if (nbits % 4 == 1) {
+    p = nbits - 1;
+    l = 1;
+  }
+  w = ((w >> l) << (p / 4 + l)) | (w >> (3 * p / 4 + l) << l) | (w & l);
+  w &= ((1ULL << nbits) - 1);
+  return w;
+}
 
-int orc_decode_codeword(uint64_t rcode, int *hamming, int *rotation) {
-  /* quick_decode_codeword with maxhamming = 2: the hash table holds every code
-   * with <= 2 flipped bits; min distance 11 makes the hit unique, so a linear
-   * popcount scan returns the same (id, hamming). */
+int orc_decode_codeword_family(const orc_family *fam, uint64_t rcode, int *hamming, int *rotation) {
+  /* quick_decode_codeword with maxhamming = 2: the hash table holds every code with <= 2 flipped bits; a minimum
+   * distance of 5 or more (rotations included) makes the hit unique, so a linear popcount scan returns the same
+   * (id, hamming). */
   for (int ridx = 0; ridx < 4; ridx++) {
-    for (int id = 0; id < orc_tag36h11_NCODES; id++) {
-      const int d = __builtin_popcountll(rcode ^ orc_tag36h11_codes[id]);
+    for (int id = 0; id < fam->ncodes; id++) {
+      const int d = __builtin_popcountll(rcode ^ fam->codes[id]);
       if (d <= 2) {
         *hamming = d;
         *rotation = ridx;
         return id;
       }
     }
-    rcode = rotate90_36(rcode);
+    rcode = rotate90(rcode, fam->nbits);
   }
   *hamming = 255;
   *rotation = 0;
   return -1;
 }
+int orc_decode_codeword(uint64_t rcode, int *hamming, int *rotation) {
+  return orc_decode_codeword_family(&k_families[0], rcode, hamming, rotation);
+}
 
 /* returns decision margin (<0: rejected) */
-static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, const double *Hm, int *id, int *hamming,
-                         int *rotation) {
-  const int wb = orc_tag36h11_WIDTH_AT_BORDER, tw = orc_tag36h11_TOTAL_WIDTH;
+float orc_i_quad_decode(const orc_config *c, const orc_family *fam, const uint8_t *im, int W, int H, const double *Hm, int *id,
+                        int *hamming, int *rotation) {
+  const int wb = fam->width_at_border, tw = fam->total_width;
   const float patterns[] = {
       -0.5f, 0.5f, 0, 1, 1, 0.5f, 0.5f, 0, 1, 0, wb + 0.5f, .5f, 0, 1, 1, wb - 0.5f, .5f, 0, 1, 0,
       0.5f, -0.5f, 1, 0, 1, 0.5f, 0.5f, 1, 0, 0, 0.5f, wb + 0.5f, 1, 0, 1, 0.5f, wb - 0.5f, 1, 0, 0};
@@ -987,16 +1026,15 @@ static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, c
   }
   gm_solve(&whitemodel);
   gm_solve(&blackmodel);
-  const int reversed_border = 0;
-  if ((gm_interp(&whitemodel, 0, 0) - gm_interp(&blackmodel, 0, 0) < 0) != reversed_border) return -1;
+  if ((gm_interp(&whitemodel, 0, 0) - gm_interp(&blackmodel, 0, 0) < 0) != fam->reversed_border) return -1;
 
   float black_score = 0, white_score = 0;
   float black_score_count = 1, white_score_count = 1;
-  double values[100];
+  double values[144];
   memset(values, 0, sizeof(values));
   const int min_coord = (wb - tw) / 2;
-  for (int i = 0; i < orc_tag36h11_NBITS; i++) {
-    const int bit_x = orc_tag36h11_bit_x[i], bit_y = orc_tag36h11_bit_y[i];
+  for (int i = 0; i < fam->nbits; i++) {
+    const int bit_x = fam->bit_x[i], bit_y = fam->bit_y[i];
     const double tagx01 = (bit_x + 0.5) / (wb);
     const double tagy01 = (bit_y + 0.5) / (wb);
     const double tagx = 2 * (tagx01 - 0.5);
@@ -1009,7 +1047,7 @@ static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, c
     values[tw * (bit_y - min_coord) + bit_x - min_coord] = v - thresh;
   }
   { /* sharpen */
-    double sharpened[100];
+    double sharpened[144];
     static const double kernel[9] = {0, -1, 0, -1, 4, -1, 0, -1, 0};
     for (int y = 0; y < tw; y++)
       for (int x = 0; x < tw; x++) {
@@ -1023,8 +1061,8 @@ static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, c
     for (int i = 0; i < tw * tw; i++) values[i] = values[i] + c->decode_sharpening * sharpened[i];
   }
   uint64_t rcode = 0;
-  for (int i = 0; i < orc_tag36h11_NBITS; i++) {
-    const int bit_x = orc_tag36h11_bit_x[i], bit_y = orc_tag36h11_bit_y[i];
+  for (int i = 0; i < fam->nbits; i++) {
+    const int bit_x = fam->bit_x[i], bit_y = fam->bit_y[i];
     rcode = (rcode << 1);
     const double v = values[(bit_y - min_coord) * tw + bit_x - min_coord];
     if (v > 0) {
@@ -1036,17 +1074,40 @@ static float quad_decode(const orc_config *c, const uint8_t *im, int W, int H, c
       black_score_count++;
     }
   }
-  *id = orc_decode_codeword(rcode, hamming, rotation);
+  *id = orc_decode_codeword_family(fam, rcode, hamming, rotation);
   return fminf(white_score / white_score_count, black_score / black_score_count);
 }
 
-static void decode_quads(const orc_config *c, orc_result *r) {
-  r->detections = (orc_detection *)calloc((size_t)r->num_corners + 1, sizeof(orc_detection));
-  r->refined = (orc_quadcorners *)calloc((size_t)r->num_corners + 1, sizeof(orc_quadcorners));
-  int nd = 0;
+/* the apriltag_detection_t quad_decode_task builds from a decoded quad (libapriltag apriltag.c, RECALLED) */
+void orc_i_fill_detection(orc_detection *d, int family, int id, int hamming, float margin, int rotation, const double *Hm) {
   /* cos/sin(rotation * M_PI / 2.0) as libm returns them for k = 0..3 */
   static const double kc[4] = {1.0, 6.123233995736766e-17, -1.0, -1.8369701987210297e-16};
   static const double ks[4] = {0.0, 1.0, 1.2246467991473532e-16, -1.0};
+  memset(d, 0, sizeof(*d));
+  d->id = id;
+  d->hamming = hamming;
+  d->decision_margin = margin;
+  d->rotation = rotation;
+  d->family = family;
+  const double cc = kc[rotation], ss = ks[rotation];
+  /* H * R, R = [c -s 0; s c 0; 0 0 1] */
+  for (int row = 0; row < 3; row++) {
+    d->H[row * 3 + 0] = Hm[row * 3 + 0] * cc + Hm[row * 3 + 1] * ss;
+    d->H[row * 3 + 1] = Hm[row * 3 + 0] * -ss + Hm[row * 3 + 1] * cc;
+    d->H[row * 3 + 2] = Hm[row * 3 + 2];
+  }
+  h_project(d->H, 0, 0, &d->c[0], &d->c[1]);
+  for (int i = 0; i < 4; i++) {
+    const int tcx = (i == 1 || i == 2) ? 1 : -1;
+    const int tcy = (i < 2) ? 1 : -1;
+    h_project(d->H, tcx, tcy, &d->p[i][0], &d->p[i][1]);
+  }
+}
+
+static void decode_quads(const orc_config *c, orc_result *r) {
+  r->detections = (orc_detection *)calloc((size_t)r->num_corners * ORC_NUM_FAMILIES + 1, sizeof(orc_detection));
+  r->refined = (orc_quadcorners *)calloc((size_t)r->num_corners + 1, sizeof(orc_quadcorners));
+  int nd = 0;
   for (int qi = 0; qi < r->num_corners; qi++) {
     float p[4][2];
     memcpy(p, r->corners[qi].corners, sizeof(p));
@@ -1067,29 +1128,17 @@ static void decode_quads(const orc_config *c, orc_result *r) {
                          Hm[2] * (Hm[3] * Hm[7] - Hm[4] * Hm[6]);
       if (!(fabs(det) > 1e-300)) continue;
     }
-    int id, hamming, rotation;
-    const float margin = quad_decode(c, r->gray, r->W, r->H, Hm, &id, &hamming, &rotation);
-    if (margin >= 0 && hamming < 255) {
-      orc_detection *d = &r->detections[nd++];
-      memset(d, 0, sizeof(*d));
-      d->id = id;
-      d->hamming = hamming;
-      d->decision_margin = margin;
-      d->rotation = rotation;
-      d->rep0 = r->corners[qi].rep0;
-      d->rep1 = r->corners[qi].rep1;
-      const double cc = kc[rotation], ss = ks[rotation];
-      /* H * R, R = [c -s 0; s c 0; 0 0 1] */
-      for (int row = 0; row < 3; row++) {
-        d->H[row * 3 + 0] = Hm[row * 3 + 0] * cc + Hm[row * 3 + 1] * ss;
-        d->H[row * 3 + 1] = Hm[row * 3 + 0] * -ss + Hm[row * 3 + 1] * cc;
-        d->H[row * 3 + 2] = Hm[row * 3 + 2];
-      }
-      h_project(d->H, 0, 0, &d->c[0], &d->c[1]);
-      for (int i = 0; i < 4; i++) {
-        const int tcx = (i == 1 || i == 2) ? 1 : -1;
-        const int tcy = (i < 2) ? 1 : -1;
-        h_project(d->H, tcx, tcy, &d->p[i][0], &d->p[i][1]);
+    for (int fi = 0; fi < ORC_NUM_FAMILIES; fi++) { /* quad_decode_task: every family of the matching polarity */
+      if (!((family_mask_of(c) >> fi) & 1u)) continue;
+      const orc_family *fam = &k_families[fi];
+      if (fam->reversed_border != r->corners[qi].reversed_border) continue;
+      int id, hamming, rotation;
+      const float margin = orc_i_quad_decode(c, fam, r->gray, r->W, r->H, Hm, &id, &hamming, &rotation);
+      if (margin >= 0 && hamming < 255) {
+        orc_detection *d = &r->detections[nd++];
+        orc_i_fill_detection(d, fi, id, hamming, margin, rotation, Hm);
+        d->rep0 = r->corners[qi].rep0;
+        d->rep1 = r->corners[qi].rep1;
       }
     }
   }
@@ -1140,14 +1189,12 @@ static int cmp_det(const void *a_, const void *b_) {
   if (a->id != b->id) return a->id - b->id;
   if (a->c[0] != b->c[0]) return a->c[0] < b->c[0] ? -1 : 1;
   if (a->c[1] != b->c[1]) return a->c[1] < b->c[1] ? -1 : 1;
-  return 0;
+  return a->family - b->family;
 }
-static void reconcile(orc_result *r) {
-  orc_detection *d = r->detections;
-  int n = r->num_detections;
+int orc_i_reconcile(orc_detection *d, int n) {
   for (int i0 = 0; i0 < n; i0++) {
     for (int i1 = i0 + 1; i1 < n; i1++) {
-      if (d[i0].id != d[i1].id) continue;
+      if (d[i0].id != d[i1].id || d[i0].family != d[i1].family) continue;
       if (!polys_overlap(d[i0].p, d[i1].p)) continue;
       int pref = 0;
       pref = prefer_smaller(pref, d[i0].hamming, d[i1].hamming);
@@ -1169,8 +1216,9 @@ static void reconcile(orc_result *r) {
     }
   }
   qsort(d, n, sizeof(orc_detection), cmp_det);
-  r->num_detections = n;
+  return n;
 }
+static void reconcile(orc_result *r) { r->num_detections = orc_i_reconcile(r->detections, r->num_detections); }
 
 /* ------------------------------------------------------------------------- */
 orc_result *orc_detect(const orc_config *c, const uint8_t *image) {
@@ -1187,10 +1235,10 @@ orc_result *orc_detect(const orc_config *c, const uint8_t *image) {
   r->quad_im = (uint8_t *)malloc(n);
   r->minmax = (uint8_t *)malloc((size_t)(w / 4) * (h / 4) * 2);
   r->thresh = (uint8_t *)malloc(n);
-  to_gray(c, image, r->gray);
-  decimate(r->gray, r->W, f, r->quad_im, w, h);
-  if (c->quad_sigma != 0) gaussian_blur(r->quad_im, w, h, c->quad_sigma);
-  threshold(r->quad_im, w, h, c->min_white_black_diff, r->minmax, r->thresh);
+  orc_i_to_gray(c, image, r->gray);
+  orc_i_decimate(r->gray, r->W, f, r->quad_im, w, h);
+  if (c->quad_sigma != 0) orc_i_gaussian_blur(r->quad_im, w, h, c->quad_sigma);
+  orc_i_threshold(r->quad_im, w, h, c->min_white_black_diff, r->minmax, r->thresh);
   if (c->max_stage <= ORC_STAGE_THRESHOLD) return r;
   r->labels = (uint32_t *)malloc(n * sizeof(uint32_t));
   r->sizes = (uint32_t *)malloc(n * sizeof(uint32_t));

@@ -46,7 +46,22 @@ typedef struct {
   double fx, cx, fy, cy;      /* CameraMatrix, apriltag_gpu.h:61-66 */
   double k1, k2, p1, p2, k3;  /* DistCoeffs, apriltag_gpu.h:68-74 */
   int max_stage;          /* stop after this stage (ORC_STAGE_*), for timing/tests */
+  uint32_t family_mask;   /* bit i = built-in family i (orc_family_get); 0 means tag36h11 only */
 } orc_config;
+
+/* apriltag_family_t (libapriltag apriltag.h), the fields the detector reads. */
+typedef struct {
+  const char *name;
+  int nbits, ncodes;
+  int width_at_border, total_width;
+  int reversed_border;
+  int h; /* minimum Hamming distance */
+  const uint64_t *codes;
+  const int32_t *bit_x, *bit_y;
+} orc_family;
+#define ORC_NUM_FAMILIES 3 /* 0 tag36h11, 1 tag25h9, 2 tag16h5 */
+const orc_family *orc_family_get(int index);
+int orc_family_index(const char *name);
 
 enum {
   ORC_STAGE_THRESHOLD = 1,
@@ -126,6 +141,8 @@ typedef struct {
   double c[2];
   double p[4][2];
   uint32_t rep0, rep1;
+  int32_t family; /* index into the built-in families */
+  int32_t pad;
 } orc_detection;
 
 typedef struct {
@@ -169,6 +186,13 @@ int orc_homography_compute(const double corr[4][4], double H[9]);
 uint64_t orc_tag36h11_code(int id);
 /* quick-decode: returns id or -1; hamming/rotation via out params */
 int orc_decode_codeword(uint64_t rcode, int *hamming, int *rotation);
+int orc_decode_codeword_family(const orc_family *fam, uint64_t rcode, int *hamming, int *rotation);
+
+/* The classic CPU detector (libapriltag apriltag_detector_detect, the reference's second detection path:
+ * test/gpu_detector_test.cu:104-157) restated in classic_detector.c.  `image` is a gray frame of cfg->width x
+ * cfg->height (cfg->format is ignored).  Writes up to `cap` detections (after reconcile, sorted by id) and returns
+ * their number; `nquads` (optional) receives the number of candidate quads. */
+int orc_classic_detect(const orc_config *cfg, const uint8_t *gray, orc_detection *out, int cap, int *nquads);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ class OrcConfig(C.Structure):
         ("max_line_fit_mse", C.c_float), ("min_white_black_diff", C.c_int),
         ("fx", C.c_double), ("cx", C.c_double), ("fy", C.c_double), ("cy", C.c_double),
         ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double), ("k3", C.c_double),
-        ("max_stage", C.c_int),
+        ("max_stage", C.c_int), ("family_mask", C.c_uint32),
     ]
 
 
@@ -46,7 +46,8 @@ FITQUAD_DT = np.dtype([("blob", "<u4"), ("rep0", "<u4"), ("rep1", "<u4"), ("vali
 CORNERS_DT = np.dtype([("corners", "<f4", (4, 2)), ("reversed_border", "<i4"), ("blob", "<u4"), ("rep0", "<u4"),
                        ("rep1", "<u4")])
 DET_DT = np.dtype([("id", "<i4"), ("hamming", "<i4"), ("decision_margin", "<f4"), ("rotation", "<i4"),
-                   ("H", "<f8", (9,)), ("c", "<f8", (2,)), ("p", "<f8", (4, 2)), ("rep0", "<u4"), ("rep1", "<u4")])
+                   ("H", "<f8", (9,)), ("c", "<f8", (2,)), ("p", "<f8", (4, 2)), ("rep0", "<u4"), ("rep1", "<u4"),
+                   ("family", "<i4"), ("pad", "<i4")])
 
 
 class OrcResult(C.Structure):
@@ -67,8 +68,8 @@ class OrcResult(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("apriltag_oracle.c", "apriltag_oracle.h", "cuda_math_emul.h",
-                                             "tag36h11_codes.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("apriltag_oracle.c", "classic_detector.c", "apriltag_oracle.h", "oracle_internal.h",
+                                             "cuda_math_emul.h", "tag_families.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
     return so
@@ -98,18 +99,32 @@ def lib():
         L.orc_tag36h11_code.restype = C.c_uint64
         L.orc_decode_codeword.argtypes = [C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_decode_codeword.restype = C.c_int
+        L.orc_classic_detect.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_classic_detect.restype = C.c_int
+        L.orc_family_index.argtypes = [C.c_char_p]
+        L.orc_family_index.restype = C.c_int
         _LIB = L
     return _LIB
 
 
+FAMILY_NAMES = ("tag36h11", "tag25h9", "tag16h5")   # bit positions of OrcConfig.family_mask
+
+
+def family_mask(families) -> int:
+    if isinstance(families, str):
+        families = [families]
+    return sum(1 << FAMILY_NAMES.index(f) for f in families)
+
+
 def make_config(width, height, fmt="yuyv", quad_decimate=2, quad_sigma=0.0, refine_edges=True, camera=None,
-                dist=None, max_stage=STAGE_DECODE, **qtp) -> OrcConfig:
+                dist=None, max_stage=STAGE_DECODE, families=("tag36h11",), **qtp) -> OrcConfig:
     cfg = OrcConfig()
     lib().orc_default_config(C.byref(cfg), width, height, FMT[fmt])
     cfg.quad_decimate = int(quad_decimate)
     cfg.quad_sigma = float(quad_sigma)
     cfg.refine_edges = int(bool(refine_edges))
     cfg.max_stage = max_stage
+    cfg.family_mask = family_mask(families)
     if camera is not None:
         cfg.fx, cfg.cx, cfg.fy, cfg.cy = camera
     if dist is not None:
@@ -172,3 +187,21 @@ def detect_raw(cfg: OrcConfig, image: np.ndarray) -> int:
     n = p.contents.num_detections
     lib().orc_free_result(p)
     return n
+
+
+def classic_detect(cfg: OrcConfig, gray: np.ndarray, cap: int = 1024):
+    """The classic CPU detector (libapriltag apriltag_detector_detect restated, oracle/classic_detector.c) on a gray
+    frame.  Returns (detections as DET_DT array, number of candidate quads)."""
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    assert gray.size == cfg.width * cfg.height, (gray.shape, cfg.width, cfg.height)
+    out = np.zeros(cap, dtype=DET_DT)
+    nq = C.c_int()
+    n = lib().orc_classic_detect(C.byref(cfg), gray.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), cap, C.byref(nq))
+    if n < 0:
+        raise ValueError("classic detector rejected the configuration")
+    return out[:min(n, cap)].copy(), nq.value
+
+
+def classic_detect_raw(cfg: OrcConfig, gray: np.ndarray) -> int:
+    """Detection count only (timing)."""
+    return lib().orc_classic_detect(C.byref(cfg), gray.ctypes.data_as(C.c_void_p), None, 0, None)

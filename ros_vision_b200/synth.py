@@ -15,13 +15,14 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .tag36h11 import BIT_X, BIT_Y, CODES
+from .tag_families import FAMILIES
 
 
 @dataclass
 class TagPose:
     tag_id: int
     corners: np.ndarray  # (4,2) image positions of tag-frame (-1,-1),(1,-1),(1,1),(-1,1)
+    family: str = "tag36h11"
 
 
 @dataclass
@@ -30,15 +31,18 @@ class Scene:
     tags: list = field(default_factory=list)
 
 
-def tag_pattern(tag_id: int) -> np.ndarray:
-    """10x10 cell image (1 = white) of tag36h11 `tag_id`, quiet zone included."""
-    pat = np.ones((10, 10), dtype=np.float64)
-    pat[1:9, 1:9] = 0.0
-    code = CODES[tag_id]
-    for i in range(36):
-        bit = (code >> (35 - i)) & 1
-        # border cell (bx, by) in [0, 8) sits at pattern cell (bx+1, by+1)
-        pat[BIT_Y[i] + 1, BIT_X[i] + 1] = float(bit)
+def tag_pattern(tag_id: int, family: str = "tag36h11") -> np.ndarray:
+    """total_width x total_width cell image (1 = white) of tag `tag_id` of `family`, one-cell quiet zone included
+    (10 x 10 for tag36h11: black border 8 x 8, data 6 x 6)."""
+    fam = FAMILIES[family]
+    tw, wb, nbits = fam["total_width"], fam["width_at_border"], fam["nbits"]
+    pat = np.ones((tw, tw), dtype=np.float64)
+    pat[1:1 + wb, 1:1 + wb] = 0.0
+    code = fam["codes"][tag_id]
+    for i in range(nbits):
+        bit = (code >> (nbits - 1 - i)) & 1
+        # border cell (bx, by) in [0, width_at_border) sits at pattern cell (bx+1, by+1)
+        pat[fam["bit_y"][i] + 1, fam["bit_x"][i] + 1] = float(bit)
     return pat
 
 
@@ -85,8 +89,10 @@ def render_tag(img: np.ndarray, pose: TagPose, white: float, black: float, ss: i
     tag_pts = [(-1.0, -1.0), (1.0, -1.0), (1.0, 1.0), (-1.0, 1.0)]
     H = solve_homography(tag_pts, [tuple(map(float, p)) for p in pose.corners])
     Hi = _invert3(H)
-    # outer extent of the quiet zone: +-1.25 in tag units
-    q = 1.25
+    fam = FAMILIES[pose.family]
+    cell = 2.0 / fam["width_at_border"]   # the black border spans [-1, 1] in tag units
+    # outer extent of the quiet zone: +-1.25 in tag units for tag36h11
+    q = 1.0 + cell
     outer = []
     for x, y in [(-q, -q), (q, -q), (q, q), (-q, q)]:
         X = H[0, 0] * x + H[0, 1] * y + H[0, 2]
@@ -112,11 +118,11 @@ def render_tag(img: np.ndarray, pose: TagPose, white: float, black: float, ss: i
     TX = (Hi[0, 0] * PX + Hi[0, 1] * PY + Hi[0, 2]) / Z
     TY = (Hi[1, 0] * PX + Hi[1, 1] * PY + Hi[1, 2]) / Z
     inside = (TX >= -q) & (TX < q) & (TY >= -q) & (TY < q) & (Z > 0)
-    cx = np.floor((TX + q) / 0.25).astype(np.int64)
-    cy = np.floor((TY + q) / 0.25).astype(np.int64)
-    np.clip(cx, 0, 9, out=cx)
-    np.clip(cy, 0, 9, out=cy)
-    pat = tag_pattern(pose.tag_id)
+    cx = np.floor((TX + q) / cell).astype(np.int64)
+    cy = np.floor((TY + q) / cell).astype(np.int64)
+    np.clip(cx, 0, fam["total_width"] - 1, out=cx)
+    np.clip(cy, 0, fam["total_width"] - 1, out=cy)
+    pat = tag_pattern(pose.tag_id, pose.family)
     val = pat[cy, cx] * (white - black) + black
     val = np.where(inside, val, 0.0)
     cov = inside.astype(np.float64)
@@ -155,7 +161,7 @@ def random_pose(rng: np.random.Generator, tag_id: int, cx: float, cy: float, sid
 def make_scene(width: int, height: int, seed: int, n_tags: int, side_range=(60.0, 300.0), ids=None,
                max_rot_deg: float = 30.0, max_tilt_deg: float = 35.0, noise_sigma: float = 4.0,
                background: float = 128.0, clutter: bool = False, salt_pepper: float = 0.0,
-               white: float = 230.0, black: float = 25.0, ss: int = 4) -> Scene:
+               white: float = 230.0, black: float = 25.0, ss: int = 4, family: str = "tag36h11") -> Scene:
     rng = np.random.default_rng(seed)
     img = np.full((height, width), float(background), dtype=np.float64)
     if clutter:
@@ -189,8 +195,9 @@ def make_scene(width: int, height: int, seed: int, n_tags: int, side_range=(60.0
         cy = float(rng.uniform(rad + 2, height - rad - 2))
         if any((cx - px) ** 2 + (cy - py) ** 2 < (rad + pr) ** 2 for px, py, pr in placed):
             continue
-        tid = int(ids[len(tags)]) if ids is not None else int(rng.integers(0, 587))
+        tid = int(ids[len(tags)]) if ids is not None else int(rng.integers(0, len(FAMILIES[family]["codes"])))
         pose = random_pose(rng, tid, cx, cy, side, max_rot_deg, max_tilt_deg)
+        pose.family = family
         render_tag(img, pose, white, black, ss)
         placed.append((cx, cy, rad))
         tags.append(pose)

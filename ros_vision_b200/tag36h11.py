@@ -1,156 +1,6 @@
-"""tag36h11 family data (generated by tools/gen_tag36h11.py -- do not edit)."""
-BIT_X = [1, 2, 3, 4, 5, 2, 3, 4, 3, 6, 6, 6, 6, 6, 5, 5, 5, 4, 6, 5, 4, 3, 2, 5, 4, 3, 4, 1, 1, 1, 1, 1, 2, 2, 2, 3]
-BIT_Y = [1, 1, 1, 1, 1, 2, 2, 2, 3, 1, 2, 3, 4, 5, 2, 3, 4, 3, 6, 6, 6, 6, 6, 5, 5, 5, 4, 6, 5, 4, 3, 2, 5, 4, 3, 4]
-NBITS = 36
-WIDTH_AT_BORDER = 8
-TOTAL_WIDTH = 10
-MIN_HAMMING = 11
-CODES = [
-    0xd7e00984b, 0xdda664ca7, 0xdc4a1c821, 0xe17b470e9,
-    0xef91d01b1, 0xf429cdd73, 0x05da29225, 0x1106cba43,
-    0x223bed79d, 0x21f51213c, 0x33eb19ca6, 0x3f76eb0f8,
-    0x469a97414, 0x45dcfe0b0, 0x4a6465f72, 0x51801db96,
-    0x5eb946b4e, 0x68a7cc2ec, 0x6f0ba2652, 0x78765559d,
-    0x87b83d129, 0x86cc4a5c5, 0x8b64df90f, 0x9c577b611,
-    0xa3810f2f5, 0xaf4d75b83, 0xb59a03fef, 0xbb1096f85,
-    0xd1b92fc76, 0xd0dd509d2, 0xe2cfda160, 0x2ff497c63,
-    0x47240671b, 0x5047a2e55, 0x635ca87c7, 0x691254166,
-    0x68f43d94a, 0x6ef24bdb6, 0x8cdd8f886, 0x9de96b718,
-    0xaff6e5a8a, 0xbae46f029, 0xd225b6d59, 0xdf8ba8c01,
-    0xe3744a22f, 0xfbb59375d, 0x18a916828, 0x22f29c1ba,
-    0x286887d58, 0x41392322e, 0x75d18ecd1, 0x87c302743,
-    0x8c6317ba9, 0x9e40f36d7, 0xc0e5a806a, 0xcc78cb87c,
-    0x12d2f2d01, 0x379f36a21, 0x6973f59ac, 0x7789ea9f4,
-    0x8f1c73e84, 0x8dd287a20, 0x94a4eee4c, 0xa455379b5,
-    0xa9e92987d, 0xbd25cb40b, 0xbe98d3582, 0xd3d5972b2,
-    0x14c53d7c7, 0x4f1796936, 0x4e71fed1a, 0x66d46fae0,
-    0xa55abb933, 0xebee1acca, 0x1ad4ba6a4, 0x305b17571,
-    0x553611351, 0x59ca62775, 0x7819cb6a1, 0xedb7bc9eb,
-    0x5b2694212, 0x72e12d185, 0xed6152e2c, 0x5bcdadbf3,
-    0x78e0aa0c6, 0xc60a0b909, 0xef9a34b0d, 0x398a6621a,
-    0xa8a27c944, 0x4b564304e, 0x52902b4e2, 0x857280b56,
-    0xa91b2c84b, 0xe91df939b, 0x1fa405f28, 0x23793ab86,
-    0x68c17729f, 0x9fbf3b840, 0x36922413c, 0x4eb5f946e,
-    0x533fe2404, 0x63de7d35e, 0x925eddc72, 0x99b8b3896,
-    0xaace4c708, 0xc22994af0, 0x8f1eae41b, 0xd95fb486c,
-    0x13fb77857, 0x4fe0983a3, 0xd559bf8a9, 0xe1855d78d,
-    0xfec8daaad, 0x71ecb6d95, 0xdc9e50e4c, 0xca3a4c259,
-    0x740d12bbf, 0xaeedd18e0, 0xb509b9c8e, 0x5232fea1c,
-    0x19282d18b, 0x76c22d67b, 0x936beb34b, 0x08a5ea8dd,
-    0x679eadc28, 0xa08e119c5, 0x20a6e3e24, 0x7eab9c239,
-    0x96632c32e, 0x470d06e44, 0x8a70212fb, 0x0a7e4251b,
-    0x9ec762cc0, 0xd8a3a1f48, 0xdb680f346, 0x4a1e93a9d,
-    0x638ddc04f, 0x4c2fcc993, 0x01ef28c95, 0xbf0d9792d,
-    0x6d27557c3, 0x623f977f4, 0x35b43be57, 0xbb0c428d5,
-    0xa6f01474d, 0x5a70c9749, 0x20ddabc3b, 0x2eabd78cf,
-    0x90aa18f88, 0xa9ea89350, 0x3cdb39b22, 0x839a08f34,
-    0x169bb814e, 0x1a575ab08, 0xa04d3d5a2, 0xbf7902f2b,
-    0x095a5e65c, 0x92e8fce94, 0x67ef48d12, 0x6400dbcac,
-    0xb12d8fb9f, 0x0347f45d3, 0xb35826f56, 0xc546ac6e4,
-    0x81cc35b66, 0x41d14bd57, 0x0c052b168, 0x7d6ce5018,
-    0xab4ed5ede, 0x5af817119, 0xd1454b182, 0x2badb090b,
-    0x03fcb4c0c, 0x2f1c28fd8, 0x93608c6f7, 0x4c93ba2b5,
-    0x07d950a5d, 0xe54b3d3fc, 0x15560cf9d, 0x189e4958a,
-    0x62140e9d2, 0x723bc1cdb, 0x2063f26fa, 0xfa08ab19f,
-    0x7955641db, 0x646b01daa, 0x71cd427cc, 0x09a42f7d4,
-    0x717edc643, 0x15eb94367, 0x8392e6bb2, 0x832408542,
-    0x2b9b874be, 0xb21f4730d, 0xb5d8f24c9, 0x7dbaf6931,
-    0x1b4e33629, 0x13452e710, 0xe974af612, 0x1df61d29a,
-    0x99f2532ad, 0xe50ec71b4, 0x5df0a36e8, 0x4934e4cea,
-    0xe34a0b4bd, 0xb7b26b588, 0x0f255118d, 0xd0c8fa31e,
-    0x06a50c94f, 0xf28aa9f06, 0x131d194d8, 0x622e3da79,
-    0xac7478303, 0xc8f2521d7, 0x6c9c881f5, 0x49e38b60a,
-    0x513d8df65, 0xd7c2b0785, 0x9f6f9d75a, 0x9f6966020,
-    0x1e1a54e33, 0xc04d63419, 0x946e04cd7, 0x1bdac5902,
-    0x56469b830, 0xffad59569, 0x86970e7d8, 0x8a4b41e12,
-    0xad4688e3b, 0x85f8f5df4, 0xd833a0893, 0x2a36fdd7c,
-    0xd6a857cf2, 0x8829bc35c, 0x5e50d79bc, 0xfbb8035e4,
-    0xc1a95bebf, 0x036b0baf8, 0xe0da964ea, 0xb6483689b,
-    0x7c8e2f4c1, 0x5b856a23b, 0x2fc183995, 0xe914b6d70,
-    0xb31041969, 0x1bb478493, 0x063e2b456, 0xf2a082b9c,
-    0x8e5e646ea, 0x08172f8f6, 0x0dacd923e, 0xe5dcf0e2e,
-    0xbf9446bae, 0x4822d50d1, 0x26e710bf5, 0xb90ba2a24,
-    0xf3b25aa73, 0x809ad589b, 0x94cc1e254, 0x5334a3adb,
-    0x592886b2f, 0xbf64704aa, 0x566dbf24c, 0x72203e692,
-    0x64e61e809, 0xd7259aad6, 0x7b924aedc, 0x2df2184e8,
-    0x353d1eca7, 0xfce30d7ce, 0xf7b0f436e, 0x57e8d8f68,
-    0x8c79e60db, 0x9c8362b2b, 0x63a5804f2, 0x9298353dc,
-    0x6f98a71c8, 0xa5731f693, 0x21ca5c870, 0x1c2107fd3,
-    0x6181f6c39, 0x19e574304, 0x329937606, 0x043d5c70d,
-    0x9b18ff162, 0x8e2ccfebf, 0x72b7b9b54, 0x9b71f4f3c,
-    0x935d7393e, 0x65938881a, 0x6a5bd6f2d, 0xa19783306,
-    0xe6472f4d7, 0x81163df5a, 0xa838e1cbd, 0x982748477,
-    0x050c54feb, 0x0d82fbb58, 0x2c4c72799, 0x97d259ad6,
-    0x22d9a43ed, 0xfdb162a9f, 0x0cb4a727d, 0x4fae2e371,
-    0x535b5be8b, 0x48795908a, 0xce7c18962, 0x4ea154d80,
-    0x50c064889, 0x8d97fc75d, 0xc8bd9ec61, 0x83ee8e8bb,
-    0xc8431419a, 0x1aa78079d, 0x8111aa4a5, 0xdfa3a69fe,
-    0x51630d83f, 0x2d930fb3f, 0x2133116e5, 0xae5395522,
-    0xbc07a4e8a, 0x57bf08ba0, 0x6cb18036a, 0xf0e2e4b75,
-    0x3eb692b6f, 0xd8178a3fa, 0x238cce6a6, 0xe97d5cdd7,
-    0xfe10d8d5e, 0xb39584a1d, 0xca03536fd, 0xaa61f3998,
-    0x72ff23ec2, 0x15aa7d770, 0x57a3a1282, 0xd1f3902dc,
-    0x6554c9388, 0xfd01283c7, 0xe8baa42c5, 0x72cee6adf,
-    0xf6614b3fa, 0x95c3778a2, 0x7da4cea7a, 0xd18a5912c,
-    0xd116426e5, 0x27c17bc1c, 0xb95b53bc1, 0xc8f937a05,
-    0xed220c9bd, 0x0c97d72ab, 0x8fb1217ae, 0x25ca8a5a1,
-    0xb261b871b, 0x1bef0a056, 0x806a51179, 0xeed249145,
-    0x3f82aeceb, 0xcc56e9acf, 0x2e78d01eb, 0x102cee17f,
-    0x37caad3d5, 0x16ac5b1ee, 0x2af164ece, 0xd4cd81dc9,
-    0x12263a7e7, 0x57ac7d117, 0x9391d9740, 0x7aedaa77f,
-    0x9675a3c72, 0x277f25191, 0xebb6e64b9, 0x7ad3ef747,
-    0x12759b181, 0x948257d4d, 0xb63a850f6, 0x3a52a8f75,
-    0x4a019532c, 0xa021a7529, 0xcc661876d, 0x4085afd05,
-    0xe7048e089, 0x3f979cdc6, 0xd9da9071b, 0xed2fc5b68,
-    0x79d64c3a1, 0xfd44e2361, 0x8eea46a74, 0x42233b9c2,
-    0xae4d1765d, 0x7303a094c, 0x2d7033abe, 0x3dcc2b0b4,
-    0x0f0967d09, 0x06f0cd7de, 0x09807aca0, 0x3a295cad3,
-    0x2b106b202, 0x3f38a828e, 0x78af46596, 0xbda2dc713,
-    0x9a8c8c9d9, 0x6a0f2ddce, 0xa76af6fe2, 0x086f66fa4,
-    0xd52d63f8d, 0x89f7a6e73, 0xcc6b23362, 0xb4ebf3c39,
-    0x564f300fa, 0xe8de3a706, 0x79a033b61, 0x765e160c5,
-    0xa266a4f85, 0xa68c38c24, 0xdca0711fb, 0x85fba85ba,
-    0x37a207b46, 0x158fcc4d0, 0x0569d79b3, 0x7b1a25555,
-    0xa8ae22468, 0x7c592bdfd, 0x0c59a5f66, 0xb1115daa3,
-    0xf17c87177, 0x6769d766b, 0x2b637356d, 0x13d8685ac,
-    0xf24cb6ec0, 0x0bd0b56d1, 0x42ff0e26d, 0xb41609267,
-    0x96f9518af, 0xc56f96636, 0x4a8e10349, 0x863512171,
-    0xea455d86c, 0xbd0e25279, 0xe65e3f761, 0x36c84a922,
-    0x85fd1b38f, 0x657c91539, 0x15033fe04, 0x09051c921,
-    0xab27d80d8, 0xf92f7d0a1, 0x8eb6bb737, 0x10b5b0f63,
-    0x6c9c7ad63, 0xf66fe70ae, 0xca579bd92, 0x956198e4d,
-    0x29e4405e5, 0xe44eb885c, 0x41612456c, 0xea45e0abf,
-    0xd326529bd, 0x7b2c33cef, 0x80bc9b558, 0x7169b9740,
-    0xc37f99209, 0x31ff6dab9, 0xc795190ed, 0xa7636e95f,
-    0x9df075841, 0x55a083932, 0xa7cbdf630, 0x409ea4ef0,
-    0x92a1991b6, 0x4b078dee9, 0xae18ce9e4, 0x5a6e1ef35,
-    0x1a403bd59, 0x31ea70a83, 0x2bc3c4f3a, 0x5c921b3cb,
-    0x042da05c5, 0x1f667d16b, 0x416a368cf, 0xfbc0a7a3b,
-    0x9419f0c7c, 0x81be2fa03, 0x34e2c172f, 0x28648d8ae,
-    0xc7acbb885, 0x45f31eb6a, 0xd1cfc0a7b, 0x42c4d260d,
-    0xcf6584097, 0x94b132b14, 0x3c5c5df75, 0x8ae596fef,
-    0xaea8054eb, 0x0ae9cc573, 0x496fb731b, 0xebf105662,
-    0xaf9c83a37, 0xc0d64cd6b, 0x7b608159a, 0xe74431642,
-    0xd6fb9d900, 0x291e99de0, 0x10500ba9a, 0x5cd05d037,
-    0xa87254fb2, 0x9d7824a37, 0x8b2c7b47c, 0x30c788145,
-    0x2f4e5a8be, 0xbadb884da, 0x026e0d5c9, 0x6fdbaa32e,
-    0x34758eb31, 0x565cd1b4f, 0x2bfd90fb0, 0x093052a6b,
-    0xd3c13c4b9, 0x2daea43bf, 0xa279762bc, 0xf1bd9f22c,
-    0x4b7fec94f, 0x545761d5a, 0x7327df411, 0x1b52a442e,
-    0x49b0ce108, 0x24c764bc8, 0x374563045, 0xa3e8f91c6,
-    0x0e6bd2241, 0xe0e52ee3c, 0x07e8e3caa, 0x96c2b7372,
-    0x33acbdfda, 0xb15d91e54, 0x464759ac1, 0x6886a1998,
-    0x57f5d3958, 0x5a1f5c1f5, 0x0b58158ad, 0xe712053fb,
-    0x5352ddb25, 0x414b98ea0, 0x74f89f546, 0x38a56b3c3,
-    0x38db0dc17, 0xaa016a755, 0xdc72366f5, 0x0cee93d75,
-    0xb2fe7a56b, 0xa847ed390, 0x8713ef88c, 0xa217cc861,
-    0x8bca25d7b, 0x455526818, 0xea3a7a180, 0xa9536e5e0,
-    0x9b64a1975, 0x5bfc756bc, 0x046aa169b, 0x53a17f76f,
-    0x4d6815274, 0xcca9cf3f6, 0x4013fcb8b, 0x3d26cdfa5,
-    0x5786231f7, 0x7d4ab09ab, 0x960b5ffbc, 0x8914df0d4,
-    0x2fc6f2213, 0xac235637e, 0x151b28ed3, 0x46f79b6db,
-    0x1382e0c9f, 0x53abf983a, 0x383c47ade, 0x3fcf88978,
-    0xeb9079df7, 0x09af0714d, 0xda19d1bb7, 0x9a02749f8,
-    0x1c62dab9b, 0x1a137e44b, 0x2867718c7, 0x35815525b,
-    0x7cd35c550, 0x2164f73a0, 0xe8b772fe0,
-]
+"""tag36h11 family data: a view of the generated table (tools/gen_families.py)."""
+from .tag_families import FAMILIES
+
+_F = FAMILIES["tag36h11"]
+BIT_X, BIT_Y, CODES = _F["bit_x"], _F["bit_y"], _F["codes"]
+NBITS, WIDTH_AT_BORDER, TOTAL_WIDTH, MIN_HAMMING = _F["nbits"], _F["width_at_border"], _F["total_width"], _F["min_hamming"]
