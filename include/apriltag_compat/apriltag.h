@@ -176,6 +176,11 @@ double estimate_tag_pose(apriltag_detection_info_t *info, apriltag_pose_t *pose)
 /* ---- tag36h11.h ---- */
 apriltag_family_t *tag36h11_create(void);
 void tag36h11_destroy(apriltag_family_t *tf);
+/* ---- tag25h9.h, tag16h5.h ---- */
+apriltag_family_t *tag25h9_create(void);
+void tag25h9_destroy(apriltag_family_t *tf);
+apriltag_family_t *tag16h5_create(void);
+void tag16h5_destroy(apriltag_family_t *tf);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200TAG_ABI_VERSION 1
+#define B200TAG_ABI_VERSION 2
 
 /* Input pixel formats.  The reference accepts YUYV only (apriltag_gpu.h:89); the
  * node converts bgr8 -> YUYV on the CPU first (apriltags_cuda_detector.cu:399-401),
@@ -90,7 +90,9 @@ typedef struct b200tag_detection {
   int32_t id;
   int32_t hamming;
   float decision_margin;
-  int32_t frame; /* index within the batch */
+  int32_t frame;  /* index within the batch */
+  int32_t family; /* index into the families the detector was created with (apriltag_detection_t.family) */
+  int32_t reserved;
   double H[9];
   double c[2];
   double p[4][2];
@@ -175,12 +177,35 @@ typedef struct b200tag_fit_quad { /* FitQuad (line_fit_filter.h:130-135) */
 
 typedef struct b200tag_detector b200tag_detector;
 
+/* A tag family: the fields of libapriltag's apriltag_family_t that detection reads (apriltag_gpu.cu:169-177 for
+ * width_at_border / reversed_border; quad_decode_index for the rest).  The reference accepts the eight families of
+ * apriltag_utils.cu:10-27; here any family of at most 64 bits and total_width <= 12 is accepted, several at once as
+ * long as they share one border polarity (the reference's own precondition, apriltag_detect.cu:108).  bit_x / bit_y
+ * are apriltag_family_t's uint32_t arrays (negative coordinates of the tagStandard / tagCircle families wrap, as in
+ * libapriltag).  The arrays are copied by b200tag_create_families. */
+typedef struct b200tag_family {
+  const char *name;
+  uint32_t nbits, ncodes;
+  const uint64_t *codes;
+  const uint32_t *bit_x, *bit_y;
+  int32_t width_at_border, total_width;
+  int32_t reversed_border;
+  int32_t max_hamming; /* bits corrected (apriltag_detector_add_family_bits; the node's add_family uses 2), 0..3 */
+} b200tag_family;
+
+/* Built-in tables: "tag36h11", "tag25h9", "tag16h5" (AprilTag 3 layouts, max_hamming 2); NULL for other names. */
+const b200tag_family *b200tag_builtin_family(const char *name);
+
 /* Fills `cfg` with libapriltag's apriltag_detector_create() defaults as the node sets them
  * (apriltags_cuda_detector.cu:142-147): decimate 2, sigma 0, refine_edges on. */
 int b200tag_default_config(b200tag_config *cfg, int width, int height, int format);
 
 /* GpuDetector::GpuDetector (apriltag_gpu.cu:111-188): allocates every device buffer up front. */
 int b200tag_create(const b200tag_config *cfg, b200tag_detector **out);
+/* The same with the caller's tag families (apriltag_detector_add_family, apriltags_cuda_detector.cu:139-140);
+ * b200tag_create == one family, the built-in tag36h11 the node configures.  B200TAG_E_INVALID for an empty list, more
+ * than 8 families, mixed border polarities or a family outside the limits above. */
+int b200tag_create_families(const b200tag_config *cfg, const b200tag_family *families, int nfamilies, b200tag_detector **out);
 /* GpuDetector::~GpuDetector (apriltag_gpu.cu:190-200). */
 void b200tag_destroy(b200tag_detector *det);
 
@@ -278,6 +303,11 @@ int b200tag_kernels_per_batch(const b200tag_detector *det);
 /* Per-kernel device time of the last b200tag_profile_device call (ms); names are static strings. */
 int b200tag_profile_device(b200tag_detector *det, const void *device_images, size_t frame_stride_bytes, int count,
                            int iters, const char **names, float *ms, int cap, int *n);
+
+/* Test hook: reconcile_detections (libapriltag; apriltag_detect.cu:660) as the engine runs it on the host after every
+ * frame, on a caller-supplied list: overlapping detections of the same family and id are reduced to the one with the
+ * lower hamming distance, then the larger decision margin; the survivors are sorted by id.  Returns their number. */
+int b200tag_debug_reconcile(b200tag_detection *dets, int count);
 
 /* Test hook: out[i] = atan2f(a[i], b[i]) (op 0) or hypotf(a[i], b[i]) (op 1) evaluated on the device. */
 int b200tag_debug_math(int op, const float *a, const float *b, float *out, int n);

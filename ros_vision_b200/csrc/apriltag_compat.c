@@ -6,7 +6,7 @@
 #include <stdio.h>
 
 #include "apriltag.h"
-#include "tag36h11_data.h"
+#include "tag_families_data.h"
 
 matd_t *matd_create(int rows, int cols) {
   matd_t *m = (matd_t *)calloc(1, sizeof(matd_t) + (size_t)rows * cols * sizeof(double));
@@ -72,26 +72,27 @@ void apriltag_detections_destroy(zarray_t *detections) {
   zarray_destroy(detections);
 }
 
-apriltag_family_t *tag36h11_create(void) {
+static apriltag_family_t *family_create(const char *name, uint32_t h, uint32_t nbits, uint32_t ncodes, const uint64_t *codes,
+                                        const int32_t *bit_x, const int32_t *bit_y, int width_at_border, int total_width) {
   apriltag_family_t *tf = (apriltag_family_t *)calloc(1, sizeof(apriltag_family_t));
-  tf->name = strdup("tag36h11");
-  tf->h = 11;
-  tf->ncodes = b200_tag36h11_NCODES;
-  tf->codes = (uint64_t *)calloc(tf->ncodes, sizeof(uint64_t));
-  memcpy(tf->codes, b200_tag36h11_codes, sizeof(b200_tag36h11_codes));
-  tf->nbits = 36;
-  tf->bit_x = (uint32_t *)calloc(tf->nbits, sizeof(uint32_t));
-  tf->bit_y = (uint32_t *)calloc(tf->nbits, sizeof(uint32_t));
-  for (int i = 0; i < 36; i++) {
-    tf->bit_x[i] = b200_tag36h11_bit_x[i];
-    tf->bit_y[i] = b200_tag36h11_bit_y[i];
+  tf->name = strdup(name);
+  tf->h = h;
+  tf->ncodes = ncodes;
+  tf->codes = (uint64_t *)calloc(ncodes, sizeof(uint64_t));
+  memcpy(tf->codes, codes, ncodes * sizeof(uint64_t));
+  tf->nbits = nbits;
+  tf->bit_x = (uint32_t *)calloc(nbits, sizeof(uint32_t));
+  tf->bit_y = (uint32_t *)calloc(nbits, sizeof(uint32_t));
+  for (uint32_t i = 0; i < nbits; i++) {
+    tf->bit_x[i] = (uint32_t)bit_x[i];
+    tf->bit_y[i] = (uint32_t)bit_y[i];
   }
-  tf->width_at_border = 8;
-  tf->total_width = 10;
+  tf->width_at_border = width_at_border;
+  tf->total_width = total_width;
   tf->reversed_border = false;
   return tf;
 }
-void tag36h11_destroy(apriltag_family_t *tf) {
+static void family_destroy(apriltag_family_t *tf) {
   if (!tf) return;
   free(tf->codes);
   free(tf->bit_x);
@@ -99,3 +100,14 @@ void tag36h11_destroy(apriltag_family_t *tf) {
   free(tf->name);
   free(tf);
 }
+
+#define B200_FAMILY(NAME)                                                                                              \
+  apriltag_family_t *NAME##_create(void) {                                                                             \
+    return family_create(#NAME, b200_##NAME##_MIN_HAMMING, b200_##NAME##_NBITS, b200_##NAME##_NCODES, b200_##NAME##_codes, \
+                         b200_##NAME##_bit_x, b200_##NAME##_bit_y, b200_##NAME##_WIDTH_AT_BORDER, b200_##NAME##_TOTAL_WIDTH); \
+  }                                                                                                                    \
+  void NAME##_destroy(apriltag_family_t *tf) { family_destroy(tf); }
+
+B200_FAMILY(tag36h11)
+B200_FAMILY(tag25h9)
+B200_FAMILY(tag16h5)

@@ -29,9 +29,7 @@
 #include "jpeg_core.h"
 #include "kernels.h"
 
-namespace b200tag {
-int upload_family();
-}
+#include "tag_families_data.h"
 
 using namespace b200tag;
 
@@ -115,6 +113,9 @@ struct b200tag_detector {
   KernelTimer timer;
   MjpgDecoder mjpg;
   NativeJpeg jpeg;
+  void *d_families = nullptr;  // DevFamily[nfamilies] followed by the code tables
+  int min_width_at_border = 8;
+  bool normal_border = true, reversed_border = false;
 };
 
 namespace b200tag {
@@ -225,6 +226,7 @@ bool det_less(const b200tag_detection &a, const b200tag_detection &b) {  // dete
   if (a.id != b.id) return a.id < b.id;
   if (a.c[0] != b.c[0]) return a.c[0] < b.c[0];
   if (a.c[1] != b.c[1]) return a.c[1] < b.c[1];
+  if (a.family != b.family) return a.family < b.family;
   return a.hamming < b.hamming;
 }
 void reconcile(std::vector<b200tag_detection> &d) {
@@ -232,7 +234,7 @@ void reconcile(std::vector<b200tag_detection> &d) {
   int n = static_cast<int>(d.size());
   for (int i0 = 0; i0 < n; i0++) {
     for (int i1 = i0 + 1; i1 < n; i1++) {
-      if (d[i0].id != d[i1].id) continue;
+      if (d[i0].id != d[i1].id || d[i0].family != d[i1].family) continue;
       if (!polys_overlap(d[i0].p, d[i1].p)) continue;
       int pref = 0;
       pref = prefer_smaller(pref, d[i0].hamming, d[i1].hamming);
@@ -281,16 +283,17 @@ void build_params(b200tag_detector *det) {
   p.w = c.width / p.f; p.h = c.height / p.f;
   p.fmt = c.format;
   p.tiles_x = p.w / 4; p.tiles_y = p.h / 4;
+  p.inv_w = static_cast<uint32_t>(((1ull << 32) + p.w - 1) / p.w);
   p.blur_ksz = c.quad_sigma != 0 ? blur_kernel(c.quad_sigma, p.blur_k) : 0;
   p.sharpen = c.quad_sigma < 0;
   p.min_white_black_diff = c.min_white_black_diff;
   p.min_cluster_pixels = static_cast<uint32_t>(std::max(24, c.min_cluster_pixels));  // apriltag_gpu.cu:529
   p.max_cluster_pixels = static_cast<uint32_t>(4 * (p.w + p.h));                      // :871 in quad-image units
-  int mtw = 8;  // tag36h11 width_at_border; apriltag_gpu.cu:169-181
+  int mtw = det->min_width_at_border;  // min over the families; apriltag_gpu.cu:169-181
   mtw = static_cast<int>(static_cast<float>(mtw) / static_cast<float>(p.f));
   if (mtw < 3) mtw = 3;
   p.min_tag_width = mtw;
-  p.normal_border = 1; p.reversed_border = 0;
+  p.normal_border = det->normal_border; p.reversed_border = det->reversed_border;
   p.cos_critical_rad = c.cos_critical_rad;
   p.max_line_fit_mse = c.max_line_fit_mse;
   p.refine_edges = c.refine_edges;
@@ -431,7 +434,122 @@ int b200tag_default_config(b200tag_config *cfg, int width, int height, int forma
   return 0;
 }
 
+namespace {
+struct Builtin {
+  b200tag_family fam;
+  std::vector<uint32_t> bx, by;
+};
+const Builtin *builtin_families() {
+  static Builtin table[3];
+  static bool ready = [] {
+    auto fill = [](Builtin &b, const char *name, uint32_t nbits, uint32_t ncodes, const uint64_t *codes, const int32_t *bx, const int32_t *by,
+                   int wb, int tw) {
+      b.bx.assign(bx, bx + nbits);
+      b.by.assign(by, by + nbits);
+      b.fam = b200tag_family{name, nbits, ncodes, codes, b.bx.data(), b.by.data(), wb, tw, 0, 2};
+    };
+    fill(table[0], "tag36h11", b200_tag36h11_NBITS, b200_tag36h11_NCODES, b200_tag36h11_codes, b200_tag36h11_bit_x, b200_tag36h11_bit_y,
+         b200_tag36h11_WIDTH_AT_BORDER, b200_tag36h11_TOTAL_WIDTH);
+    fill(table[1], "tag25h9", b200_tag25h9_NBITS, b200_tag25h9_NCODES, b200_tag25h9_codes, b200_tag25h9_bit_x, b200_tag25h9_bit_y,
+         b200_tag25h9_WIDTH_AT_BORDER, b200_tag25h9_TOTAL_WIDTH);
+    fill(table[2], "tag16h5", b200_tag16h5_NBITS, b200_tag16h5_NCODES, b200_tag16h5_codes, b200_tag16h5_bit_x, b200_tag16h5_bit_y,
+         b200_tag16h5_WIDTH_AT_BORDER, b200_tag16h5_TOTAL_WIDTH);
+    return true;
+  }();
+  (void)ready;
+  return table;
+}
+
+// Validates the caller's families (apriltag_gpu.cu:169-177, apriltag_detect.cu:108) and builds the device tables.
+int install_families(b200tag_detector *det, const b200tag_family *fams, int n) {
+  if (!fams || n < 1 || n > kMaxFamilies) {
+    det->err = "between 1 and 8 tag families are required";
+    return B200TAG_E_INVALID;
+  }
+  bool normal = false, reversed = false;
+  int min_wb = 1000000;
+  size_t total_codes = 0;
+  for (int i = 0; i < n; i++) {
+    const b200tag_family &f = fams[i];
+    if (f.nbits < 1 || f.nbits > static_cast<uint32_t>(kMaxFamilyBits) || f.ncodes < 1 || !f.codes || !f.bit_x || !f.bit_y ||
+        f.width_at_border < 1 || f.width_at_border > 8 || f.total_width < f.width_at_border || f.total_width > kMaxTotalWidth ||
+        f.max_hamming < 0 || f.max_hamming > 3) {
+      det->err = std::string("tag family ") + (f.name ? f.name : "?") + ": outside the supported limits (nbits <= 64, width_at_border <= 8, "
+                 "total_width <= 12, max_hamming <= 3)";
+      return B200TAG_E_INVALID;
+    }
+    const int lo = (f.width_at_border - f.total_width) / 2, hi = lo + f.total_width;
+    for (uint32_t b = 0; b < f.nbits; b++) {
+      const int x = static_cast<int32_t>(f.bit_x[b]), y = static_cast<int32_t>(f.bit_y[b]);
+      if (x < lo || x >= hi || y < lo || y >= hi) {
+        det->err = std::string("tag family ") + (f.name ? f.name : "?") + ": a bit lies outside the tag";
+        return B200TAG_E_INVALID;
+      }
+    }
+    normal |= !f.reversed_border;
+    reversed |= f.reversed_border != 0;
+    min_wb = std::min(min_wb, f.width_at_border);
+    total_codes += f.ncodes;
+  }
+  if (normal && reversed) {  // apriltag_detect.cu:108: exactly one border polarity across the families
+    det->err = "tag families with normal and with reversed borders cannot be mixed (apriltag_detect.cu:108)";
+    return B200TAG_E_INVALID;
+  }
+  std::vector<uint8_t> host(sizeof(DevFamily) * kMaxFamilies + total_codes * sizeof(uint64_t));
+  DevFamily *df = reinterpret_cast<DevFamily *>(host.data());
+  uint64_t *codes = reinterpret_cast<uint64_t *>(host.data() + sizeof(DevFamily) * kMaxFamilies);
+  uint32_t off = 0;
+  for (int i = 0; i < n; i++) {
+    const b200tag_family &f = fams[i];
+    memset(&df[i], 0, sizeof(DevFamily));
+    df[i].nbits = f.nbits; df[i].ncodes = f.ncodes;
+    df[i].width_at_border = f.width_at_border; df[i].total_width = f.total_width;
+    df[i].reversed_border = f.reversed_border != 0; df[i].max_hamming = f.max_hamming;
+    df[i].codes_off = off;
+    for (uint32_t b = 0; b < f.nbits; b++) {
+      df[i].bit_x[b] = static_cast<int8_t>(static_cast<int32_t>(f.bit_x[b]));
+      df[i].bit_y[b] = static_cast<int8_t>(static_cast<int32_t>(f.bit_y[b]));
+    }
+    memcpy(codes + off, f.codes, f.ncodes * sizeof(uint64_t));
+    off += f.ncodes;
+  }
+  if (cudaMalloc(&det->d_families, host.size()) != cudaSuccess ||
+      cudaMemcpy(det->d_families, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    det->err = "uploading the tag families failed";
+    return B200TAG_E_CUDA;
+  }
+  det->fp.families = static_cast<const DevFamily *>(det->d_families);
+  det->fp.family_codes = reinterpret_cast<const uint64_t *>(static_cast<const uint8_t *>(det->d_families) + sizeof(DevFamily) * kMaxFamilies);
+  det->fp.nfamilies = n;
+  det->min_width_at_border = min_wb;
+  det->normal_border = normal;
+  det->reversed_border = reversed;
+  return 0;
+}
+}  // namespace
+
+const b200tag_family *b200tag_builtin_family(const char *name) {
+  if (!name) return nullptr;
+  const Builtin *t = builtin_families();
+  for (int i = 0; i < 3; i++)
+    if (strcmp(name, t[i].fam.name) == 0) return &t[i].fam;
+  return nullptr;
+}
+
 int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
+  return b200tag_create_families(cfg, b200tag_builtin_family("tag36h11"), 1, out);
+}
+
+int b200tag_debug_reconcile(b200tag_detection *dets, int count) {
+  if (!dets || count < 0) return B200TAG_E_INVALID;
+  std::vector<b200tag_detection> v(dets, dets + count);
+  reconcile(v);
+  std::copy(v.begin(), v.end(), dets);
+  return static_cast<int>(v.size());
+}
+
+int b200tag_create_families(const b200tag_config *cfg, const b200tag_family *families, int nfamilies, b200tag_detector **out) {
   if (!cfg || !out) return B200TAG_E_INVALID;
   *out = nullptr;
   std::string why;
@@ -462,7 +580,13 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
     return fail(B200TAG_E_NO_DEVICE);
   }
   DeviceGuard on_device(det->device);  // the caller's current device is left as it was
-  build_params(det);
+  {
+    FrameParams keep;  // install_families fills det->fp's family fields; build_params starts from a clean struct
+    if (int rc = install_families(det, families, nfamilies)) return fail(rc);
+    keep = det->fp;
+    build_params(det);
+    det->fp.families = keep.families; det->fp.family_codes = keep.family_codes; det->fp.nfamilies = keep.nfamilies;
+  }
   FrameParams &p = det->fp;
   const size_t N = static_cast<size_t>(p.W) * p.H, n = static_cast<size_t>(p.w) * p.h;
   const size_t tiles = static_cast<size_t>(p.tiles_x) * p.tiles_y;
@@ -580,10 +704,6 @@ int b200tag_create(const b200tag_config *cfg, b200tag_detector **out) {
   if (!ck(cudaHostGetDevicePointer(reinterpret_cast<void **>(&det->d_dets_alias), det->h_dets, 0), "cudaHostGetDevicePointer"))
     return fail(B200TAG_E_CUDA);
   p.dets = det->d_dets_alias;  // the decode kernel writes detections straight into pinned host memory
-  if (upload_family() != 0) {
-    det->err = "uploading the tag family failed";
-    return fail(B200TAG_E_CUDA);
-  }
   if (const char *e = getenv("B200TAG_NO_GRAPH")) det->use_graphs = !(e[0] == '1');
   launch_blobs_init(det->stream);  // one-time attributes / tables, outside any later graph capture
   launch_hash_clear(p, B, det->stream);
@@ -621,6 +741,7 @@ void b200tag_destroy(b200tag_detector *det) {
   if (det->mjpg.lib) dlclose(det->mjpg.lib);
 #endif
   if (det->arena) cudaFree(det->arena);
+  if (det->d_families) cudaFree(det->d_families);
   if (det->h_counters) cudaFreeHost(det->h_counters);
   if (det->h_dets) cudaFreeHost(det->h_dets);
   delete det;

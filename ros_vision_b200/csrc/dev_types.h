@@ -103,6 +103,19 @@ struct alignas(16) WorkItem {
   uint32_t blob, offset, count, pad;
 };
 
+// A tag family on the device (apriltag_family_t, the fields quad_decode reads).
+constexpr int kMaxFamilies = 8;
+constexpr int kMaxFamilyBits = 64;
+constexpr int kMaxTotalWidth = 12;
+struct DevFamily {
+  uint32_t nbits, ncodes;
+  int32_t width_at_border, total_width;
+  int32_t reversed_border, max_hamming;
+  uint32_t codes_off;  // first code in FrameParams::family_codes
+  uint32_t pad;
+  int8_t bit_x[kMaxFamilyBits], bit_y[kMaxFamilyBits];
+};
+
 struct FrameParams {
   // geometry
   int32_t W, H;        // full resolution
@@ -110,6 +123,7 @@ struct FrameParams {
   int32_t f;           // quad_decimate
   int32_t fmt;
   int32_t tiles_x, tiles_y;  // 4x4 threshold tiles
+  uint32_t inv_w;      // ceil(2^32 / w): x / w == __umulhi(x, inv_w) for x < 2^20
   int32_t blur_ksz;    // 0 = no blur
   uint8_t blur_k[32];
   int32_t sharpen;     // quad_sigma < 0
@@ -161,6 +175,9 @@ struct FrameParams {
   b200tag_fit_quad *fit_quads;  // blob_cap
   b200tag_quad *quads;  // quad_cap
   b200tag_detection *dets;  // det_cap
+  const DevFamily *families;      // nfamilies (device memory, owned by the detector)
+  const uint64_t *family_codes;   // all families' code tables back to back
+  int32_t nfamilies;
   Counters *counters;
 };
 

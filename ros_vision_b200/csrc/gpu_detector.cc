@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace frc971::apriltag {
 namespace {
@@ -52,14 +53,28 @@ void GpuDetector::Init(size_t width, size_t height, apriltag_detector_t *td, Cam
   cfg.min_white_black_diff = td->qtp.min_white_black_diff;
   cfg.fx = cam.fx; cfg.cx = cam.cx; cfg.fy = cam.fy; cfg.cy = cam.cy;
   cfg.k1 = dist.k1; cfg.k2 = dist.k2; cfg.p1 = dist.p1; cfg.p2 = dist.p2; cfg.k3 = dist.k3;
-  // apriltag_gpu.cu:169-177: the family decides border polarity and the minimum tag width.
-  // This engine decodes tag36h11 (width_at_border 8, normal border), the family the node configures.
-  if (td->tag_families == nullptr || zarray_size(td->tag_families) != 1) Fatal("constructor", "exactly one tag family (tag36h11) is supported");
-  apriltag_family_t *family;
-  zarray_get(td->tag_families, 0, &family);
-  if (family->nbits != 36 || family->width_at_border != 8 || family->total_width != 10 || family->reversed_border)
-    Fatal("constructor", "only tag36h11 is supported");
-  const int rc = b200tag_create(&cfg, &handle_);
+  // apriltag_gpu.cu:169-177: the families decide border polarity and the minimum tag width; the decoder reads their
+  // codes and bit layout.  Every family the caller added is handed over as it is (the eight of apriltag_utils.cu:10-27
+  // or any other of at most 64 bits); mixed border polarities abort like the reference's CHECK (apriltag_detect.cu:108).
+  if (td->tag_families == nullptr || zarray_size(td->tag_families) < 1) Fatal("constructor", "the detector has no tag family");
+  std::vector<b200tag_family> fams;
+  for (int i = 0; i < zarray_size(td->tag_families); i++) {
+    apriltag_family_t *family;
+    zarray_get(td->tag_families, i, &family);
+    b200tag_family f;
+    f.name = family->name;
+    f.nbits = family->nbits;
+    f.ncodes = family->ncodes;
+    f.codes = family->codes;
+    f.bit_x = family->bit_x;
+    f.bit_y = family->bit_y;
+    f.width_at_border = family->width_at_border;
+    f.total_width = family->total_width;
+    f.reversed_border = family->reversed_border ? 1 : 0;
+    f.max_hamming = 2;  // apriltag_detector_add_family (bits_corrected = 2), apriltags_cuda_detector.cu:140
+    fams.push_back(f);
+  }
+  const int rc = b200tag_create_families(&cfg, fams.data(), static_cast<int>(fams.size()), &handle_);
   if (rc != 0) Fatal(b200tag_error_string(rc), b200tag_last_error(nullptr));
   detections_ = zarray_create(sizeof(apriltag_detection_t *));
   zarray_ensure_capacity(detections_, static_cast<int>(kMaxBlobs));
@@ -103,10 +118,10 @@ void GpuDetector::Collect(int rc) {
   quad_corners_host_.clear();
   int n = 0;
   const b200tag_detection *d = b200tag_detections(handle_, 0, &n);
-  apriltag_family_t *family = nullptr;
-  zarray_get(tag_detector_->tag_families, 0, &family);
   for (int i = 0; i < n; i++) {  // already reconciled and sorted by id (apriltag_detect.cu:660-662)
     apriltag_detection_t *det = static_cast<apriltag_detection_t *>(calloc(1, sizeof(apriltag_detection_t)));
+    apriltag_family_t *family = nullptr;
+    zarray_get(tag_detector_->tag_families, d[i].family, &family);
     det->family = family;
     det->id = d[i].id;
     det->hamming = d[i].hamming;

@@ -12,23 +12,8 @@
 
 #include "dev_types.h"
 #include "kernels.h"
-#include "tag36h11_data.h"
 
 namespace b200tag {
-
-// The table is uploaded once from the host copy in tag36h11_data.h (see upload_family()).
-__device__ uint64_t d_family_codes[b200_tag36h11_NCODES];
-__device__ uint8_t d_bit_x[b200_tag36h11_NBITS];
-__device__ uint8_t d_bit_y[b200_tag36h11_NBITS];
-
-int upload_family() {
-  cudaError_t e = cudaMemcpyToSymbol(d_family_codes, b200_tag36h11_codes, sizeof(b200_tag36h11_codes));
-  if (e != cudaSuccess) return -1;
-  e = cudaMemcpyToSymbol(d_bit_x, b200_tag36h11_bit_x, sizeof(b200_tag36h11_bit_x));
-  if (e != cudaSuccess) return -1;
-  e = cudaMemcpyToSymbol(d_bit_y, b200_tag36h11_bit_y, sizeof(b200_tag36h11_bit_y));
-  return e == cudaSuccess ? 0 : -1;
-}
 
 // ReDistort, apriltag_detect.cu:307-331
 __device__ void redistort(double *x, double *y, const FrameParams &c) {
@@ -195,13 +180,181 @@ struct DecodeShared {
   int e_ns[4];
   double gm_x[64], gm_y[64];
   int gm_v[64];  // -1 = sample outside the image
-  double values[100], sharp[100];
+  double values[kMaxTotalWidth * kMaxTotalWidth], sharp[kMaxTotalWidth * kMaxTotalWidth];
   double H[9];
   double A[72];  // homography system
   GrayModel white, black;
   uint32_t cur;
   int ok;
+  DevFamily fam[kMaxFamilies];  // the detector's families (bit layout; the code tables stay in global memory)
 };
+
+// quad_decode + the detection record for one family (libapriltag apriltag.c, RECALLED).  WB / TW / NB are the
+// family's width_at_border / total_width / nbits as compile-time constants (tag36h11, the family the node configures:
+// divisions and loop bounds fold), or 0 to take them from the family at run time.
+template <int WB, int TW, int NB>
+__device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared &S, const DevFamily &fam, int fi, const uint8_t *im,
+                                              int W, int H, Counters *ctr, b200tag_detection *dets, int frame, int lane) {
+  const int wb = WB ? WB : fam.width_at_border, tw = TW ? TW : fam.total_width, nbits = NB ? NB : static_cast<int>(fam.nbits);
+  const uint64_t *codes = p.family_codes + fam.codes_off;
+  __syncwarp();
+
+    // quad_decode: gray model from 8 border lines x width_at_border samples (width_at_border <= 8 is checked when the
+    // detector is created; every libapriltag family has 5..8)
+    const int per_line = wb;
+    for (int j = lane; j < 64; j += 32) {
+      const int pi = j >> 3, i = j & 7;
+      float p0, p1, p2, p3;
+      switch (pi) {
+        case 0: p0 = -0.5f;     p1 = 0.5f;      p2 = 0; p3 = 1; break;
+        case 1: p0 = 0.5f;      p1 = 0.5f;      p2 = 0; p3 = 1; break;
+        case 2: p0 = wb + 0.5f; p1 = .5f;       p2 = 0; p3 = 1; break;
+        case 3: p0 = wb - 0.5f; p1 = .5f;       p2 = 0; p3 = 1; break;
+        case 4: p0 = 0.5f;      p1 = -0.5f;     p2 = 1; p3 = 0; break;
+        case 5: p0 = 0.5f;      p1 = 0.5f;      p2 = 1; p3 = 0; break;
+        case 6: p0 = 0.5f;      p1 = wb + 0.5f; p2 = 1; p3 = 0; break;
+        default: p0 = 0.5f;     p1 = wb - 0.5f; p2 = 1; p3 = 0; break;
+      }
+      const double tagx01 = (p0 + i * p2) / (wb);
+      const double tagy01 = (p1 + i * p3) / (wb);
+      const double tagx = 2 * (tagx01 - 0.5);
+      const double tagy = 2 * (tagy01 - 0.5);
+      double px, py;
+      h_project(S.H, tagx, tagy, &px, &py);
+      const int ix = static_cast<int>(px), iy = static_cast<int>(py);
+      int v = -1;
+      if (i < per_line && !(ix < 0 || iy < 0 || ix >= W || iy >= H)) v = im[static_cast<size_t>(iy) * W + ix];
+      S.gm_x[j] = tagx;
+      S.gm_y[j] = tagy;
+      S.gm_v[j] = v;
+    }
+    for (int j = lane; j < tw * tw; j += 32) S.values[j] = 0.0;
+    __syncwarp();
+    if (lane < 2) {  // lane 0 fits the white model, lane 1 the black one (each sums its samples in order)
+      GrayModel m;
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) m.A[i][j] = 0;
+        m.B[i] = m.C[i] = 0;
+      }
+      for (int j = 0; j < 64; j++) {
+        if (S.gm_v[j] < 0) continue;
+        const int is_white = ((j >> 3) & 1) == 0;  // patterns alternate white, black
+        if (is_white == (lane == 0)) gm_add(&m, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
+      }
+      gm_solve(&m);
+      if (lane == 0) S.white = m; else S.black = m;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int reversed_border = fam.reversed_border != 0;
+      S.ok = !((gm_interp(&S.white, 0, 0) - gm_interp(&S.black, 0, 0) < 0) != reversed_border);
+    }
+    __syncwarp();
+    if (!S.ok) return;
+
+    const int min_coord = (wb - tw) / 2;
+    for (int i = lane; i < nbits; i += 32) {
+      const int bit_x = fam.bit_x[i], bit_y = fam.bit_y[i];
+      const double tagx01 = (bit_x + 0.5) / (wb);
+      const double tagy01 = (bit_y + 0.5) / (wb);
+      const double tagx = 2 * (tagx01 - 0.5);
+      const double tagy = 2 * (tagy01 - 0.5);
+      double px, py;
+      h_project(S.H, tagx, tagy, &px, &py);
+      const double v = value_for_pixel(im, W, H, px, py);
+      if (v == -1) continue;
+      const double thresh = (gm_interp(&S.black, tagx, tagy) + gm_interp(&S.white, tagx, tagy)) / 2.0;
+      S.values[tw * (bit_y - min_coord) + bit_x - min_coord] = v - thresh;
+    }
+    __syncwarp();
+    for (int c = lane; c < tw * tw; c += 32) {  // sharpen()
+      const int y = c / tw, x = c % tw;
+      const double kernel[9] = {0, -1, 0, -1, 4, -1, 0, -1, 0};
+      double acc = 0;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+          if ((y + i - 1) < 0 || (y + i - 1) > tw - 1 || (x + j - 1) < 0 || (x + j - 1) > tw - 1) continue;
+          acc += S.values[(y + i - 1) * tw + (x + j - 1)] * kernel[i * 3 + j];
+        }
+      S.sharp[c] = acc;
+    }
+    __syncwarp();
+    for (int c = lane; c < tw * tw; c += 32) S.values[c] = S.values[c] + p.decode_sharpening * S.sharp[c];
+    __syncwarp();
+
+    // bits and decision margin, folded in bit order by every lane redundantly (nbits steps)
+    float black_score = 0, white_score = 0;
+    float black_score_count = 1, white_score_count = 1;
+    uint64_t rcode = 0;
+    for (int i = 0; i < nbits; i++) {
+      const int bit_x = fam.bit_x[i], bit_y = fam.bit_y[i];
+      rcode = (rcode << 1);
+      const double v = S.values[(bit_y - min_coord) * tw + bit_x - min_coord];
+      if (v > 0) {
+        white_score += static_cast<float>(v);
+        white_score_count++;
+        rcode |= 1;
+      } else {
+        black_score -= static_cast<float>(v);
+        black_score_count++;
+      }
+    }
+    // quick_decode_codeword: lane-parallel popcount scan over the family's codes, first rotation that hits
+    // (the hash table of libapriltag holds every code with <= max_hamming flipped bits; with the families' minimum
+    // distances the hit is unique, so the smallest id within reach is the same answer)
+    int id = -1, hamming = 255, rotation = 0;
+    const int ncodes = static_cast<int>(fam.ncodes), maxh = fam.max_hamming;
+    for (int ridx = 0; ridx < 4 && id < 0; ridx++) {
+      int found = 0x7fffffff, fh = 255;
+      for (int c = lane; c < ncodes; c += 32) {
+        const int d = __popcll(rcode ^ __ldg(codes + c));
+        if (d <= maxh && c < found) { found = c; fh = d; }
+      }
+      const int best = __reduce_min_sync(0xffffffffu, found);
+      if (best != 0x7fffffff) {
+        const uint32_t who = __ballot_sync(0xffffffffu, found == best);
+        hamming = __shfl_sync(0xffffffffu, fh, __ffs(who) - 1);
+        id = best;
+        rotation = ridx;
+      } else {  // rotate90 (libapriltag apriltag.c)
+        int pp = nbits;
+        uint64_t l = 0;
+        if (nbits % 4 == 1) { pp = nbits - 1; l = 1; }
+        rcode = ((rcode >> l) << (pp / 4 + l)) | (rcode >> (3 * pp / 4 + l) << l) | (rcode & l);
+        rcode &= nbits >= 64 ? ~0ull : ((1ull << nbits) - 1);
+      }
+    }
+    const float margin = fminf(white_score / white_score_count, black_score / black_score_count);
+    if (lane == 0 && margin >= 0 && hamming < 255) {
+      const uint32_t di = atomicAdd(&ctr->num_detections, 1u);
+      if (di < p.det_cap) {
+        b200tag_detection &d = dets[di];
+        d.id = id;
+        d.hamming = hamming;
+        d.decision_margin = margin;
+        d.frame = frame;
+        d.family = fi;
+        d.reserved = 0;
+        // cos/sin(rotation * M_PI / 2.0) as the host libm returns them
+        const double kc[4] = {1.0, 6.123233995736766e-17, -1.0, -1.8369701987210297e-16};
+        const double ks[4] = {0.0, 1.0, 1.2246467991473532e-16, -1.0};
+        const double cc = kc[rotation], ss = ks[rotation];
+        for (int row = 0; row < 3; row++) {
+          d.H[row * 3 + 0] = S.H[row * 3 + 0] * cc + S.H[row * 3 + 1] * ss;
+          d.H[row * 3 + 1] = S.H[row * 3 + 0] * -ss + S.H[row * 3 + 1] * cc;
+          d.H[row * 3 + 2] = S.H[row * 3 + 2];
+        }
+        h_project(d.H, 0, 0, &d.c[0], &d.c[1]);
+        for (int i = 0; i < 4; i++) {
+          const int tcx = (i == 1 || i == 2) ? 1 : -1;
+          const int tcy = (i < 2) ? 1 : -1;
+          h_project(d.H, tcx, tcy, &d.p[i][0], &d.p[i][1]);
+        }
+      } else {
+        atomicOr(&ctr->status, B200TAG_ST_DETS_OVERFLOW);
+      }
+    }
+}
 
 __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
   __shared__ DecodeShared S;
@@ -213,7 +366,12 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
   b200tag_detection *dets = p.dets + static_cast<size_t>(frame) * p.det_cap;
   const uint32_t nquads = min(ctr->num_quads, p.quad_cap);
   const int W = p.W, H = p.H;
-  const int wb = b200_tag36h11_WIDTH_AT_BORDER, tw = b200_tag36h11_TOTAL_WIDTH;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.families);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(S.fam);
+    for (uint32_t i = lane; i < p.nfamilies * (sizeof(DevFamily) / 4); i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncwarp();
 
   uint32_t nxt = 0;
   if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);
@@ -365,150 +523,15 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
     __syncwarp();
     if (!S.ok) continue;
 
-    // quad_decode: gray model from 8 border lines x 8 samples
-    for (int j = lane; j < 64; j += 32) {
-      const int pi = j >> 3, i = j & 7;
-      float p0, p1, p2, p3;
-      switch (pi) {
-        case 0: p0 = -0.5f;     p1 = 0.5f;      p2 = 0; p3 = 1; break;
-        case 1: p0 = 0.5f;      p1 = 0.5f;      p2 = 0; p3 = 1; break;
-        case 2: p0 = wb + 0.5f; p1 = .5f;       p2 = 0; p3 = 1; break;
-        case 3: p0 = wb - 0.5f; p1 = .5f;       p2 = 0; p3 = 1; break;
-        case 4: p0 = 0.5f;      p1 = -0.5f;     p2 = 1; p3 = 0; break;
-        case 5: p0 = 0.5f;      p1 = 0.5f;      p2 = 1; p3 = 0; break;
-        case 6: p0 = 0.5f;      p1 = wb + 0.5f; p2 = 1; p3 = 0; break;
-        default: p0 = 0.5f;     p1 = wb - 0.5f; p2 = 1; p3 = 0; break;
-      }
-      const double tagx01 = (p0 + i * p2) / (wb);
-      const double tagy01 = (p1 + i * p3) / (wb);
-      const double tagx = 2 * (tagx01 - 0.5);
-      const double tagy = 2 * (tagy01 - 0.5);
-      double px, py;
-      h_project(S.H, tagx, tagy, &px, &py);
-      const int ix = static_cast<int>(px), iy = static_cast<int>(py);
-      int v = -1;
-      if (!(ix < 0 || iy < 0 || ix >= W || iy >= H)) v = im[static_cast<size_t>(iy) * W + ix];
-      S.gm_x[j] = tagx;
-      S.gm_y[j] = tagy;
-      S.gm_v[j] = v;
-    }
-    for (int j = lane; j < 100; j += 32) S.values[j] = 0.0;
-    __syncwarp();
-    if (lane < 2) {  // lane 0 fits the white model, lane 1 the black one (each sums its samples in order)
-      GrayModel m;
-      for (int i = 0; i < 3; i++) {
-        for (int j = 0; j < 3; j++) m.A[i][j] = 0;
-        m.B[i] = m.C[i] = 0;
-      }
-      for (int j = 0; j < 64; j++) {
-        if (S.gm_v[j] < 0) continue;
-        const int is_white = ((j >> 3) & 1) == 0;  // patterns alternate white, black
-        if (is_white == (lane == 0)) gm_add(&m, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
-      }
-      gm_solve(&m);
-      if (lane == 0) S.white = m; else S.black = m;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const int reversed_border = 0;
-      S.ok = !((gm_interp(&S.white, 0, 0) - gm_interp(&S.black, 0, 0) < 0) != reversed_border);
-    }
-    __syncwarp();
-    if (!S.ok) continue;
-
-    const int min_coord = (wb - tw) / 2;
-    for (int i = lane; i < b200_tag36h11_NBITS; i += 32) {
-      const int bit_x = d_bit_x[i], bit_y = d_bit_y[i];
-      const double tagx01 = (bit_x + 0.5) / (wb);
-      const double tagy01 = (bit_y + 0.5) / (wb);
-      const double tagx = 2 * (tagx01 - 0.5);
-      const double tagy = 2 * (tagy01 - 0.5);
-      double px, py;
-      h_project(S.H, tagx, tagy, &px, &py);
-      const double v = value_for_pixel(im, W, H, px, py);
-      if (v == -1) continue;
-      const double thresh = (gm_interp(&S.black, tagx, tagy) + gm_interp(&S.white, tagx, tagy)) / 2.0;
-      S.values[tw * (bit_y - min_coord) + bit_x - min_coord] = v - thresh;
-    }
-    __syncwarp();
-    for (int c = lane; c < tw * tw; c += 32) {  // sharpen()
-      const int y = c / tw, x = c % tw;
-      const double kernel[9] = {0, -1, 0, -1, 4, -1, 0, -1, 0};
-      double acc = 0;
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-          if ((y + i - 1) < 0 || (y + i - 1) > tw - 1 || (x + j - 1) < 0 || (x + j - 1) > tw - 1) continue;
-          acc += S.values[(y + i - 1) * tw + (x + j - 1)] * kernel[i * 3 + j];
-        }
-      S.sharp[c] = acc;
-    }
-    __syncwarp();
-    for (int c = lane; c < tw * tw; c += 32) S.values[c] = S.values[c] + p.decode_sharpening * S.sharp[c];
-    __syncwarp();
-
-    // bits and decision margin, folded in bit order by every lane redundantly (36 steps)
-    float black_score = 0, white_score = 0;
-    float black_score_count = 1, white_score_count = 1;
-    uint64_t rcode = 0;
-    for (int i = 0; i < b200_tag36h11_NBITS; i++) {
-      const int bit_x = d_bit_x[i], bit_y = d_bit_y[i];
-      rcode = (rcode << 1);
-      const double v = S.values[(bit_y - min_coord) * tw + bit_x - min_coord];
-      if (v > 0) {
-        white_score += static_cast<float>(v);
-        white_score_count++;
-        rcode |= 1;
-      } else {
-        black_score -= static_cast<float>(v);
-        black_score_count++;
-      }
-    }
-    // quick_decode_codeword with maxhamming 2: lane-parallel popcount scan, first rotation that hits
-    int id = -1, hamming = 255, rotation = 0;
-    for (int ridx = 0; ridx < 4 && id < 0; ridx++) {
-      int found = 0x7fffffff, fh = 255;
-      for (int c = lane; c < b200_tag36h11_NCODES; c += 32) {
-        const int d = __popcll(rcode ^ d_family_codes[c]);
-        if (d <= 2 && c < found) { found = c; fh = d; }
-      }
-      const int best = __reduce_min_sync(0xffffffffu, found);
-      if (best != 0x7fffffff) {
-        const uint32_t who = __ballot_sync(0xffffffffu, found == best);
-        hamming = __shfl_sync(0xffffffffu, fh, __ffs(who) - 1);
-        id = best;
-        rotation = ridx;
-      } else {
-        rcode = ((rcode << 9) | (rcode >> 27)) & ((1ull << 36) - 1);  // rotate90
-      }
-    }
-    const float margin = fminf(white_score / white_score_count, black_score / black_score_count);
-    if (lane == 0 && margin >= 0 && hamming < 255) {
-      const uint32_t di = atomicAdd(&ctr->num_detections, 1u);
-      if (di < p.det_cap) {
-        b200tag_detection &d = dets[di];
-        d.id = id;
-        d.hamming = hamming;
-        d.decision_margin = margin;
-        d.frame = frame;
-        // cos/sin(rotation * M_PI / 2.0) as the host libm returns them
-        const double kc[4] = {1.0, 6.123233995736766e-17, -1.0, -1.8369701987210297e-16};
-        const double ks[4] = {0.0, 1.0, 1.2246467991473532e-16, -1.0};
-        const double cc = kc[rotation], ss = ks[rotation];
-        for (int row = 0; row < 3; row++) {
-          d.H[row * 3 + 0] = S.H[row * 3 + 0] * cc + S.H[row * 3 + 1] * ss;
-          d.H[row * 3 + 1] = S.H[row * 3 + 0] * -ss + S.H[row * 3 + 1] * cc;
-          d.H[row * 3 + 2] = S.H[row * 3 + 2];
-        }
-        h_project(d.H, 0, 0, &d.c[0], &d.c[1]);
-        for (int i = 0; i < 4; i++) {
-          const int tcx = (i == 1 || i == 2) ? 1 : -1;
-          const int tcy = (i < 2) ? 1 : -1;
-          h_project(d.H, tcx, tcy, &d.p[i][0], &d.p[i][1]);
-        }
-      } else {
-        atomicOr(&ctr->status, B200TAG_ST_DETS_OVERFLOW);
-      }
-    }
+    // quad_decode_task: every family of the quad's border polarity gets its own decode of the same homography
+    for (int fi = 0; fi < p.nfamilies; fi++) {
+      const DevFamily &fam = S.fam[fi];
+      if ((fam.reversed_border != 0) != (quad.reversed_border != 0)) continue;
+      if (fam.width_at_border == 8 && fam.total_width == 10 && fam.nbits == 36)
+        decode_family<8, 10, 36>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
+      else
+        decode_family<0, 0, 0>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
+    }  // families
   }
 }
 

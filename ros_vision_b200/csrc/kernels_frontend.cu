@@ -11,6 +11,7 @@
 // here is a contraction; the bound is HBM/L2 bandwidth and atomics latency.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dev_types.h"
 #include "kernels.h"
@@ -662,34 +663,79 @@ __global__ void __launch_bounds__(256) k_ccl_handoff(FrameParams p, uint32_t til
   }
 }
 
-// K5: every pixel jumps to its root and learns whether its component is large enough to bound a blob
-// (sizes are final after k_ccl_handoff).  4 pixels (16 bytes of labels) per thread; 16 bytes in, 16 bytes out.
-__global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
-  const int frame = blockIdx.y;
+// K5: every pixel gets its final label word: root | colour | "component has at least 25 pixels" (sizes are final
+// after k_ccl_handoff).  One CTA per CCL tile: after k_ccl_local every pixel of a tile points at one of the tile's own
+// roots, so only those (a few hundred per 2048 pixels) are chased through the merged trees -- once each, into a
+// shared-memory table indexed by the root's position in the tile -- and every pixel then takes its word from the
+// table.  16 bytes of labels in, 16 bytes out per thread and pass; the dependent global accesses (parent chain, size
+// of the final root) happen once per tile root instead of once per pixel.
+constexpr int kFinThreads = 256;
+constexpr int kFinPasses = kCclTW * kCclTH / 4 / kFinThreads;
+constexpr uint32_t kFinUnused = 0xffffffffu, kFinNeeded = 0xfffffffeu;
+__global__ void __launch_bounds__(kFinThreads) k_ccl_final(FrameParams p) {
+  __shared__ uint32_t s_out[kCclTW * kCclTH];
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
   const size_t n = static_cast<size_t>(p.w) * p.h;
   uint32_t *labels = p.labels + frame * n;
   const uint32_t *sizes = p.sizes + frame * n;
-  const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  const uint4 l = __ldcg(reinterpret_cast<const uint4 *>(labels + i4));
-  uint32_t lab[4] = {l.x, l.y, l.z, l.w};
-  // neighbouring pixels mostly alternate between two tile roots (a white and a black component): chase each once
-  uint32_t m_lab0 = 0xffffffffu, m_out0 = 0, m_lab1 = 0xffffffffu, m_out1 = 0;
+  const int tid = threadIdx.x;
+  const uint32_t origin = static_cast<uint32_t>(y0) * p.w + x0;
+  for (int i = tid; i < kCclTW * kCclTH / 4; i += kFinThreads)
+    reinterpret_cast<uint4 *>(s_out)[i] = make_uint4(kFinUnused, kFinUnused, kFinUnused, kFinUnused);
+  uint32_t lab[kFinPasses][4], pos[kFinPasses][4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if ((lab[k] >> kColourShift) == 2) continue;  // 127-pixels: own index, never large enough
-    uint32_t out;
-    if (lab[k] == m_lab0) out = m_out0;
-    else if (lab[k] == m_lab1) out = m_out1;
-    else {
-      const uint32_t root = gfind(labels, lab[k]);
-      out = root | (__ldg(sizes + (root & kLabelMask)) >= kMinBlobPixels ? kLabelBig : 0u);
-      m_lab1 = m_lab0; m_out1 = m_out0;
-      m_lab0 = lab[k]; m_out0 = out;
-    }
-    lab[k] = out;
+  for (int k = 0; k < kFinPasses; k++) {
+    const int i = tid + k * kFinThreads;
+    const int r = i / (kCclTW / 4), xq = (i % (kCclTW / 4)) * 4;
+    const int gy = y0 + r, gx = x0 + xq;
+    uint4 l = make_uint4(kColourGray, kColourGray, kColourGray, kColourGray);
+    if (gy < p.h && gx < p.w) l = __ldcg(reinterpret_cast<const uint4 *>(labels + static_cast<size_t>(gy) * p.w + gx));
+    lab[k][0] = l.x; lab[k][1] = l.y; lab[k][2] = l.z; lab[k][3] = l.w;
   }
-  *reinterpret_cast<uint4 *>(labels + i4) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+  __syncthreads();
+  // (1) which positions of the tile are roots some pixel points at
+#pragma unroll
+  for (int k = 0; k < kFinPasses; k++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      pos[k][q] = kFinUnused;
+      if ((lab[k][q] >> kColourShift) == 2) continue;  // 127-pixels: own index, never large enough
+      // position in the tile of the root this pixel points at.  A tile root that a cross-tile merge dethroned
+      // points OUT of the tile (at its new parent): it is resolved from its own position.
+      const uint32_t delta = (lab[k][q] & kLabelMask) - origin;
+      const uint32_t dy = __umulhi(delta, p.inv_w);  // delta / w: exact below 2^20, and >= kCclTH beyond (or on wrap-around)
+      const uint32_t dx = delta - dy * p.w;
+      const int i = tid + k * kFinThreads;
+      const uint32_t own = static_cast<uint32_t>(i / (kCclTW / 4)) * kCclTW + (i % (kCclTW / 4)) * 4 + q;
+      pos[k][q] = (dy < kCclTH && dx < kCclTW) ? dy * kCclTW + dx : own;
+      s_out[pos[k][q]] = kFinNeeded;
+    }
+  }
+  __syncthreads();
+  // (2) resolve them: final root of the merged tree, size of that root
+  for (int i = tid; i < kCclTW * kCclTH; i += kFinThreads) {
+    if (s_out[i] != kFinNeeded) continue;
+    const uint32_t self = origin + static_cast<uint32_t>(i / kCclTW) * p.w + (i % kCclTW);
+    // (loading the root's own size side by side with its cell, on the guess that it was never dethroned, was
+    //  measured: the extra gathers cost more than the shorter chains save -- 0.149 -> 0.167 ms per 128 frames)
+    const uint32_t root = gfind(labels, __ldcg(labels + self)) & ~kLabelBig;
+    const uint32_t size = __ldg(sizes + (root & kLabelMask));
+    s_out[i] = root | (size >= kMinBlobPixels ? kLabelBig : 0u);
+  }
+  __syncthreads();
+  // (3) every pixel takes the word of its tile root
+#pragma unroll
+  for (int k = 0; k < kFinPasses; k++) {
+    const int i = tid + k * kFinThreads;
+    const int r = i / (kCclTW / 4), xq = (i % (kCclTW / 4)) * 4;
+    const int gy = y0 + r, gx = x0 + xq;
+    if (gy >= p.h || gx >= p.w) continue;
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) o[q] = pos[k][q] == kFinUnused ? lab[k][q] : s_out[pos[k][q]];
+    *reinterpret_cast<uint4 *>(labels + static_cast<size_t>(gy) * p.w + gx) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -707,9 +753,7 @@ __global__ void __launch_bounds__(256) k_ccl_final(FrameParams p) {
 // pair (C1, C2); extents (C3) are computed per blob by the fit kernels, where a whole blob sits
 // in one warp / CTA and the reductions are shuffles instead of atomics.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBpTW = 64, kBpTH = 16, kBpThreads = 256;
-constexpr int kBpMaxPts = kBpTW * kBpTH * 4;
-constexpr uint32_t kBpLH = 1024;        // local blob-pair table (power of two)
+constexpr int kBpTW = 64;               // tile width: one 64-bit emission mask per (row, direction)
 constexpr uint32_t kBpMaxProbe = 48;    // longer probe sequences take the direct-to-global path
 constexpr uint32_t kBpDirect = 0xffffffffu;
 
@@ -740,7 +784,13 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
 }
 
 // staged cell = label word: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
-__global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
+// TH = tile height (16 or 8 rows); 16 threads per row.
+template <int TH>
+__global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
+  constexpr int kBpTH = TH, kBpThreads = TH * 16;
+  constexpr int kBpMaxPts = kBpTW * kBpTH * 4;
+  constexpr uint32_t kBpLH = TH * 64;    // local blob-pair table (power of two, <= 1024: 10-bit entry index in s_loc)
+  static_assert(kBpLH <= 1024 && (kBpLH & (kBpLH - 1)) == 0, "local table size");
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
   __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
   __shared__ uint32_t s_loc[kBpMaxPts];             // [9:0] local entry | [31:10] rank among the tile's points of that entry
@@ -854,11 +904,13 @@ __global__ void __launch_bounds__(kBpThreads) k_boundary(FrameParams p) {
     }
     s_ebase[ry][d] = incl - cnt;
     if (tid == 31) s_half = incl;
-    if (tid == 63) s_npts = incl;  // second half only; completed below
+    if (tid == kBpTH * 4 - 1) s_npts = incl;  // (with two warps: the second half only; completed below)
   }
-  __syncthreads();
-  if (tid >= 32 && tid < kBpTH * 4) s_ebase[tid >> 2][tid & 3] += s_half;
-  if (tid == 0) s_npts += s_half;
+  if constexpr (kBpTH * 4 > 32) {
+    __syncthreads();
+    if (tid >= 32 && tid < kBpTH * 4) s_ebase[tid >> 2][tid & 3] += s_half;
+    if (tid == 0) s_npts += s_half;
+  }
   __syncthreads();
   {  // list entries: one thread per 16-bit quarter of an emission word walks its set bits (3 on average)
     static_assert(kBpThreads == kBpTH * 4 * 4 && kBpTW == 64, "one thread per (row, direction, quarter)");
@@ -1013,12 +1065,17 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   k_ccl_handoff<<<dim3(cdiv(cgrid.x * cgrid.y, 8), frames), 256, 0, s>>>(p, cgrid.x * cgrid.y);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_final", s);
-  k_ccl_final<<<dim3(cdiv(static_cast<unsigned>((static_cast<size_t>(p.w) * p.h + 3) / 4), 256), frames), 256, 0, s>>>(p);
+  k_ccl_final<<<cgrid, kFinThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   launches += 4;
 
   if (kt) kt->begin("boundary", s);
-  k_boundary<<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, kBpTH), frames), kBpThreads, 0, s>>>(p);
+  {  // tile height: 16 rows (256 threads) or 8 rows (128 threads, half the shared memory: more CTAs per SM)
+    // (measured on config 2, 128 frames: 0.384 ms with 16 rows, 0.363 ms with 8; B200TAG_BP_TH=16 selects the former)
+    static const int th = [] { const char *e = getenv("B200TAG_BP_TH"); return (e && atoi(e) == 16) ? 16 : 8; }();
+    if (th == 8) k_boundary<8><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
+    else k_boundary<16><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 16), frames), 256, 0, s>>>(p);
+  }
   if (kt) kt->end(s);
   launches++;
   return launches;

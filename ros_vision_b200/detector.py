@@ -50,7 +50,14 @@ class FrameInfo(C.Structure):
 
 
 DETECTION_DT = np.dtype([("id", "<i4"), ("hamming", "<i4"), ("decision_margin", "<f4"), ("frame", "<i4"),
-                         ("H", "<f8", (9,)), ("c", "<f8", (2,)), ("p", "<f8", (4, 2))])
+                         ("family", "<i4"), ("reserved", "<i4"), ("H", "<f8", (9,)), ("c", "<f8", (2,)), ("p", "<f8", (4, 2))])
+
+
+class Family(C.Structure):
+    """b200tag_family: the fields of libapriltag's apriltag_family_t that detection reads."""
+    _fields_ = [("name", C.c_char_p), ("nbits", C.c_uint32), ("ncodes", C.c_uint32), ("codes", C.POINTER(C.c_uint64)),
+                ("bit_x", C.POINTER(C.c_uint32)), ("bit_y", C.POINTER(C.c_uint32)), ("width_at_border", C.c_int32),
+                ("total_width", C.c_int32), ("reversed_border", C.c_int32), ("max_hamming", C.c_int32)]
 QUAD_DT = np.dtype([("corners", "<f4", (4, 2)), ("reversed_border", "<i4"), ("blob_index", "<u4"), ("rep0", "<u4"),
                     ("rep1", "<u4")])
 POINT_DT = np.dtype([("slot", "<u4"), ("x", "<u2"), ("y", "<u2"), ("dir", "u1"), ("black_to_white", "u1"),
@@ -89,6 +96,10 @@ def load_library():
     vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
     L.b200tag_default_config.argtypes = [C.POINTER(Config), i32, i32, i32]
     L.b200tag_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.b200tag_create_families.argtypes = [C.POINTER(Config), C.POINTER(Family), i32, C.POINTER(vp)]
+    L.b200tag_builtin_family.argtypes = [C.c_char_p]
+    L.b200tag_builtin_family.restype = C.POINTER(Family)
+    L.b200tag_debug_reconcile.argtypes = [vp, i32]
     L.b200tag_destroy.argtypes = [vp]
     L.b200tag_destroy.restype = None
     L.b200tag_detect.argtypes = [vp, vp]
@@ -204,7 +215,7 @@ class GpuDetector:
 
     def __init__(self, width, height, fmt="yuyv", quad_decimate=2, quad_sigma=0.0, refine_edges=True,
                  camera_matrix=None, distortion_coefficients=None, max_batch=1, device=-1, keep_stages=False,
-                 max_points=0, max_blobs=0, max_detections=0, test_flags=0, **qtp):
+                 max_points=0, max_blobs=0, max_detections=0, test_flags=0, families=("tag36h11",), **qtp):
         self._lib = load_library()
         cfg = default_config(width, height, fmt)
         cfg.quad_decimate = int(quad_decimate)
@@ -228,7 +239,27 @@ class GpuDetector:
         self.frame_bytes = width * height * BYTES_PER_PIXEL[fmt]
         self.max_batch = int(max_batch)
         h = C.c_void_p()
-        rc = self._lib.b200tag_create(C.byref(cfg), C.byref(h))
+        # tag families (apriltag_detector_add_family): names of built-in tables or dicts in the layout of
+        # ros_vision_b200.tag_families.FAMILIES entries (+ optional "reversed_border", "max_hamming", "name")
+        if isinstance(families, (str, dict)):
+            families = [families]
+        self.families = list(families)
+        fams = (Family * len(self.families))()
+        keep = []
+        for i, f in enumerate(self.families):
+            if isinstance(f, str):
+                b = self._lib.b200tag_builtin_family(f.encode())
+                if not b:
+                    raise ValueError(f"no built-in tag family {f!r}")
+                fams[i] = b.contents
+            else:
+                codes = (C.c_uint64 * len(f["codes"]))(*f["codes"])
+                bx = (C.c_uint32 * f["nbits"])(*[v & 0xffffffff for v in f["bit_x"]])
+                by = (C.c_uint32 * f["nbits"])(*[v & 0xffffffff for v in f["bit_y"]])
+                keep.append((codes, bx, by))
+                fams[i] = Family(f.get("name", "custom").encode(), f["nbits"], len(f["codes"]), codes, bx, by, f["width_at_border"],
+                                 f["total_width"], int(f.get("reversed_border", 0)), int(f.get("max_hamming", 2)))
+        rc = self._lib.b200tag_create_families(C.byref(cfg), fams, len(self.families), C.byref(h))
         if rc:
             msg = self._lib.b200tag_last_error(None).decode()
             raise B200TagError(f"b200tag_create: {self._lib.b200tag_error_string(rc).decode()}: {msg}")

@@ -24,7 +24,7 @@ def test_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in sorted(names):
         assert hasattr(lib, n), f"libb200tag.so does not export {n}"
-    assert lib.b200tag_version() == 1
+    assert lib.b200tag_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
