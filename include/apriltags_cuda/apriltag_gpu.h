@@ -7,10 +7,12 @@
 // C ABI in include/b200tag.h (libb200tag.so); nothing CUDA-specific leaks into this header, so callers no
 // longer need nvcc/clang-cuda to include it.
 //
-// Not carried over: the debug copies typed to the reference's packed device structs
-// (QuadBoundaryPoint / IndexPoint / LineFitPoint / Peak, apriltag_gpu.h:111-183) -- their 20-bit blob ids
-// and 10-bit coordinates cannot represent frames beyond 1024x1024 quad pixels.  The same stages are
-// available, unpacked, through b200tag_copy_stage().
+// The debug copies typed to the reference's packed device structs (QuadBoundaryPoint / IndexPoint / LineFitPoint /
+// Peak / FitQuad, apriltag_gpu.h:111-183) are here too: reference_types.h holds the record types, the accessors convert
+// the engine's own (wider) stage records on the host.  They need a detector that keeps its debug stages
+// (GpuDetector::KeepDebugStages(true) before construction, or B200TAG_KEEP_STAGES=1) and a frame that fits the
+// reference's bit fields (quad image <= 1024 x 1024, <= 4096 blob pairs); the same stages are available without those
+// limits, unpacked, through b200tag_copy_stage().
 #ifndef B200TAG_APRILTAGS_CUDA_APRILTAG_GPU_H_
 #define B200TAG_APRILTAGS_CUDA_APRILTAG_GPU_H_
 
@@ -22,6 +24,7 @@ extern "C" {
 #include "apriltag.h"
 }
 #include "b200tag.h"
+#include "apriltags_cuda/reference_types.h"
 
 namespace frc971::apriltag {
 
@@ -85,6 +88,26 @@ class GpuDetector {
   int NumQuads() const;                       // :135  number of blob pairs
   int NumSelectedPairs() const;               // :146  points of the selected blobs
   int NumFitQuads() const;                    // :179
+
+  // The typed debug copies of apriltag_gpu.h:111-183 (see reference_types.h for their limits).  Blob indices are
+  // positions in the list of blob pairs sorted by (rep1, rep0), the order the reference's radix sort produces.
+  void CopyUnionMarkerPairTo(QuadBoundaryPoint *output) const;            // :111  dense, 4 (w-2) (h-2) entries
+  void CopyCompressedUnionMarkerPairTo(QuadBoundaryPoint *output) const;  // :115  NumCompressedUnionMarkerPairs()
+  std::vector<QuadBoundaryPoint> CopySortedUnionMarkerPair() const;       // :119
+  std::vector<MinMaxExtents> CopyExtents() const;                         // :137  NumQuads() blob pairs
+  std::vector<cub::KeyValuePair<long, MinMaxExtents>> CopySelectedExtents() const;  // :141
+  std::vector<IndexPoint> CopySelectedBlobs() const;                      // :148  NumSelectedPairs() points
+  std::vector<IndexPoint> CopySortedSelectedBlobs() const;                // :152
+  std::vector<LineFitPoint> CopyLineFitPoints() const;                    // :156
+  std::vector<double> CopyErrors() const;                                 // :160
+  std::vector<double> CopyFilteredErrors() const;                         // :164
+  std::vector<Peak> CopyPeaks() const;                                    // :167
+  int NumCompressedPeaks() const;                                         // :171
+  std::vector<Peak> CopyCompressedPeaks() const;                          // :175
+  std::vector<FitQuad> CopyFitQuads() const;                              // :181
+  // Detectors constructed after KeepDebugStages(true) keep every intermediate stage (slower: extra kernels and
+  // copies); the typed accessors above abort on a detector that does not.
+  static void KeepDebugStages(bool keep);
 
   void AdjustCenter(float corners[4][2]) const;  // :185
 

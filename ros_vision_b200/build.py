@@ -73,17 +73,19 @@ CORE_LIB = os.path.join(LIBDIR, "libapriltags_cuda_core.so")
 def build_cpp_class(force: bool = False) -> str:
     """libapriltags_cuda_core.so: frc971::apriltag::GpuDetector (+ libapriltag stand-ins) over libb200tag.so."""
     inc = os.path.join(HERE, "..", "include")
-    srcs = [os.path.join(CSRC, "gpu_detector.cc"), os.path.join(CSRC, "apriltag_compat.c")]
-    deps = srcs + [os.path.join(inc, "apriltags_cuda", "apriltag_gpu.h"), os.path.join(inc, "apriltag_compat", "apriltag.h"),
+    srcs = [os.path.join(CSRC, "gpu_detector.cc"), os.path.join(CSRC, "apriltag_compat.c"), os.path.join(CSRC, "gpu_detector_debug.cc")]
+    deps = srcs + [os.path.join(inc, "apriltags_cuda", "apriltag_gpu.h"), os.path.join(inc, "apriltags_cuda", "reference_types.h"), os.path.join(inc, "apriltag_compat", "apriltag.h"),
                    os.path.join(inc, "b200tag.h"), LIB]
     if not force and os.path.exists(CORE_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(CORE_LIB) for d in deps):
         return CORE_LIB
     flags = ["-O2", "-fPIC", "-I", inc, "-I", os.path.join(inc, "apriltag_compat"), "-I", CSRC]
     o1 = os.path.join(LIBDIR, "gpu_detector.o")
     o2 = os.path.join(LIBDIR, "apriltag_compat.o")
+    o3 = os.path.join(LIBDIR, "gpu_detector_debug.o")
     subprocess.check_call(["g++", "-std=c++17", *flags, "-c", srcs[0], "-o", o1])
     subprocess.check_call(["gcc", "-std=c11", "-D_GNU_SOURCE", *flags, "-c", srcs[1], "-o", o2])
-    subprocess.check_call(["g++", "-shared", "-o", CORE_LIB, o1, o2, "-L", LIBDIR, "-lb200tag", "-Wl,-rpath,$ORIGIN", "-lm"])
+    subprocess.check_call(["g++", "-std=c++17", *flags, "-c", srcs[2], "-o", o3])
+    subprocess.check_call(["g++", "-shared", "-o", CORE_LIB, o1, o2, o3, "-L", LIBDIR, "-lb200tag", "-Wl,-rpath,$ORIGIN", "-lm"])
     return CORE_LIB
 
 
@@ -92,6 +94,10 @@ def build_cpp_test() -> str:
     exe = os.path.join(LIBDIR, "gpu_detector_test")
     src = os.path.join(HERE, "..", "tests", "cpp", "gpu_detector_test.cc")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", inc, "-I", os.path.join(inc, "apriltag_compat"), src, "-o", exe,
+                           "-L", LIBDIR, "-lapriltags_cuda_core", "-lb200tag", "-Wl,-rpath,$ORIGIN"])
+    exe2 = os.path.join(LIBDIR, "debug_accessors_test")
+    src2 = os.path.join(HERE, "..", "tests", "cpp", "debug_accessors_test.cc")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", inc, "-I", os.path.join(inc, "apriltag_compat"), src2, "-o", exe2,
                            "-L", LIBDIR, "-lapriltags_cuda_core", "-lb200tag", "-Wl,-rpath,$ORIGIN"])
     return exe
 

@@ -11,6 +11,7 @@
 
 namespace frc971::apriltag {
 namespace {
+bool g_keep_debug_stages = false;
 
 [[noreturn]] void Fatal(const char *what, const char *detail) {
   // the reference aborts through glog LOG(FATAL) / CHECK (cuda_frc971.h:14-17)
@@ -51,6 +52,8 @@ void GpuDetector::Init(size_t width, size_t height, apriltag_detector_t *td, Cam
   cfg.cos_critical_rad = td->qtp.cos_critical_rad;
   cfg.max_line_fit_mse = td->qtp.max_line_fit_mse;
   cfg.min_white_black_diff = td->qtp.min_white_black_diff;
+  if (const char *e = std::getenv("B200TAG_KEEP_STAGES")) g_keep_debug_stages = g_keep_debug_stages || e[0] == '1';
+  cfg.keep_stages = g_keep_debug_stages ? 1 : 0;
   cfg.fx = cam.fx; cfg.cx = cam.cx; cfg.fy = cam.fy; cfg.cy = cam.cy;
   cfg.k1 = dist.k1; cfg.k2 = dist.k2; cfg.p1 = dist.p1; cfg.p2 = dist.p2; cfg.k3 = dist.k3;
   // apriltag_gpu.cu:169-177: the families decide border polarity and the minimum tag width; the decoder reads their
@@ -79,6 +82,8 @@ void GpuDetector::Init(size_t width, size_t height, apriltag_detector_t *td, Cam
   detections_ = zarray_create(sizeof(apriltag_detection_t *));
   zarray_ensure_capacity(detections_, static_cast<int>(kMaxBlobs));
 }
+
+void GpuDetector::KeepDebugStages(bool keep) { g_keep_debug_stages = keep; }
 
 GpuDetector::~GpuDetector() {
   ClearDetections();

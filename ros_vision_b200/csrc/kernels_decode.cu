@@ -180,14 +180,14 @@ struct DecodeShared {
   int e_ns[4];
   double gm_x[64], gm_y[64];
   int gm_v[64];  // -1 = sample outside the image
-  double values[kMaxTotalWidth * kMaxTotalWidth], sharp[kMaxTotalWidth * kMaxTotalWidth];
+  // (the tag's cell values and their sharpened copy live in sx / sy: the refinement samples are dead by then)
   double H[9];
   double A[72];  // homography system
   GrayModel white, black;
   uint32_t cur;
   int ok;
-  DevFamily fam[kMaxFamilies];  // the detector's families (bit layout; the code tables stay in global memory)
 };
+static_assert(kSampleChunk >= kMaxTotalWidth * kMaxTotalWidth, "cell values alias the sample buffers");
 
 // quad_decode + the detection record for one family (libapriltag apriltag.c, RECALLED).  WB / TW / NB are the
 // family's width_at_border / total_width / nbits as compile-time constants (tag36h11, the family the node configures:
@@ -197,6 +197,7 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
                                               int W, int H, Counters *ctr, b200tag_detection *dets, int frame, int lane) {
   const int wb = WB ? WB : fam.width_at_border, tw = TW ? TW : fam.total_width, nbits = NB ? NB : static_cast<int>(fam.nbits);
   const uint64_t *codes = p.family_codes + fam.codes_off;
+  double *values = S.sx, *sharp = S.sy;
   __syncwarp();
 
     // quad_decode: gray model from 8 border lines x width_at_border samples (width_at_border <= 8 is checked when the
@@ -228,7 +229,7 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
       S.gm_y[j] = tagy;
       S.gm_v[j] = v;
     }
-    for (int j = lane; j < tw * tw; j += 32) S.values[j] = 0.0;
+    for (int j = lane; j < tw * tw; j += 32) values[j] = 0.0;
     __syncwarp();
     if (lane < 2) {  // lane 0 fits the white model, lane 1 the black one (each sums its samples in order)
       GrayModel m;
@@ -264,7 +265,7 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
       const double v = value_for_pixel(im, W, H, px, py);
       if (v == -1) continue;
       const double thresh = (gm_interp(&S.black, tagx, tagy) + gm_interp(&S.white, tagx, tagy)) / 2.0;
-      S.values[tw * (bit_y - min_coord) + bit_x - min_coord] = v - thresh;
+      values[tw * (bit_y - min_coord) + bit_x - min_coord] = v - thresh;
     }
     __syncwarp();
     for (int c = lane; c < tw * tw; c += 32) {  // sharpen()
@@ -274,12 +275,12 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
       for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
           if ((y + i - 1) < 0 || (y + i - 1) > tw - 1 || (x + j - 1) < 0 || (x + j - 1) > tw - 1) continue;
-          acc += S.values[(y + i - 1) * tw + (x + j - 1)] * kernel[i * 3 + j];
+          acc += values[(y + i - 1) * tw + (x + j - 1)] * kernel[i * 3 + j];
         }
-      S.sharp[c] = acc;
+      sharp[c] = acc;
     }
     __syncwarp();
-    for (int c = lane; c < tw * tw; c += 32) S.values[c] = S.values[c] + p.decode_sharpening * S.sharp[c];
+    for (int c = lane; c < tw * tw; c += 32) values[c] = values[c] + p.decode_sharpening * sharp[c];
     __syncwarp();
 
     // bits and decision margin, folded in bit order by every lane redundantly (nbits steps)
@@ -289,7 +290,7 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
     for (int i = 0; i < nbits; i++) {
       const int bit_x = fam.bit_x[i], bit_y = fam.bit_y[i];
       rcode = (rcode << 1);
-      const double v = S.values[(bit_y - min_coord) * tw + bit_x - min_coord];
+      const double v = values[(bit_y - min_coord) * tw + bit_x - min_coord];
       if (v > 0) {
         white_score += static_cast<float>(v);
         white_score_count++;
@@ -366,13 +367,6 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
   b200tag_detection *dets = p.dets + static_cast<size_t>(frame) * p.det_cap;
   const uint32_t nquads = min(ctr->num_quads, p.quad_cap);
   const int W = p.W, H = p.H;
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.families);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(S.fam);
-    for (uint32_t i = lane; i < p.nfamilies * (sizeof(DevFamily) / 4); i += 32) dst[i] = __ldg(src + i);
-  }
-  __syncwarp();
-
   uint32_t nxt = 0;
   if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);
   while (true) {
@@ -525,7 +519,7 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
 
     // quad_decode_task: every family of the quad's border polarity gets its own decode of the same homography
     for (int fi = 0; fi < p.nfamilies; fi++) {
-      const DevFamily &fam = S.fam[fi];
+      const DevFamily &fam = p.families[fi];
       if ((fam.reversed_border != 0) != (quad.reversed_border != 0)) continue;
       if (fam.width_at_border == 8 && fam.total_width == 10 && fam.nbits == 36)
         decode_family<8, 10, 36>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
