@@ -47,6 +47,8 @@ enum {
   B200TAG_ST_BLOBS_OVERFLOW = 1u << 2,
   B200TAG_ST_QUADS_OVERFLOW = 1u << 3,
   B200TAG_ST_DETS_OVERFLOW = 1u << 4,
+  B200TAG_ST_JPEG_TRUNCATED = 1u << 5, /* MJPG input: the bitstream does not end with an EOI marker (a cut-off frame: the
+                                          missing part of the image decodes as flat gray).  Does not fail the call. */
 };
 
 /* b200tag_config.test_flags: results must be identical with and without them. */

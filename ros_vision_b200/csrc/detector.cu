@@ -113,6 +113,7 @@ struct b200tag_detector {
   KernelTimer timer;
   MjpgDecoder mjpg;
   NativeJpeg jpeg;
+  std::vector<uint32_t> host_status;  // per frame of the last batch: status bits raised on the host (B200TAG_ST_JPEG_TRUNCATED)
   void *d_families = nullptr;  // DevFamily[nfamilies] followed by the code tables
   int min_width_at_border = 8;
   bool normal_border = true, reversed_border = false;
@@ -349,7 +350,8 @@ int record_sequence(b200tag_detector *det, const void *device_images, size_t str
 // The launch sequence of a (input buffer, frame count) pair never changes, so it is captured once into a CUDA
 // graph and replayed: one graph launch instead of 15 stream operations per batch (what matters for the
 // single-frame latency path, where the kernels are short).
-int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt) {
+int enqueue_impl(b200tag_detector *det, const void *device_images, size_t stride, int count, KernelTimer *kt, bool keep_host_status = false) {
+  if (!keep_host_status) det->host_status.assign(static_cast<size_t>(count), 0u);
   det->last_images = static_cast<const uint8_t *>(device_images);
   det->last_stride = stride ? stride : det->in_bytes;
   int launches = 0;
@@ -863,6 +865,7 @@ static int mjpg_open(b200tag_detector *det) {
 static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const size_t *sizes, int count) {
   NativeJpeg &J = det->jpeg;
   J.parsed.resize(count);
+  det->host_status.assign(static_cast<size_t>(count), 0u);
   std::vector<int> set_of(count, 0);
   std::vector<int> set_owner;  // frame whose tables define each distinct set
   size_t bytes = 0;
@@ -874,6 +877,12 @@ static int mjpg_native(b200tag_detector *det, const uint8_t *const *jpegs, const
     if (rc != kJpegOk) {
       det->err = "frame " + std::to_string(f) + ": not a JPEG bitstream this decoder can parse (" + why + ")";
       return B200TAG_E_INVALID;
+    }
+    {  // a complete frame ends with EOI (FF D9), possibly followed by padding; a cut-off one is decoded as far as it
+       // goes (the rest of the plane stays flat gray) and flagged, so that the caller can drop it
+      size_t e = sizes[f];
+      while (e > 2 && e + 16 > sizes[f] && jpegs[f][e - 1] == 0) e--;
+      if (e < 2 || jpegs[f][e - 2] != 0xff || jpegs[f][e - 1] != 0xd9) det->host_status[f] |= B200TAG_ST_JPEG_TRUNCATED;
     }
     const JpegFrame &fr = J.parsed[f].frame;
     if (fr.width != det->cfg.width || fr.height != det->cfg.height) {
@@ -1031,7 +1040,7 @@ int b200tag_enqueue_mjpg(b200tag_detector *det, const uint8_t *const *jpegs, con
     if (rc < 0) return rc;
     if (rc == 0) {
       det->jpeg.last_native = true;
-      return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr);
+      return enqueue_impl(det, det->d_in, det->fp.in_stride, count, nullptr, true);
     }
   }
   det->jpeg.last_native = false;
@@ -1160,7 +1169,7 @@ const b200tag_detection *b200tag_detections(const b200tag_detector *det, int fra
 int b200tag_frame_info_get(const b200tag_detector *det, int frame, b200tag_frame_info *info) {
   if (!det || !info || frame < 0 || frame >= det->last_count || det->pending) return B200TAG_E_INVALID;
   const Counters &c = det->h_counters[frame];
-  info->status = c.status;
+  info->status = c.status | (static_cast<size_t>(frame) < det->host_status.size() ? det->host_status[frame] : 0u);
   info->num_points = std::min(c.num_points, det->fp.point_cap);
   info->num_clusters = alloc_clusters(c.alloc);
   info->num_blobs = c.num_selected_blobs;

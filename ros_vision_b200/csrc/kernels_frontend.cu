@@ -222,57 +222,97 @@ __global__ void __launch_bounds__(256) k_pre_bgr_dec1(FrameParams p) {
   *reinterpret_cast<uint4 *>(quad + g16 * 16) = o4;
 }
 
-// K1b: separable Gaussian with upstream's border rule (convolve(): indices [ksz/2, sz-ksz+ksz/2)
-// are filtered, the rest copied), rows first then columns.  One CTA = 64x32 output pixels: the
-// input tile with its halo is staged in shared memory, the row pass writes a second shared tile
-// (all rows the column pass needs), the column pass writes the result.
+// K1b: separable Gaussian with upstream's border rule (convolve(): indices [ksz/2, sz-ksz+ksz/2) are filtered, the
+// rest copied), rows first then columns.  One CTA = 64x32 output pixels.  The input tile with its halo is staged in
+// shared memory with 4-byte loads (the halo is rounded up to a multiple of 4 columns so every word is aligned); both
+// passes work on words: a thread filters 4 neighbouring pixels from the bytes it has in registers (row pass) or from
+// aligned word loads of the rows above and below (column pass) and stores one word.  KSZ = filter length as a
+// compile-time constant (3, 5, 7: quad_sigma up to 1.9), or 0 to take it from the parameters.
 constexpr int kBlurTW = 64, kBlurTH = 32;  // (the host caps the filter radius at 15: detector.cu blur_kernel)
+template <int KSZ>
 __global__ void __launch_bounds__(256) k_blur(FrameParams p) {
-  extern __shared__ uint8_t s_blur[];
-  const int ksz = p.blur_ksz, r = ksz >> 1;
-  const int sw = kBlurTW + 2 * r, sh = kBlurTH + 2 * r;  // staged input tile
-  uint8_t *s_in = s_blur;                                  // [sh][sw]
-  uint8_t *s_row = s_blur + sh * sw;                       // [sh][kBlurTW]: row-filtered
+  extern __shared__ __align__(16) uint8_t s_blur[];
+  const int ksz = KSZ ? KSZ : p.blur_ksz, r = ksz >> 1, r4 = (r + 3) & ~3;
+  const int sw = kBlurTW + 2 * r4, sh = kBlurTH + 2 * r;   // staged input tile, sw a multiple of 4
+  uint8_t *s_in = s_blur;                                   // [sh][sw]
+  uint8_t *s_row = s_blur + sh * sw;                        // [sh][kBlurTW]: row-filtered
   const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
   const int frame = blockIdx.z;
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *src = p.quad_tmp + frame * n;
   uint8_t *dst = p.quad + frame * n;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < sh * sw; i += 256) {
-    const int yy = i / sw, xx = i % sw;
-    const int gx = x0 - r + xx, gy = y0 - r + yy;
-    s_in[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h) ? src[static_cast<size_t>(gy) * p.w + gx] : 0;
-  }
-  __syncthreads();
-  for (int i = tid; i < sh * kBlurTW; i += 256) {
-    const int yy = i / kBlurTW, xx = i % kBlurTW;
-    const int gx = x0 + xx;
-    uint32_t v = s_in[yy * sw + xx + r];
-    if (gx >= r && gx < p.w - ksz + r) {
-      uint32_t acc = 0;
-      for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * s_in[yy * sw + xx + j];
-      v = (acc >> 8) & 0xff;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  // stage: warp = row (stride 8), lane = word of the row
+  for (int yy = wrp; yy < sh; yy += 8) {
+    const int gy = y0 - r + yy;
+    for (int cw = lane; cw < sw / 4; cw += 32) {
+      const int gx = x0 - r4 + 4 * cw;
+      uint32_t v = 0;
+      if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) v = __ldg(reinterpret_cast<const uint32_t *>(src + static_cast<size_t>(gy) * p.w + gx));
+      reinterpret_cast<uint32_t *>(s_in + yy * sw)[cw] = v;
     }
-    s_row[i] = static_cast<uint8_t>(v);
   }
   __syncthreads();
-  for (int i = tid; i < kBlurTH * kBlurTW; i += 256) {
-    const int yy = i / kBlurTW, xx = i % kBlurTW;
-    const int gx = x0 + xx, gy = y0 + yy;
+  uint32_t kk[KSZ ? KSZ : 32];
+#pragma unroll
+  for (int j = 0; j < (KSZ ? KSZ : 32); j++) kk[j] = j < ksz ? p.blur_k[j] : 0u;
+  // row pass: thread = 4 pixels of a staged row (16 words per row, 16 rows per sweep)
+  const int q = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  for (int yy = rsub; yy < sh; yy += 16) {
+    const uint8_t *row = s_in + yy * sw + r4 + 4 * q;   // the thread's first pixel
+    uint32_t out = 0;
+#pragma unroll
+    for (int px = 0; px < 4; px++) {
+      const int gx = x0 + 4 * q + px;
+      uint32_t v = row[px];
+      if (gx >= r && gx < p.w - ksz + r) {
+        uint32_t acc = 0;
+        if constexpr (KSZ != 0) {
+#pragma unroll
+          for (int j = 0; j < KSZ; j++) acc += kk[j] * row[px - r + j];
+        } else {
+          for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * row[px - r + j];
+        }
+        v = (acc >> 8) & 0xff;
+      }
+      out |= v << (8 * px);
+    }
+    reinterpret_cast<uint32_t *>(s_row + yy * kBlurTW)[q] = out;
+  }
+  __syncthreads();
+  // column pass: thread = one word of an output row, aligned word loads of the ksz rows it needs
+  for (int yy = rsub; yy < kBlurTH; yy += 16) {
+    const int gx = x0 + 4 * q, gy = y0 + yy;
     if (gx >= p.w || gy >= p.h) continue;
-    uint32_t v = s_row[(yy + r) * kBlurTW + xx];
+    uint32_t out = reinterpret_cast<const uint32_t *>(s_row + (yy + r) * kBlurTW)[q];
     if (gy >= r && gy < p.h - ksz + r) {
-      uint32_t acc = 0;
-      for (int j = 0; j < ksz; j++) acc += static_cast<uint32_t>(p.blur_k[j]) * s_row[(yy + j) * kBlurTW + xx];
-      v = (acc >> 8) & 0xff;
+      uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      if constexpr (KSZ != 0) {
+#pragma unroll
+        for (int j = 0; j < KSZ; j++) {
+          const uint32_t wv = reinterpret_cast<const uint32_t *>(s_row + (yy + j) * kBlurTW)[q];
+          a0 += kk[j] * (wv & 0xff); a1 += kk[j] * ((wv >> 8) & 0xff); a2 += kk[j] * ((wv >> 16) & 0xff); a3 += kk[j] * (wv >> 24);
+        }
+      } else {
+        for (int j = 0; j < ksz; j++) {
+          const uint32_t wv = reinterpret_cast<const uint32_t *>(s_row + (yy + j) * kBlurTW)[q], kj = p.blur_k[j];
+          a0 += kj * (wv & 0xff); a1 += kj * ((wv >> 8) & 0xff); a2 += kj * ((wv >> 16) & 0xff); a3 += kj * (wv >> 24);
+        }
+      }
+      out = ((a0 >> 8) & 0xff) | (((a1 >> 8) & 0xff) << 8) | (((a2 >> 8) & 0xff) << 16) | (((a3 >> 8) & 0xff) << 24);
     }
     if (p.sharpen) {
-      int sv = 2 * static_cast<int>(s_in[(yy + r) * sw + xx + r]) - static_cast<int>(v);
-      sv = max(0, min(255, sv));
-      v = static_cast<uint32_t>(sv);
+      const uint32_t orig = reinterpret_cast<const uint32_t *>(s_in + (yy + r) * sw + r4)[q];
+      uint32_t o = 0;
+#pragma unroll
+      for (int px = 0; px < 4; px++) {
+        int sv = 2 * static_cast<int>((orig >> (8 * px)) & 0xff) - static_cast<int>((out >> (8 * px)) & 0xff);
+        sv = max(0, min(255, sv));
+        o |= static_cast<uint32_t>(sv) << (8 * px);
+      }
+      out = o;
     }
-    dst[static_cast<size_t>(gy) * p.w + gx] = static_cast<uint8_t>(v);
+    *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(gy) * p.w + gx) = out;
   }
 }
 
@@ -1041,9 +1081,15 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
     }
     if (p.blur_ksz) {
       if (kt) kt->begin("blur", s);
-      const int r = p.blur_ksz >> 1;
-      const size_t smem = static_cast<size_t>(kBlurTH + 2 * r) * (kBlurTW + 2 * r) + static_cast<size_t>(kBlurTH + 2 * r) * kBlurTW;
-      k_blur<<<dim3(cdiv(p.w, kBlurTW), cdiv(p.h, kBlurTH), frames), 256, smem, s>>>(p);
+      const int r = p.blur_ksz >> 1, r4 = (r + 3) & ~3;
+      const size_t smem = static_cast<size_t>(kBlurTH + 2 * r) * (kBlurTW + 2 * r4) + static_cast<size_t>(kBlurTH + 2 * r) * kBlurTW;
+      const dim3 bgrid(cdiv(p.w, kBlurTW), cdiv(p.h, kBlurTH), frames);
+      switch (p.blur_ksz) {
+        case 3: k_blur<3><<<bgrid, 256, smem, s>>>(p); break;
+        case 5: k_blur<5><<<bgrid, 256, smem, s>>>(p); break;
+        case 7: k_blur<7><<<bgrid, 256, smem, s>>>(p); break;
+        default: k_blur<0><<<bgrid, 256, smem, s>>>(p); break;
+      }
       if (kt) kt->end(s);
       launches++;
     }

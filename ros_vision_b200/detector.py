@@ -23,7 +23,7 @@ BYTES_PER_PIXEL = {"gray": 1, "yuyv": 2, "bgr": 3}
  STAGE_SORTED_POINTS, STAGE_LINE_FIT_POINTS, STAGE_ERRORS, STAGE_FILTERED_ERRORS, STAGE_FIT_QUADS, STAGE_QUADS,
  STAGE_RAW_DETECTIONS, STAGE_MINMAX, STAGE_CLUSTERS) = range(16)
 
-ST_POINTS_OVERFLOW, ST_HASH_OVERFLOW, ST_BLOBS_OVERFLOW, ST_QUADS_OVERFLOW, ST_DETS_OVERFLOW = 1, 2, 4, 8, 16
+ST_POINTS_OVERFLOW, ST_HASH_OVERFLOW, ST_BLOBS_OVERFLOW, ST_QUADS_OVERFLOW, ST_DETS_OVERFLOW, ST_JPEG_TRUNCATED = 1, 2, 4, 8, 16, 32
 
 
 class B200TagError(RuntimeError):

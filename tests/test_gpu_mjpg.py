@@ -235,6 +235,11 @@ def test_corrupt_entropy_data_does_not_hang_or_crash(D, monkeypatch):
     det = D.GpuDetector(w, h, "gray", quad_decimate=2, max_batch=3)
     det.DetectMjpg([bytes(bad), good, good[:len(good) // 2]], allow_overflow=True)
     assert {int(i) for i in det.Detections(1)["id"]} == {int(t.tag_id) for t in sc.tags}
+    # the cut-off frame is flagged so that the caller can drop it; complete frames are not
+    assert det.FrameInfo(2).status & D.ST_JPEG_TRUNCATED
+    assert not det.FrameInfo(1).status & D.ST_JPEG_TRUNCATED and not det.FrameInfo(0).status & D.ST_JPEG_TRUNCATED
+    det.DetectMjpg([good])
+    assert det.FrameInfo(0).status == 0
     det.close()
 
 

@@ -185,6 +185,22 @@ def test_blob_overflow_with_huge_blobs(D, oracle):
     det.close()
 
 
+@pytest.mark.parametrize("sigma", [0.8, 1.2, 1.6, 2.6, -0.8, -1.3])
+def test_quad_sigma_variants(D, oracle, sigma):
+    """The Gaussian quad_sigma filter (upstream image_u8_gaussian_blur; negative = sharpen) for every filter length the
+    kernel specialises (3, 5, 7) and the generic one, at decimate 1 and 2, on a frame whose quad image is not a
+    multiple of the blur tile."""
+    from ros_vision_b200 import synth
+    for w, h, fmt, dec in ((360, 248, "gray", 1), (656, 496, "yuyv", 2)):
+        sc = synth.make_scene(w, h, 21, 2, side_range=(60, 110), noise_sigma=4.0)
+        frame = _pack(sc.gray, fmt)
+        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, sigma), frame)
+        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, quad_sigma=sigma, keep_stages=True)
+        det.Detect(frame)
+        compare_all(det, orc, 0, fmt)
+        det.close()
+
+
 def test_other_decimation_factors(D, oracle):
     """quad_decimate 3 and 4 (the reference supports only 2): every stage against the oracle."""
     from ros_vision_b200 import synth

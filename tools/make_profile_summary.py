@@ -21,8 +21,9 @@ B = line["config"].get("frames_per_batch", line["config"]["frames_per_step_per_g
 rows = [r for r in csv.reader(open(launches_path)) if len(r) > 14 and r[0].isdigit()]
 names = [re.sub(r"\(.*", "", r[4]).replace("void ", "").split("<")[0] for r in rows]
 times = [float(r[14]) for r in rows]
-alias = {"k_pre_yuyv_dec2": "pre_yuyv_dec2", "k_threshold": "threshold", "k_ccl_local": "ccl_local", "k_ccl_merge": "ccl_merge",
-         "k_ccl_final": "ccl_final", "k_boundary": "boundary", "k_select": "select", "k_scatter": "scatter",
+alias = {"k_pre_yuyv_dec2": "pre_yuyv_dec2", "k_pre_gray_dec2": "pre_gray_dec2", "k_pre_bgr_dec2": "pre_bgr_dec2", "k_pre_bgr_dec1": "pre_bgr_dec1",
+         "k_pre_generic": "pre_generic", "k_blur": "blur", "k_tile_minmax": "tile_minmax", "k_ccl_local": "ccl_local", "k_ccl_merge": "ccl_merge",
+         "k_ccl_handoff": "ccl_handoff", "k_ccl_final": "ccl_final", "k_boundary": "boundary", "k_select": "select", "k_scatter": "scatter",
          "k_fit_small": "fit_small", "k_decode": "decode", "k_quads": "quads"}
 # batched launches are the slow ones: per kernel name take the maximum-duration launches' median
 per = collections.defaultdict(list)
@@ -41,10 +42,10 @@ tot_ev = sum(k["ms"] for k in kern)
 tot_ncu = sum(ncu_ms.get(k["kernel"], 0.0) for k in kern)
 
 out = []
-out.append(f"# Round 1, version {tag}\n")
-out.append(f"bench.py, B200, {B} frames/step of config 2: **{line['value']:.0f} frames/s device-resident, "
+out.append(f"# {tag}: {line['config']['workload']}\n")
+out.append(f"bench.py, B200, {B} frames per batch: **{line['value']:.0f} frames/s device-resident, "
            f"{line['e2e']['value']:.0f} frames/s end to end, p50 single-frame latency {line.get('p50_latency_ms', 0):.3f} ms**"
-           + (f", CPU oracle port {line['cpu_baseline']['value']:.0f} frames/s on {line['cpu_baseline']['cores']} threads" if line.get("cpu_baseline") else "")
+           + (f", CPU classic detector (port) {line['cpu_baseline']['value']:.0f} frames/s on {line['cpu_baseline']['cores']} threads" if line.get("cpu_baseline") and "value" in line["cpu_baseline"] else "")
            + (f", reference kernels recompiled for sm_100a (decode excluded) {line['reference_gpu']['value']:.0f} frames/s" if line.get("reference_gpu") and "value" in line["reference_gpu"] else "")
            + ".\n")
 out.append("Per-kernel CUDA-event time per step (bench.py `roofline.kernels`) vs the ncu launch list "
@@ -73,7 +74,10 @@ for rep in reps:
         key = alias.get(name.split("<")[0], name)
         if name.startswith("k_fit_cta"): key = "fit_medium" if block == "128" else ("fit_huge" if block == "512" else "fit_large")
         rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
-        traffic[key] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "report": os.path.basename(rep)}
+        traffic[key] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "report": os.path.basename(rep),
+                        "issue_active_pct": float(g("smsp__issue_active.avg.pct_of_peak_sustained_active")),
+                        "warps_active_pct": float(g("sm__warps_active.avg.pct_of_peak_sustained_active")),
+                        "duration_us": float(g("gpu__time_duration.sum")), "frames_per_launch": B, "workload": line["config"]["workload"]}
         st = []
         for i, h in enumerate(hdr):
             if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
@@ -91,7 +95,7 @@ for rep in reps:
                    + (f" (algorithmic {alg / 1e6:.1f} MB)" if alg else "") + "; stalls: "
                    + ", ".join(f"{n} {100 * v / tot:.0f} %" for v, n in sorted(st, reverse=True)[:6]) + ".\n")
 open(os.path.join(ROOT, "profiles", f"summary_{tag}.md"), "w").write("\n".join(out) + "\n")
-tpath = os.path.join(ROOT, "profiles", "traffic.json")
+tpath = os.path.join(ROOT, "profiles", os.environ.get("TRAFFIC_JSON", "traffic.json"))
 old = json.load(open(tpath)) if os.path.exists(tpath) else {}
 for k, v in traffic.items():
     v["tag"] = tag

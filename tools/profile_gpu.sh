@@ -6,7 +6,7 @@ set -u
 KERNEL=${1:-k_fit_small}
 TAG=${2:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --latency-iters 20 --no-cpu --no-extra"
+CMD="python bench.py --config ${CONFIG:-2} --steps 2 --warmup 3 --latency-iters 20 --no-cpu --no-extra"
 $CMD > gpurun_out/bench_plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/bench_plain_$TAG.log; exit 1; }
 tail -1 gpurun_out/bench_plain_$TAG.log | cut -c1-400
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
