@@ -118,6 +118,8 @@ def main():
         if n > have:
             continue
         for mode in ("procs", "threads", "procs+2M"):
+            if mode == "procs+2M" and n not in (1, max(int(x) for x in args.gpus.split(",") if int(x) <= have)):
+                continue
             t0 = time.time()
             try:
                 if mode == "threads":
