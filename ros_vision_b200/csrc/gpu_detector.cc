@@ -9,6 +9,30 @@
 #include <cstring>
 #include <vector>
 
+// The libapriltag record layouts this layer was written against (upstream AprilTag 3.x, LP64).  In this repo they come
+// from the stand-in include/apriltag_compat/apriltag.h; in the real workspace this file is compiled against
+// libapriltag's own headers and these assertions make a differing fork fail at compile time
+// instead of silently reading the wrong bytes.  -DB200TAG_SKIP_LAYOUT_CHECKS turns them off.
+#ifndef B200TAG_SKIP_LAYOUT_CHECKS
+#include <cstddef>
+static_assert(offsetof(zarray_t, el_sz) == 0 && offsetof(zarray_t, size) == 8 && offsetof(zarray_t, alloc) == 12 &&
+                  offsetof(zarray_t, data) == 16 && sizeof(zarray_t) == 24, "zarray_t layout");
+static_assert(offsetof(matd_t, nrows) == 0 && offsetof(matd_t, ncols) == 4 && offsetof(matd_t, data) == 8, "matd_t layout");
+static_assert(offsetof(apriltag_detection_t, family) == 0 && offsetof(apriltag_detection_t, id) == 8 &&
+                  offsetof(apriltag_detection_t, hamming) == 12 && offsetof(apriltag_detection_t, decision_margin) == 16 &&
+                  offsetof(apriltag_detection_t, H) == 24 && offsetof(apriltag_detection_t, c) == 32 &&
+                  offsetof(apriltag_detection_t, p) == 48 && sizeof(apriltag_detection_t) == 112, "apriltag_detection_t layout");
+static_assert(offsetof(apriltag_family_t, ncodes) == 0 && offsetof(apriltag_family_t, codes) == 8 &&
+                  offsetof(apriltag_family_t, width_at_border) == 16 && offsetof(apriltag_family_t, total_width) == 20 &&
+                  offsetof(apriltag_family_t, reversed_border) == 24 && offsetof(apriltag_family_t, nbits) == 28 &&
+                  offsetof(apriltag_family_t, bit_x) == 32 && offsetof(apriltag_family_t, bit_y) == 40 &&
+                  offsetof(apriltag_family_t, name) == 56, "apriltag_family_t layout");
+static_assert(sizeof(static_cast<apriltag_detector_t *>(nullptr)->quad_decimate) == sizeof(float) &&
+                  sizeof(static_cast<apriltag_detector_t *>(nullptr)->decode_sharpening) == sizeof(double) &&
+                  sizeof(static_cast<apriltag_detector_t *>(nullptr)->qtp.cos_critical_rad) == sizeof(float),
+              "apriltag_detector_t field types");
+#endif
+
 namespace frc971::apriltag {
 namespace {
 bool g_keep_debug_stages = false;

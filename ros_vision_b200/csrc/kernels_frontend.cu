@@ -405,9 +405,9 @@ constexpr uint32_t kCclRootCap = 2 * kCclTW + 2 * kCclTH;
 // (labeling_allegretti_2019_BKE.cu:114-300).  One CTA = a 32x64 tile of the quad image = 8x16 threshold tiles.
 //   (T) thread = one 4x4 threshold tile: 3x3 dilation of the raw tile min/max (edge tiles skip missing
 //       neighbours), threshold value into shared memory;
-//   (A) thread = 4 pixels of a row (one 4-byte load): byte-wise compare (__vcmpgtu4) gives the thresholded word,
-//       stored as is; its white / black nibbles are OR-reduced over the 8 lanes of the row into the two 32-bit run
-//       masks of the row -- the labelling never reads the thresholded image back;
+//   (A) thread = half a row (one 16-byte load): byte-wise compares (__vcmpgtu4) give the thresholded words, stored
+//       as they are, and the white / black bits of the row's two 32-bit run masks -- the labelling never reads the
+//       thresholded image back;
 //   (B) union-find on RUNS: nodes are the first pixels of the horizontal runs; one thread per (row, colour) walks
 //       the runs of its mask with ffs/clz and unites each with the runs it touches in the row above (white:
 //       8-connected, i.e. the run dilated by one pixel; black: 4-connected);
@@ -465,42 +465,50 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   }
   __syncthreads();
 
-  // (A) thresholded pixels + run masks: 8 lanes per row, 4 rows per warp, 16 rows per pass; all four pixel loads
-  //     of a thread are issued before the first use.  Pixels outside the image join nothing.
+  // (A) thresholded pixels + run masks: thread = half a row (16 pixels: one 16-byte load, one 16-byte store); the
+  //     byte-wise compare of each 4-pixel word gives the thresholded word and a nibble of the white / black masks; the
+  //     two halves of a row meet with one shuffle.  Pixels outside the image join nothing.
   {
-    constexpr int kPasses = kCclTH / (kCclThreads / 8);
-    const int xq = tid & 7, rsub = tid >> 3;
-    const int gx = x0 + 4 * xq;
-    const uint32_t row_lanes = 0xffu << (lane & 24);
-    uint32_t d[kPasses];
+    static_assert(kCclThreads == 2 * kCclTH && kCclTW == 32, "two threads per row");
+    const int r = tid >> 1, half = tid & 1;
+    const int gy = y0 + r, gx = x0 + 16 * half;
+    uint32_t d[4] = {0, 0, 0, 0};
+    const bool row_in = gy < p.h;
+    const bool vec = row_in && (p.w & 15) == 0 && gx + 16 <= p.w;
+    const uint8_t *src = quad + static_cast<size_t>(gy) * p.w + gx;
+    if (vec) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else if (row_in) {
 #pragma unroll
-    for (int k = 0; k < kPasses; k++) {
-      const int gy = y0 + rsub + k * (kCclThreads / 8);
-      d[k] = 0;
-      if (gy < p.h && gx < p.w) d[k] = __ldg(reinterpret_cast<const uint32_t *>(quad + static_cast<size_t>(gy) * p.w + gx));
+      for (int g = 0; g < 4; g++)
+        if (gx + 4 * g < p.w) d[g] = __ldg(reinterpret_cast<const uint32_t *>(src + 4 * g));
     }
+    uint32_t o[4], wm16 = 0, bm16 = 0;
 #pragma unroll
-    for (int k = 0; k < kPasses; k++) {
-      const int r = rsub + k * (kCclThreads / 8);
-      const int gy = y0 + r;
-      const bool inside = gy < p.h && gx < p.w;
-      const uint32_t t = s_thr[r >> 2][xq];
-      uint32_t wn = 0, bn = 0;
-      if (inside) {
-        uint32_t o = 0x7f7f7f7fu;
-        if (t != 0xffffu) {
-          o = __vcmpgtu4(d[k], t * 0x01010101u);  // 0xff where v > thresh (threshold.cu:138-142)
-          wn = ((o & 0x01010101u) * 0x01020408u) >> 24;  // one bit per byte, byte 0 -> bit 0
-          bn = wn ^ 0xfu;
-        }
-        *reinterpret_cast<uint32_t *>(th + static_cast<size_t>(gy) * p.w + gx) = o;
+    for (int g = 0; g < 4; g++) {
+      const uint32_t t = s_thr[r >> 2][4 * half + g];
+      o[g] = 0x7f7f7f7fu;
+      if (t != 0xffffu && row_in && gx + 4 * g < p.w) {
+        o[g] = __vcmpgtu4(d[g], t * 0x01010101u);  // 0xff where v > thresh (threshold.cu:138-142)
+        const uint32_t wn = ((o[g] & 0x01010101u) * 0x01020408u) >> 24;  // one bit per byte, byte 0 -> bit 0
+        wm16 |= wn << (4 * g);
+        bm16 |= (wn ^ 0xfu) << (4 * g);
       }
-      const uint32_t wm = __reduce_or_sync(row_lanes, wn << (4 * xq));
-      const uint32_t bm = __reduce_or_sync(row_lanes, bn << (4 * xq));
-      if (xq == 0) {
-        s_mask[1][r] = wm;
-        s_mask[0][r] = bm;
-      }
+    }
+    uint8_t *dst = th + static_cast<size_t>(gy) * p.w + gx;
+    if (vec) {
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else if (row_in) {
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+        if (gx + 4 * g < p.w) *reinterpret_cast<uint32_t *>(dst + 4 * g) = o[g];
+    }
+    const uint32_t both = wm16 | (bm16 << 16);
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, both, 1);
+    if (half == 0) {
+      s_mask[1][r] = (both & 0xffffu) | (other << 16);
+      s_mask[0][r] = (both >> 16) | (other & 0xffff0000u);
     }
   }
   for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
