@@ -157,3 +157,39 @@ def test_bad_arguments(D):
     assert lib.b200tag_estimate_poses(det.ctypes.data_as(C.c_void_p), 1, 0.0, FX, FY, CX, CY, out.ctypes.data_as(C.c_void_p)) != 0
     assert lib.b200tag_estimate_poses(None, 1, TAGSIZE, FX, FY, CX, CY, out.ctypes.data_as(C.c_void_p)) != 0
     assert len(D.estimate_poses(np.zeros(0, dtype=D.DETECTION_DT), TAGSIZE, FX, FY, CX, CY)) == 0
+
+
+def test_pose_against_opencv_ippe():
+    """Third opinion for the pose step: OpenCV's planar-square solver (cv2.solvePnPGeneric, SOLVEPNP_IPPE_SQUARE, which
+    like estimate_tag_pose returns both local minima of the planar problem, best first) on noisy projections.  The
+    better pose of each must agree: rotation within 0.5 degrees, translation within 0.5 % (the two solvers minimise
+    different errors -- object space here, image space there -- so with pixel noise they agree to the pose's own
+    uncertainty, not exactly: tags at 0.5-1.5 m, 0.02 px noise)."""
+    cv2 = pytest.importorskip("cv2")
+    from ros_vision_b200 import detector as D
+    D.load_library()
+    rng = np.random.default_rng(7)
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], dtype=np.float64)
+    obj = _object_points(TAGSIZE)
+    worst_r, worst_t, n = 0.0, 0.0, 0
+    for _ in range(120):
+        R = _rot(*rng.uniform(-0.9, 0.9, 3))
+        t = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(0.5, 1.5)])
+        det = _detection(R, t, noise=rng.normal(0, 0.02, (4, 2)))
+        ours = D.estimate_poses(det, TAGSIZE, FX, FY, CX, CY)[0]
+        ok, rvecs, tvecs, errs = cv2.solvePnPGeneric(obj, det["p"][0].astype(np.float64), K, None, flags=cv2.SOLVEPNP_IPPE_SQUARE)
+        assert ok and len(rvecs) >= 1
+        Rcv, _ = cv2.Rodrigues(rvecs[0])
+        tcv = tvecs[0].reshape(3)
+        # when the two minima are nearly as good as each other the solvers may rank them differently: skip those
+        if len(errs) > 1 and float(errs[1]) < 1.5 * float(errs[0]) + 1e-6:
+            continue
+        if np.isfinite(ours["err_other"]) and ours["err_other"] < 2.0 * ours["err"] + 1e-12:
+            continue
+        dR = ours["R"] @ Rcv.T
+        ang = np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+        worst_r = max(worst_r, ang)
+        worst_t = max(worst_t, float(np.linalg.norm(ours["t"] - tcv) / np.linalg.norm(tcv)))
+        n += 1
+    assert n >= 60, n
+    assert worst_r < 0.5 and worst_t < 5e-3, (worst_r, worst_t)
