@@ -416,7 +416,6 @@ constexpr uint32_t kCclRootCap = 2 * kCclTW + 2 * kCclTH;
 //   (D) write-out per pixel, 16-byte stores: label = global index of the root of the pixel's run | colour, sizes =
 //       count at tile roots, 0 elsewhere; tile roots that touch the border go to the tile's root list, from which
 //       k_ccl_handoff moves the counts of merged-away roots to the final roots.
-template <bool LOCKSTEP>
 __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   __shared__ uint32_t s_mask[2][kCclTH];  // [0] black, [1] white
   __shared__ uint32_t s_par[kCclTH * kCclTW];
@@ -518,91 +517,6 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   }
   __syncthreads();
 
-  if constexpr (LOCKSTEP) {
-    // (B'/C'/D') lane = column, each warp walks its 16 rows: every lane of a row does the same thing at the same time
-    // (one bit test, at most two unions, one store), instead of one thread per (row, colour) walking its runs at its
-    // own pace.
-    const int lane_ = tid & 31, warp_ = tid >> 5;
-    constexpr int kRowsPerWarp = kCclTH / kCclWarps;
-    const uint32_t lt = (1u << lane_) - 1u;  // the columns left of this lane
-    // (B') A run of this row and a run of the row above are neighbours iff they share a column -- found at the first
-    //      column of their overlap -- or, white only, touch corner to corner without sharing one.
-    for (int k = 0; k < kRowsPerWarp; k++) {
-      const int r = warp_ * kRowsPerWarp + k;
-      if (r == 0) continue;
-      const uint32_t wm = s_mask[1][r], bm = s_mask[0][r], uw = s_mask[1][r - 1], ub = s_mask[0][r - 1];
-      const bool iw = (wm >> lane_) & 1u, ib = (bm >> lane_) & 1u;
-      uint32_t partner[2] = {0xffffffffu, 0xffffffffu};
-      uint32_t node = 0;
-      if (iw || ib) {
-        const uint32_t m = iw ? wm : bm, up = iw ? uw : ub;
-        const uint32_t below = ~m & lt;
-        node = r * kCclTW + (below ? 32 - __clz(static_cast<int>(below)) : 0);  // first pixel of my run
-        const bool upx = (up >> lane_) & 1u;
-        if (upx) {
-          if (!(((m & up) << 1) >> lane_ & 1u)) {  // not both set one column to the left: the overlap starts here
-            const uint32_t bu = ~up & lt;
-            partner[0] = (r - 1) * kCclTW + (bu ? 32 - __clz(static_cast<int>(bu)) : 0);
-          }
-        } else if (iw) {
-          // corner contacts: my run ends here and a run above starts one column to the right / my run starts here and
-          // a run above ends one column to the left
-          if (lane_ < 31 && ((up >> (lane_ + 1)) & 1u) && !((m >> (lane_ + 1)) & 1u)) partner[0] = (r - 1) * kCclTW + lane_ + 1;
-          if (lane_ > 0 && ((up >> (lane_ - 1)) & 1u) && !((m >> (lane_ - 1)) & 1u)) {
-            const uint32_t bu = ~up & (lt >> 1);
-            partner[1] = (r - 1) * kCclTW + (bu ? 32 - __clz(static_cast<int>(bu)) : 0);
-          }
-        }
-      }
-#pragma unroll 1
-      for (int q = 0; q < 2; q++)
-        if (partner[q] != 0xffffffffu) node = sunite(s_par, node, partner[q]);
-      __syncwarp();
-    }
-    __syncthreads();
-    // (C') run starts compress to their roots and add their length to the root's count
-    for (int k = 0; k < kRowsPerWarp; k++) {
-      const int r = warp_ * kRowsPerWarp + k;
-      const bool edge_row = r == 0 || r == kCclTH - 1;
-#pragma unroll
-      for (int colour = 0; colour < 2; colour++) {
-        const uint32_t m = s_mask[colour][r];
-        if (((m & ~(m << 1)) >> lane_) & 1u) {  // a run starts here
-          const uint32_t inv = ~(m >> lane_);
-          const int len = inv ? __ffs(static_cast<int>(inv)) - 1 : 32 - lane_;
-          const uint32_t node = r * kCclTW + lane_;
-          const uint32_t root = sfind(s_par, node);
-          if (root != node) s_par[node] = root;
-          const uint32_t touches = (edge_row || lane_ == 0 || lane_ + len == kCclTW) ? 0x10000u : 0u;
-          atomicAdd(&s_cnt[root], static_cast<uint32_t>(len) | touches);
-        }
-      }
-    }
-    __syncthreads();
-    // (D') write out: one row per step, 128 bytes of labels and of sizes per warp and step
-    for (int k = 0; k < kRowsPerWarp; k++) {
-      const int r = warp_ * kRowsPerWarp + k;
-      const int gy = y0 + r, gx = x0 + lane_;
-      if (gy >= p.h || gx >= p.w) continue;
-      const uint32_t wm = s_mask[1][r], bm = s_mask[0][r];
-      const size_t g = static_cast<size_t>(gy) * p.w + gx;
-      uint32_t lab = static_cast<uint32_t>(g) | kColourGray, sz = 0;
-      const bool iw = (wm >> lane_) & 1u, ib = (bm >> lane_) & 1u;
-      if (iw || ib) {
-        const uint32_t below = ~(iw ? wm : bm) & lt;
-        const int s0 = below ? 32 - __clz(static_cast<int>(below)) : 0;
-        const uint32_t root = s_par[r * kCclTW + s0];
-        lab = static_cast<uint32_t>((y0 + (root / kCclTW)) * p.w + x0 + (root % kCclTW)) | (iw ? 1u << kColourShift : 0u);
-        if (root == static_cast<uint32_t>(r * kCclTW + lane_)) {
-          const uint32_t c = s_cnt[root];
-          sz = c & 0xffffu;
-          if (c >> 16) s_roots[atomicAdd(&s_nroots, 1u)] = static_cast<uint32_t>(g);
-        }
-      }
-      labels[g] = lab;
-      sizes[g] = sz;
-    }
-  } else {
   // (B) unions with the row above: thread = (row, colour)
   const int row = tid >> 1, colour = tid & 1;
   const uint32_t mine = s_mask[colour][row];
@@ -676,7 +590,6 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
     }
     *reinterpret_cast<uint4 *>(labels + g) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
     *reinterpret_cast<uint4 *>(sizes + g) = make_uint4(sz[0], sz[1], sz[2], sz[3]);
-  }
   }
   __syncthreads();
   {
@@ -1213,11 +1126,7 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   }
   const dim3 cgrid(cdiv(p.w, kCclTW), cdiv(p.h, kCclTH), frames);
   if (kt) kt->begin("ccl_local", s);
-  {
-    static const bool lockstep = [] { const char *e = getenv("B200TAG_CCL_LOCKSTEP"); return e && e[0] == '1'; }();
-    if (lockstep) k_ccl_local<true><<<cgrid, kCclThreads, 0, s>>>(p);
-    else k_ccl_local<false><<<cgrid, kCclThreads, 0, s>>>(p);
-  }
+  k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_merge", s);
   k_ccl_merge<<<cgrid, kCclMergeThreads, 0, s>>>(p);
