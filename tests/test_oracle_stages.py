@@ -167,3 +167,29 @@ def test_undistort_redistort_roundtrip(oracle):
     u, v = C.c_double(12.25), C.c_double(99.5)
     L.orc_undistort(C.byref(u), C.byref(v), C.byref(ident))
     assert (u.value, v.value) == (12.25, 99.5)
+
+
+def test_gaussian_blur_against_opencv(oracle):
+    """Row x1 (quad_sigma): the blur follows upstream image_u8_gaussian_blur from memory -- an 8-bit integer kernel
+    `k[i] = (uint8)(255 * g[i] / sum g)` applied along rows, then columns, each pass `>> 8`.  Its SHAPE is pinned here
+    against OpenCV's float Gaussian of the same length and sigma: the integer kernel sums to a little under 256 and the
+    shift divides by 256, so a pass darkens by sum(k) / 256; with that gain applied to OpenCV's result the two agree
+    within 3 grey levels on every interior pixel, 1 level lower on average (half a level of truncation per pass)."""
+    cv2 = pytest.importorskip("cv2")
+    from ros_vision_b200 import synth
+    sc = synth.make_scene(640, 480, 3, 4, side_range=(40, 100), noise_sigma=5.0)
+    for sigma in (0.8, 1.2, 1.6, 2.6):
+        r = oracle.detect(oracle.make_config(640, 480, "gray", 1, sigma, max_stage=oracle.STAGE_THRESHOLD), sc.gray)
+        ksz = int(4 * sigma)
+        ksz += (ksz % 2 == 0)
+        g = np.exp(-0.5 * ((np.arange(ksz) - ksz // 2) / sigma) ** 2)
+        k = np.floor(255 * g / g.sum()).astype(np.int64)
+        gain = (k.sum() / 256.0) ** 2
+        ref = cv2.GaussianBlur(sc.gray.astype(np.float64), (ksz, ksz), sigma, borderType=cv2.BORDER_REPLICATE) * gain
+        # OpenCV's kernel is the normalised float Gaussian; the integer one differs from it by < 1/255 per tap
+        d = r.quad_im.astype(np.float64)[ksz:-ksz, ksz:-ksz] - ref[ksz:-ksz, ksz:-ksz]
+        assert np.abs(d).max() <= 3.0, (sigma, np.abs(d).max())     # observed 2.1 ... 2.7
+        assert -1.3 <= d.mean() <= -0.7, (sigma, d.mean())         # two truncations of half a level each: observed -0.99
+        # border rule of convolve(): the first and last ksz/2 pixels of a line are copied, not filtered
+        rr = ksz // 2
+        assert np.array_equal(r.quad_im[:rr, :rr], sc.gray[:rr, :rr]) and np.array_equal(r.quad_im[-rr:, -rr:], sc.gray[-rr:, -rr:])
