@@ -414,7 +414,11 @@ __device__ __forceinline__ int point_weight(const uint8_t *im, int w, int h, int
   if (ix > 0 && ix + 1 < w && iy > 0 && iy + 1 < h) {
     const int gx = static_cast<int>(__ldg(im + iy * w + ix + 1)) - static_cast<int>(__ldg(im + iy * w + ix - 1));
     const int gy = static_cast<int>(__ldg(im + (iy + 1) * w + ix)) - static_cast<int>(__ldg(im + (iy - 1) * w + ix));
-    W = static_cast<int>(hypotf(static_cast<float>(gx), static_cast<float>(gy)) + 1);
+    // (int)(hypotf(gx, gy) + 1) of the reference.  gx, gy are integers in [-255, 255]: the square root of the exact
+    // integer gx^2 + gy^2 is either an integer or at least 1 / (2 * 361) away from one, so the correctly rounded
+    // single-precision root gives the same truncation as libdevice's hypotf -- checked for all 511^2 inputs against
+    // the oracle's bit-exact hypotf emulation (tests/test_gpu_math.py) -- at a fraction of its instructions.
+    W = static_cast<int>(__fsqrt_rn(static_cast<float>(gx * gx + gy * gy)) + 1);
   }
   return W;
 }
@@ -972,15 +976,19 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
     const PeakTable &T = S.t;
     const uint32_t b = T.blob, cnt = T.cnt, npk = T.npk;
 
-  // (7) side-fit table: every ordered pair of chosen peaks (<= 90 fits instead of 4 per combination)
+  // (7) side-fit table: every ordered pair of chosen peaks (<= 90 fits instead of 4 per combination), enumerated
+  //     densely (pair t = (a, c'), c' skipping a) so that nm (nm - 1) fits take ceil(nm (nm - 1) / 32) rounds.  Only
+  //     forward pairs (a < c) can be a first or second side, whose normals the corner test needs; the others are
+  //     closing sides (peak m3 back to m0): error only.
   const int nm = static_cast<int>(T.nsel);
   const double max_mse = static_cast<double>(p.max_line_fit_mse);
-  for (int t = lane; t < kMaxPeaks * kMaxPeaks; t += 32) {
-    const int a = t / kMaxPeaks, c = t % kMaxPeaks;
-    if (a == c || a >= nm || c >= nm) continue;
+  for (int t = lane; t < nm * (nm - 1); t += 32) {
+    const int a = t / (nm - 1);
+    int c = t - a * (nm - 1);
+    c += c >= a;
     const Mom mo = table_moments(T, a, c);
-    double err, mse, nrm[2];
-    fit_line(mo, nullptr, nrm, &err, &mse);
+    double err, mse, nrm[2] = {0.0, 0.0};
+    fit_line(mo, nullptr, a < c ? nrm : nullptr, &err, &mse);
     S.seg_err[a][c] = (mse > max_mse) ? kDblMax : err;  // line_fit_filter.cu:964-966,1009,1027,1035
     S.seg_nx[a][c] = nrm[0];
     S.seg_ny[a][c] = nrm[1];

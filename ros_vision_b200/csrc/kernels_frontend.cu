@@ -847,6 +847,8 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   constexpr int kBpTH = TH, kBpThreads = TH * 16;
   constexpr int kBpMaxPts = kBpTW * kBpTH * 4;
   constexpr uint32_t kBpLH = TH * 64;    // local blob-pair table (power of two, <= 1024: 10-bit entry index in s_loc)
+  constexpr int kBpLHBits = TH == 16 ? 10 : 9;
+  static_assert((1u << kBpLHBits) == kBpLH, "table size");
   static_assert(kBpLH <= 1024 && (kBpLH & (kBpLH - 1)) == 0, "local table size");
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
   __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
@@ -1000,7 +1002,8 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
     const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
     const uint32_t ra = min(r0, r1), rb = max(r0, r1);
     const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
-    uint32_t h = hash_pair(ra, rb) & (kBpLH - 1);
+    // (the CTA-local table only has to spread the few dozen pairs of one tile: two multiplies, top bits)
+    uint32_t h = ((ra * 0x9E3779B1u) ^ (rb * 0x85EBCA77u)) >> (32 - kBpLHBits);
     uint32_t loc = kBpDirect;  // crowded local table (adversarial input): handled in (4)
     const uint32_t max_probe = (p.test_flags & B200TAG_TEST_DIRECT_HASH) ? 0u : kBpMaxProbe;
     for (uint32_t probe = 0; probe < max_probe; probe++) {

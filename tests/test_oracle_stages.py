@@ -193,3 +193,19 @@ def test_gaussian_blur_against_opencv(oracle):
         # border rule of convolve(): the first and last ksz/2 pixels of a line are copied, not filtered
         rr = ksz // 2
         assert np.array_equal(r.quad_im[:rr, :rr], sc.gray[:rr, :rr]) and np.array_equal(r.quad_im[-rr:, -rr:], sc.gray[-rr:, -rr:])
+
+
+def test_point_weight_root_equals_hypotf(oracle):
+    """The fit kernels compute the point weight (int)(hypotf(gx, gy) + 1) (apriltag_gpu.cu:644-657) as
+    (int)(sqrt_rn((float)(gx^2 + gy^2)) + 1): equal for every pair of pixel differences, against the bit-exact emulation
+    of CUDA's hypotf and against the integer square root."""
+    import ctypes as C
+    import math
+    L = oracle.lib()
+    for gx in range(0, 256):          # hypotf is even in both arguments
+        for gy in range(gx, 256):     # and symmetric
+            h = L.orc_emul_hypotf(C.c_float(gx), C.c_float(gy))
+            s = gx * gx + gy * gy
+            w_ref = int(np.float32(h) + np.float32(1))
+            w_new = int(np.float32(np.sqrt(np.float32(s))) + np.float32(1))
+            assert w_ref == w_new == math.isqrt(s) + 1, (gx, gy)
