@@ -281,8 +281,8 @@ def test_largest_coordinates(D, oracle):
 
 
 def test_random_scenes(D, oracle):
-    """Forty random frames -- sizes, formats, decimation, noise level, tag count and size all drawn at random --
-    every stage against the oracle.  Rare paths (equal angles, crowded buckets, blobs on tile corners) get their
+    """Forty random frames -- sizes, formats, decimation, blur, tag family, noise level, tag count and size all drawn
+    at random -- every stage against the oracle.  Rare paths (equal angles, crowded buckets, blobs on tile corners) get their
     chance here."""
     from ros_vision_b200 import synth
     import os
@@ -301,12 +301,14 @@ def test_random_scenes(D, oracle):
                 continue
         ntags = int(rng.integers(0, 5))
         smax = max(24.0, min(w, h) / 2.5)
+        sigma = float(rng.choice([0.0, 0.0, 0.0, 0.8, 1.4, 2.2, -0.9]))
+        fam = str(rng.choice(["tag36h11", "tag36h11", "tag25h9", "tag16h5"]))
         sc = synth.make_scene(w, h, 7000 + k + (seed % 100000) * 1000 * (seed != 20261018), ntags, side_range=(min(20.0 * dec, smax), smax),
                               noise_sigma=float(rng.uniform(0.0, 8.0)), clutter=bool(rng.integers(0, 2)),
-                              salt_pepper=float(rng.choice([0.0, 0.0, 0.01])))
+                              salt_pepper=float(rng.choice([0.0, 0.0, 0.01])), family=fam)
         frame = _pack(sc.gray, fmt, np.random.default_rng(k))
-        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, 0.0), frame)
-        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, keep_stages=True)
+        orc = oracle.detect(oracle.make_config(w, h, fmt, dec, sigma, families=[fam]), frame)
+        det = D.GpuDetector(w, h, fmt, quad_decimate=dec, quad_sigma=sigma, keep_stages=True, families=[fam])
         det.Detect(frame)
         compare_all(det, orc, 0, fmt)
         det.close()
