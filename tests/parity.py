@@ -124,9 +124,15 @@ def compare_quads(det: D.GpuDetector, orc, blobs, frame=0):
 
 
 # decision_margin: the mean of bilinear samples minus the gray-model threshold.  The sample positions move with the
-# refined corners (observed difference between device and host single-precision trigonometry: 6.1e-5 px), the image
-# gradient is at most 255 grey levels per pixel: 255 * 2e-4 px (three times the observed corner difference).
-MARGIN_TOL = 255 * 2e-4
+# refined corners (typical difference between device and host single-precision trigonometry: 6.1e-5 px; more on tiny or
+# ill-conditioned quads, always below CORNER_TOL_PX), the image gradient is at most 255 grey levels per pixel: the
+# tolerance is 255 levels/px times three times the corner difference actually observed on that detection, with a floor
+# of 2e-4 px.
+MARGIN_FLOOR_PX = 2e-4
+
+
+def margin_tolerance(corner_diff_px):
+    return 255.0 * np.maximum(MARGIN_FLOOR_PX, 3.0 * np.asarray(corner_diff_px))
 
 
 def _project(H, x, y):
@@ -212,7 +218,9 @@ def compare_detections(det: D.GpuDetector, orc, frame=0):
         assert np.abs(got["c"] - ref["c"]).max() <= CORNER_TOL_PX, "centres"
         for g, r in zip(got, ref):
             compare_homography(g["H"], r["H"])
-        assert np.abs(got["decision_margin"] - ref["decision_margin"]).max() <= MARGIN_TOL, "decision margin"
+        dp = np.abs(got["p"] - ref["p"]).reshape(len(ref), -1).max(axis=1)
+        dm = np.abs(got["decision_margin"].astype(np.float64) - ref["decision_margin"].astype(np.float64))
+        assert (dm <= margin_tolerance(dp)).all(), f"decision margin: diff {dm.tolist()} at corner diff {dp.tolist()}"
     check_detection_geometry(got)
     check_detection_geometry(ref)
     return got
