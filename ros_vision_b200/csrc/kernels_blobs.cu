@@ -1260,6 +1260,13 @@ constexpr int kHugeThreads = 512;
 constexpr uint32_t kHugeCap = 8192;
 using HugeShared = CtaShared<kHugeThreads, kHugeCap, 0>;
 #define K_FIT_HUGE(KEEP) k_fit_cta<kHugeThreads, kHugeCap, 0, kSortCap + 1, 0xffffffffu, 1, KEEP>
+// large tier for one or a few frames at a time (the node's case: one Detect per camera frame): the same blobs on 512
+// threads.  A frame has a few dozen of them, far fewer than SMs, so the time of the blob stage is the time of ONE blob;
+// twice the threads nearly halve it (single frame: 111 -> 6x us), while in batches, where CTAs outnumber SMs many times,
+// the 256-thread kernel above is the better one.
+using Large512Shared = CtaShared<kHugeThreads, kSortCap, 0>;
+#define K_FIT_LARGE512(KEEP) k_fit_cta<kHugeThreads, kSortCap, 0, kMediumCap + 1, kSortCap, 1, KEEP>
+constexpr int kLowLatencyFrames = 4;  // batches up to this size take the 512-thread large tier
 
 void launch_blobs_init(cudaStream_t s) {
   static bool dev_ready[64] = {false};
@@ -1276,6 +1283,8 @@ void launch_blobs_init(cudaStream_t s) {
     cudaFuncSetAttribute(K_FIT_LARGE(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LargeShared)));
     cudaFuncSetAttribute(K_FIT_HUGE(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HugeShared)));
     cudaFuncSetAttribute(K_FIT_HUGE(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HugeShared)));
+    cudaFuncSetAttribute(K_FIT_LARGE512(false), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Large512Shared)));
+    cudaFuncSetAttribute(K_FIT_LARGE512(true), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Large512Shared)));
     k_init_combos<<<1, 1, 0, s>>>();
     dev_ready[dev] = true;
   }
@@ -1313,7 +1322,11 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
-  {
+  if (frames <= kLowLatencyFrames) {
+    const dim3 g(max(1u, min(148u, cdivu(592u, frames))), frames);
+    if (p.keep_stages) K_FIT_LARGE512(true)<<<g, kHugeThreads, sizeof(Large512Shared), s_large>>>(p, 1);
+    else K_FIT_LARGE512(false)<<<g, kHugeThreads, sizeof(Large512Shared), s_large>>>(p, 1);
+  } else {
     const dim3 g(max(3u, min(444u, cdivu(1776u, frames))), frames);
     if (p.keep_stages) K_FIT_LARGE(true)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);
     else K_FIT_LARGE(false)<<<g, kLargeThreads, sizeof(LargeShared), s_large>>>(p, 1);

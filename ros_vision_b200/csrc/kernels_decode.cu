@@ -357,10 +357,23 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
     }
 }
 
-__global__ void __launch_bounds__(32) k_decode(FrameParams p) {
+// WARPS warps per candidate quad.  One warp (batches: quads outnumber the warps an SM can hold, so per-quad latency is
+// hidden) or four (one or a few frames at a time: a frame has about a hundred quads for 148 SMs, so the time of this
+// kernel is the time of ONE quad): the refinement samples -- the bulk of the work, independent of each other -- are
+// spread over all threads; the ordered sums, the homography and the decode proper stay on the first warp, exactly as
+// in the one-warp kernel, so the results are the same bit for bit.
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_decode(FrameParams p) {
   __shared__ DecodeShared S;
+  constexpr int NT = 32 * WARPS;
+  auto csync = [] {
+    if constexpr (WARPS == 1) __syncwarp();
+    else __syncthreads();
+  };
   const int frame = blockIdx.y;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid;  // (the first warp's lane index wherever "lane < k" picks workers below)
+  const bool first_warp = tid < 32;
   Counters *ctr = p.counters + frame;
   const uint8_t *im = p.gray + frame * p.gray_stride;
   const b200tag_quad *quads = p.quads + static_cast<size_t>(frame) * p.quad_cap;
@@ -368,15 +381,17 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
   const uint32_t nquads = min(ctr->num_quads, p.quad_cap);
   const int W = p.W, H = p.H;
   uint32_t nxt = 0;
-  if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);
+  if (tid == 0) nxt = atomicAdd(&ctr->next_quad, 1u);
   while (true) {
-    __syncwarp();
-    const uint32_t qi = __shfl_sync(0xffffffffu, nxt, 0);
+    csync();
+    if (tid == 0) S.cur = nxt;
+    csync();
+    const uint32_t qi = S.cur;
     if (qi >= nquads) break;
-    if (lane == 0) nxt = atomicAdd(&ctr->next_quad, 1u);  // the next item's round trip overlaps this quad
+    if (tid == 0) nxt = atomicAdd(&ctr->next_quad, 1u);  // the next item's round trip overlaps this quad
     const b200tag_quad quad = quads[qi];
-    if (lane < 8) S.p[lane >> 1][lane & 1] = quad.corners[lane >> 1][lane & 1];
-    __syncwarp();
+    if (tid < 8) S.p[tid >> 1][tid & 1] = quad.corners[tid >> 1][tid & 1];
+    csync();
 
     if (p.refine_edges) {  // RefineEdges, apriltag_detect.cu:405-564
       // The four edges only read the unrefined corners, so they are refined side by side: lanes 0..3 own one edge
@@ -396,7 +411,7 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
         S.e_ny[lane] = ny;
         S.e_ns[lane] = nsamples;
       }
-      __syncwarp();
+      csync();
       const int ns0 = S.e_ns[0], ns1 = S.e_ns[1], ns2 = S.e_ns[2], ns3 = S.e_ns[3];
       const int off1 = ns0, off2 = ns0 + ns1, off3 = ns0 + ns1 + ns2, total = off3 + ns3;
       double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;  // lanes 0..3: sums of their edge
@@ -404,7 +419,7 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
       const int my_hi = lane == 0 ? off1 : (lane == 1 ? off2 : (lane == 2 ? off3 : total));
       for (int base = 0; base < total; base += kSampleChunk) {
         const int lim = min(kSampleChunk, total - base);
-        for (int j = lane; j < lim; j += 32) {
+        for (int j = tid; j < lim; j += NT) {
           const int g = base + j;
           const int edge = (g >= off1) + (g >= off2) + (g >= off3);
           const int s = g - (edge == 0 ? 0 : (edge == 1 ? off1 : (edge == 2 ? off2 : off3)));
@@ -459,7 +474,7 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
           S.sy[j] = besty;
           S.sv[j] = valid;
         }
-        __syncwarp();
+        csync();
         if (lane < 4) {  // this chunk's samples of my edge, in sample order
           const int lo = max(base, my_lo) - base, hi = min(base + lim, my_hi) - base;
           for (int j = lo; j < hi; j++) {
@@ -468,7 +483,7 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
             Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N++;
           }
         }
-        __syncwarp();
+        csync();
       }
       if (lane < 4) {
         const double Ex = Mx / N, Ey = My / N;
@@ -502,38 +517,43 @@ __global__ void __launch_bounds__(32) k_decode(FrameParams p) {
       __syncwarp();
     }
 
-    // quad_update_homographies
-    {
-      int ok = homography_compute_warp(S.A, S.p, S.H, lane) == 0;
-      if (ok) {
-        const double *Hm = S.H;
-        const double det = Hm[0] * (Hm[4] * Hm[8] - Hm[5] * Hm[7]) - Hm[1] * (Hm[3] * Hm[8] - Hm[5] * Hm[6]) +
-                           Hm[2] * (Hm[3] * Hm[7] - Hm[4] * Hm[6]);
-        if (!(fabs(det) > 1e-300)) ok = 0;
+    // the rest -- homography, gray model, bit samples, code scan, detection record -- is the first warp's
+    if (first_warp) {
+      // quad_update_homographies
+      {
+        int ok = homography_compute_warp(S.A, S.p, S.H, lane) == 0;
+        if (ok) {
+          const double *Hm = S.H;
+          const double det = Hm[0] * (Hm[4] * Hm[8] - Hm[5] * Hm[7]) - Hm[1] * (Hm[3] * Hm[8] - Hm[5] * Hm[6]) +
+                             Hm[2] * (Hm[3] * Hm[7] - Hm[4] * Hm[6]);
+          if (!(fabs(det) > 1e-300)) ok = 0;
+        }
+        __syncwarp();
+        if (lane == 0) S.ok = ok;
       }
       __syncwarp();
-      if (lane == 0) S.ok = ok;
+      if (S.ok) {
+        // quad_decode_task: every family of the quad's border polarity gets its own decode of the same homography
+        for (int fi = 0; fi < p.nfamilies; fi++) {
+          const DevFamily &fam = p.families[fi];
+          if ((fam.reversed_border != 0) != (quad.reversed_border != 0)) continue;
+          if (fam.width_at_border == 8 && fam.total_width == 10 && fam.nbits == 36)
+            decode_family<8, 10, 36>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
+          else
+            decode_family<0, 0, 0>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
+        }
+      }
     }
-    __syncwarp();
-    if (!S.ok) continue;
-
-    // quad_decode_task: every family of the quad's border polarity gets its own decode of the same homography
-    for (int fi = 0; fi < p.nfamilies; fi++) {
-      const DevFamily &fam = p.families[fi];
-      if ((fam.reversed_border != 0) != (quad.reversed_border != 0)) continue;
-      if (fam.width_at_border == 8 && fam.total_width == 10 && fam.nbits == 36)
-        decode_family<8, 10, 36>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
-      else
-        decode_family<0, 0, 0>(p, S, fam, fi, im, W, H, ctr, dets, frame, lane);
-    }  // families
   }
 }
 
 int launch_decode(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt) {
   if (kt) kt->begin("decode", s);
-  // one warp per CTA; about 2400 CTAs in total (a frame has ~100 candidate quads), all 148 SMs for a single frame
+  // batches: one warp per CTA, about 2400 CTAs in total (a frame has ~100 candidate quads); up to four frames: four
+  // warps per quad, all 148 SMs
   const unsigned per_frame = static_cast<unsigned>(frames) >= 16 ? (2368u + frames - 1) / frames : 148u;
-  k_decode<<<dim3(per_frame < 8u ? 8u : per_frame, frames), 32, 0, s>>>(p);
+  if (frames <= 4) k_decode<4><<<dim3(148u, frames), 128, 0, s>>>(p);
+  else k_decode<1><<<dim3(per_frame < 8u ? 8u : per_frame, frames), 32, 0, s>>>(p);
   if (kt) kt->end(s);
   return 1;
 }
