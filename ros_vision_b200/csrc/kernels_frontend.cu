@@ -611,10 +611,26 @@ __device__ __forceinline__ uint32_t gfind(const uint32_t *par, uint32_t a) {
   return a;
 }
 
+// The same with path halving: every other node on the way is re-pointed at its grandparent.  The plain stores are
+// safe next to concurrent atomicMin links for the reason given at sfind.  Worth it only when the chains are walked
+// on the critical path of a single frame (a component that spans many tiles is a chain of tile roots): in batches the
+// extra stores cost more than the shorter chains save (measured in round 1).
+__device__ __forceinline__ uint32_t gfind_halving(uint32_t *par, uint32_t a) {
+  uint32_t q = __ldcg(par + (a & kLabelMask));
+  while (q != a) {
+    const uint32_t qq = __ldcg(par + (q & kLabelMask));
+    if (qq != q) par[a & kLabelMask] = qq;
+    a = q;
+    q = qq;
+  }
+  return a;
+}
+
+template <bool HALVING>
 __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
   while (true) {
-    a = gfind(par, a);
-    b = gfind(par, b);
+    a = HALVING ? gfind_halving(par, a) : gfind(par, a);
+    b = HALVING ? gfind_halving(par, b) : gfind(par, b);
     if (a == b) return;
     if (a < b) {
       const uint32_t t = a;
@@ -633,6 +649,7 @@ __device__ __forceinline__ void gunite(uint32_t *par, uint32_t a, uint32_t b) {
 // tile-local trees (equal raw labels on both sides -- on thresholded noise the same giant component shows up at
 // every other border pixel) are deduplicated with __match_any_sync, so only one lane walks the parent chains.
 constexpr int kCclMergeThreads = ((kCclTW + 2 * kCclTH + 31) / 32) * 32;
+template <bool HALVING>
 __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * kCclTW, y0 = blockIdx.y * kCclTH;
@@ -684,7 +701,7 @@ __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
     if (!has) continue;
     const unsigned long long key = (static_cast<unsigned long long>(min(mine, theirs[k])) << 32) | max(mine, theirs[k]);
     const uint32_t group = __match_any_sync(active, key);
-    if (lane == __ffs(group) - 1 && mine != theirs[k]) gunite(labels, mine, theirs[k]);
+    if (lane == __ffs(group) - 1 && mine != theirs[k]) gunite<HALVING>(labels, mine, theirs[k]);
   }
 }
 
@@ -1132,7 +1149,8 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_merge", s);
-  k_ccl_merge<<<cgrid, kCclMergeThreads, 0, s>>>(p);
+  if (frames <= 4) k_ccl_merge<true><<<cgrid, kCclMergeThreads, 0, s>>>(p);   // single-frame latency: see gfind_halving
+  else k_ccl_merge<false><<<cgrid, kCclMergeThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_handoff", s);
   k_ccl_handoff<<<dim3(cdiv(cgrid.x * cgrid.y, 8), frames), 256, 0, s>>>(p, cgrid.x * cgrid.y);
