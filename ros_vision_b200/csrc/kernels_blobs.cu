@@ -1264,8 +1264,10 @@ using HugeShared = CtaShared<kHugeThreads, kHugeCap, 0>;
 // threads.  A frame has a few dozen of them, far fewer than SMs, so the time of the blob stage is the time of ONE blob;
 // twice the threads nearly halve it (single frame: 111 -> 6x us), while in batches, where CTAs outnumber SMs many times,
 // the 256-thread kernel above is the better one.
-using Large512Shared = CtaShared<kHugeThreads, kSortCap, 0>;
-#define K_FIT_LARGE512(KEEP) k_fit_cta<kHugeThreads, kSortCap, 0, kMediumCap + 1, kSortCap, 1, KEEP>
+// With one CTA per SM there is room for the prefix moments in shared memory too (36 B x 4096 points = 147 KB of 216 KB).
+using Large512Shared = CtaShared<kHugeThreads, kSortCap, kSortCap>;
+#define K_FIT_LARGE512(KEEP) k_fit_cta<kHugeThreads, kSortCap, kSortCap, kMediumCap + 1, kSortCap, 1, KEEP>
+static_assert(sizeof(Large512Shared) <= 227 * 1024, "shared memory of the low-latency large tier");
 constexpr int kLowLatencyFrames = 4;  // batches up to this size take the 512-thread large tier
 
 void launch_blobs_init(cudaStream_t s) {
