@@ -344,6 +344,36 @@ def test_production_variant_matches_oracle(D, oracle):
         det.close()
 
 
+def test_detector_driven_from_other_threads(D, oracle):
+    """A detector created on one thread and driven from others (a ROS executor does that): every entry point selects
+    the detector's own device and restores the caller's (csrc/detector.cu DeviceGuard)."""
+    import threading
+    from ros_vision_b200 import synth
+    sc = synth.make_scene(640, 480, 77, 3, side_range=(60, 130), noise_sigma=3.0)
+    want = [int(d["id"]) for d in oracle.detect(oracle.make_config(640, 480, "gray", 2, 0.0), sc.gray).detections]
+    det = D.GpuDetector(640, 480, "gray", device=0)
+    got, errs = {}, []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                with lock:
+                    det.Detect(sc.gray)
+                    got[k] = [int(i) for i in det.Detections()["id"]]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    lock = threading.Lock()   # a detector is not re-entrant (same contract as the reference): one call at a time
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert all(v == want for v in got.values()) and len(got) == 4
+    det.close()
+
+
 def test_invalid_configurations_are_rejected(D):
     with pytest.raises(D.B200TagError):
         D.GpuDetector(642, 480, "gray")  # quad image width not a multiple of 4
