@@ -6,12 +6,19 @@
   python bench.py --impl reference ...                            the CPU implementation of the same path
 
 A "step" is one pass of the hot path over one batch of synthetic frames of BASELINE config 2
-(Arducam-style 1280x800 YUYV stream, tag36h11, quad_decimate=2).
+(Arducam-style 1280x800 YUYV stream, tag36h11, quad_decimate=2) on each of `--device-lanes` detectors.
   value      frames/s with the frames already resident in HBM when the timed region starts
   e2e        frames/s through the public API with HOST (pinned) frame buffers: H2D copies, all kernels
              and the result read-back inside the timed region
-  roofline   dominant kernel: algorithmic bytes per launch / measured launch duration vs measured HBM peak
-  cpu_baseline  the CPU oracle (a port of the reference algorithm) on a bounded sample of the same frames
+  p50/p99    host frame in -> detections out, one frame at a time
+  roofline   the slowest FRONT-END kernel: algorithmic bytes per launch / measured launch duration vs the measured HBM
+             peak; the front end as a whole (per-kernel bytes and compulsory bytes); per kernel the CUDA-event time and,
+             from the committed ncu table (profiles/traffic.json), DRAM bytes and issue-slot utilisation
+  step_stats min / median / max of the step time
+  cpu_baseline  the classic CPU detector (libapriltag's apriltag_detector_detect restated in oracle/classic_detector.c,
+             kind "port") on a bounded sample of the same frames: one thread and all threads, CPU model printed
+  e2e_mjpg   the same scenes as JPEG bitstreams in host memory (the camera wire format), at every N
+  extra      BASELINE configs 4 (one 1600x1200 stream per GPU) and 5 (4K clutter scene, batch 16 per GPU), at every N
 Multi-GPU (torchrun): frames shard by rank, no collective on the data path (SURVEY.md section 8e);
 time = max over ranks, value = total frames / that time.
 """
