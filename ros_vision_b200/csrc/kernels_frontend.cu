@@ -389,11 +389,6 @@ __device__ __forceinline__ uint32_t sunite(uint32_t *par, uint32_t a, uint32_t b
   }
 }
 
-// bits [lo, lo + len) of a 32-bit word, 1 <= len <= 32
-__device__ __forceinline__ uint32_t bit_span(int lo, int len) {
-  return (len >= 32 ? ~0u : ((1u << len) - 1u)) << lo;
-}
-
 constexpr uint32_t kLabelMask = 0x0fffffffu;   // [27:0] label
 constexpr uint32_t kLabelBig = 1u << 28;       // component has >= kMinBlobPixels pixels (set by k_ccl_final)
 constexpr int kColourShift = 29;               // [30:29] 0 black, 1 white, 2 gray
@@ -517,27 +512,25 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   }
   __syncthreads();
 
-  // (B) unions with the row above: thread = (row, colour)
+  // (B) unions with the row above: thread = (row, colour).  Runs come off the mask by carry propagation: adding the
+  //     lowest set bit to a mask ripples through the run that starts there, so `m & ~(m + low)` IS that run.
   const int row = tid >> 1, colour = tid & 1;
   const uint32_t mine = s_mask[colour][row];
   if (row > 0) {
     const uint32_t up = s_mask[colour][row - 1];
     uint32_t m = mine;
     while (m) {
-      const int s = __ffs(static_cast<int>(m)) - 1;
-      const uint32_t inv = ~(m >> s);
-      const int len = inv ? __ffs(static_cast<int>(inv)) - 1 : 32 - s;
-      const uint32_t run = bit_span(s, len);
-      m &= ~run;
+      const uint32_t low = m & (0u - m), rest = m + low;
+      const uint32_t run = m & ~rest;
+      m &= rest;
+      const int s = 31 - __clz(static_cast<int>(low));
       uint32_t ov = up & (colour ? (run | (run << 1) | (run >> 1)) : run);
       uint32_t node = row * kCclTW + s;  // replaced by its current root after every union: later finds start there
       while (ov) {
-        const int bpos = __ffs(static_cast<int>(ov)) - 1;
-        const uint32_t below = ~up & ((1u << bpos) - 1u);
+        const uint32_t b = ov & (0u - ov);          // lowest overlapping column
+        ov &= ~(up & ~(up + b));                     // ... and the rest of that upper run (from b upwards) is done
+        const uint32_t below = ~up & (b - 1u);       // the upper run starts after the last zero below b
         const int us = below ? 32 - __clz(static_cast<int>(below)) : 0;
-        const uint32_t above = ~up >> bpos;
-        const int ulen = above ? __ffs(static_cast<int>(above)) - 1 : 32 - bpos;
-        ov &= ~bit_span(bpos, ulen);
         node = sunite(s_par, node, (row - 1) * kCclTW + us);
       }
     }
@@ -549,15 +542,16 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
     uint32_t m = mine;
     const bool edge_row = row == 0 || row == kCclTH - 1;
     while (m) {
-      const int s = __ffs(static_cast<int>(m)) - 1;
-      const uint32_t inv = ~(m >> s);
-      const int len = inv ? __ffs(static_cast<int>(inv)) - 1 : 32 - s;
-      m &= ~bit_span(s, len);
+      const uint32_t low = m & (0u - m), rest = m + low;
+      const uint32_t run = m & ~rest;
+      m &= rest;
+      const int s = 31 - __clz(static_cast<int>(low));
+      const uint32_t len = static_cast<uint32_t>(__popc(run));
       const uint32_t node = row * kCclTW + s;
       const uint32_t root = sfind(s_par, node);
       if (root != node) s_par[node] = root;
-      const uint32_t touches = (edge_row || s == 0 || s + len == kCclTW) ? 0x10000u : 0u;
-      atomicAdd(&s_cnt[root], static_cast<uint32_t>(len) | touches);
+      const uint32_t touches = (edge_row || ((run & 0x80000001u) != 0)) ? 0x10000u : 0u;
+      atomicAdd(&s_cnt[root], len | touches);
     }
   }
   __syncthreads();
