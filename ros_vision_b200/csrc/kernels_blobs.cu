@@ -312,7 +312,8 @@ struct Mom {
 
 // Prefix moments live either in global memory as b200tag_lfp records (large tiers) or, for blobs of at most
 // 768 points, in shared memory as six separate arrays: Mxx/Myy/Mxy 64 bit, Mx/My/W 32 bit unsigned
-// (W <= 768 * 361 and Mx, My <= W * 8192 < 2^32), 36 bytes per point instead of 48 and conflict-free.
+// (W <= 768 * 361 and Mx, My <= W * 8192 < 2^32; the 4096-point low-latency tier is launched only where the same
+// bound holds, see launch_blobs), 36 bytes per point instead of 48 and conflict-free.
 struct LfStore {
   b200tag_lfp *aos;            // global records, or nullptr
   unsigned long long *m64;     // shared: [3][cap]
@@ -431,11 +432,12 @@ __device__ __forceinline__ uint32_t float_order(float f) {  // monotone float ->
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr double kDblMax = 1.7976931348623157e308;
 
-// Per-blob scratch of the fit kernels (always in shared memory).
+// Per-blob scratch of the fit kernels (always in shared memory); WARPS = warps working on the blob.
+template <int WARPS>
 struct BlobScratch {
   uint32_t peak_idx[kMaxPeaks];
-  uint32_t red_u[16][4];  // per-warp partial extents (CTA tiers, up to 512 threads)
-  int red_i[16][3];
+  uint32_t red_u[WARPS > 1 ? WARPS : 1][4];  // per-warp partial extents (CTA tiers only)
+  int red_i[WARPS > 1 ? WARPS : 1][3];
   uint32_t npeaks;   // all strict local maxima
   uint32_t nsel;     // min(10, npeaks)
   uint32_t cur;      // work-list position being processed
@@ -520,7 +522,7 @@ constexpr uint32_t kMaxBucketLoad = 24;  // fuller buckets (thin, elongated blob
 // kernels carry no debug code in their instruction stream.
 template <int GS, bool AOS, bool KEEP>
 __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Counters *ctr, uint32_t b, uint32_t cnt, uint32_t off,
-                                             b200tag_blob *blob_rec, const BlobWork &wk, BlobScratch &S, long long *scan, uint32_t gt) {
+                                             b200tag_blob *blob_rec, const BlobWork &wk, BlobScratch<GS / 32> &S, long long *scan, uint32_t gt) {
   const size_t n = static_cast<size_t>(p.w) * p.h;
   const uint8_t *quad = p.quad + frame * n;
   const size_t pbase = static_cast<size_t>(frame) * p.point_cap + off;
@@ -583,8 +585,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     //     spread around the whole circle, so a bucket sort does it in O(cnt): B >= cnt buckets over the
     //     theta range (monotone map), in-bucket rank from the counting atomicAdd, exclusive scan, scatter,
     //     then each thread insertion-sorts the few elements of its own buckets on the full 64-bit key.
-    uint32_t N = 1;
-    while (N < cnt) N <<= 1;
+    const uint32_t N = 1u << (32 - __clz(static_cast<int>(cnt - 1)));  // next power of two (cnt >= 24)
     const uint32_t B = min(N, wk.hist_cap);
     // bucket = theta >> bk_shift: theta < 2 * pi * 8e6 + 1 < 2^26, so the B power-of-two buckets cover [0, 2^26) and
     // three quarters of them are in use (average load <= 4/3); a shift instead of a 64-bit multiply and divide
@@ -710,96 +711,168 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     for (uint32_t i = gt; i < cnt; i += GS) out[i] = wk.keys[i];
   }
 
-  // (2) weights (independent gathers, strided) then inclusive prefix moments over contiguous chunks,
-  //     C7 (apriltag_gpu.cu:631-687,984-987).  Weights are parked in the still unused error buffer.
+  // (2) weights and inclusive prefix moments, C7 (apriltag_gpu.cu:631-687,984-987).  Every thread owns a contiguous
+  //     chunk of L points (L odd: consecutive threads then hit distinct shared-memory banks): a first pass gathers
+  //     the weights and sums the chunk, one scan over the THREADS' totals (a warp scan per warp, the warps' totals
+  //     through shared memory) gives each thread its carry-in, a second pass writes the running sums.  Integer sums:
+  //     any order gives the reference's values.  (Scanning every 32 points across the warp, as the global-memory
+  //     variant below does for the sake of coalesced stores, costs 45 shuffles per 32 points instead of 45 per warp.)
+  //     Products: W <= 361, coordinates <= 8192, so W*x fits 32 bits and W*x*x is one 32x32->64 multiply.
   int *wbuf = reinterpret_cast<int *>(wk.errs);
-#pragma unroll 2
-  for (uint32_t i = gt; i < cnt; i += GS) {
-    const unsigned long long k = wk.keys[i];
-    const uint32_t d = key_dir(k);
-    const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
-    wbuf[i] = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
-  }
-  gsync<GS>();
-  // Inclusive prefix sums by warp scans over 32 consecutive points per step (consecutive lanes touch
-  // consecutive shared-memory words: no bank conflicts).  Each warp owns a contiguous range of the blob;
-  // in the CTA tiers a first sweep computes the warps' totals, their exclusive scan gives each warp its
-  // carry-in.  Products: W <= 361, coordinates <= 8192, so W*x fits 32 bits and W*x*x one 32x32->64 multiply.
-  {
-    constexpr int kWarps = GS / 32;
-    const int wi = static_cast<int>(gt >> 5);
-    const uint32_t per_warp = ((cnt + kWarps - 1) / kWarps + 31u) & ~31u;
-    const uint32_t w_lo = min(cnt, wi * per_warp), w_hi = min(cnt, w_lo + per_warp);
-    unsigned long long c_Mxx = 0, c_Myy = 0, c_Mxy = 0, c_Mx = 0, c_My = 0, c_W = 0;  // carry-in of this warp
-    if constexpr (GS > 32) {
+  if constexpr (!AOS) {
+    {
+      const int wi = static_cast<int>(gt >> 5);
+      const uint32_t L = ((cnt + GS - 1) / GS) | 1u;
+      const uint32_t c_lo = min(cnt, gt * L), c_hi = min(cnt, c_lo + L);
       unsigned long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0;
-      uint32_t t_Mx = 0, t_My = 0, t_W = 0;  // per lane: at most per_warp / 32 <= 128 points of < 2^22 each
-      for (uint32_t i = w_lo + lane; i < w_hi; i += 32) {
+      uint32_t t_Mx = 0, t_My = 0, t_W = 0;  // per chunk: L <= 65 points of < 2^22 each
+  #pragma unroll 2
+      for (uint32_t i = c_lo; i < c_hi; i++) {
         const unsigned long long k = wk.keys[i];
         const uint32_t d = key_dir(k);
         const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
-        const uint32_t W = static_cast<uint32_t>(wbuf[i]);
+        const uint32_t W = static_cast<uint32_t>(point_weight(quad, p.w, p.h, static_cast<int>(ix2 / 2), static_cast<int>(iy2 / 2)));
+        wbuf[i] = static_cast<int>(W);
         const uint32_t wx = W * ix2, wy = W * iy2;
         t_Mx += wx; t_My += wy; t_W += W;
         t_Mxx += static_cast<unsigned long long>(wx) * ix2;
         t_Mxy += static_cast<unsigned long long>(wx) * iy2;
         t_Myy += static_cast<unsigned long long>(wy) * iy2;
       }
-      unsigned long long r_Mx = t_Mx, r_My = t_My, r_W = t_W;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        t_Mxx += __shfl_xor_sync(0xffffffffu, t_Mxx, o);
-        t_Myy += __shfl_xor_sync(0xffffffffu, t_Myy, o);
-        t_Mxy += __shfl_xor_sync(0xffffffffu, t_Mxy, o);
-        r_Mx += __shfl_xor_sync(0xffffffffu, r_Mx, o);
-        r_My += __shfl_xor_sync(0xffffffffu, r_My, o);
-        r_W += __shfl_xor_sync(0xffffffffu, r_W, o);
+      // inclusive scan of the threads' totals across the warp (64 bit: a blob's Mx, My reach 2^32 above ~1400 points)
+      unsigned long long s_Mxx = t_Mxx, s_Myy = t_Myy, s_Mxy = t_Mxy, s_Mx = t_Mx, s_My = t_My, s_W = t_W;
+  #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u_Mxx = __shfl_up_sync(0xffffffffu, s_Mxx, o), u_Myy = __shfl_up_sync(0xffffffffu, s_Myy, o);
+        const unsigned long long u_Mxy = __shfl_up_sync(0xffffffffu, s_Mxy, o);
+        // (32-bit shuffles: Mx, My, W of a blob in shared memory stay below 2^32 -- they are stored as 32-bit words)
+        const uint32_t u_Mx = __shfl_up_sync(0xffffffffu, static_cast<uint32_t>(s_Mx), o), u_My = __shfl_up_sync(0xffffffffu, static_cast<uint32_t>(s_My), o);
+        const uint32_t u_W = __shfl_up_sync(0xffffffffu, static_cast<uint32_t>(s_W), o);
+        if (lane >= o) { s_Mx += u_Mx; s_My += u_My; s_W += u_W; s_Mxx += u_Mxx; s_Myy += u_Myy; s_Mxy += u_Mxy; }
       }
-      unsigned long long *tot = reinterpret_cast<unsigned long long *>(scan);  // [kWarps][6]
-      if (lane == 0) {
-        tot[wi * 6 + 0] = t_Mxx; tot[wi * 6 + 1] = t_Myy; tot[wi * 6 + 2] = t_Mxy;
-        tot[wi * 6 + 3] = r_Mx;  tot[wi * 6 + 4] = r_My;  tot[wi * 6 + 5] = r_W;
+      unsigned long long c_Mxx = s_Mxx - t_Mxx, c_Myy = s_Myy - t_Myy, c_Mxy = s_Mxy - t_Mxy;  // carry-in of this thread
+      unsigned long long c_Mx = s_Mx - t_Mx, c_My = s_My - t_My, c_W = s_W - t_W;
+      if constexpr (GS > 32) {
+        unsigned long long *tot = reinterpret_cast<unsigned long long *>(scan);  // [GS / 32][6]
+        if (lane == 31) {
+          tot[wi * 6 + 0] = s_Mxx; tot[wi * 6 + 1] = s_Myy; tot[wi * 6 + 2] = s_Mxy;
+          tot[wi * 6 + 3] = s_Mx;  tot[wi * 6 + 4] = s_My;  tot[wi * 6 + 5] = s_W;
+        }
+        __syncthreads();
+        for (int w = 0; w < wi; w++) {
+          c_Mxx += tot[w * 6 + 0]; c_Myy += tot[w * 6 + 1]; c_Mxy += tot[w * 6 + 2];
+          c_Mx += tot[w * 6 + 3];  c_My += tot[w * 6 + 4];  c_W += tot[w * 6 + 5];
+        }
       }
-      __syncthreads();
-      for (int w = 0; w < wi; w++) {
-        c_Mxx += tot[w * 6 + 0]; c_Myy += tot[w * 6 + 1]; c_Mxy += tot[w * 6 + 2];
-        c_Mx += tot[w * 6 + 3];  c_My += tot[w * 6 + 4];  c_W += tot[w * 6 + 5];
-      }
-    }
-#pragma unroll 1
-    for (uint32_t base = w_lo; base < w_hi; base += 32) {
-      const uint32_t i = base + lane;
-      uint32_t s_Mx = 0, s_My = 0, s_W = 0;
-      unsigned long long s_Mxx = 0, s_Myy = 0, s_Mxy = 0;
-      if (i < w_hi) {
+  #pragma unroll 2
+      for (uint32_t i = c_lo; i < c_hi; i++) {
         const unsigned long long k = wk.keys[i];
         const uint32_t d = key_dir(k);
         const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
         const uint32_t W = static_cast<uint32_t>(wbuf[i]);
         const uint32_t wx = W * ix2, wy = W * iy2;
-        s_Mx = wx; s_My = wy; s_W = W;
-        s_Mxx = static_cast<unsigned long long>(wx) * ix2;
-        s_Mxy = static_cast<unsigned long long>(wx) * iy2;
-        s_Myy = static_cast<unsigned long long>(wy) * iy2;
-      }
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {  // 32 points of < 2^22 (Mx, My) stay below 2^27: 32-bit scans
-        const uint32_t u_Mx = __shfl_up_sync(0xffffffffu, s_Mx, o), u_My = __shfl_up_sync(0xffffffffu, s_My, o);
-        const uint32_t u_W = __shfl_up_sync(0xffffffffu, s_W, o);
-        const unsigned long long u_Mxx = __shfl_up_sync(0xffffffffu, s_Mxx, o), u_Myy = __shfl_up_sync(0xffffffffu, s_Myy, o);
-        const unsigned long long u_Mxy = __shfl_up_sync(0xffffffffu, s_Mxy, o);
-        if (lane >= o) { s_Mx += u_Mx; s_My += u_My; s_W += u_W; s_Mxx += u_Mxx; s_Myy += u_Myy; s_Mxy += u_Mxy; }
-      }
-      if (i < w_hi) {
+        c_Mx += wx; c_My += wy; c_W += W;
+        c_Mxx += static_cast<unsigned long long>(wx) * ix2;
+        c_Mxy += static_cast<unsigned long long>(wx) * iy2;
+        c_Myy += static_cast<unsigned long long>(wy) * iy2;
         b200tag_lfp o;
-        o.Mxx = static_cast<long long>(c_Mxx + s_Mxx); o.Myy = static_cast<long long>(c_Myy + s_Myy);
-        o.Mxy = static_cast<long long>(c_Mxy + s_Mxy);
-        o.Mx = static_cast<long long>(c_Mx + s_Mx); o.My = static_cast<long long>(c_My + s_My); o.W = static_cast<long long>(c_W + s_W);
+        o.Mxx = static_cast<long long>(c_Mxx); o.Myy = static_cast<long long>(c_Myy); o.Mxy = static_cast<long long>(c_Mxy);
+        o.Mx = static_cast<long long>(c_Mx); o.My = static_cast<long long>(c_My); o.W = static_cast<long long>(c_W);
         lf_store<AOS>(wk.lf, i, o);
       }
-      c_Mxx += __shfl_sync(0xffffffffu, s_Mxx, 31); c_Myy += __shfl_sync(0xffffffffu, s_Myy, 31);
-      c_Mxy += __shfl_sync(0xffffffffu, s_Mxy, 31);
-      c_Mx += __shfl_sync(0xffffffffu, s_Mx, 31); c_My += __shfl_sync(0xffffffffu, s_My, 31); c_W += __shfl_sync(0xffffffffu, s_W, 31);
+    }
+  } else {
+    // Prefix moments in global memory (blobs above the shared-memory capacity): records of 48 bytes, written
+    // coalesced -- consecutive lanes own consecutive points.  Weights first (independent strided gathers), then
+    // each warp scans its contiguous range 32 points at a time; a first sweep gives the warps' totals.
+  #pragma unroll 2
+    for (uint32_t i = gt; i < cnt; i += GS) {
+      const unsigned long long k = wk.keys[i];
+      const uint32_t d = key_dir(k);
+      const int ix2 = static_cast<int>(2 * key_bx(k)) + dir_dx(d) + 1, iy2 = static_cast<int>(2 * key_by(k)) + dir_dy(d) + 1;
+      wbuf[i] = point_weight(quad, p.w, p.h, ix2 / 2, iy2 / 2);
+    }
+    gsync<GS>();
+    // Inclusive prefix sums by warp scans over 32 consecutive points per step (consecutive lanes touch
+    // consecutive shared-memory words: no bank conflicts).  Each warp owns a contiguous range of the blob;
+    // in the CTA tiers a first sweep computes the warps' totals, their exclusive scan gives each warp its
+    // carry-in.  Products: W <= 361, coordinates <= 8192, so W*x fits 32 bits and W*x*x one 32x32->64 multiply.
+    {
+      constexpr int kWarps = GS / 32;
+      const int wi = static_cast<int>(gt >> 5);
+      const uint32_t per_warp = ((cnt + kWarps - 1) / kWarps + 31u) & ~31u;
+      const uint32_t w_lo = min(cnt, wi * per_warp), w_hi = min(cnt, w_lo + per_warp);
+      unsigned long long c_Mxx = 0, c_Myy = 0, c_Mxy = 0, c_Mx = 0, c_My = 0, c_W = 0;  // carry-in of this warp
+      if constexpr (GS > 32) {
+        unsigned long long t_Mxx = 0, t_Myy = 0, t_Mxy = 0;
+        uint32_t t_Mx = 0, t_My = 0, t_W = 0;  // per lane: at most per_warp / 32 <= 128 points of < 2^22 each
+        for (uint32_t i = w_lo + lane; i < w_hi; i += 32) {
+          const unsigned long long k = wk.keys[i];
+          const uint32_t d = key_dir(k);
+          const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
+          const uint32_t W = static_cast<uint32_t>(wbuf[i]);
+          const uint32_t wx = W * ix2, wy = W * iy2;
+          t_Mx += wx; t_My += wy; t_W += W;
+          t_Mxx += static_cast<unsigned long long>(wx) * ix2;
+          t_Mxy += static_cast<unsigned long long>(wx) * iy2;
+          t_Myy += static_cast<unsigned long long>(wy) * iy2;
+        }
+        unsigned long long r_Mx = t_Mx, r_My = t_My, r_W = t_W;
+  #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          t_Mxx += __shfl_xor_sync(0xffffffffu, t_Mxx, o);
+          t_Myy += __shfl_xor_sync(0xffffffffu, t_Myy, o);
+          t_Mxy += __shfl_xor_sync(0xffffffffu, t_Mxy, o);
+          r_Mx += __shfl_xor_sync(0xffffffffu, r_Mx, o);
+          r_My += __shfl_xor_sync(0xffffffffu, r_My, o);
+          r_W += __shfl_xor_sync(0xffffffffu, r_W, o);
+        }
+        unsigned long long *tot = reinterpret_cast<unsigned long long *>(scan);  // [kWarps][6]
+        if (lane == 0) {
+          tot[wi * 6 + 0] = t_Mxx; tot[wi * 6 + 1] = t_Myy; tot[wi * 6 + 2] = t_Mxy;
+          tot[wi * 6 + 3] = r_Mx;  tot[wi * 6 + 4] = r_My;  tot[wi * 6 + 5] = r_W;
+        }
+        __syncthreads();
+        for (int w = 0; w < wi; w++) {
+          c_Mxx += tot[w * 6 + 0]; c_Myy += tot[w * 6 + 1]; c_Mxy += tot[w * 6 + 2];
+          c_Mx += tot[w * 6 + 3];  c_My += tot[w * 6 + 4];  c_W += tot[w * 6 + 5];
+        }
+      }
+  #pragma unroll 1
+      for (uint32_t base = w_lo; base < w_hi; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t s_Mx = 0, s_My = 0, s_W = 0;
+        unsigned long long s_Mxx = 0, s_Myy = 0, s_Mxy = 0;
+        if (i < w_hi) {
+          const unsigned long long k = wk.keys[i];
+          const uint32_t d = key_dir(k);
+          const uint32_t ix2 = 2 * key_bx(k) + dir_dx(d) + 1, iy2 = 2 * key_by(k) + dir_dy(d) + 1;
+          const uint32_t W = static_cast<uint32_t>(wbuf[i]);
+          const uint32_t wx = W * ix2, wy = W * iy2;
+          s_Mx = wx; s_My = wy; s_W = W;
+          s_Mxx = static_cast<unsigned long long>(wx) * ix2;
+          s_Mxy = static_cast<unsigned long long>(wx) * iy2;
+          s_Myy = static_cast<unsigned long long>(wy) * iy2;
+        }
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // 32 points of < 2^22 (Mx, My) stay below 2^27: 32-bit scans
+          const uint32_t u_Mx = __shfl_up_sync(0xffffffffu, s_Mx, o), u_My = __shfl_up_sync(0xffffffffu, s_My, o);
+          const uint32_t u_W = __shfl_up_sync(0xffffffffu, s_W, o);
+          const unsigned long long u_Mxx = __shfl_up_sync(0xffffffffu, s_Mxx, o), u_Myy = __shfl_up_sync(0xffffffffu, s_Myy, o);
+          const unsigned long long u_Mxy = __shfl_up_sync(0xffffffffu, s_Mxy, o);
+          if (lane >= o) { s_Mx += u_Mx; s_My += u_My; s_W += u_W; s_Mxx += u_Mxx; s_Myy += u_Myy; s_Mxy += u_Mxy; }
+        }
+        if (i < w_hi) {
+          b200tag_lfp o;
+          o.Mxx = static_cast<long long>(c_Mxx + s_Mxx); o.Myy = static_cast<long long>(c_Myy + s_Myy);
+          o.Mxy = static_cast<long long>(c_Mxy + s_Mxy);
+          o.Mx = static_cast<long long>(c_Mx + s_Mx); o.My = static_cast<long long>(c_My + s_My); o.W = static_cast<long long>(c_W + s_W);
+          lf_store<AOS>(wk.lf, i, o);
+        }
+        c_Mxx += __shfl_sync(0xffffffffu, s_Mxx, 31); c_Myy += __shfl_sync(0xffffffffu, s_Myy, 31);
+        c_Mxy += __shfl_sync(0xffffffffu, s_Mxy, 31);
+        c_Mx += __shfl_sync(0xffffffffu, s_Mx, 31); c_My += __shfl_sync(0xffffffffu, s_My, 31); c_W += __shfl_sync(0xffffffffu, s_W, 31);
+      }
     }
   }
   gsync<GS>();
@@ -1132,11 +1205,11 @@ struct SmallWarpShared {
   unsigned long long lf64[3 * kSmallBlobPoints];  // prefix moments (LfStore); bucket-sort scratch before that
   uint32_t lf32[3 * kSmallBlobPoints];
   alignas(16) float errs[kSmallBlobPoints];   // weights -> errors -> peak list (8-byte keys)
-  BlobScratch scratch;
+  BlobScratch<1> scratch;
 };
 
 template <bool KEEP>
-__global__ void __launch_bounds__(kSmallWarps * 32, 5) k_fit_small(FrameParams p) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 6) k_fit_small(FrameParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallWarpShared &S = reinterpret_cast<SmallWarpShared *>(smem_raw)[threadIdx.x >> 5];
   const int frame = blockIdx.y;
@@ -1184,8 +1257,9 @@ struct CtaShared {
   uint32_t lf32[LF_CAP > 0 ? 3 * LF_CAP : 1];
   alignas(16) float errs[KEY_CAP];  // also holds 8-byte peak keys
   // warp totals of the prefix scan; in the large tier also the bucket counters of the angle sort (KEY_CAP words)
-  long long scan[(LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP / 2 : 6 * THREADS];
-  BlobScratch scratch;
+  // (with the prefix moments in shared memory the bucket counters alias them: only the warp totals remain)
+  long long scan[LF_CAP > 0 ? 6 * (THREADS / 32) : (KEY_CAP / 2 > 6 * THREADS ? KEY_CAP / 2 : 6 * THREADS)];
+  BlobScratch<THREADS / 32> scratch;
 };
 
 template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP, uint32_t MIN_CNT, uint32_t MAX_CNT, int MIN_CTAS, bool KEEP>
@@ -1252,7 +1326,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
 
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
 using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
-#define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 5, KEEP>
+// six CTAs of either tier per SM: 228 KB less 1 KB per CTA
+static_assert(sizeof(MediumShared) <= 37888, "shared memory of the medium tier");
+#define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 6, KEEP>
 #define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, kSortCap, 3, KEEP>
 // huge: 512 threads, blobs above 4096 points (clutter, image-spanning edges); keys / errors / peaks in shared memory up
 // to 8192 points (one CTA per SM), beyond that in place in the global arrays
@@ -1324,7 +1400,10 @@ int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *
   }
   if (kt) kt->end(s);
   if (kt) kt->begin("fit_large", s);
-  if (frames <= kLowLatencyFrames) {
+  // (the shared-memory prefix moments keep Mx, My, W as 32-bit words: kSortCap points of weight <= 361 must not reach
+  //  2^32, which holds for quad images up to 1451 pixels a side -- larger frames take the 256-thread kernel)
+  const bool lf32_ok = static_cast<uint64_t>(kSortCap) * 361u * (2u * static_cast<uint32_t>(max(p.w, p.h)) + 1u) < (1ull << 32);
+  if (frames <= kLowLatencyFrames && lf32_ok) {
     const dim3 g(max(1u, min(148u, cdivu(592u, frames))), frames);
     if (p.keep_stages) K_FIT_LARGE512(true)<<<g, kHugeThreads, sizeof(Large512Shared), s_large>>>(p, 1);
     else K_FIT_LARGE512(false)<<<g, kHugeThreads, sizeof(Large512Shared), s_large>>>(p, 1);
