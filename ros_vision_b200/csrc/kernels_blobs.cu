@@ -1250,17 +1250,33 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 6) k_fit_small(FrameParams p
 //   large : 256 threads, blobs above 768 points; sort / errors / peaks in shared memory up to 4096 points,
 //           prefix moments in the blob's own L2-resident segment (3 CTAs per SM)
 // k_select sorts the blobs into the tiers' work lists (medium from the front of large_list, large from its back).
+// Shared memory of a CTA tier: one buffer, carved per blob in one of two ways --
+//   layout A (blobs of at most LF_CAP points, everything in shared memory):
+//       keys[LF_CAP] u64 | prefix moments 3 x u64[LF_CAP], 3 x u32[LF_CAP] | errs[LF_CAP] f32     (48 bytes per point)
+//   layout B (blobs of at most KEY_CAP > LF_CAP points, prefix moments in the blob's global segment):
+//       keys[KEY_CAP] u64 | errs[KEY_CAP] f32 | bucket counters / warp totals of the scans
+// so that a tier whose size range spans both (large: A up to 1536 points, B up to 4096) pays for the larger of the two,
+// not their sum.
 template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP>
 struct CtaShared {
-  unsigned long long keys[KEY_CAP];
-  unsigned long long lf64[LF_CAP > 0 ? 3 * LF_CAP : 1];  // prefix moments (LfStore); bucket-sort scratch before that
-  uint32_t lf32[LF_CAP > 0 ? 3 * LF_CAP : 1];
-  alignas(16) float errs[KEY_CAP];  // also holds 8-byte peak keys
-  // warp totals of the prefix scan; in the large tier also the bucket counters of the angle sort (KEY_CAP words)
-  // (with the prefix moments in shared memory the bucket counters alias them: only the warp totals remain)
-  long long scan[LF_CAP > 0 ? 6 * (THREADS / 32) : (KEY_CAP / 2 > 6 * THREADS ? KEY_CAP / 2 : 6 * THREADS)];
+  static constexpr bool kHasB = KEY_CAP > LF_CAP;
+  // layout B scratch (64-bit words): KEY_CAP bucket counters of the angle sort if that beats the warp totals' 6 * THREADS
+  static constexpr uint32_t kScanWords = kHasB ? (KEY_CAP / 2 > 6 * THREADS ? KEY_CAP / 2 : 6 * THREADS) : 0;
+  static constexpr size_t kBytesA = static_cast<size_t>(LF_CAP) * 48;
+  static constexpr size_t kBytesB = kHasB ? static_cast<size_t>(KEY_CAP) * 12 + static_cast<size_t>(kScanWords) * 8 : 0;
+  alignas(16) unsigned char buf[kBytesA > kBytesB ? kBytesA : kBytesB];
+  long long tot[6 * (THREADS / 32)];  // layout A: warp totals of the prefix scan
   BlobScratch<THREADS / 32> scratch;
+
+  __device__ unsigned long long *a_keys() { return reinterpret_cast<unsigned long long *>(buf); }
+  __device__ unsigned long long *a_lf64() { return reinterpret_cast<unsigned long long *>(buf) + LF_CAP; }
+  __device__ uint32_t *a_lf32() { return reinterpret_cast<uint32_t *>(buf + static_cast<size_t>(LF_CAP) * 32); }
+  __device__ float *a_errs() { return reinterpret_cast<float *>(buf + static_cast<size_t>(LF_CAP) * 44); }
+  __device__ unsigned long long *b_keys() { return reinterpret_cast<unsigned long long *>(buf); }
+  __device__ float *b_errs() { return reinterpret_cast<float *>(buf + static_cast<size_t>(KEY_CAP) * 8); }
+  __device__ long long *b_scan() { return reinterpret_cast<long long *>(buf + static_cast<size_t>(KEY_CAP) * 12); }
 };
+static_assert(kMediumCap % 4 == 0 && kSortCap % 4 == 0, "16-byte alignment of the carved arrays");
 
 template <int THREADS, uint32_t KEY_CAP, uint32_t LF_CAP, uint32_t MIN_CNT, uint32_t MAX_CNT, int MIN_CTAS, bool KEEP>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, int tier) {
@@ -1275,7 +1291,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
   const WorkItem *list = (tier == 2 ? p.small_list : p.large_list) + static_cast<size_t>(frame) * p.blob_cap;
   const uint32_t nlist = min(tier == 0 ? ctr->num_medium : (tier == 1 ? ctr->num_large : ctr->num_huge), p.blob_cap);
   // bucket counters of blobs whose prefix moments live in global memory: the scan scratch, largest power of two
-  constexpr uint32_t kScanHist = (LF_CAP == 0 && KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP : ((6u * THREADS * 2u >= 2048u) ? 2048u : 1024u);
+  constexpr uint32_t kScanHist = (KEY_CAP / 2 > 6 * THREADS) ? KEY_CAP : ((6u * THREADS * 2u >= 2048u) ? 2048u : 1024u);
   uint32_t *next = tier == 0 ? &ctr->next_medium : (tier == 1 ? &ctr->next_large : &ctr->next_huge);
   uint32_t nxt = 0;
   if (tid == 0) nxt = atomicAdd(next, 1u);
@@ -1296,40 +1312,46 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_fit_cta(FrameParams p, in
     constexpr bool kHasSmemLf = LF_CAP > 0;
     constexpr bool kHasGlobalLf = MAX_CNT > LF_CAP;
     constexpr bool kHasInPlace = MAX_CNT > KEY_CAP;
-    if (kHasSmemLf && blob_cnt <= LF_CAP) {  // everything in shared memory
-      wk.keys = S.keys; wk.errs = S.errs;
-      wk.lf.aos = nullptr; wk.lf.m64 = S.lf64; wk.lf.m32 = S.lf32; wk.lf.cap = LF_CAP;
-      wk.filt = reinterpret_cast<double *>(S.keys);
-      wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
+    // layout A keeps Mx, My, W as 32-bit words: cnt points of weight <= 361 and coordinate <= 2 max(w, h) + 1 must stay
+    // below 2^32 (always true up to 1452 points; tiers without a fallback are launched only where it holds)
+    const bool lf32_ok = LF_CAP <= 1452 || !kHasGlobalLf ||
+                         static_cast<uint64_t>(blob_cnt) * 361u * (2u * static_cast<uint32_t>(max(p.w, p.h)) + 1u) < (1ull << 32);
+    if (kHasSmemLf && blob_cnt <= LF_CAP && lf32_ok) {  // everything in shared memory
+      wk.keys = S.a_keys(); wk.errs = S.a_errs();
+      wk.lf.aos = nullptr; wk.lf.m64 = S.a_lf64(); wk.lf.m32 = S.a_lf32(); wk.lf.cap = LF_CAP;
+      wk.filt = reinterpret_cast<double *>(S.a_keys());
+      wk.peaks = reinterpret_cast<unsigned long long *>(S.a_errs());
       wk.keys_in_place = false;
-      wk.hist = reinterpret_cast<uint32_t *>(S.lf64); wk.hist_cap = next_pow2(LF_CAP > 0 ? LF_CAP : 1); wk.tmp = wk.hist + next_pow2(LF_CAP > 0 ? LF_CAP : 1);
-      fit_one_blob<THREADS, false, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
+      wk.hist = reinterpret_cast<uint32_t *>(S.a_lf64()); wk.hist_cap = next_pow2(LF_CAP > 0 ? LF_CAP : 1); wk.tmp = wk.hist + next_pow2(LF_CAP > 0 ? LF_CAP : 1);
+      fit_one_blob<THREADS, false, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.tot, tid);
     } else if (kHasGlobalLf && KEY_CAP > LF_CAP && blob_cnt <= KEY_CAP) {  // prefix moments in the blob's global segment
-      wk.keys = S.keys; wk.errs = S.errs;
+      wk.keys = S.b_keys(); wk.errs = S.b_errs();
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
-      wk.filt = reinterpret_cast<double *>(S.keys);
-      wk.peaks = reinterpret_cast<unsigned long long *>(S.errs);
+      wk.filt = reinterpret_cast<double *>(S.b_keys());
+      wk.peaks = reinterpret_cast<unsigned long long *>(S.b_errs());
       wk.keys_in_place = false;
-      wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
+      wk.hist = reinterpret_cast<uint32_t *>(S.b_scan()); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.b_scan(), tid);
     } else if (kHasInPlace) {  // too large for shared memory: work in place in the global arrays
       wk.keys = reinterpret_cast<unsigned long long *>(p.seg_keys + pbase);
       wk.lf.aos = p.lfp + pbase; wk.lf.m64 = nullptr; wk.lf.m32 = nullptr; wk.lf.cap = 0;
       wk.errs = p.errs + pbase; wk.filt = p.filt + pbase;
       wk.peaks = reinterpret_cast<unsigned long long *>(p.peak_ws + static_cast<size_t>(frame) * (p.point_cap / 2 + 1) + blob_off / 2);
       wk.keys_in_place = true;
-      wk.hist = reinterpret_cast<uint32_t *>(S.scan); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
-      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.scan, tid);
+      wk.hist = reinterpret_cast<uint32_t *>(S.b_scan()); wk.hist_cap = kScanHist; wk.tmp = reinterpret_cast<uint32_t *>(p.lfp + pbase);
+      fit_one_blob<THREADS, true, KEEP>(p, frame, ctr, b, blob_cnt, blob_off, blobs + b, wk, S.scratch, S.b_scan(), tid);
     }
   }
 }
 
 using MediumShared = CtaShared<128, kMediumCap, kMediumCap>;
-using LargeShared = CtaShared<kLargeThreads, kSortCap, 0>;
+constexpr uint32_t kLargeLfCap = 1536;  // large tier: blobs up to here entirely in shared memory (72 KB = the 4096-point layout B + 8 KB)
+using LargeShared = CtaShared<kLargeThreads, kSortCap, kLargeLfCap>;
+static_assert(sizeof(LargeShared) <= 76800 - 1024, "three CTAs of the large tier per SM");
 // six CTAs of either tier per SM: 228 KB less 1 KB per CTA
 static_assert(sizeof(MediumShared) <= 37888, "shared memory of the medium tier");
 #define K_FIT_MEDIUM(KEEP) k_fit_cta<128, kMediumCap, kMediumCap, kSmallBlobPoints + 1, kMediumCap, 6, KEEP>
-#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, 0, kMediumCap + 1, kSortCap, 3, KEEP>
+#define K_FIT_LARGE(KEEP) k_fit_cta<kLargeThreads, kSortCap, kLargeLfCap, kMediumCap + 1, kSortCap, 3, KEEP>
 // huge: 512 threads, blobs above 4096 points (clutter, image-spanning edges); keys / errors / peaks in shared memory up
 // to 8192 points (one CTA per SM), beyond that in place in the global arrays
 constexpr int kHugeThreads = 512;
