@@ -466,8 +466,11 @@ __global__ void k_init_combos() {
         }
 }
 
-// The 10 strongest of MANY (> 32) peaks: ten rounds of a warp-wide minimum over the list; position-ordered
-// insertion by lane 0.  Rare for small blobs, kept out of line so it does not sit in the hot instruction stream.
+constexpr int kPeakRegs = 8;  // peak keys a lane holds in registers during the selection (32 * 8 = 256 peaks)
+
+// The 10 strongest of MANY (> 256) peaks: ten rounds of a warp-wide minimum over the list; position-ordered
+// insertion by lane 0.  Rare (blobs of thousands of points), kept out of line so it does not sit in the hot
+// instruction stream.
 __device__ __noinline__ uint32_t top_peaks_many(const unsigned long long *peaks, uint32_t npk, uint32_t *peak_idx, int lane) {
   unsigned long long last = 0;
   uint32_t nsel = 0;
@@ -958,6 +961,57 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       nsel = min(npk, static_cast<uint32_t>(kMaxPeaks));
       // position order: rank of this lane's point index among the chosen ones
       const uint32_t my_idx = static_cast<uint32_t>(v & 0xffffffffu);
+      uint32_t rank = 0;
+#pragma unroll
+      for (int m = 0; m < kMaxPeaks; m++) {
+        const uint32_t o = __shfl_sync(0xffffffffu, my_idx, m);
+        rank += (m < static_cast<int>(nsel)) && (o < my_idx);
+      }
+      if (lane < static_cast<int>(nsel)) S.peak_idx[rank] = my_idx;
+    } else if (npk <= 32 * kPeakRegs) {
+      // Every lane holds its (up to kPeakRegs) keys of the list in registers, smallest first; ten rounds of "warp
+      // minimum over the lanes' heads, the owner pops" pick the ten smallest keys -- keys are unique (the point
+      // index is their low word), so the owner is the lane whose head equals the minimum.  Round r leaves its
+      // key in lane r: lanes 0..nsel-1 end up with the chosen peaks, strongest first.
+      unsigned long long k[kPeakRegs];
+#pragma unroll
+      for (int j = 0; j < kPeakRegs; j++) k[j] = kNoKey;
+      {
+#pragma unroll
+        for (int j = 0; j < kPeakRegs; j++) {
+          const uint32_t q = static_cast<uint32_t>(lane) + 32u * j;
+          if (q < npk) k[j] = wk.peaks[q];
+        }
+        // 19-comparator sorting network for 8 inputs
+        constexpr int net[19][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
+                                    {0, 4}, {3, 7}, {1, 5}, {2, 6}, {1, 4}, {3, 6}, {2, 4}, {3, 5}, {3, 4}};
+        static_assert(kPeakRegs == 8, "the network below sorts 8 registers");
+#pragma unroll
+        for (int c = 0; c < 19; c++) {
+          const unsigned long long a = k[net[c][0]], b2 = k[net[c][1]];
+          k[net[c][0]] = a < b2 ? a : b2;
+          k[net[c][1]] = a < b2 ? b2 : a;
+        }
+      }
+      unsigned long long chosen = kNoKey;
+#pragma unroll 1
+      for (int round = 0; round < kMaxPeaks; round++) {
+        const uint32_t hi = static_cast<uint32_t>(k[0] >> 32);
+        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+        const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(k[0]) : 0xffffffffu;
+        const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+        const unsigned long long best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+        if (best == kNoKey) break;
+        nsel++;
+        if (lane == round) chosen = best;
+        if (k[0] == best) {
+#pragma unroll
+          for (int j = 0; j + 1 < kPeakRegs; j++) k[j] = k[j + 1];
+          k[kPeakRegs - 1] = kNoKey;
+        }
+      }
+      // position order: rank of this lane's point index among the chosen ones
+      const uint32_t my_idx = static_cast<uint32_t>(chosen & 0xffffffffu);
       uint32_t rank = 0;
 #pragma unroll
       for (int m = 0; m < kMaxPeaks; m++) {
