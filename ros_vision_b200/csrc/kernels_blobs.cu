@@ -1109,8 +1109,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
   //     closing sides (peak m3 back to m0): error only.
   const int nm = static_cast<int>(T.nsel);
   const double max_mse = static_cast<double>(p.max_line_fit_mse);
+  const uint32_t inv_nm1 = nm > 1 ? 65535u / static_cast<uint32_t>(nm - 1) + 1u : 0u;  // t / (nm - 1) for t < 90, exactly
   for (int t = lane; t < nm * (nm - 1); t += 32) {
-    const int a = t / (nm - 1);
+    const int a = static_cast<int>((static_cast<uint32_t>(t) * inv_nm1) >> 16);
     int c = t - a * (nm - 1);
     c += c >= a;
     const Mom mo = table_moments(T, a, c);
@@ -1197,25 +1198,26 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
       }
       bad = __any_sync(0xffffffffu, bad);
       __syncwarp();
+      // the six edge lengths of the two triangles of the area test, one lane each (hypotf is the expensive part of the
+      // tests below): (0,1) (1,2) (2,0) | (2,3) (3,0) (0,2)
+      float elen = 0;
+      if (lane < 6) {
+        const int a = (0x032210 >> (4 * lane)) & 0xf, c = (0x203021 >> (4 * lane)) & 0xf;
+        elen = hypotf(S.corners[c][0] - S.corners[a][0], S.corners[c][1] - S.corners[a][1]);
+      }
+      float elens[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) elens[i] = __shfl_sync(0xffffffffu, elen, i);
       if (lane == 0 && !bad) {
         float cr[4][2];
         for (int j = 0; j < 4; j++) { cr[j][0] = S.corners[j][0]; cr[j][1] = S.corners[j][1]; }
         {  // :171-207
           float area = 0;
-          float length[3], pp;
-          for (int i = 0; i < 3; i++) {
-            const int a = i, c = (i + 1) % 3;
-            length[i] = hypotf(cr[c][0] - cr[a][0], cr[c][1] - cr[a][1]);
-          }
-          pp = (length[0] + length[1] + length[2]) / 2;
-          area += sqrtf(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
-          const int idxs[4] = {2, 3, 0, 2};
-          for (int i = 0; i < 3; i++) {
-            const int a = idxs[i], c = idxs[i + 1];
-            length[i] = hypotf(cr[c][0] - cr[a][0], cr[c][1] - cr[a][1]);
-          }
-          pp = (length[0] + length[1] + length[2]) / 2;
-          area += sqrtf(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
+          float pp;
+          pp = (elens[0] + elens[1] + elens[2]) / 2;
+          area += sqrtf(pp * (pp - elens[0]) * (pp - elens[1]) * (pp - elens[2]));
+          pp = (elens[3] + elens[4] + elens[5]) / 2;
+          area += sqrtf(pp * (pp - elens[3]) * (pp - elens[4]) * (pp - elens[5]));
           if (static_cast<double>(area) < 0.95 * p.min_tag_width * p.min_tag_width) bad = true;
         }
         if (!bad) {  // :209-238

@@ -237,10 +237,10 @@ __device__ __forceinline__ void decode_family(const FrameParams &p, DecodeShared
         for (int j = 0; j < 3; j++) m.A[i][j] = 0;
         m.B[i] = m.C[i] = 0;
       }
-      for (int j = 0; j < 64; j++) {
+      for (int jj = 0; jj < 32; jj++) {  // patterns alternate white, black: this lane's are 0, 2, 4, 6 or 1, 3, 5, 7
+        const int j = (((jj >> 3) << 1) | lane) * 8 + (jj & 7);
         if (S.gm_v[j] < 0) continue;
-        const int is_white = ((j >> 3) & 1) == 0;  // patterns alternate white, black
-        if (is_white == (lane == 0)) gm_add(&m, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
+        gm_add(&m, S.gm_x[j], S.gm_y[j], S.gm_v[j]);
       }
       gm_solve(&m);
       if (lane == 0) S.white = m; else S.black = m;
