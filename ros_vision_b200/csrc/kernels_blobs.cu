@@ -1077,7 +1077,7 @@ __device__ __forceinline__ Mom table_moments(const PeakTable &T, int a, int c) {
 
 constexpr int kQuadWarps = 4;
 
-__global__ void __launch_bounds__(kQuadWarps * 32, 9) k_quads(FrameParams p) {
+__global__ void __launch_bounds__(kQuadWarps * 32, 8) k_quads(FrameParams p) {
   __shared__ QuadScratch s_q[kQuadWarps];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
