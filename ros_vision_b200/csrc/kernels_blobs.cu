@@ -468,6 +468,55 @@ __global__ void k_init_combos() {
 
 constexpr int kPeakRegs = 8;  // peak keys a lane holds in registers during the selection (32 * 8 = 256 peaks)
 
+// The 10 strongest of up to 32 K peaks.  Every lane holds its (up to K) keys of the list in registers, smallest first;
+// ten rounds of "warp minimum over the lanes' heads, the owner pops" pick the ten smallest keys -- keys are unique (the
+// point index is their low word), so the owner is the lane whose head equals the minimum.  Round r leaves its key in
+// lane r: lanes 0..nsel-1 return the chosen peaks, strongest first.
+template <int K>
+__device__ __forceinline__ unsigned long long top_peaks_regs(const unsigned long long *peaks, uint32_t npk, int lane, uint32_t *nsel_out) {
+  static_assert(K == 2 || K == 4 || K == 8, "sorting networks below");
+  unsigned long long k[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const uint32_t q = static_cast<uint32_t>(lane) + 32u * j;
+    k[j] = q < npk ? peaks[q] : kNoKey;
+  }
+  // optimal sorting networks: 1, 5, 19 comparators
+  constexpr int net2[1][2] = {{0, 1}};
+  constexpr int net4[5][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}, {1, 2}};
+  constexpr int net8[19][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
+                               {0, 4}, {3, 7}, {1, 5}, {2, 6}, {1, 4}, {3, 6}, {2, 4}, {3, 5}, {3, 4}};
+  constexpr int ncmp = K == 2 ? 1 : (K == 4 ? 5 : 19);
+#pragma unroll
+  for (int c = 0; c < ncmp; c++) {
+    const int i0 = K == 2 ? net2[c % 1][0] : (K == 4 ? net4[c % 5][0] : net8[c][0]);
+    const int i1 = K == 2 ? net2[c % 1][1] : (K == 4 ? net4[c % 5][1] : net8[c][1]);
+    const unsigned long long a = k[i0 % K], b2 = k[i1 % K];
+    k[i0 % K] = a < b2 ? a : b2;
+    k[i1 % K] = a < b2 ? b2 : a;
+  }
+  unsigned long long chosen = kNoKey;
+  uint32_t nsel = 0;
+#pragma unroll 1
+  for (int round = 0; round < kMaxPeaks; round++) {
+    const uint32_t hi = static_cast<uint32_t>(k[0] >> 32);
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(k[0]) : 0xffffffffu;
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+    const unsigned long long best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+    if (best == kNoKey) break;
+    nsel++;
+    if (lane == round) chosen = best;
+    if (k[0] == best) {
+#pragma unroll
+      for (int j = 0; j + 1 < K; j++) k[j] = k[j + 1];
+      k[K - 1] = kNoKey;
+    }
+  }
+  *nsel_out = nsel;
+  return chosen;
+}
+
 // The 10 strongest of MANY (> 256) peaks: ten rounds of a warp-wide minimum over the list; position-ordered
 // insertion by lane 0.  Rare (blobs of thousands of points), kept out of line so it does not sit in the hot
 // instruction stream.
@@ -969,47 +1018,10 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       }
       if (lane < static_cast<int>(nsel)) S.peak_idx[rank] = my_idx;
     } else if (npk <= 32 * kPeakRegs) {
-      // Every lane holds its (up to kPeakRegs) keys of the list in registers, smallest first; ten rounds of "warp
-      // minimum over the lanes' heads, the owner pops" pick the ten smallest keys -- keys are unique (the point
-      // index is their low word), so the owner is the lane whose head equals the minimum.  Round r leaves its
-      // key in lane r: lanes 0..nsel-1 end up with the chosen peaks, strongest first.
-      unsigned long long k[kPeakRegs];
-#pragma unroll
-      for (int j = 0; j < kPeakRegs; j++) k[j] = kNoKey;
-      {
-#pragma unroll
-        for (int j = 0; j < kPeakRegs; j++) {
-          const uint32_t q = static_cast<uint32_t>(lane) + 32u * j;
-          if (q < npk) k[j] = wk.peaks[q];
-        }
-        // 19-comparator sorting network for 8 inputs
-        constexpr int net[19][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
-                                    {0, 4}, {3, 7}, {1, 5}, {2, 6}, {1, 4}, {3, 6}, {2, 4}, {3, 5}, {3, 4}};
-        static_assert(kPeakRegs == 8, "the network below sorts 8 registers");
-#pragma unroll
-        for (int c = 0; c < 19; c++) {
-          const unsigned long long a = k[net[c][0]], b2 = k[net[c][1]];
-          k[net[c][0]] = a < b2 ? a : b2;
-          k[net[c][1]] = a < b2 ? b2 : a;
-        }
-      }
-      unsigned long long chosen = kNoKey;
-#pragma unroll 1
-      for (int round = 0; round < kMaxPeaks; round++) {
-        const uint32_t hi = static_cast<uint32_t>(k[0] >> 32);
-        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-        const uint32_t lo = (hi == mhi) ? static_cast<uint32_t>(k[0]) : 0xffffffffu;
-        const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
-        const unsigned long long best = (static_cast<unsigned long long>(mhi) << 32) | mlo;
-        if (best == kNoKey) break;
-        nsel++;
-        if (lane == round) chosen = best;
-        if (k[0] == best) {
-#pragma unroll
-          for (int j = 0; j + 1 < kPeakRegs; j++) k[j] = k[j + 1];
-          k[kPeakRegs - 1] = kNoKey;
-        }
-      }
+      // registers per lane sized to the list: 2 (up to 64 peaks), 4 (128) or 8 (256)
+      const unsigned long long chosen = npk <= 64    ? top_peaks_regs<2>(wk.peaks, npk, lane, &nsel)
+                                        : npk <= 128 ? top_peaks_regs<4>(wk.peaks, npk, lane, &nsel)
+                                                     : top_peaks_regs<8>(wk.peaks, npk, lane, &nsel);
       // position order: rank of this lane's point index among the chosen ones
       const uint32_t my_idx = static_cast<uint32_t>(chosen & 0xffffffffu);
       uint32_t rank = 0;
