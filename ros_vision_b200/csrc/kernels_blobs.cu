@@ -586,6 +586,11 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
   //     points are parked in the still unused error buffer.
   uint32_t *raw = reinterpret_cast<uint32_t *>(wk.errs);
   {
+    // bucket counters of the angle sort (phase 1), zeroed here so that the barrier of the extent reduction covers them too
+    const uint32_t N = 1u << (32 - __clz(static_cast<int>(cnt - 1)));  // next power of two (cnt >= 24)
+    const uint32_t B = min(N, wk.hist_cap);
+    for (uint32_t i = gt; i < B; i += GS) wk.hist[i] = 0;
+    if (gt == 0) S.npeaks = 0;
     const uint32_t *sp = p.seg_pts + pbase;
     uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
     int sgx = 0, sgy = 0, sdot = 0;
@@ -628,7 +633,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
       }
     }
     if (!sel) return;  // uniform across the group
-    gsync<GS>();
+    if constexpr (GS == 32) __syncwarp();  // (CTA tiers: the barrier inside the reduction above)
     // MinMaxExtents::cx/cy, line_fit_filter.h:44-49
     const double cx = static_cast<double>(static_cast<float>(static_cast<int>(mnx + mxx)) * 0.5f) + 0.05118;
     const double cy = static_cast<double>(static_cast<float>(static_cast<int>(mny + mxy)) * 0.5f) + -0.028581;
@@ -637,14 +642,9 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     //     spread around the whole circle, so a bucket sort does it in O(cnt): B >= cnt buckets over the
     //     theta range (monotone map), in-bucket rank from the counting atomicAdd, exclusive scan, scatter,
     //     then each thread insertion-sorts the few elements of its own buckets on the full 64-bit key.
-    const uint32_t N = 1u << (32 - __clz(static_cast<int>(cnt - 1)));  // next power of two (cnt >= 24)
-    const uint32_t B = min(N, wk.hist_cap);
     // bucket = theta >> bk_shift: theta < 2 * pi * 8e6 + 1 < 2^26, so the B power-of-two buckets cover [0, 2^26) and
     // three quarters of them are in use (average load <= 4/3); a shift instead of a 64-bit multiply and divide
     const uint32_t bk_shift = 26u - (31u - static_cast<uint32_t>(__clz(static_cast<int>(B))));
-    for (uint32_t i = gt; i < B; i += GS) wk.hist[i] = 0;
-    if (gt == 0) S.npeaks = 0;
-    gsync<GS>();
     uint32_t *th_tmp = wk.tmp, *rk_tmp = wk.tmp + cnt;
 #pragma unroll 1
     for (uint32_t i = gt; i < cnt; i += GS) {
@@ -678,7 +678,7 @@ __device__ __forceinline__ void fit_one_blob(const FrameParams &p, int frame, Co
     mx = __reduce_max_sync(0xffffffffu, mx);
     if constexpr (GS > 32) {
       const int wi = gt >> 5;
-      __syncthreads();  // red_u was read by every thread above
+      // (red_u is free: every thread read its phase-0 contents before the barrier that ended the key loop)
       if (lane == 31) S.red_u[wi][0] = incl;
       if (lane == 0) S.red_u[wi][1] = mx;
       __syncthreads();
