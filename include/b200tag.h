@@ -292,6 +292,22 @@ int b200tag_estimate_pose(const b200tag_detection *det, double tagsize, double f
 int b200tag_estimate_poses(const b200tag_detection *dets, int count, double tagsize, double fx, double fy, double cx,
                            double cy, b200tag_pose *out);
 
+/* The rest of the node's per-frame step (apriltags_cuda_detector.cu:421-462,595-599): every detection's pose, the tag
+ * position in the camera frame (the pose's t), in the robot frame (rotation * t + offset, transformCameraToRobot) and
+ * its Euclidean distance from the camera; the records come back closest first, as the node publishes them (ties
+ * keep the detections' order).  `rotation` is a row-major 3x3 matrix and `offset` a 3-vector, the camera's
+ * "extrinsics" entry; NULL means identity / zero (the node's defaults, :36-37). */
+typedef struct b200tag_tag_position {
+  int index;          /* position of the detection in the input list */
+  int id;
+  double camera[3];   /* tag origin in the camera frame */
+  double robot[3];    /* the same point in the robot frame */
+  double distance;    /* |camera| */
+  double err;         /* object-space error of the pose (estimate_tag_pose's return value) */
+} b200tag_tag_position;
+int b200tag_locate_tags(const b200tag_detection *dets, int count, double tagsize, double fx, double fy, double cx,
+                        double cy, const double *rotation, const double *offset, b200tag_tag_position *out);
+
 /* Pinned host staging memory, so b200tag_detect* can overlap H2D with compute. */
 void *b200tag_alloc_pinned(size_t bytes);
 /* Write-combined pinned memory: for buffers the CPU (or a capture driver) only ever WRITES, such as a camera ring

@@ -13,6 +13,7 @@
 //      t = tan(beta / 2), refine that candidate by orthogonal iteration too,
 //   4. return the pose with the smaller object-space error.
 // Host code: a handful of 3x3 operations per detection.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -340,6 +341,26 @@ int b200tag_estimate_poses(const b200tag_detection *dets, int count, double tags
   if (count < 0 || (count > 0 && (!dets || !out))) return B200TAG_E_INVALID;
   for (int i = 0; i < count; i++)
     if (int rc = b200tag_estimate_pose(dets + i, tagsize, fx, fy, cx, cy, out + i)) return rc;
+  return 0;
+}
+
+int b200tag_locate_tags(const b200tag_detection *dets, int count, double tagsize, double fx, double fy, double cx,
+                        double cy, const double *rotation, const double *offset, b200tag_tag_position *out) {
+  if (count < 0 || (count > 0 && (!dets || !out))) return B200TAG_E_INVALID;
+  static const double kEye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, kZero[3] = {0, 0, 0};
+  const double *Rx = rotation ? rotation : kEye, *ox = offset ? offset : kZero;
+  for (int i = 0; i < count; i++) {
+    b200tag_pose pose;
+    if (int rc = b200tag_estimate_pose(dets + i, tagsize, fx, fy, cx, cy, &pose)) return rc;
+    b200tag_tag_position &o = out[i];
+    o.index = i;
+    o.id = dets[i].id;
+    for (int k = 0; k < 3; k++) o.camera[k] = pose.t[k];
+    for (int r = 0; r < 3; r++) o.robot[r] = Rx[3 * r] * pose.t[0] + Rx[3 * r + 1] * pose.t[1] + Rx[3 * r + 2] * pose.t[2] + ox[r];
+    o.distance = std::sqrt(pose.t[0] * pose.t[0] + pose.t[1] * pose.t[1] + pose.t[2] * pose.t[2]);
+    o.err = pose.err;
+  }
+  std::stable_sort(out, out + count, [](const b200tag_tag_position &a, const b200tag_tag_position &b) { return a.distance < b.distance; });
   return 0;
 }
 

@@ -80,6 +80,8 @@ _STAGE_DTYPES = {
 }
 
 POSE_DT = np.dtype([("R", "<f8", (3, 3)), ("t", "<f8", (3,)), ("err", "<f8"), ("err_other", "<f8")])
+TAG_POSITION_DT = np.dtype([("index", "<i4"), ("id", "<i4"), ("camera", "<f8", (3,)), ("robot", "<f8", (3,)),
+                            ("distance", "<f8"), ("err", "<f8")])  # b200tag_tag_position
 
 _lib = None
 
@@ -142,6 +144,7 @@ def load_library():
     L.b200tag_last_error.argtypes = [vp]
     L.b200tag_last_error.restype = C.c_char_p
     L.b200tag_estimate_poses.argtypes = [vp, i32] + [C.c_double] * 5 + [vp]
+    L.b200tag_locate_tags.argtypes = [vp, i32] + [C.c_double] * 5 + [vp, vp, vp]
     L.b200tag_version.restype = i32
     _lib = L
     return L
@@ -178,6 +181,25 @@ def estimate_poses(detections: np.ndarray, tagsize: float, fx: float, fy: float,
                                         float(cx), float(cy), out.ctypes.data_as(C.c_void_p))
         if rc:
             raise B200TagError(f"b200tag_estimate_poses: {lib.b200tag_error_string(rc).decode()}")
+    return out
+
+
+def locate_tags(detections: np.ndarray, tagsize: float, fx: float, fy: float, cx: float, cy: float,
+                rotation=None, offset=None) -> np.ndarray:
+    """The node's per-frame step behind Detect (apriltags_cuda_detector.cu:421-462,595-599): pose of every detection, tag
+    position in the camera frame and -- through the camera's extrinsic `rotation` (3x3) and `offset` (3) -- in the robot
+    frame, distance from the camera; TAG_POSITION_DT records, closest first."""
+    lib = load_library()
+    dets = np.ascontiguousarray(detections, dtype=DETECTION_DT)
+    out = np.zeros(len(dets), dtype=TAG_POSITION_DT)
+    rot = None if rotation is None else np.ascontiguousarray(rotation, dtype=np.float64).reshape(9)
+    off = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64).reshape(3)
+    rc = lib.b200tag_locate_tags(dets.ctypes.data_as(C.c_void_p) if len(dets) else None, len(dets), float(tagsize), float(fx),
+                                 float(fy), float(cx), float(cy), None if rot is None else rot.ctypes.data_as(C.c_void_p),
+                                 None if off is None else off.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p) if len(dets) else None)
+    if rc:
+        raise B200TagError(f"b200tag_locate_tags: {lib.b200tag_error_string(rc).decode()}")
     return out
 
 

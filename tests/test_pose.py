@@ -182,7 +182,7 @@ def test_pose_against_opencv_ippe():
         Rcv, _ = cv2.Rodrigues(rvecs[0])
         tcv = tvecs[0].reshape(3)
         # when the two minima are nearly as good as each other the solvers may rank them differently: skip those
-        if len(errs) > 1 and float(errs[1]) < 1.5 * float(errs[0]) + 1e-6:
+        if len(errs) > 1 and float(np.ravel(errs[1])[0]) < 1.5 * float(np.ravel(errs[0])[0]) + 1e-6:
             continue
         if np.isfinite(ours["err_other"]) and ours["err_other"] < 2.0 * ours["err"] + 1e-12:
             continue
@@ -193,3 +193,45 @@ def test_pose_against_opencv_ippe():
         n += 1
     assert n >= 60, n
     assert worst_r < 0.5 and worst_t < 5e-3, (worst_r, worst_t)
+
+
+def test_locate_tags_robot_frame_and_distance_order(D):
+    """The rest of the node's step (apriltags_cuda_detector.cu:421-462,595-599): robot = rotation * t + offset, records closest first."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    dets, truth = [], []
+    for i, z in enumerate([2.5, 0.8, 4.0, 1.6, 0.8]):  # two tags at the same depth: different x keeps the distances distinct
+        R = _rot(*rng.uniform(-0.4, 0.4, 3))
+        t = np.array([0.1 * i - 0.2, 0.05 * i - 0.1, z])
+        d = _detection(R, t)
+        d["id"][0] = 100 + i
+        dets.append(d)
+        truth.append(t)
+    dets = np.concatenate(dets)
+    rotation = _rot(0.3, -1.1, 0.7)
+    offset = np.array([0.25, -0.1, 0.6])
+    got = D.locate_tags(dets, TAGSIZE, FX, FY, CX, CY, rotation, offset)
+    poses = D.estimate_poses(dets, TAGSIZE, FX, FY, CX, CY)
+    dist = np.linalg.norm(np.array(truth), axis=1)
+    order = np.argsort(dist, kind="stable")
+    assert list(got["index"]) == list(order)
+    assert list(got["id"]) == [100 + int(i) for i in order]
+    assert np.all(np.diff(got["distance"]) >= 0)
+    for rec in got:
+        i = int(rec["index"])
+        assert np.array_equal(rec["camera"], poses["t"][i]) and rec["err"] == poses["err"][i]
+        assert np.allclose(rec["camera"], truth[i], atol=1e-6)
+        assert np.allclose(rec["robot"], rotation @ poses["t"][i] + offset, rtol=0, atol=1e-12)
+        assert rec["distance"] == pytest.approx(np.linalg.norm(poses["t"][i]), abs=1e-12)
+    # the node's defaults (identity rotation, zero offset): robot frame == camera frame
+    plain = D.locate_tags(dets, TAGSIZE, FX, FY, CX, CY)
+    assert np.array_equal(plain["robot"], plain["camera"]) and list(plain["index"]) == list(order)
+    # equal distances keep the detections' order (std::sort in the node is unstable; either order is legal there)
+    twin = np.concatenate([dets[:1], dets[:1]])
+    twin["id"][1] = 7
+    assert list(D.locate_tags(twin, TAGSIZE, FX, FY, CX, CY)["index"]) == [0, 1]
+    assert len(D.locate_tags(np.zeros(0, dtype=D.DETECTION_DT), TAGSIZE, FX, FY, CX, CY)) == 0
+    out = np.zeros(1, dtype=D.TAG_POSITION_DT)
+    lib = D.load_library()
+    assert lib.b200tag_locate_tags(None, 1, TAGSIZE, FX, FY, CX, CY, None, None, out.ctypes.data_as(C.c_void_p)) != 0
+    assert lib.b200tag_locate_tags(dets.ctypes.data_as(C.c_void_p), 1, -1.0, FX, FY, CX, CY, None, None, out.ctypes.data_as(C.c_void_p)) != 0
