@@ -55,6 +55,8 @@ enum {
 enum {
   B200TAG_TEST_DIRECT_HASH = 1,   /* k_boundary: every point bypasses the CTA-local blob-pair table */
   B200TAG_TEST_BITONIC_SORT = 2,  /* fit kernels: angle sort by the bitonic network instead of the bucket sort */
+  B200TAG_TEST_SMALL_CHUNKS = 4,  /* k_boundary: a tile's points go through the blob-pair grouping 96 at a time (the path of
+                                     tiles with more than two points per pixel) */
 };
 
 /* Mirrors the fields of apriltag_detector_t / apriltag_quad_thresh_params that the

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,18 @@ struct SideStreams {
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
 };
+
+// Measurement switches (bit mask in the environment variable B200TAG_EXP, read once): select another variant of a
+// kernel so that both can be timed in one run (tools/exp_kernels.py).  Unset = the production variants.
+//    1: k_scatter with one point in flight per thread (production: 4)      32: ... with 8
+//    2: k_boundary with the uncapped point list and a 512-entry CTA-local table (9 CTAs per SM; production: 16)
+//    4: k_boundary with the capped list and a 512-entry table (12 CTAs per SM)
+//    8: k_ccl_final without the 32-register cap (6 CTAs per SM; production: 8)
+//   16: k_ccl_local without the 32-register cap (12 CTAs per SM; production: 16)
+inline int exp_flags() {
+  static const int f = [] { const char *e = getenv("B200TAG_EXP"); return e ? atoi(e) : 0; }();
+  return f;
+}
 
 // Each returns the number of kernels it launched.
 int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt);

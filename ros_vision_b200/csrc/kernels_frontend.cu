@@ -389,6 +389,24 @@ __device__ __forceinline__ uint32_t sunite(uint32_t *par, uint32_t a, uint32_t b
   }
 }
 
+// Phase (C) of k_ccl_local keeps a root's counters in the upper bits of its own parent word (no second array: 9 KB of
+// shared memory per CTA instead of 17, 16 CTAs per SM instead of 12): finds mask the index, and only non-roots -- whose
+// words carry no counters -- are ever re-pointed.
+constexpr int kParBits = 11;                    // a tile has 2^11 pixels
+constexpr uint32_t kParMask = (1u << kParBits) - 1u;
+constexpr int kParTouchShift = kParBits + 12;   // the pixel count takes 12 bits (<= 2048)
+static_assert(kCclTW * kCclTH == (1 << kParBits), "tile size");
+__device__ __forceinline__ uint32_t sfind_counted(uint32_t *par, uint32_t a) {
+  uint32_t q = par[a] & kParMask;
+  while (q != a) {
+    const uint32_t qq = par[q] & kParMask;
+    if (qq != q) par[a] = qq;
+    a = q;
+    q = qq;
+  }
+  return a;
+}
+
 constexpr uint32_t kLabelMask = 0x0fffffffu;   // [27:0] label
 constexpr uint32_t kLabelBig = 1u << 28;       // component has >= kMinBlobPixels pixels (set by k_ccl_final)
 constexpr int kColourShift = 29;               // [30:29] 0 black, 1 white, 2 gray
@@ -406,15 +424,17 @@ constexpr uint32_t kCclRootCap = 2 * kCclTW + 2 * kCclTH;
 //   (B) union-find on RUNS: nodes are the first pixels of the horizontal runs; one thread per (row, colour) walks
 //       the runs of its mask with ffs/clz and unites each with the runs it touches in the row above (white:
 //       8-connected, i.e. the run dilated by one pixel; black: 4-connected);
-//   (C) a second walk compresses every run start to its root and adds the run length to the root's pixel count
-//       (upper half of the counter: how many of the runs touch the tile border);
+//   (C) a second walk compresses every run start to its root and adds the run length to the root's pixel count, kept
+//       above the index in the root's own parent word (and above that: how many of the runs touch the tile border);
 //   (D) write-out per pixel, 16-byte stores: label = global index of the root of the pixel's run | colour, sizes =
 //       count at tile roots, 0 elsewhere; tile roots that touch the border go to the tile's root list, from which
 //       k_ccl_handoff moves the counts of merged-away roots to the final roots.
-__global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kCclThreads, MIN_CTAS) k_ccl_local(FrameParams p) {
   __shared__ uint32_t s_mask[2][kCclTH];  // [0] black, [1] white
+  // parent links; from phase (C) on a ROOT's word also carries its counters above the index (kParBits):
+  // [10:0] parent | [22:11] pixels of the component (<= 2048) | [30:23] runs of it that touch the tile border (<= 192)
   __shared__ uint32_t s_par[kCclTH * kCclTW];
-  __shared__ uint32_t s_cnt[kCclTH * kCclTW];
   __shared__ uint16_t s_thr[kCclTH / 4][kCclTW / 4];  // threshold of the 4x4 tile; 0xffff = flat (all 127)
   __shared__ uint32_t s_roots[kCclRootCap];
   __shared__ uint32_t s_nroots;
@@ -506,10 +526,8 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
       s_mask[0][r] = (both >> 16) | (other & 0xffff0000u);
     }
   }
-  for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads) {
+  for (int i = tid; i < kCclTH * kCclTW / 4; i += kCclThreads)
     reinterpret_cast<uint4 *>(s_par)[i] = make_uint4(4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3);
-    reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
-  }
   __syncthreads();
 
   // (B) unions with the row above: thread = (row, colour).  Runs come off the mask by carry propagation: adding the
@@ -537,7 +555,7 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
   }
   __syncthreads();
 
-  // (C) compress run starts to their roots, per-root pixel counts (low half) and border-touching runs (high half)
+  // (C) compress run starts to their roots; per-root pixel counts and border-touching runs in the roots' parent words
   {
     uint32_t m = mine;
     const bool edge_row = row == 0 || row == kCclTH - 1;
@@ -548,10 +566,10 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
       const int s = 31 - __clz(static_cast<int>(low));
       const uint32_t len = static_cast<uint32_t>(__popc(run));
       const uint32_t node = row * kCclTW + s;
-      const uint32_t root = sfind(s_par, node);
-      if (root != node) s_par[node] = root;
-      const uint32_t touches = (edge_row || ((run & 0x80000001u) != 0)) ? 0x10000u : 0u;
-      atomicAdd(&s_cnt[root], len | touches);
+      const uint32_t root = sfind_counted(s_par, node);
+      if (root != node) s_par[node] = root;  // (a non-root: its word has no counters)
+      const uint32_t touches = (edge_row || ((run & 0x80000001u) != 0)) ? (1u << kParTouchShift) : 0u;
+      atomicAdd(&s_par[root], (len << kParBits) | touches);
     }
   }
   __syncthreads();
@@ -573,12 +591,12 @@ __global__ void __launch_bounds__(kCclThreads) k_ccl_local(FrameParams p) {
       if (isw || isb) {
         const uint32_t below = ~(isw ? wm : bm) & ((1u << x) - 1u);
         const int s = below ? 32 - __clz(static_cast<int>(below)) : 0;
-        const uint32_t root = s_par[r * kCclTW + s];
+        const uint32_t word = s_par[r * kCclTW + s];
+        const uint32_t root = word & kParMask;
         lab[k] = static_cast<uint32_t>((y0 + (root / kCclTW)) * p.w + x0 + (root % kCclTW)) | (isw ? 1u << kColourShift : 0u);
-        if (root == static_cast<uint32_t>(r * kCclTW + x)) {
-          const uint32_t c = s_cnt[root];
-          sz[k] = c & 0xffffu;
-          if (c >> 16) s_roots[atomicAdd(&s_nroots, 1u)] = static_cast<uint32_t>(g + k);
+        if (root == static_cast<uint32_t>(r * kCclTW + x)) {  // the pixel is its run's start and the root: `word` is the root's own
+          sz[k] = (word >> kParBits) & 0xfffu;
+          if (word >> kParTouchShift) s_roots[atomicAdd(&s_nroots, 1u)] = static_cast<uint32_t>(g + k);
         }
       }
     }
@@ -731,7 +749,8 @@ __global__ void __launch_bounds__(256) k_ccl_handoff(FrameParams p, uint32_t til
 constexpr int kFinThreads = 256;
 constexpr int kFinPasses = kCclTW * kCclTH / 4 / kFinThreads;
 constexpr uint32_t kFinUnused = 0xffffffffu, kFinNeeded = 0xfffffffeu;
-__global__ void __launch_bounds__(kFinThreads) k_ccl_final(FrameParams p) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kFinThreads, MIN_CTAS) k_ccl_final(FrameParams p) {
   __shared__ uint32_t s_out[kCclTW * kCclTH];
   __shared__ uint16_t s_list[kCclTW * kCclTH];
   __shared__ uint32_t s_nlist;
@@ -853,13 +872,17 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
 
 // staged cell = label word: [27:0] label | [28] big enough | [30:29] colour class (0 black, 1 white, 2 gray)
 // TH = tile height (16 or 8 rows); 16 threads per row.
-template <int TH>
+// CAP = points of the tile that phases (2)-(4) take in one go.  A tile can emit up to four points per pixel, thresholded
+// sensor noise emits 0.75, long one-pixel stripes 2: the list buffers hold CAP = 2 points per pixel and a tile with more
+// goes through (2)-(4) in several rounds, each with a fresh CTA-local table (ranks stay consistent: every round adds its
+// counts to the global table before its records are written).  Half the list memory = 12 instead of 9 CTAs per SM.
+template <int TH, int CAP, int LHBITS>
 __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   constexpr int kBpTH = TH, kBpThreads = TH * 16;
-  constexpr int kBpMaxPts = kBpTW * kBpTH * 4;
-  constexpr uint32_t kBpLH = TH * 64;    // local blob-pair table (power of two, <= 1024: 10-bit entry index in s_loc)
-  constexpr int kBpLHBits = TH == 16 ? 10 : 9;
-  static_assert((1u << kBpLHBits) == kBpLH, "table size");
+  constexpr int kBpMaxPts = CAP;
+  static_assert(CAP <= kBpTW * TH * 4 && CAP % 32 == 0, "list capacity");
+  constexpr uint32_t kBpLH = 1u << LHBITS;  // local blob-pair table (power of two, <= 1024: 10-bit entry index in s_loc)
+  constexpr int kBpLHBits = LHBITS;
   static_assert(kBpLH <= 1024 && (kBpLH & (kBpLH - 1)) == 0, "local table size");
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
   __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
@@ -985,88 +1008,101 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
     if (tid == 0) s_npts += s_half;
   }
   __syncthreads();
-  {  // list entries: one thread per 16-bit quarter of an emission word walks its set bits (3 on average)
-    static_assert(kBpThreads == kBpTH * 4 * 4 && kBpTW == 64, "one thread per (row, direction, quarter)");
-    const int ry = tid >> 4, d = (tid >> 2) & 3, q = tid & 3;
-    const unsigned long long e = s_emit[ry][d];
-    uint32_t piece = static_cast<uint32_t>(e >> (16 * q)) & 0xffffu;
-    const uint32_t bw = static_cast<uint32_t>(s_b2w[ry][d] >> (16 * q));
-    uint32_t pos = s_ebase[ry][d] + __popcll(e & ((1ull << (16 * q)) - 1ull));
-    const uint32_t head = (static_cast<uint32_t>(ry * kBpTW + 16 * q) << 3) | (d << 1);
-    while (piece) {
-      const int b = __ffs(static_cast<int>(piece)) - 1;
-      piece &= piece - 1;
-      s_pts[pos++] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
-    }
-  }
-  __syncthreads();
   const uint32_t npts = s_npts;
   if (npts == 0) return;
   if (tid == 0) s_gbase = atomicAdd(&ctr->num_points, npts);
-
-  // (2) local blob-pair table: entry + local rank per point
-  for (uint32_t i = tid; i < npts; i += kBpThreads) {
-    const uint32_t e = s_pts[i];
-    const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
-    const int ry = pix / kBpTW, txp = pix % kBpTW;
-    const uint32_t r0 = s_cell[ry][txp + 1] & 0x0fffffffu;
-    const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
-    const uint32_t ra = min(r0, r1), rb = max(r0, r1);
-    const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
-    // (the CTA-local table only has to spread the few dozen pairs of one tile: two multiplies, top bits)
-    uint32_t h = ((ra * 0x9E3779B1u) ^ (rb * 0x85EBCA77u)) >> (32 - kBpLHBits);
-    uint32_t loc = kBpDirect;  // crowded local table (adversarial input): handled in (4)
-    const uint32_t max_probe = (p.test_flags & B200TAG_TEST_DIRECT_HASH) ? 0u : kBpMaxProbe;
-    for (uint32_t probe = 0; probe < max_probe; probe++) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_lkey[h]);
-      if (cur == kEmptyKey) {
-        cur = atomicCAS(&s_lkey[h], kEmptyKey, key);
-        if (cur == kEmptyKey) s_used[atomicAdd(&s_nused, 1u)] = static_cast<uint16_t>(h);  // claimed: list it
+  const uint32_t cap = (p.test_flags & B200TAG_TEST_SMALL_CHUNKS) ? 96u : static_cast<uint32_t>(CAP);
+  for (uint32_t c0 = 0; c0 < npts; c0 += cap) {  // one round unless the tile has more than CAP points
+    if (c0 > 0) {
+      __syncthreads();  // the previous round's records are written: list and table are free again
+      for (int i = tid; i < static_cast<int>(kBpLH); i += kBpThreads) {
+        s_lkey[i] = kEmptyKey;
+        s_lcnt[i] = 0;
       }
-      if (cur == key || cur == kEmptyKey) {
-        loc = h | (atomicAdd(&s_lcnt[h], 1u) << 10);
-        break;
-      }
-      h = (h + 1) & (kBpLH - 1);
+      if (tid == 0) s_nused = 0;
     }
-    s_loc[i] = loc;
-  }
-  __syncthreads();
+    {  // list entries: one thread per 16-bit quarter of an emission word walks its set bits (3 on average)
+      static_assert(kBpThreads == kBpTH * 4 * 4 && kBpTW == 64, "one thread per (row, direction, quarter)");
+      const int ry = tid >> 4, d = (tid >> 2) & 3, q = tid & 3;
+      const unsigned long long e = s_emit[ry][d];
+      uint32_t piece = static_cast<uint32_t>(e >> (16 * q)) & 0xffffu;
+      const uint32_t bw = static_cast<uint32_t>(s_b2w[ry][d] >> (16 * q));
+      uint32_t pos = s_ebase[ry][d] + __popcll(e & ((1ull << (16 * q)) - 1ull)) - c0;  // (wraps below c0: not in this round)
+      const uint32_t head = (static_cast<uint32_t>(ry * kBpTW + 16 * q) << 3) | (d << 1);
+      while (piece) {
+        const int b = __ffs(static_cast<int>(piece)) - 1;
+        piece &= piece - 1;
+        if (pos < cap) s_pts[pos] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
+        pos++;
+      }
+    }
+    __syncthreads();
+    const uint32_t m = min(cap, npts - c0);
 
-  // (3) one global find-or-claim and one global count update per local entry
-  const uint32_t nused = s_nused;
-  for (uint32_t u = tid; u < nused; u += kBpThreads) {
-    const uint32_t e = s_used[u];
-    const unsigned long long key = s_lkey[e];
-    const uint32_t slot = hash_insert(p, h_key, key, static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(key), ctr, occupied);
-    s_lkey[e] = slot;
-    s_lcnt[e] = slot != kInvalidSlot ? atomicAdd(h_count + slot, s_lcnt[e]) : 0u;
-  }
-  __syncthreads();
-
-  // (4) point records
-  const uint32_t gbase = s_gbase;
-  for (uint32_t i = tid; i < npts; i += kBpThreads) {
-    const uint32_t e = s_pts[i];
-    const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
-    const int ry = pix / kBpTW, txp = pix % kBpTW;
-    const uint32_t loc = s_loc[i];
-    uint32_t slot, rank;
-    if (loc != kBpDirect) {
-      slot = static_cast<uint32_t>(s_lkey[loc & (kBpLH - 1)]);
-      rank = s_lcnt[loc & (kBpLH - 1)] + (loc >> 10);
-    } else {
+    // (2) local blob-pair table: entry + local rank per point
+    for (uint32_t i = tid; i < m; i += kBpThreads) {
+      const uint32_t e = s_pts[i];
+      const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
+      const int ry = pix / kBpTW, txp = pix % kBpTW;
       const uint32_t r0 = s_cell[ry][txp + 1] & 0x0fffffffu;
       const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
       const uint32_t ra = min(r0, r1), rb = max(r0, r1);
-      slot = hash_insert(p, h_key, (static_cast<unsigned long long>(ra) << 32) | rb, ra, rb, ctr, occupied);
-      rank = slot != kInvalidSlot ? atomicAdd(h_count + slot, 1u) : 0u;
+      const unsigned long long key = (static_cast<unsigned long long>(ra) << 32) | rb;
+      // (the CTA-local table only has to spread the few dozen pairs of one tile: two multiplies, top bits)
+      uint32_t h = ((ra * 0x9E3779B1u) ^ (rb * 0x85EBCA77u)) >> (32 - kBpLHBits);
+      uint32_t loc = kBpDirect;  // crowded local table (adversarial input): handled in (4)
+      const uint32_t max_probe = (p.test_flags & B200TAG_TEST_DIRECT_HASH) ? 0u : kBpMaxProbe;
+      for (uint32_t probe = 0; probe < max_probe; probe++) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_lkey[h]);
+        if (cur == kEmptyKey) {
+          cur = atomicCAS(&s_lkey[h], kEmptyKey, key);
+          if (cur == kEmptyKey) s_used[atomicAdd(&s_nused, 1u)] = static_cast<uint16_t>(h);  // claimed: list it
+        }
+        if (cur == key || cur == kEmptyKey) {
+          loc = h | (atomicAdd(&s_lcnt[h], 1u) << 10);
+          break;
+        }
+        h = (h + 1) & (kBpLH - 1);
+      }
+      s_loc[i] = loc;
     }
-    const uint32_t pos = gbase + i;
-    if (pos < p.point_cap) {
-      points[pos] = pack_point(slot, rank, static_cast<uint32_t>(x0 + txp), static_cast<uint32_t>(y0 + ry), d, e & 1u);
-    } else {
-      atomicOr(&ctr->status, B200TAG_ST_POINTS_OVERFLOW);
+    __syncthreads();
+
+    // (3) one global find-or-claim and one global count update per local entry
+    const uint32_t nused = s_nused;
+    for (uint32_t u = tid; u < nused; u += kBpThreads) {
+      const uint32_t e = s_used[u];
+      const unsigned long long key = s_lkey[e];
+      const uint32_t slot = hash_insert(p, h_key, key, static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(key), ctr, occupied);
+      s_lkey[e] = slot;
+      s_lcnt[e] = slot != kInvalidSlot ? atomicAdd(h_count + slot, s_lcnt[e]) : 0u;
+    }
+    __syncthreads();
+
+    // (4) point records
+    const uint32_t gbase = s_gbase + c0;
+    for (uint32_t i = tid; i < m; i += kBpThreads) {
+      const uint32_t e = s_pts[i];
+      const uint32_t d = (e >> 1) & 3u, pix = e >> 3;
+      const int ry = pix / kBpTW, txp = pix % kBpTW;
+      const uint32_t loc = s_loc[i];
+      uint32_t slot, rank;
+      if (loc != kBpDirect) {
+        slot = static_cast<uint32_t>(s_lkey[loc & (kBpLH - 1)]);
+        rank = s_lcnt[loc & (kBpLH - 1)] + (loc >> 10);
+      } else {
+        const uint32_t r0 = s_cell[ry][txp + 1] & 0x0fffffffu;
+        const uint32_t r1 = s_cell[ry + dir_dy(d)][txp + 1 + dir_dx(d)] & 0x0fffffffu;
+        const uint32_t ra = min(r0, r1), rb = max(r0, r1);
+        slot = hash_insert(p, h_key, (static_cast<unsigned long long>(ra) << 32) | rb, ra, rb, ctr, occupied);
+        rank = slot != kInvalidSlot ? atomicAdd(h_count + slot, 1u) : 0u;
+      }
+      const uint32_t pos = gbase + i;
+      if (pos < p.point_cap) {
+        points[pos] = pack_point(slot, rank, static_cast<uint32_t>(x0 + txp), static_cast<uint32_t>(y0 + ry), d, e & 1u);
+      } else {
+        atomicOr(&ctr->status, B200TAG_ST_POINTS_OVERFLOW);
+      }
     }
   }
 }
@@ -1140,7 +1176,8 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   }
   const dim3 cgrid(cdiv(p.w, kCclTW), cdiv(p.h, kCclTH), frames);
   if (kt) kt->begin("ccl_local", s);
-  k_ccl_local<<<cgrid, kCclThreads, 0, s>>>(p);
+  if (exp_flags() & 16) k_ccl_local<12><<<cgrid, kCclThreads, 0, s>>>(p);
+  else k_ccl_local<16><<<cgrid, kCclThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_merge", s);
   if (frames <= 4) k_ccl_merge<true><<<cgrid, kCclMergeThreads, 0, s>>>(p);   // single-frame latency: see gfind_halving
@@ -1150,7 +1187,8 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   k_ccl_handoff<<<dim3(cdiv(cgrid.x * cgrid.y, 8), frames), 256, 0, s>>>(p, cgrid.x * cgrid.y);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_final", s);
-  k_ccl_final<<<cgrid, kFinThreads, 0, s>>>(p);
+  if (exp_flags() & 8) k_ccl_final<1><<<cgrid, kFinThreads, 0, s>>>(p);
+  else k_ccl_final<8><<<cgrid, kFinThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   launches += 4;
 
@@ -1158,8 +1196,10 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   {  // tile height: 16 rows (256 threads) or 8 rows (128 threads, half the shared memory: more CTAs per SM)
     // (measured on config 2, 128 frames: 0.384 ms with 16 rows, 0.363 ms with 8; B200TAG_BP_TH=16 selects the former)
     static const int th = [] { const char *e = getenv("B200TAG_BP_TH"); return (e && atoi(e) == 16) ? 16 : 8; }();
-    if (th == 8) k_boundary<8><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
-    else k_boundary<16><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 16), frames), 256, 0, s>>>(p);
+    if (th == 8 && (exp_flags() & 2)) k_boundary<8, 2048, 9><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
+    else if (th == 8 && (exp_flags() & 4)) k_boundary<8, 1024, 9><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
+    else if (th == 8) k_boundary<8, 1024, 8><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
+    else k_boundary<16, 4096, 10><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 16), frames), 256, 0, s>>>(p);
   }
   if (kt) kt->end(s);
   launches++;

@@ -123,10 +123,11 @@ def test_edge_cases(D, oracle):
     det.close()
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 7])
 def test_fallback_paths_give_identical_results(D, oracle, flags):
-    """The rarely taken paths -- points counted straight in the global blob-pair hash (crowded CTA-local table)
-    and the bitonic angle sort (crowded theta buckets) -- forced on, every stage still equal to the oracle."""
+    """The rarely taken paths -- points counted straight in the global blob-pair hash (crowded CTA-local table),
+    the bitonic angle sort (crowded theta buckets) and a boundary tile's points grouped in several rounds (more points
+    than its list holds) -- forced on, every stage still equal to the oracle."""
     from ros_vision_b200 import synth
     for w, h, fmt, dec, seed, ntags, side in [(640, 480, "yuyv", 2, 31, 3, (50, 140)), (1280, 800, "gray", 1, 32, 2, (300, 600))]:
         sc = synth.make_scene(w, h, seed, ntags, side_range=side, noise_sigma=4.0)
