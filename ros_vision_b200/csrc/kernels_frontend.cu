@@ -913,49 +913,58 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
     s_lcnt[i] = 0;
   }
   if (tid == 0) s_nused = 0;
-  {  // halo tile: the label words already are the cells (k_ccl_final); outside the image = gray
-    constexpr int kCells = (kBpTH + 1) * (kBpTW + 2);
-    constexpr int kPer = (kCells + kBpThreads - 1) / kBpThreads;
-    uint32_t cell[kPer];
+  // halo tile: the label words already are the cells (k_ccl_final); outside the image = gray.  A warp stages whole rows
+  // (two coalesced 128-byte loads + the two halo cells), so the row masks of (1) -- three 64-bit masks per staged row:
+  // white, black, component big enough, plus the same three bits for the two halo columns -- come from ballots over the
+  // words it still holds in registers.
+  {
+    constexpr int kWarps = kBpThreads / 32;
+    constexpr int kRowsPer = (kBpTH + 1 + kWarps - 1) / kWarps;
+    const int wrp = tid >> 5;
+    uint32_t c0[kRowsPer], c1[kRowsPer], ch[kRowsPer];
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-      const int i = tid + k * kBpThreads;
-      const int r = i / (kBpTW + 2), c = i % (kBpTW + 2);
-      const int gx = x0 - 1 + c, gy = y0 + r;
-      cell[k] = kColourGray;
-      if (i < kCells && gx >= 0 && gx < p.w && gy < p.h) cell[k] = __ldg(labels + static_cast<size_t>(gy) * p.w + gx);
+    for (int k = 0; k < kRowsPer; k++) {
+      const int r = wrp + k * kWarps, gy = y0 + r;
+      c0[k] = c1[k] = ch[k] = kColourGray;
+      if (r <= kBpTH && gy < p.h) {
+        const uint32_t *row = labels + static_cast<size_t>(gy) * p.w;
+        const int gx0 = x0 + lane, gx1 = x0 + 32 + lane;
+        const int gxh = lane == 0 ? x0 - 1 : x0 + kBpTW;  // lanes 0 / 1: left / right halo column
+        if (gx0 < p.w) c0[k] = __ldg(row + gx0);
+        if (gx1 < p.w) c1[k] = __ldg(row + gx1);
+        if (lane < 2 && gxh >= 0 && gxh < p.w) ch[k] = __ldg(row + gxh);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-      const int i = tid + k * kBpThreads;
-      if (i < kCells) (&s_cell[0][0])[i] = cell[k];
+    for (int k = 0; k < kRowsPer; k++) {
+      const int r = wrp + k * kWarps;
+      if (r > kBpTH) continue;  // (warp-uniform)
+      s_cell[r][1 + lane] = c0[k];
+      s_cell[r][33 + lane] = c1[k];
+      if (lane < 2) {  // halo columns: bit 0 white, 1 black, 2 big
+        s_cell[r][lane ? kBpTW + 1 : 0] = ch[k];
+        const uint32_t col = ch[k] >> 29;
+        s_halo[r][lane] = static_cast<uint8_t>((col == 1 ? 1u : 0u) | (col == 0 ? 2u : 0u) | (((ch[k] >> 28) & 1u) << 2));
+      }
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const uint32_t c = half ? c1[k] : c0[k];
+        const uint32_t col = c >> 29;
+        const uint32_t wm = __ballot_sync(0xffffffffu, col == 1), bm = __ballot_sync(0xffffffffu, col == 0);
+        const uint32_t gm = __ballot_sync(0xffffffffu, (c >> 28) & 1u);
+        if (lane == 0) {
+          s_rowm[r][0][half] = wm;
+          s_rowm[r][1][half] = bm;
+          s_rowm[r][2][half] = gm;
+        }
+      }
     }
   }
   __syncthreads();
 
-  // (1) which directions emit a point -- on row bit masks.  Three 64-bit masks per staged row (white, black,
-  //     component big enough) plus the two halo columns; one thread per (row, direction) combines them into the
+  // (1) which directions emit a point -- on row bit masks: one thread per (row, direction) combines the masks into the
   //     emission mask of apriltag_gpu.cu:276-357 with shifts and ANDs; popcounts give every point its place in the
   //     list without shuffles or atomics.
-  for (int t = tid >> 5; t < (kBpTH + 1) * 2; t += kBpThreads / 32) {
-    const int r = t >> 1, half = t & 1;
-    const uint32_t c = s_cell[r][1 + 32 * half + lane];
-    const uint32_t col = c >> 29;
-    const uint32_t wm = __ballot_sync(0xffffffffu, col == 1), bm = __ballot_sync(0xffffffffu, col == 0);
-    const uint32_t gm = __ballot_sync(0xffffffffu, (c >> 28) & 1u);
-    if (lane == 0) {
-      s_rowm[r][0][half] = wm;
-      s_rowm[r][1][half] = bm;
-      s_rowm[r][2][half] = gm;
-    }
-  }
-  if (tid < (kBpTH + 1) * 2) {  // halo columns: bit 0 white, 1 black, 2 big
-    const int r = tid >> 1, side = tid & 1;
-    const uint32_t c = s_cell[r][side ? kBpTW + 1 : 0];
-    const uint32_t col = c >> 29;
-    s_halo[r][side] = static_cast<uint8_t>((col == 1 ? 1u : 0u) | (col == 0 ? 2u : 0u) | (((c >> 28) & 1u) << 2));
-  }
-  __syncthreads();
   if (tid < kBpTH * 4) {
     const int ry = tid >> 2, d = tid & 3;
     const int y = y0 + ry;
