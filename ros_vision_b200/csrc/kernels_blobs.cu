@@ -52,7 +52,10 @@ __device__ __forceinline__ bool select_blob(const FrameParams &p, uint32_t count
 // spent 97 % of its time waiting for them).  Only the count limits of SelectBlobs
 // (apriltag_gpu.cu:536-541) are applied here; the extent and polarity tests need the blob's
 // points and run at the top of the fit kernels.
-__global__ void __launch_bounds__(256) k_select(FrameParams p) {
+// (a latency kernel -- two barriers and one round of atomics per trip: eight CTAs per SM and a grid that fills them
+//  once, so that every CTA makes as few trips as possible)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_select(FrameParams p) {
   __shared__ uint32_t s_warp[8][6];  // per-warp totals: occupied, candidates, small, points, medium, huge
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_pbase, s_mbase, s_lbase, s_hbase;
@@ -1475,7 +1478,8 @@ void launch_blobs_init(cudaStream_t s) {
 
 int launch_blobs(const FrameParams &p, int frames, cudaStream_t s, KernelTimer *kt, const SideStreams *side) {
   if (kt) kt->begin("select", s);
-  k_select<<<dim3(max(1u, min(16u, cdivu(148u * 4u, frames))), frames), 256, 0, s>>>(p);
+  if (exp_flags() & 64) k_select<1><<<dim3(max(1u, min(16u, cdivu(148u * 4u, frames))), frames), 256, 0, s>>>(p);
+  else k_select<8><<<dim3(max(1u, min(16u, 148u * 8u / static_cast<unsigned>(frames))), frames), 256, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("scatter", s);
   if (exp_flags() & 1) k_scatter<1><<<dim3(max(8u, min(592u, cdivu(4736u, frames))), frames), 256, 0, s>>>(p);
