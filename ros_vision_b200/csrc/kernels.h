@@ -57,7 +57,6 @@ struct SideStreams {
 //    2: k_boundary with the uncapped point list and a 512-entry CTA-local table (9 CTAs per SM; production: 16)
 //    4: k_boundary with the capped list and a 512-entry table (12 CTAs per SM)
 //    8: k_ccl_final without the 32-register cap (6 CTAs per SM; production: 8)
-//   16: k_ccl_local without the 32-register cap (12 CTAs per SM; production: 16)
 //   64: k_select at 5 instead of 8 CTAs per SM, grid sized for 4 per SM
 inline int exp_flags() {
   static const int f = [] { const char *e = getenv("B200TAG_EXP"); return e ? atoi(e) : 0; }();

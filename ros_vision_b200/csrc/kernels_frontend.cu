@@ -429,6 +429,9 @@ constexpr uint32_t kCclRootCap = 2 * kCclTW + 2 * kCclTH;
 //   (D) write-out per pixel, 16-byte stores: label = global index of the root of the pixel's run | colour, sizes =
 //       count at tile roots, 0 elsewhere; tile roots that touch the border go to the tile's root list, from which
 //       k_ccl_handoff moves the counts of merged-away roots to the final roots.
+// (tried: a run's first link to the row above as ONE atomicMin on the run's own word -- it still is its own root unless a
+//  run below has linked it already, and any smaller index of the other component keeps the forest valid -- instead of two
+//  finds and the atomicMin: correct, but the links to non-roots make the later finds longer, 0.269 -> 0.298 ms)
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kCclThreads, MIN_CTAS) k_ccl_local(FrameParams p) {
   __shared__ uint32_t s_mask[2][kCclTH];  // [0] black, [1] white
@@ -559,6 +562,9 @@ __global__ void __launch_bounds__(kCclThreads, MIN_CTAS) k_ccl_local(FrameParams
   {
     uint32_t m = mine;
     const bool edge_row = row == 0 || row == kCclTH - 1;
+    // consecutive runs of a row often end under the same root (the percolating white component of thresholded noise):
+    // their counts are added up in a register and reach the root's word -- a hot address -- in one atomic
+    uint32_t acc = 0, acc_root = 0;
     while (m) {
       const uint32_t low = m & (0u - m), rest = m + low;
       const uint32_t run = m & ~rest;
@@ -569,8 +575,14 @@ __global__ void __launch_bounds__(kCclThreads, MIN_CTAS) k_ccl_local(FrameParams
       const uint32_t root = sfind_counted(s_par, node);
       if (root != node) s_par[node] = root;  // (a non-root: its word has no counters)
       const uint32_t touches = (edge_row || ((run & 0x80000001u) != 0)) ? (1u << kParTouchShift) : 0u;
-      atomicAdd(&s_par[root], (len << kParBits) | touches);
+      if (root != acc_root && acc) {
+        atomicAdd(&s_par[acc_root], acc);
+        acc = 0;
+      }
+      acc_root = root;
+      acc += (len << kParBits) | touches;
     }
+    if (acc) atomicAdd(&s_par[acc_root], acc);
   }
   __syncthreads();
 
@@ -878,7 +890,9 @@ __device__ uint32_t hash_insert(const FrameParams &p, unsigned long long *keys, 
 // sensor noise emits 0.75, long one-pixel stripes 2: the list buffers hold CAP = 2 points per pixel and a tile with more
 // goes through (2)-(4) in several rounds, each with a fresh CTA-local table (ranks stay consistent: every round adds its
 // counts to the global table before its records are written).  Half the list memory = 12 instead of 9 CTAs per SM.
-template <int TH, int CAP, int LHBITS>
+// SMALL_ROUNDS: the test variant that takes 96 points per round (B200TAG_TEST_SMALL_CHUNKS), its own instantiation so
+// that the production kernel compares against a compile-time capacity.
+template <int TH, int CAP, int LHBITS, bool SMALL_ROUNDS>
 __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   constexpr int kBpTH = TH, kBpThreads = TH * 16;
   constexpr int kBpMaxPts = CAP;
@@ -889,8 +903,8 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   __shared__ uint32_t s_cell[kBpTH + 1][kBpTW + 2];
   __shared__ uint16_t s_pts[kBpMaxPts];             // [12:3] pixel of the tile | [2:1] dir | [0] black_to_white
   __shared__ uint32_t s_loc[kBpMaxPts];             // [9:0] local entry | [31:10] rank among the tile's points of that entry
-  __shared__ unsigned long long s_lkey[kBpLH];      // blob-pair key; after (3): the global slot
-  __shared__ uint32_t s_lcnt[kBpLH];                // points of the entry in this tile; after (3): base rank
+  __shared__ __align__(16) unsigned long long s_lkey[kBpLH];  // blob-pair key; after (3): the global slot
+  __shared__ __align__(16) uint32_t s_lcnt[kBpLH];            // points of the entry in this tile; after (3): base rank
   __shared__ uint16_t s_used[kBpLH];                // entries in use, in claim order: (3) runs over these, densely
   __shared__ uint32_t s_nused;
   __shared__ uint32_t s_npts, s_gbase, s_half;
@@ -910,11 +924,14 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   uint32_t *occupied = p.occupied + hoff;
   const int tid = threadIdx.x, lane = tid & 31;
 
-  for (int i = tid; i < static_cast<int>(kBpLH); i += kBpThreads) {
-    s_lkey[i] = kEmptyKey;
-    s_lcnt[i] = 0;
-  }
-  if (tid == 0) s_nused = 0;
+  auto clear_table = [&]() {  // 16-byte stores
+    static_assert(kEmptyKey == 0xFFFFFFFFFFFFFFFFull, "all ones");
+    for (int i = tid; i < static_cast<int>(kBpLH / 2); i += kBpThreads)
+      reinterpret_cast<uint4 *>(s_lkey)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int i = tid; i < static_cast<int>(kBpLH / 4); i += kBpThreads) reinterpret_cast<uint4 *>(s_lcnt)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) s_nused = 0;
+  };
+  clear_table();
   // halo tile: the label words already are the cells (k_ccl_final); outside the image = gray.  A warp stages whole rows
   // (two coalesced 128-byte loads + the two halo cells), so the row masks of (1) -- three 64-bit masks per staged row:
   // white, black, component big enough, plus the same three bits for the two halo columns -- come from ballots over the
@@ -1022,15 +1039,12 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
   const uint32_t npts = s_npts;
   if (npts == 0) return;
   if (tid == 0) s_gbase = atomicAdd(&ctr->num_points, npts);
-  const uint32_t cap = (p.test_flags & B200TAG_TEST_SMALL_CHUNKS) ? 96u : static_cast<uint32_t>(CAP);
+  constexpr uint32_t cap = SMALL_ROUNDS ? 96u : static_cast<uint32_t>(CAP);
+  const bool one_round = npts <= cap;  // (CTA-uniform)
   for (uint32_t c0 = 0; c0 < npts; c0 += cap) {  // one round unless the tile has more than CAP points
     if (c0 > 0) {
       __syncthreads();  // the previous round's records are written: list and table are free again
-      for (int i = tid; i < static_cast<int>(kBpLH); i += kBpThreads) {
-        s_lkey[i] = kEmptyKey;
-        s_lcnt[i] = 0;
-      }
-      if (tid == 0) s_nused = 0;
+      clear_table();
     }
     {  // list entries: one thread per 16-bit quarter of an emission word walks its set bits (3 on average)
       static_assert(kBpThreads == kBpTH * 4 * 4 && kBpTW == 64, "one thread per (row, direction, quarter)");
@@ -1040,11 +1054,19 @@ __global__ void __launch_bounds__(TH * 16) k_boundary(FrameParams p) {
       const uint32_t bw = static_cast<uint32_t>(s_b2w[ry][d] >> (16 * q));
       uint32_t pos = s_ebase[ry][d] + __popcll(e & ((1ull << (16 * q)) - 1ull)) - c0;  // (wraps below c0: not in this round)
       const uint32_t head = (static_cast<uint32_t>(ry * kBpTW + 16 * q) << 3) | (d << 1);
-      while (piece) {
-        const int b = __ffs(static_cast<int>(piece)) - 1;
-        piece &= piece - 1;
-        if (pos < cap) s_pts[pos] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
-        pos++;
+      if (one_round) {
+        while (piece) {
+          const int b = __ffs(static_cast<int>(piece)) - 1;
+          piece &= piece - 1;
+          s_pts[pos++] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
+        }
+      } else {
+        while (piece) {
+          const int b = __ffs(static_cast<int>(piece)) - 1;
+          piece &= piece - 1;
+          if (pos < cap) s_pts[pos] = static_cast<uint16_t>(head + (b << 3) + ((bw >> b) & 1u));
+          pos++;
+        }
       }
     }
     __syncthreads();
@@ -1187,8 +1209,7 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   }
   const dim3 cgrid(cdiv(p.w, kCclTW), cdiv(p.h, kCclTH), frames);
   if (kt) kt->begin("ccl_local", s);
-  if (exp_flags() & 16) k_ccl_local<12><<<cgrid, kCclThreads, 0, s>>>(p);
-  else k_ccl_local<16><<<cgrid, kCclThreads, 0, s>>>(p);
+  k_ccl_local<16><<<cgrid, kCclThreads, 0, s>>>(p);
   if (kt) kt->end(s);
   if (kt) kt->begin("ccl_merge", s);
   if (frames <= 4) k_ccl_merge<true><<<cgrid, kCclMergeThreads, 0, s>>>(p);   // single-frame latency: see gfind_halving
@@ -1207,10 +1228,12 @@ int launch_frontend(const FrameParams &p, int frames, cudaStream_t s, KernelTime
   {  // tile height: 16 rows (256 threads) or 8 rows (128 threads, half the shared memory: more CTAs per SM)
     // (measured on config 2, 128 frames: 0.384 ms with 16 rows, 0.363 ms with 8; B200TAG_BP_TH=16 selects the former)
     static const int th = [] { const char *e = getenv("B200TAG_BP_TH"); return (e && atoi(e) == 16) ? 16 : 8; }();
-    if (th == 8 && (exp_flags() & 2)) k_boundary<8, 2048, 9><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
-    else if (th == 8 && (exp_flags() & 4)) k_boundary<8, 1024, 9><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
-    else if (th == 8) k_boundary<8, 1024, 8><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames), 128, 0, s>>>(p);
-    else k_boundary<16, 4096, 10><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 16), frames), 256, 0, s>>>(p);
+    const dim3 g8(cdiv(p.w, kBpTW), cdiv(p.h, 8), frames);
+    if (th == 8 && (p.test_flags & B200TAG_TEST_SMALL_CHUNKS)) k_boundary<8, 1024, 8, true><<<g8, 128, 0, s>>>(p);
+    else if (th == 8 && (exp_flags() & 2)) k_boundary<8, 2048, 9, false><<<g8, 128, 0, s>>>(p);
+    else if (th == 8 && (exp_flags() & 4)) k_boundary<8, 1024, 9, false><<<g8, 128, 0, s>>>(p);
+    else if (th == 8) k_boundary<8, 1024, 8, false><<<g8, 128, 0, s>>>(p);
+    else k_boundary<16, 4096, 10, false><<<dim3(cdiv(p.w, kBpTW), cdiv(p.h, 16), frames), 256, 0, s>>>(p);
   }
   if (kt) kt->end(s);
   launches++;
