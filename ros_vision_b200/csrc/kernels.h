@@ -58,6 +58,7 @@ struct SideStreams {
 //    4: k_boundary with the capped list and a 512-entry table (12 CTAs per SM)
 //    8: k_ccl_final without the 32-register cap (6 CTAs per SM; production: 8)
 //   64: k_select at 5 instead of 8 CTAs per SM, grid sized for 4 per SM
+//  512: the shared-memory tile blur for filter lengths 3, 5, 7 (production: k_blur_strip)
 inline int exp_flags() {
   static const int f = [] { const char *e = getenv("B200TAG_EXP"); return e ? atoi(e) : 0; }();
   return f;
