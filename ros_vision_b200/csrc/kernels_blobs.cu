@@ -1444,7 +1444,10 @@ static_assert(sizeof(MediumShared) <= 37888, "shared memory of the medium tier")
 constexpr int kHugeThreads = 512;
 constexpr uint32_t kHugeCap = 8192;
 using HugeShared = CtaShared<kHugeThreads, kHugeCap, 0>;
-#define K_FIT_HUGE(KEEP) k_fit_cta<kHugeThreads, kHugeCap, 0, kSortCap + 1, 0xffffffffu, 1, KEEP>
+// (held to 64 registers -- this instance has the global-memory path only and fits without spills -- so that a resident
+//  huge-tier CTA leaves half the register file to the other tiers' CTAs; a 256-thread variant was slower: 0.46 -> 0.67 ms
+//  per 16 config-5 frames)
+#define K_FIT_HUGE(KEEP) k_fit_cta<kHugeThreads, kHugeCap, 0, kSortCap + 1, 0xffffffffu, (KEEP) ? 1 : 2, KEEP>
 // large tier for one or a few frames at a time (the node's case: one Detect per camera frame): the same blobs on 512
 // threads.  A frame has a few dozen of them, far fewer than SMs, so the time of the blob stage is the time of ONE blob;
 // twice the threads nearly halve it (single frame: 111 -> 6x us), while in batches, where CTAs outnumber SMs many times,

@@ -820,6 +820,8 @@ __global__ void __launch_bounds__(kCclMergeThreads) k_ccl_merge(FrameParams p) {
   if (live) i = static_cast<uint32_t>(y * p.w + x);
   const uint32_t mine = __ldcg(labels + i);
   const uint32_t colour = mine >> kColourShift;  // 0 black, 1 white, 2 gray
+  // (fetching the diagonal neighbours from the geometry alone, side by side with this pixel's word instead of after its
+  //  colour is known, was measured: one round trip less per chain, but a third more loads -- 0.079 -> 0.086 ms)
   if (live && colour != 2) {
     if (kind == 0) {
       if (y > 0) {  // every "up" neighbour is in another tile
@@ -871,9 +873,10 @@ __global__ void __launch_bounds__(256) k_ccl_handoff(FrameParams p, uint32_t til
   for (uint32_t e = threadIdx.x % TPT; e < nr; e += TPT) {
     const uint32_t self = list[e];
     const uint32_t me = __ldcg(labels + self);
+    const uint32_t mine = sizes[self];  // (fetched next to the label, not after the chain)
     if ((me & kLabelMask) == self) continue;  // still a root
     const uint32_t root = gfind(labels, me) & kLabelMask;
-    atomicAdd(sizes + root, sizes[self]);
+    atomicAdd(sizes + root, mine);
     sizes[self] = 0;
   }
 }
