@@ -123,6 +123,28 @@ def test_edge_cases(D, oracle):
     det.close()
 
 
+def test_boundary_tile_with_more_points_than_its_list(D, oracle):
+    """k_boundary's point list holds two points per pixel of its 64x8 tile.  A comb -- one-pixel teeth whose tips sit on a
+    tile's last row -- emits four points at every tip and two everywhere else: 1056 points in a tile, so the production
+    kernel (not the B200TAG_TEST_SMALL_CHUNKS variant) takes that tile in two rounds."""
+    w, h = 256, 64
+    img = np.zeros((h, w), np.uint8)
+    img[8:12, :] = 255          # the bar that joins the teeth into one component
+    img[12:24, 0::2] = 255      # teeth in the even columns, tips on row 23 = last row of the tiles covering rows 16..23
+    orc = oracle.detect(oracle.make_config(w, h, "gray", 1, 0.0), img)
+    per_tile = np.bincount((orc.points["by"] // 8) * (w // 64) + orc.points["bx"] // 64)
+    assert per_tile.max() > 1024, per_tile.max()
+    for batch in (1, 3):
+        det = D.GpuDetector(w, h, "gray", quad_decimate=1, keep_stages=True, max_batch=batch)
+        if batch > 1:
+            det.DetectBatch([img] * batch)
+        else:
+            det.Detect(img)
+        for f in range(batch):
+            compare_all(det, orc, f, "gray")
+        det.close()
+
+
 @pytest.mark.parametrize("flags", [1, 2, 3, 4, 7])
 def test_fallback_paths_give_identical_results(D, oracle, flags):
     """The rarely taken paths -- points counted straight in the global blob-pair hash (crowded CTA-local table),
