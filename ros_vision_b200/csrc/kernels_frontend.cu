@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(kFinThreads, MIN_CTAS) k_ccl_final(FrameParams
 // ---------------------------------------------------------------------------------------------
 // K6: boundary points, grouped by blob pair.
 //
-// One CTA = one 64x16 pixel tile (halo staged in shared memory as label | big | colour).
+// One CTA = one 64x8 (or 64x16) pixel tile (halo staged in shared memory as label | big | colour).
 //   (1) per pixel: which of the 4 directions emit a point (apriltag_gpu.cu:276-357); the points
 //       are compacted into a shared-memory list, so everything after this runs with full warps;
 //   (2) per point: blob-pair key -> entry of a CTA-local hash table, local rank by one
