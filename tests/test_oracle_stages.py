@@ -84,9 +84,24 @@ def test_components_match_scipy(oracle, seed):
     assert np.array_equal(sizes, r.sizes)
 
 
-def test_boundary_points_bruteforce(oracle):
-    sc = synth.make_scene(128, 96, 7, 1, side_range=(50, 60), noise_sigma=3.0)
-    r = oracle.detect(oracle.make_config(128, 96, "gray", 2, 0.0, max_stage=oracle.STAGE_BLOBS), sc.gray)
+def _comb(w=256, h=64):
+    """One-pixel teeth hanging from a bar, tips on row 23: four boundary points at every tip, two per pixel along the teeth
+    (the densest pattern the boundary rule produces over a whole 64x8 tile: 1056 points in 512 pixels)."""
+    img = np.zeros((h, w), np.uint8)
+    img[8:12, :] = 255
+    img[12:24, 0::2] = 255
+    return img
+
+
+@pytest.mark.parametrize("case", ["scene", "comb"])
+def test_boundary_points_bruteforce(oracle, case):
+    if case == "scene":
+        sc = synth.make_scene(128, 96, 7, 1, side_range=(50, 60), noise_sigma=3.0)
+        r = oracle.detect(oracle.make_config(128, 96, "gray", 2, 0.0, max_stage=oracle.STAGE_BLOBS), sc.gray)
+    else:
+        r = oracle.detect(oracle.make_config(256, 64, "gray", 1, 0.0, max_stage=oracle.STAGE_BLOBS), _comb())
+        per_tile = np.bincount((r.points["by"] // 8) * 4 + r.points["bx"] // 64)
+        assert per_tile.max() == 1056   # 7 rows x 64 px x 2 + 32 tips x 4 + 32 gaps x 1
     t, L, S = r.thresh, r.labels.reshape(r.h, r.w), r.sizes
     pts = set()
     for y in range(1, r.h - 1):
